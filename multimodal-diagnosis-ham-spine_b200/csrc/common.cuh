@@ -1,0 +1,98 @@
+// Shared device/host helpers for the sm_100a kernels of the multimodal hot path.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#define MDHS_OK 0
+#define MDHS_ERR_ARG 1001      // bad argument (shape / alignment / null pointer)
+#define MDHS_ERR_DRIVER 1002   // driver entry point (tensor map encode) unavailable
+
+// Returns the cudaError_t of the last launch as the C-ABI status.
+#define MDHS_RETURN_LAST()                          \
+  do {                                              \
+    cudaError_t e__ = cudaGetLastError();           \
+    return e__ == cudaSuccess ? MDHS_OK : (int)e__; \
+  } while (0)
+
+typedef __nv_bfloat16 bf16;
+typedef __nv_bfloat162 bf162;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide sum for blockDim.x <= 1024; `red` is >= 32 floats of shared memory.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float r = (lane < nw) ? red[lane] : 0.f;
+  r = warp_sum(r);
+  return r;
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float r = (lane < nw) ? red[lane] : -INFINITY;
+  r = warp_max(r);
+  return r;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
+  float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+// 8 x bf16 <-> 8 x float through one 128-bit access.
+struct alignas(16) bf16x8 {
+  bf162 v[4];
+};
+__device__ __forceinline__ void load8(const bf16* p, float* f) {
+  bf16x8 t = *reinterpret_cast<const bf16x8*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    float2 x = __bfloat1622float2(t.v[i]);
+    f[2 * i] = x.x;
+    f[2 * i + 1] = x.y;
+  }
+}
+__device__ __forceinline__ void store8(bf16* p, const float* f) {
+  bf16x8 t;
+#pragma unroll
+  for (int i = 0; i < 4; i++) t.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  *reinterpret_cast<bf16x8*>(p) = t;
+}
+
+// Counter-based RNG for fused dropout: one 32-bit hash per (seed, element index).
+__device__ __forceinline__ uint32_t hash_u32(uint64_t seed, uint64_t idx) {
+  uint64_t z = seed + idx * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (uint32_t)(z >> 32);
+}
+// keep-mask scale: returns 0 or 1/(1-p). p == 0 -> always 1.
+__device__ __forceinline__ float dropout_scale(uint64_t seed, uint64_t idx, float p, float inv_keep) {
+  if (p <= 0.f) return 1.f;
+  float u = (float)(hash_u32(seed, idx) >> 8) * (1.0f / 16777216.0f);
+  return u < p ? 0.f : inv_keep;
+}
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

@@ -1,0 +1,522 @@
+// bf16 GEMM for sm_100a: tcgen05.mma with TMEM accumulators, TMA-fed shared-memory pipeline,
+// persistent warp-specialised CTAs (one per SM).  See include/mdhs_b200.h for the contract.
+//
+//   warp 0      : TMA producer (one elected lane) -> smem ring of STAGES {A tile, B tile}
+//   warp 1      : MMA issuer (one lane) -> tcgen05.mma into one of two TMEM accumulator stages
+//   warp 2      : TMEM allocator / deallocator
+//   warps 4..7  : epilogue: tcgen05.ld -> registers -> per-warp smem transpose -> fused
+//                 bias / activation / act' / residual / BN column statistics -> coalesced stores
+//
+// Tiles are 128 x BN x 64 (BN in {64,128,256}); operands are staged with the 128-byte TMA/UMMA
+// swizzle; both operands may be K-major or MN-major so forward, dgrad and wgrad need no transposes.
+#include <cuda.h>
+#include "common.cuh"
+#include "../../include/mdhs_b200.h"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_WARP0 = 4;
+constexpr int STAGE_ROW = 66;                                // padded fp32 row of the transpose buffer
+constexpr int STAGING_BYTES = 4 * 32 * STAGE_ROW * 4;        // one 32x64 fp32 tile per epilogue warp
+constexpr int A_TILE_BYTES = BM * BK * 2;                    // 16 KiB
+constexpr int SMEM_LIMIT = 232448;                           // 227 KiB opt-in maximum
+
+template <int BN> struct Cfg {
+  static constexpr int B_TILE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES;
+  static_assert(SMEM_BYTES <= SMEM_LIMIT, "shared memory budget exceeded");
+};
+
+struct Params {
+  int M, N, K;
+  int num_m, num_n, splits, kb_total, kb_per_split;
+  void* D; int64_t ldd; int d_f32; int accumulate;
+  const float* bias;
+  bf16* aux_out; int64_t ld_aux_out;
+  const bf16* aux_in; int64_t ld_aux_in;
+  int act, dact;
+  const void* residual; int64_t ldr; int r_f32;
+  double* colsum; double* colsumsq;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor, 128-byte swizzle, sm_100 version bit set.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+
+// ------------------------------------------------------------------ kernel
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t tiles_base = smem_base;
+  float* staging = reinterpret_cast<float*>(smem_gen + C::STAGES * C::STAGE_BYTES);
+  const uint32_t bars = smem_base + C::STAGES * C::STAGE_BYTES + STAGING_BYTES;
+  // barrier layout: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem base address
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * C::STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * C::STAGES + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * C::STAGES + 4);
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + C::STAGES * C::STAGE_BYTES + STAGING_BYTES + 8 * (2 * C::STAGES + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; s++) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  const int total_tiles = p.num_m * p.num_n * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------ TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int split = t % p.splits;
+      const int mn = t / p.splits;
+      const int n_blk = mn % p.num_n, m_blk = mn / p.num_n;
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      for (int kb = kb0; kb < kb1; kb++) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t fb = full_bar(stage);
+        mbar_expect_tx(fb, C::STAGE_BYTES);
+        const uint32_t sA = tiles_base + stage * C::STAGE_BYTES;
+        const uint32_t sB = sA + A_TILE_BYTES;
+        if (!A_MN) {
+          tma_load_2d(sA, &tmA, fb, kb * BK, m_blk * BM);
+        } else {
+          tma_load_2d(sA, &tmA, fb, m_blk * BM, kb * BK);
+          tma_load_2d(sA + 8192, &tmA, fb, m_blk * BM + 64, kb * BK);
+        }
+        if (!B_MN) {
+          tma_load_2d(sB, &tmB, fb, kb * BK, n_blk * BN);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 64; j++) tma_load_2d(sB + j * 8192, &tmB, fb, n_blk * BN + j * 64, kb * BK);
+        }
+        if (++stage == C::STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int split = t % p.splits;
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = kb0; kb < kb1; kb++) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t sA = tiles_base + stage * C::STAGE_BYTES;
+        const uint32_t sB = sA + A_TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; k++) {
+          // K-major: 16 elements = 32 bytes inside the swizzle row; 8-row groups 1024 B apart.
+          // MN-major: 16 k-rows = 2048 bytes; 64-element MN groups 8192 B apart (LBO).
+          const uint64_t ad = A_MN ? umma_desc(sA + k * 2048, 8192, 1024) : umma_desc(sA + k * 32, 0, 1024);
+          const uint64_t bd = B_MN ? umma_desc(sB + k * 2048, 8192, 1024) : umma_desc(sB + k * 32, 0, 1024);
+          tc_mma(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+        }
+        tc_commit(empty_bar(stage));
+        if (kb == kb1 - 1) tc_commit(tfull_bar(acc));
+        if (++stage == C::STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ------------------------------------------------------------ epilogue
+    const int wq = warp - EPI_WARP0;  // TMEM lane quarter owned by this warp
+    float* buf = staging + wq * 32 * STAGE_ROW;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int split = t % p.splits;
+      const int mn = t / p.splits;
+      const int n_blk = mn % p.num_n, m_blk = mn / p.num_n;
+      const int n_tile0 = n_blk * BN;
+      const int m_row0 = m_blk * BM + wq * 32;
+      const int n_valid = min(BN, p.N - n_tile0);
+      const int chunks = (n_valid + 63) / 64;
+      const bool add_bias = (p.bias != nullptr) && (split == 0);
+
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN);
+
+      for (int c = 0; c < chunks; c++) {
+        uint32_t r[64];
+        tmem_ld32(taddr + c * 64, r);
+        tmem_ld32(taddr + c * 64 + 32, r + 32);
+        tmem_ld_wait();
+        if (c == chunks - 1) {
+          // accumulator fully read: hand the TMEM stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+        // transpose through shared memory: thread = row  ->  lane = column pair
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          *reinterpret_cast<float2*>(&buf[lane * STAGE_ROW + 2 * j]) =
+              make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+        }
+        __syncwarp();
+        const int n = n_tile0 + c * 64 + 2 * lane;
+        const bool ncol_ok = n < p.N;
+        float b0 = 0.f, b1 = 0.f;
+        if (add_bias && ncol_ok) {
+          const float2 bb = *reinterpret_cast<const float2*>(p.bias + n);
+          b0 = bb.x;
+          b1 = bb.y;
+        }
+        float cs0 = 0.f, cs1 = 0.f, cq0 = 0.f, cq1 = 0.f;
+        const int rows = min(32, p.M - m_row0);
+        for (int i = 0; i < rows; i++) {
+          const float2 v = *reinterpret_cast<const float2*>(&buf[i * STAGE_ROW + 2 * lane]);
+          if (!ncol_ok) continue;
+          const int64_t m = m_row0 + i;
+          float x0 = v.x + b0, x1 = v.y + b1;
+          if (p.aux_out) {
+            *reinterpret_cast<bf162*>(p.aux_out + m * p.ld_aux_out + n) = __floats2bfloat162_rn(x0, x1);
+          }
+          if (p.act == MDHS_ACT_RELU) {
+            x0 = fmaxf(x0, 0.f);
+            x1 = fmaxf(x1, 0.f);
+          } else if (p.act == MDHS_ACT_GELU) {
+            x0 = gelu_erf(x0);
+            x1 = gelu_erf(x1);
+          }
+          if (p.dact != MDHS_ACT_NONE) {
+            const float2 a = __bfloat1622float2(*reinterpret_cast<const bf162*>(p.aux_in + m * p.ld_aux_in + n));
+            if (p.dact == MDHS_ACT_RELU) {
+              x0 = a.x > 0.f ? x0 : 0.f;
+              x1 = a.y > 0.f ? x1 : 0.f;
+            } else {
+              x0 *= gelu_erf_grad(a.x);
+              x1 *= gelu_erf_grad(a.y);
+            }
+          }
+          if (p.residual && split == 0) {
+            if (p.r_f32) {
+              const float2 rr = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(p.residual) + m * p.ldr + n);
+              x0 += rr.x;
+              x1 += rr.y;
+            } else {
+              const float2 rr =
+                  __bfloat1622float2(*reinterpret_cast<const bf162*>(reinterpret_cast<const bf16*>(p.residual) + m * p.ldr + n));
+              x0 += rr.x;
+              x1 += rr.y;
+            }
+          }
+          if (p.d_f32) {
+            float* dp = reinterpret_cast<float*>(p.D) + m * p.ldd + n;
+            if (p.accumulate) {
+              atomicAdd(dp, x0);
+              atomicAdd(dp + 1, x1);
+            } else {
+              *reinterpret_cast<float2*>(dp) = make_float2(x0, x1);
+            }
+          } else {
+            const bf162 o = __floats2bfloat162_rn(x0, x1);
+            *reinterpret_cast<bf162*>(reinterpret_cast<bf16*>(p.D) + m * p.ldd + n) = o;
+            if (p.colsum) {  // statistics of exactly what the next kernel will read back
+              const float2 q = __bfloat1622float2(o);
+              x0 = q.x;
+              x1 = q.y;
+            }
+          }
+          if (p.colsum) {
+            cs0 += x0;
+            cs1 += x1;
+            cq0 += x0 * x0;
+            cq1 += x1 * x1;
+          }
+        }
+        if (p.colsum && ncol_ok && rows > 0) {
+          atomicAdd(p.colsum + n, (double)cs0);
+          atomicAdd(p.colsum + n + 1, (double)cs1);
+          atomicAdd(p.colsumsq + n, (double)cq0);
+          atomicAdd(p.colsumsq + n + 1, (double)cq1);
+        }
+        __syncwarp();
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+    }
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map: `inner` contiguous elements per row, `outer` rows `ld` elements apart.
+int make_map(CUtensorMap* map, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_inner, int box_outer) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return MDHS_ERR_DRIVER;
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MDHS_OK : MDHS_ERR_ARG;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch(const mdhs_gemm_args* a, const Params& p0, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  Params p = p0;
+  p.num_m = ceil_div(a->M, BM);
+  p.num_n = ceil_div(a->N, BN);
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!A_MN) rc = make_map(&tmA, a->A, a->K, a->M, a->lda, BK, BM);
+  else       rc = make_map(&tmA, a->A, a->M, a->K, a->lda, 64, BK);
+  if (rc) return rc;
+  if (!B_MN) rc = make_map(&tmB, a->B, a->K, a->N, a->ldb, BK, BN);
+  else       rc = make_map(&tmB, a->B, a->N, a->K, a->ldb, 64, BK);
+  if (rc) return rc;
+  static bool attr_set = false;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int total = p.num_m * p.num_n * p.splits;
+  const int grid = total < num_sms() ? total : num_sms();
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  MDHS_RETURN_LAST();
+}
+
+template <int BN>
+int dispatch_major(const mdhs_gemm_args* a, const Params& p, cudaStream_t s) {
+  if (a->a_mn_major) {
+    return a->b_mn_major ? launch<BN, true, true>(a, p, s) : launch<BN, true, false>(a, p, s);
+  }
+  return a->b_mn_major ? launch<BN, false, true>(a, p, s) : launch<BN, false, false>(a, p, s);
+}
+
+}  // namespace
+
+int64_t g_mdhs_launches = 0;
+
+extern "C" int mdhs_abi_version(void) { return MDHS_ABI_VERSION; }
+extern "C" int64_t mdhs_launch_count(void) { return g_mdhs_launches; }
+
+extern "C" int mdhs_gemm_bf16(const mdhs_gemm_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!a || !a->A || !a->B || !a->D) return MDHS_ERR_ARG;
+  if (a->M <= 0 || a->N <= 0 || a->K <= 0) return MDHS_ERR_ARG;
+  if ((a->K % 8) || (a->N % 2) || (a->lda % 8) || (a->ldb % 8)) return MDHS_ERR_ARG;
+  if (a->a_mn_major && (a->M % 8)) return MDHS_ERR_ARG;
+  if (a->b_mn_major && (a->N % 8)) return MDHS_ERR_ARG;
+  if (((uintptr_t)a->A & 15) || ((uintptr_t)a->B & 15)) return MDHS_ERR_ARG;
+  if (a->accumulate && a->d_dtype != MDHS_DT_F32) return MDHS_ERR_ARG;
+  if (a->split_k > 1 && (!a->accumulate || a->act || a->dact || a->aux_out || a->colsum)) return MDHS_ERR_ARG;
+  if (a->dact != MDHS_ACT_NONE && !a->aux_in) return MDHS_ERR_ARG;
+  if ((a->colsum == nullptr) != (a->colsumsq == nullptr)) return MDHS_ERR_ARG;
+  if ((a->ldd % 2) || (a->residual && (a->ldr % 2))) return MDHS_ERR_ARG;
+
+  Params p;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.kb_total = ceil_div(a->K, BK);
+  int splits = a->split_k > 1 ? a->split_k : 1;
+  if (splits > p.kb_total) splits = p.kb_total;
+  p.kb_per_split = ceil_div(p.kb_total, splits);
+  p.splits = ceil_div(p.kb_total, p.kb_per_split);
+  p.D = a->D; p.ldd = a->ldd; p.d_f32 = (a->d_dtype == MDHS_DT_F32); p.accumulate = a->accumulate;
+  p.bias = a->bias;
+  p.aux_out = reinterpret_cast<bf16*>(a->aux_out); p.ld_aux_out = a->ld_aux_out;
+  p.aux_in = reinterpret_cast<const bf16*>(a->aux_in); p.ld_aux_in = a->ld_aux_in;
+  p.act = a->act; p.dact = a->dact;
+  p.residual = a->residual; p.ldr = a->ldr; p.r_f32 = (a->r_dtype == MDHS_DT_F32);
+  p.colsum = a->colsum; p.colsumsq = a->colsumsq;
+  p.num_m = p.num_n = 0;
+
+  int bn = a->bn_hint;
+  if (bn != 64 && bn != 128 && bn != 256) {
+    // pick the tile width with the best wave efficiency on this GPU; prefer wider tiles on ties
+    const int sms = num_sms();
+    const int cand[3] = {256, 128, 64};
+    double best = -1.0;
+    bn = 128;
+    for (int i = 0; i < 3; i++) {
+      const int c = cand[i];
+      if (c > 64 && a->N <= c / 2) continue;
+      const int64_t tiles = (int64_t)ceil_div(a->M, BM) * ceil_div(a->N, c) * p.splits;
+      const int64_t waves = (tiles + sms - 1) / sms;
+      double eff = (double)tiles / (double)(waves * sms);
+      // wider tiles re-read A less often and keep the tensor pipe busier per smem byte
+      eff *= (c == 256 ? 1.0 : (c == 128 ? 0.93 : 0.80));
+      // padding waste inside the last column block
+      eff *= (double)a->N / (double)((int64_t)ceil_div(a->N, c) * c);
+      if (eff > best) {
+        best = eff;
+        bn = c;
+      }
+    }
+  }
+  g_mdhs_launches++;
+  switch (bn) {
+    case 256: return dispatch_major<256>(a, p, stream);
+    case 128: return dispatch_major<128>(a, p, stream);
+    default:  return dispatch_major<64>(a, p, stream);
+  }
+}

@@ -1,0 +1,104 @@
+"""Parity of the tcgen05 GEMM (include/mdhs_b200.h: mdhs_gemm_bf16) against fp32 matmul on the same
+bf16-rounded inputs.  Tolerance: fp32 accumulation of bf16 products -> max abs err <= 2e-2 * scale for
+bf16 outputs (one bf16 rounding of the result), <= 2e-3 relative for fp32 outputs."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(a, b, a_mn, b_mn):
+    A = a.float().t() if a_mn else a.float()
+    B = b.float().t() if b_mn else b.float()
+    return A @ B.t()
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K,bn", [
+    (128, 64, 64, 64), (256, 128, 128, 128), (384, 256, 192, 256), (200, 136, 72, 0),
+    (1000, 264, 520, 0), (8192, 768, 768, 0), (136, 2304, 768, 256),
+])
+def test_gemm_layouts(mdhs, M, N, K, bn, a_mn, b_mn):
+    from mdhs_b200 import ops
+    torch.manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn((K, M) if a_mn else (M, K), device="cuda").bfloat16()
+    b = torch.randn((K, N) if b_mn else (N, K), device="cuda").bfloat16()
+    ref = _ref(a, b, a_mn, b_mn)
+    out = ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn, out_dtype=torch.float32, bn_hint=bn)
+    torch.cuda.synchronize()
+    err = (out - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 2e-3 * scale + 1e-3, (err, scale)
+    out16 = ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn, bn_hint=bn)
+    err16 = (out16.float() - ref).abs().max().item()
+    assert err16 <= 1e-2 * scale, (err16, scale)
+
+
+def test_gemm_epilogues(mdhs):
+    from mdhs_b200 import ops
+    torch.manual_seed(0)
+    M, N, K = 520, 328, 264
+    a = torch.randn(M, K, device="cuda").bfloat16()
+    w = (torch.randn(N, K, device="cuda") * 0.1).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda").bfloat16()
+    pre = a.float() @ w.float().t() + bias
+    # bias + gelu + residual, with the pre-activation saved
+    aux = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    out = ops.gemm(a, w, bias=bias, act=ops.ACT_GELU, residual=res, aux_out=aux, out_dtype=torch.float32)
+    ref = torch.nn.functional.gelu(pre) + res.float()
+    assert (out - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
+    assert (aux.float() - pre).abs().max().item() <= 1e-2 * pre.abs().max().item()
+    # relu + colsum statistics on bf16 output
+    cs = torch.zeros(N, device="cuda", dtype=torch.float64)
+    cq = torch.zeros(N, device="cuda", dtype=torch.float64)
+    out = ops.gemm(a, w, bias=bias, act=ops.ACT_RELU, colsum=cs, colsumsq=cq)
+    ref = torch.relu(pre)
+    assert (out.float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+    assert torch.allclose(cs, out.double().sum(0), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(cq, (out.double() ** 2).sum(0), rtol=1e-5, atol=1e-3)
+    # dgrad-style: multiply by gelu'(aux_in)
+    g = ops.gemm(a, w, aux_in=aux, dact=ops.ACT_GELU, out_dtype=torch.float32)
+    x = aux.float()
+    gp = 0.5 * (1 + torch.erf(x / 2 ** 0.5)) + x * torch.exp(-0.5 * x * x) / (2 * torch.pi) ** 0.5
+    ref = (a.float() @ w.float().t()) * gp
+    assert (g - ref).abs().max().item() <= 3e-3 * ref.abs().max().item()
+    # relu' mask
+    g = ops.gemm(a, w, aux_in=aux, dact=ops.ACT_RELU, out_dtype=torch.float32)
+    ref = (a.float() @ w.float().t()) * (aux.float() > 0)
+    assert (g - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
+
+
+def test_gemm_splitk_accumulate(mdhs):
+    from mdhs_b200 import ops
+    torch.manual_seed(1)
+    # wgrad shape: dW[N,K] = dY^T[N,M] . X[M,K]  (both operands MN-major, reduction over M rows)
+    rows, n_out, k_in = 4096 + 40, 264, 200
+    dy = torch.randn(rows, n_out, device="cuda").bfloat16()
+    x = torch.randn(rows, k_in, device="cuda").bfloat16()
+    acc = torch.ones(n_out, k_in, device="cuda")
+    ops.gemm(dy, x, a_mn=True, b_mn=True, out=acc, accumulate=True, split_k=8)
+    ref = dy.float().t() @ x.float() + 1.0
+    assert (acc - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
+
+
+def test_gemm_strided_views(mdhs):
+    from mdhs_b200 import ops
+    torch.manual_seed(2)
+    # operands that are column slices of a wider buffer (fused QKV style)
+    buf = torch.randn(300, 768, device="cuda").bfloat16()
+    a = buf[:, 256:512]
+    w = torch.randn(128, 256, device="cuda").bfloat16()
+    out = torch.zeros(300, 512, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, out=out[:, 128:256])
+    ref = a.float() @ w.float().t()
+    assert (out[:, 128:256].float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+    assert out[:, :128].abs().max().item() == 0 and out[:, 256:].abs().max().item() == 0
+
+
+def test_gemm_rejects_bad_args(mdhs):
+    from mdhs_b200 import ops, _lib
+    a = torch.randn(64, 60, device="cuda").bfloat16()  # K % 8 != 0
+    b = torch.randn(64, 60, device="cuda").bfloat16()
+    with pytest.raises(_lib.MdhsError):
+        ops.gemm(a, b)
