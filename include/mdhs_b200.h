@@ -37,7 +37,8 @@ int64_t mdhs_launch_count(void);
  *   mibf_net/model_resnet.py:15), ConNexT/models/block/kan1.py:156-160 (base+spline GEMMs).
  * Epilogue order: +bias[n] -> (store pre-activation to aux_out) -> act -> *act'(aux_in) -> +residual
  *   -> store bf16 / fp32 / atomic fp32 add (split-K and gradient accumulation).
- * Requirements: K % 8 == 0, N % 2 == 0, lda/ldb % 8 == 0, 16-byte aligned A/B.
+ * Epilogue order: +bias -> aux_out -> act -> *act'(aux_in) -> dropout -> +residual -> store (-> colsum).
+ * Requirements: N % 8 == 0, all leading dimensions % 8 == 0, 16-byte aligned pointers (K is free).
  */
 enum { MDHS_ACT_NONE = 0, MDHS_ACT_RELU = 1, MDHS_ACT_GELU = 2 };
 enum { MDHS_DT_BF16 = 0, MDHS_DT_F32 = 1 };
@@ -57,8 +58,111 @@ typedef struct {
   int32_t bn_hint;                            /* 0 = auto; else 64/128/256 tile width */
   double* colsum; double* colsumsq;           /* optional fp64 [N] atomics: per-column sum / sum of
                                                  squares of the stored value (train-mode BN stats) */
+  float dropout_p; uint64_t dropout_seed;     /* inverted dropout after act/act' (mask = hash(seed, m*N+n)) */
 } mdhs_gemm_args;
 int mdhs_gemm_bf16(const mdhs_gemm_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * LayerNorm (nn.LayerNorm in modules/fusion_blocks.py:18,22,34,113,211,240; modules/heads.py:35;
+ * transformers BertEmbeddings/BertSelfOutput/BertOutput LayerNorm, eps 1e-12).  x is bf16 or fp32
+ * [rows, C]; statistics fp32; optional inverted dropout on the output (BERT embeddings).
+ * Backward accumulates (+=) dgamma/dbeta and can emit a second dx copy masked by the dropout of the
+ * dense branch that fed the residual sum.  C % 8 == 0, C <= 2048.
+ */
+int mdhs_layernorm_fwd(const void* x, int x_f32, int64_t ldx, const float* gamma, const float* beta, void* y_bf16,
+                       int64_t ldy, float* y_f32, float* mean, float* rstd, int rows, int C, float eps,
+                       float drop_p, uint64_t seed, void* stream);
+int mdhs_layernorm_bwd(const void* dy, int dy_f32, int64_t lddy, const void* x, int x_f32, int64_t ldx,
+                       const float* mean, const float* rstd, const float* gamma, void* dx_bf16, int64_t lddx,
+                       void* dx_drop_bf16, float* dx_f32, float* dgamma, float* dbeta, int rows, int C,
+                       float drop_p, uint64_t seed, float drop2_p, uint64_t seed2, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * BatchNorm2d on NHWC bf16 [rows = B*H*W, C] (torchvision ResNet: encoder.py:61-68,
+ * mibf_net/model_resnet.py:15; eps 1e-5, momentum 0.1).  Train mode: the conv GEMM epilogue (or
+ * mdhs_col_stats) produces fp64 per-channel sums; finalize turns them into mean/invstd, updates the
+ * running statistics and emits scale/shift; apply fuses normalise + residual add + ReLU.
+ * mdhs_bn_bwd = two passes (reduce, apply); relu != 0 masks dy with (y > 0); dz optionally receives the
+ * masked dy (gradient of the identity branch); dgamma/dbeta accumulate (+=).
+ */
+int mdhs_bn_finalize(const double* colsum, const double* colsumsq, int64_t count, const float* gamma,
+                     const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                     float* mean, float* invstd, float* scale, float* shift, int C, int training, void* stream);
+int mdhs_bn_apply(const void* x, const float* scale, const float* shift, const void* residual, void* y,
+                  int64_t rows, int C, int relu, void* stream);
+int mdhs_bn_bwd(const void* dy, const void* x, const void* y, const float* mean, const float* invstd,
+                const float* gamma, double* sum_dy, double* sum_dy_xhat, void* dx, void* dz, float* dgamma,
+                float* dbeta, int64_t rows, int C, int relu, void* stream);
+/* column sums of a bf16 [rows, C] matrix: fp64 sum / sum of squares (BN statistics) and/or fp32 += (bias grads) */
+int mdhs_col_stats(const void* x, int64_t ldx, double* sum64, double* sumsq64, float* sum32, int64_t rows, int C,
+                   void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Convolution plumbing (NHWC bf16).  Non-1x1 convolutions are lowered to mdhs_gemm_bf16 on patch
+ * matrices: col[(b,ho,wo), (r*S+s)*C + c].  col2im is the gather-form gradient (optionally + `add`).
+ * 3x3/2 max-pool keeps the winning tap index for a deterministic backward.  (torchvision ResNet stem /
+ * Bottleneck convs used by encoder.py:61-72 and mibf_net/model_resnet.py:15.)
+ */
+int mdhs_im2col_nchw_f32(const float* x, void* col, int B, int C, int H, int W, int R, int S, int stride, int pad,
+                         int ldc, void* stream);
+int mdhs_im2col_nhwc(const void* x, void* col, int B, int H, int W, int C, int R, int S, int stride, int pad,
+                     void* stream);
+int mdhs_col2im_nhwc(const void* dcol, const void* add, void* dx, int B, int H, int W, int C, int R, int S,
+                     int stride, int pad, void* stream);
+int mdhs_maxpool3x3s2_fwd(const void* x, void* y, void* idx, int B, int H, int W, int C, void* stream);
+int mdhs_maxpool3x3s2_bwd(const void* dy, const void* idx, void* dx, int B, int H, int W, int C, void* stream);
+/* mean over tokens (encoder.py tokens -> model.py:283-290 pooling, fusion_blocks.py:96-98,143-145) */
+int mdhs_mean_tokens_fwd(const void* x, float* y32, void* y16, int B, int T, int C, float scale, int accumulate,
+                         void* stream);
+int mdhs_mean_tokens_bwd(const float* dy32, const void* dy16, void* dx, int B, int T, int C, float scale,
+                         void* stream);
+/* weight re-layout OIHW fp32 <-> GEMM operand [O, (r*S+s)*I + i] (row stride ldk) */
+int mdhs_conv_weight_pack(const float* w, void* wp, int O, int I, int R, int S, int ldk, void* stream);
+int mdhs_conv_weight_pack_dgrad(const float* w, void* wt, int O, int I, int R, int S, void* stream);
+int mdhs_conv_wgrad_unpack(const float* gp, float* g, int O, int I, int R, int S, int ldk, void* stream);
+int mdhs_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream);
+int mdhs_cast_bf16_f32(const void* x, float* y, int64_t n, void* stream);
+int mdhs_nhwc_bf16_to_nchw_f32(const void* x, float* y, int B, int H, int W, int C, void* stream);
+int mdhs_nchw_f32_to_nhwc_bf16(const float* x, void* y, int B, int H, int W, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused multi-head attention, forward and backward, for short sequences (Sk <= 512, D in {32, 64}):
+ * softmax(scale * Q K^T + key mask) (dropout) V.  Replaces the eager attention of transformers
+ * BertSelfAttention (encoder.py:130-134) and nn.MultiheadAttention (fusion_blocks.py:19-32,107-112).
+ * Token-major bf16 buffers [B*S, ld], head h in columns [h*D,(h+1)*D); key_mask [B,Sk] 1 = attend.
+ */
+int mdhs_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
+                       int64_t ldo, const uint8_t* key_mask, float* lse, int B, int H, int Sq, int Sk, int D,
+                       float scale, float drop_p, uint64_t seed, void* stream);
+int mdhs_attention_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                       const void* o, const void* d_o, int64_t ldo, const uint8_t* key_mask, const float* lse,
+                       void* dq, void* dk, void* dv, float* dk32, float* dv32, int B, int H, int Sq, int Sk, int D,
+                       float scale, float drop_p, uint64_t seed, void* stream);
+
+/* BERT embeddings (transformers BertEmbeddings via encoder.py:130-134): gather + gradient scatter */
+int mdhs_embed_gather(const int64_t* ids, const int64_t* type_ids, const float* word, const float* pos,
+                      const float* type, float* e, int rows, int S, int C, int vocab, void* stream);
+int mdhs_embed_scatter(const float* de, const int64_t* ids, const int64_t* type_ids, float* gword, float* gpos,
+                       float* gtype, int rows, int S, int C, int vocab, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Small fp32 head kernels: nn.Linear with few outputs (model.py:195-200 classifier, gating.py:10-14),
+ * cross entropy with label smoothing / class weights / focal form (scripts/train.py:46-61,252-254).
+ */
+int mdhs_linear_f32_fwd(const float* X, int64_t ldx, const float* W, const float* bias, float* Y, int64_t ldy, int M,
+                        int N, int K, int act, void* stream);
+int mdhs_linear_f32_bwd(const float* dY, int64_t lddy, const float* X, int64_t ldx, const float* W, float* dX,
+                        int64_t lddx, int accumulate_dx, float* dW, float* db, int M, int N, int K, void* stream);
+int mdhs_ce_loss(const float* logits, int64_t ld, const int64_t* labels, const float* class_weights, float* loss,
+                 float* dlogits, int B, int C, float label_smoothing, int focal, float gamma, void* stream);
+int mdhs_axpby_f32(const float* x, float* y, int64_t n, const float* a_dev, float a, float b, void* stream);
+
+/* Fused optimizer step on the flat parameter buffer (scripts/train.py:257-309) */
+int mdhs_adam_flat(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, int64_t n,
+                   float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                   int adamw, int zero_grad, void* stream);
+int mdhs_sgd_flat(float* params, float* grads, float* momentum_buf, void* shadow_bf16, int64_t n, float lr,
+                  float momentum, float weight_decay, float grad_scale, int first_step, int zero_grad, void* stream);
 
 #ifdef __cplusplus
 }

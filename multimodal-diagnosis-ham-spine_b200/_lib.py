@@ -29,7 +29,46 @@ class GemmArgs(ctypes.Structure):
         ("residual", ctypes.c_void_p), ("ldr", ctypes.c_int64), ("r_dtype", ctypes.c_int32),
         ("split_k", ctypes.c_int32), ("bn_hint", ctypes.c_int32),
         ("colsum", ctypes.c_void_p), ("colsumsq", ctypes.c_void_p),
+        ("dropout_p", ctypes.c_float), ("dropout_seed", ctypes.c_uint64),
     ]
+
+
+# Argument signatures of include/mdhs_b200.h: p = pointer, i = int32, l = int64, f = float, u = uint64.
+# Every function returns int status and takes the stream as its last pointer.
+SIGNATURES = {
+    "mdhs_gemm_bf16": "pp",
+    "mdhs_layernorm_fwd": "pilpppl" "ppp" "iiffup",
+    "mdhs_layernorm_bwd": "pilpilppp" "plpppp" "iifufup",
+    "mdhs_bn_finalize": "pplppppffppppiip",
+    "mdhs_bn_apply": "pppppliip",
+    "mdhs_bn_bwd": "pppppppppppp" "liip",
+    "mdhs_col_stats": "plppplip",
+    "mdhs_im2col_nchw_f32": "ppiiiiiiiiip",
+    "mdhs_im2col_nhwc": "ppiiiiiiiip",
+    "mdhs_col2im_nhwc": "pppiiiiiiiip",
+    "mdhs_maxpool3x3s2_fwd": "pppiiiip",
+    "mdhs_maxpool3x3s2_bwd": "pppiiiip",
+    "mdhs_mean_tokens_fwd": "pppiiifip",
+    "mdhs_mean_tokens_bwd": "pppiiifp",
+    "mdhs_conv_weight_pack": "ppiiiiip",
+    "mdhs_conv_weight_pack_dgrad": "ppiiiip",
+    "mdhs_conv_wgrad_unpack": "ppiiiiip",
+    "mdhs_cast_f32_bf16": "pplp",
+    "mdhs_cast_bf16_f32": "pplp",
+    "mdhs_nhwc_bf16_to_nchw_f32": "ppiiiip",
+    "mdhs_nchw_f32_to_nhwc_bf16": "ppiiiip",
+    "mdhs_attention_fwd": "plplplplpp" "iiiii" "ffup",
+    "mdhs_attention_bwd": "plplplpplpp" "ppppp" "iiiii" "ffup",
+    "mdhs_embed_gather": "ppppppiiiip",
+    "mdhs_embed_scatter": "ppppppiiiip",
+    "mdhs_linear_f32_fwd": "plpppliiiip",
+    "mdhs_linear_f32_bwd": "plplppli" "pp" "iiip",
+    "mdhs_ce_loss": "plppppiififp",
+    "mdhs_axpby_f32": "pplpffp",
+    "mdhs_adam_flat": "ppppplfffffifiip",
+    "mdhs_sgd_flat": "pppplffffiip",
+}
+_CT = {"p": ctypes.c_void_p, "i": ctypes.c_int32, "l": ctypes.c_int64, "f": ctypes.c_float, "u": ctypes.c_uint64}
 
 
 def lib():
@@ -43,7 +82,18 @@ def lib():
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.mdhs_abi_version.restype = ctypes.c_int
         _lib.mdhs_launch_count.restype = ctypes.c_int64
+        for name, sig in SIGNATURES.items():
+            fn = getattr(_lib, name)  # AttributeError here = header / library mismatch
+            fn.argtypes = [_CT[c] for c in sig]
+            fn.restype = ctypes.c_int
     return _lib
+
+
+def call(name, *args):
+    """Invoke one C-ABI entry point; raises MdhsError on a non-zero status."""
+    rc = getattr(lib(), name)(*args)
+    if rc != 0:
+        raise MdhsError(f"{name} failed with status {rc}")
 
 
 def check(rc, what):

@@ -1,0 +1,442 @@
+// Data-movement kernels around the implicit-GEMM convolutions of the image encoder (NHWC bf16):
+// patch gather (im2col) / scatter-free col2im, 3x3/2 max-pool, token pooling, weight re-layout.
+// All are HBM-bound: 16-byte vectors along the channel axis, grid sized from the element count.
+#include "common.cuh"
+#include "../../include/mdhs_b200.h"
+
+extern int64_t g_mdhs_launches;
+
+namespace {
+
+int grid_for(int64_t items, int block) {
+  int64_t g = (items + block - 1) / block;
+  const int64_t cap = 148 * 32;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+// NCHW fp32 image -> im2col rows for the stem (C_in = 3 is too narrow for channel vectors).
+// col[(b,ho,wo), (r*S+s)*C + c] ; columns >= R*S*C are zero padding up to ldc.
+__global__ void __launch_bounds__(256) im2col_nchw_f32_kernel(const float* __restrict__ x, bf16* __restrict__ col, int B, int C,
+                                                              int H, int W, int R, int S, int stride, int pad, int Ho, int Wo,
+                                                              int ldc) {
+  const int64_t total = (int64_t)B * Ho * Wo * ldc;
+  const int K = R * S * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % ldc);
+    const int64_t row = i / ldc;
+    float v = 0.f;
+    if (k < K) {
+      const int c = k % C, rs = k / C, s = rs % S, r = rs / S;
+      const int wo = (int)(row % Wo);
+      const int ho = (int)((row / Wo) % Ho);
+      const int b = (int)(row / ((int64_t)Wo * Ho));
+      const int h = ho * stride - pad + r, w = wo * stride - pad + s;
+      if (h >= 0 && h < H && w >= 0 && w < W) v = x[(((int64_t)b * C + c) * H + h) * W + w];
+    }
+    col[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// NHWC bf16 -> im2col rows, 8 channels per thread.  col[(b,ho,wo), (r*S+s)*C + c].
+__global__ void __launch_bounds__(256) im2col_nhwc_kernel(const bf16* __restrict__ x, bf16* __restrict__ col, int B, int H, int W,
+                                                          int C, int R, int S, int stride, int pad, int Ho, int Wo) {
+  const int cvec = C >> 3;
+  const int64_t total = (int64_t)B * Ho * Wo * R * S * cvec;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvec);
+    int64_t t = i / cvec;
+    const int rs = (int)(t % (R * S));
+    t /= (R * S);
+    const int wo = (int)(t % Wo);
+    t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    const int r = rs / S, s = rs % S;
+    const int h = ho * stride - pad + r, w = wo * stride - pad + s;
+    uint4 v = zero;
+    if (h >= 0 && h < H && w >= 0 && w < W)
+      v = *reinterpret_cast<const uint4*>(x + (((int64_t)b * H + h) * W + w) * C + cv * 8);
+    *reinterpret_cast<uint4*>(col + i * 8) = v;
+  }
+}
+
+// Gradient of im2col as a gather (no atomics): dx[b,h,w,c] = sum over the taps that read this pixel.
+// If `add` is given (same shape as dx) it is summed in (residual-branch gradient).
+__global__ void __launch_bounds__(256) col2im_nhwc_kernel(const bf16* __restrict__ dcol, const bf16* __restrict__ add,
+                                                          bf16* __restrict__ dx, int B, int H, int W, int C, int R, int S,
+                                                          int stride, int pad, int Ho, int Wo) {
+  const int cvec = C >> 3;
+  const int64_t total = (int64_t)B * H * W * cvec;
+  const int64_t ldc = (int64_t)R * S * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvec);
+    int64_t t = i / cvec;
+    const int w = (int)(t % W);
+    t /= W;
+    const int h = (int)(t % H);
+    const int b = (int)(t / H);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = 0.f;
+    if (add) load8(add + i * 8, acc);
+    for (int r = 0; r < R; r++) {
+      const int hn = h + pad - r;
+      if (hn < 0 || (hn % stride) != 0) continue;
+      const int ho = hn / stride;
+      if (ho >= Ho) continue;
+      for (int s = 0; s < S; s++) {
+        const int wn = w + pad - s;
+        if (wn < 0 || (wn % stride) != 0) continue;
+        const int wo = wn / stride;
+        if (wo >= Wo) continue;
+        float v[8];
+        load8(dcol + (((int64_t)b * Ho + ho) * Wo + wo) * ldc + (int64_t)(r * S + s) * C + cv * 8, v);
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] += v[k];
+      }
+    }
+    store8(dx + i * 8, acc);
+  }
+}
+
+// 3x3 stride-2 pad-1 max-pool (torchvision ResNet stem), NHWC bf16; records the winning tap (0..8, first
+// maximum in row-major window order like ATen) so that the backward pass is a deterministic gather.
+__global__ void __launch_bounds__(256) maxpool3x3s2_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
+                                                               uint8_t* __restrict__ idx, int B, int H, int W, int C, int Ho,
+                                                               int Wo) {
+  const int cvec = C >> 3;
+  const int64_t total = (int64_t)B * Ho * Wo * cvec;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvec);
+    int64_t t = i / cvec;
+    const int wo = (int)(t % Wo);
+    t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    float best[8];
+    uint8_t bi[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      best[k] = -INFINITY;
+      bi[k] = 0;
+    }
+    for (int r = 0; r < 3; r++) {
+      const int h = ho * 2 - 1 + r;
+      if (h < 0 || h >= H) continue;
+      for (int s = 0; s < 3; s++) {
+        const int w = wo * 2 - 1 + s;
+        if (w < 0 || w >= W) continue;
+        float v[8];
+        load8(x + (((int64_t)b * H + h) * W + w) * C + cv * 8, v);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          if (v[k] > best[k]) {
+            best[k] = v[k];
+            bi[k] = (uint8_t)(r * 3 + s);
+          }
+        }
+      }
+    }
+    store8(y + i * 8, best);
+    uint2 packed;
+    packed.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | ((uint32_t)bi[3] << 24);
+    packed.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | ((uint32_t)bi[7] << 24);
+    *reinterpret_cast<uint2*>(idx + i * 8) = packed;
+  }
+}
+
+__global__ void __launch_bounds__(256) maxpool3x3s2_bwd_kernel(const bf16* __restrict__ dy, const uint8_t* __restrict__ idx,
+                                                               bf16* __restrict__ dx, int B, int H, int W, int C, int Ho,
+                                                               int Wo) {
+  const int cvec = C >> 3;
+  const int64_t total = (int64_t)B * H * W * cvec;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvec);
+    int64_t t = i / cvec;
+    const int w = (int)(t % W);
+    t /= W;
+    const int h = (int)(t % H);
+    const int b = (int)(t / H);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = 0.f;
+    for (int r = 0; r < 3; r++) {
+      const int hn = h + 1 - r;
+      if (hn < 0 || (hn & 1)) continue;
+      const int ho = hn >> 1;
+      if (ho >= Ho) continue;
+      for (int s = 0; s < 3; s++) {
+        const int wn = w + 1 - s;
+        if (wn < 0 || (wn & 1)) continue;
+        const int wo = wn >> 1;
+        if (wo >= Wo) continue;
+        const int64_t o = ((((int64_t)b * Ho + ho) * Wo + wo) * cvec + cv) * 8;
+        const uint2 packed = *reinterpret_cast<const uint2*>(idx + o);
+        float v[8];
+        load8(dy + o, v);
+        const uint32_t tap = (uint32_t)(r * 3 + s);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const uint32_t word = k < 4 ? packed.x : packed.y;
+          if (((word >> ((k & 3) * 8)) & 0xffu) == tap) acc[k] += v[k];
+        }
+      }
+    }
+    store8(dx + i * 8, acc);
+  }
+}
+
+// Mean over the token axis: x [B, T, C] bf16 -> y [B, C] (fp32 and/or bf16), scaled by `scale`
+// (1/T for a mean; multi-scale fusion averages three pooled vectors with an extra 1/3).
+__global__ void __launch_bounds__(256) mean_tokens_fwd_kernel(const bf16* __restrict__ x, float* __restrict__ y32,
+                                                              bf16* __restrict__ y16, int B, int T, int C, float scale,
+                                                              int accumulate) {
+  const int cvec = C >> 3;
+  const int64_t total = (int64_t)B * cvec;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvec);
+    const int b = (int)(i / cvec);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = 0.f;
+    const bf16* p = x + (int64_t)b * T * C + cv * 8;
+    for (int t = 0; t < T; t++) {
+      float v[8];
+      load8(p + (int64_t)t * C, v);
+#pragma unroll
+      for (int k = 0; k < 8; k++) acc[k] += v[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] *= scale;
+    if (y32) {
+      float* o = y32 + (int64_t)b * C + cv * 8;
+#pragma unroll
+      for (int k = 0; k < 8; k++) o[k] = accumulate ? o[k] + acc[k] : acc[k];
+    }
+    if (y16) store8(y16 + (int64_t)b * C + cv * 8, acc);
+  }
+}
+
+// dx[b,t,c] = scale * dy[b,c]  (dy fp32 or bf16), optionally added to an existing gradient.
+__global__ void __launch_bounds__(256) mean_tokens_bwd_kernel(const float* __restrict__ dy32, const bf16* __restrict__ dy16,
+                                                              bf16* __restrict__ dx, int B, int T, int C, float scale) {
+  const int cvec = C >> 3;
+  const int64_t total = (int64_t)B * T * cvec;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvec);
+    const int b = (int)(i / ((int64_t)cvec * T));
+    float v[8];
+    if (dy32) {
+      const float* p = dy32 + (int64_t)b * C + cv * 8;
+#pragma unroll
+      for (int k = 0; k < 8; k++) v[k] = p[k] * scale;
+    } else {
+      load8(dy16 + (int64_t)b * C + cv * 8, v);
+#pragma unroll
+      for (int k = 0; k < 8; k++) v[k] *= scale;
+    }
+    store8(dx + i * 8, v);
+  }
+}
+
+// Conv weight OIHW fp32 -> [O, (r*S+s)*I + i] bf16 with row stride ldk (zero padded), and the inverse
+// accumulation of the GEMM-layout fp32 gradient back into the OIHW fp32 grad.
+__global__ void conv_weight_pack_kernel(const float* __restrict__ w, bf16* __restrict__ wp, int O, int I, int R, int S, int ldk) {
+  const int64_t total = (int64_t)O * ldk;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % ldk);
+    const int o = (int)(i / ldk);
+    float v = 0.f;
+    if (k < R * S * I) {
+      const int c = k % I, rs = k / I;
+      v = w[((int64_t)o * I + c) * R * S + rs];
+    }
+    wp[i] = __float2bfloat16_rn(v);
+  }
+}
+// dgrad operand for stride-1 "same" convolutions: wt[c_in, ((R-1-r)*S + (S-1-s))*O + o] = w[o, c_in, r, s]
+__global__ void conv_weight_pack_dgrad_kernel(const float* __restrict__ w, bf16* __restrict__ wt, int O, int I, int R, int S) {
+  const int64_t total = (int64_t)O * I * R * S;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int o = (int)(i % O);
+    int64_t t = i / O;
+    const int rs = (int)(t % (R * S));
+    const int c = (int)(t / (R * S));
+    const int r = R - 1 - rs / S, s = S - 1 - rs % S;
+    wt[i] = __float2bfloat16_rn(w[(((int64_t)o * I + c) * R + r) * S + s]);
+  }
+}
+__global__ void conv_wgrad_unpack_kernel(const float* __restrict__ gp, float* __restrict__ g, int O, int I, int R, int S, int ldk) {
+  const int64_t total = (int64_t)O * I * R * S;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int rs = (int)(i % (R * S));
+    const int64_t oc = i / (R * S);
+    const int c = (int)(oc % I);
+    const int o = (int)(oc / I);
+    g[i] += gp[(int64_t)o * ldk + (int64_t)rs * I + c];
+  }
+}
+
+// fp32 -> bf16 (weights after an optimizer step) and bf16 -> fp32.
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, int64_t n) {
+  const int64_t nv = n >> 3;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 a = *reinterpret_cast<const float4*>(x + i * 8), b = *reinterpret_cast<const float4*>(x + i * 8 + 4);
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    store8(y + i * 8, v);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
+    const int64_t j = (nv << 3) + threadIdx.x;
+    y[j] = __float2bfloat16_rn(x[j]);
+  }
+}
+__global__ void __launch_bounds__(256) cast_bf16_f32_kernel(const bf16* __restrict__ x, float* __restrict__ y, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = __bfloat162float(x[i]);
+}
+
+// NHWC bf16 [B,H,W,C] -> NCHW fp32 (module boundary for hooks / Grad-CAM) and back.
+__global__ void nhwc_bf16_to_nchw_f32_kernel(const bf16* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C) {
+  const int64_t total = (int64_t)B * C * H * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    int64_t t = i / W;
+    const int h = (int)(t % H);
+    t /= H;
+    const int c = (int)(t % C);
+    const int b = (int)(t / C);
+    y[i] = __bfloat162float(x[(((int64_t)b * H + h) * W + w) * C + c]);
+  }
+}
+__global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, int B, int H, int W, int C) {
+  const int64_t total = (int64_t)B * C * H * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    int64_t t = i / C;
+    const int w = (int)(t % W);
+    t /= W;
+    const int h = (int)(t % H);
+    const int b = (int)(t / H);
+    y[i] = __float2bfloat16_rn(x[(((int64_t)b * C + c) * H + h) * W + w]);
+  }
+}
+
+}  // namespace
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int mdhs_im2col_nchw_f32(const float* x, void* col, int B, int C, int H, int W, int R, int S, int stride, int pad,
+                                    int ldc, void* stream) {
+  if (!x || !col || ldc < R * S * C) return MDHS_ERR_ARG;
+  const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
+  g_mdhs_launches++;
+  im2col_nchw_f32_kernel<<<grid_for((int64_t)B * Ho * Wo * ldc, 256), 256, 0, ST(stream)>>>(x, (bf16*)col, B, C, H, W, R, S, stride,
+                                                                                            pad, Ho, Wo, ldc);
+  MDHS_RETURN_LAST();
+}
+
+extern "C" int mdhs_im2col_nhwc(const void* x, void* col, int B, int H, int W, int C, int R, int S, int stride, int pad,
+                                void* stream) {
+  if (!x || !col || (C % 8)) return MDHS_ERR_ARG;
+  const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
+  g_mdhs_launches++;
+  im2col_nhwc_kernel<<<grid_for((int64_t)B * Ho * Wo * R * S * (C / 8), 256), 256, 0, ST(stream)>>>((const bf16*)x, (bf16*)col, B, H,
+                                                                                                    W, C, R, S, stride, pad, Ho, Wo);
+  MDHS_RETURN_LAST();
+}
+
+extern "C" int mdhs_col2im_nhwc(const void* dcol, const void* add, void* dx, int B, int H, int W, int C, int R, int S, int stride,
+                                int pad, void* stream) {
+  if (!dcol || !dx || (C % 8)) return MDHS_ERR_ARG;
+  const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
+  g_mdhs_launches++;
+  col2im_nhwc_kernel<<<grid_for((int64_t)B * H * W * (C / 8), 256), 256, 0, ST(stream)>>>((const bf16*)dcol, (const bf16*)add,
+                                                                                          (bf16*)dx, B, H, W, C, R, S, stride, pad,
+                                                                                          Ho, Wo);
+  MDHS_RETURN_LAST();
+}
+
+extern "C" int mdhs_maxpool3x3s2_fwd(const void* x, void* y, void* idx, int B, int H, int W, int C, void* stream) {
+  if (!x || !y || !idx || (C % 8)) return MDHS_ERR_ARG;
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  g_mdhs_launches++;
+  maxpool3x3s2_fwd_kernel<<<grid_for((int64_t)B * Ho * Wo * (C / 8), 256), 256, 0, ST(stream)>>>((const bf16*)x, (bf16*)y,
+                                                                                                 (uint8_t*)idx, B, H, W, C, Ho, Wo);
+  MDHS_RETURN_LAST();
+}
+
+extern "C" int mdhs_maxpool3x3s2_bwd(const void* dy, const void* idx, void* dx, int B, int H, int W, int C, void* stream) {
+  if (!dy || !dx || !idx || (C % 8)) return MDHS_ERR_ARG;
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  g_mdhs_launches++;
+  maxpool3x3s2_bwd_kernel<<<grid_for((int64_t)B * H * W * (C / 8), 256), 256, 0, ST(stream)>>>((const bf16*)dy, (const uint8_t*)idx,
+                                                                                               (bf16*)dx, B, H, W, C, Ho, Wo);
+  MDHS_RETURN_LAST();
+}
+
+extern "C" int mdhs_mean_tokens_fwd(const void* x, float* y32, void* y16, int B, int T, int C, float scale, int accumulate,
+                                    void* stream) {
+  if (!x || (!y32 && !y16) || (C % 8)) return MDHS_ERR_ARG;
+  g_mdhs_launches++;
+  mean_tokens_fwd_kernel<<<grid_for((int64_t)B * (C / 8), 128), 128, 0, ST(stream)>>>((const bf16*)x, y32, (bf16*)y16, B, T, C, scale,
+                                                                                      accumulate);
+  MDHS_RETURN_LAST();
+}
+
+extern "C" int mdhs_mean_tokens_bwd(const float* dy32, const void* dy16, void* dx, int B, int T, int C, float scale, void* stream) {
+  if ((!dy32 && !dy16) || !dx || (C % 8)) return MDHS_ERR_ARG;
+  g_mdhs_launches++;
+  mean_tokens_bwd_kernel<<<grid_for((int64_t)B * T * (C / 8), 256), 256, 0, ST(stream)>>>(dy32, (const bf16*)dy16, (bf16*)dx, B, T, C,
+                                                                                          scale);
+  MDHS_RETURN_LAST();
+}
+
+extern "C" int mdhs_conv_weight_pack(const float* w, void* wp, int O, int I, int R, int S, int ldk, void* stream) {
+  if (!w || !wp || ldk < R * S * I) return MDHS_ERR_ARG;
+  g_mdhs_launches++;
+  conv_weight_pack_kernel<<<grid_for((int64_t)O * ldk, 256), 256, 0, ST(stream)>>>(w, (bf16*)wp, O, I, R, S, ldk);
+  MDHS_RETURN_LAST();
+}
+
+extern "C" int mdhs_conv_weight_pack_dgrad(const float* w, void* wt, int O, int I, int R, int S, void* stream) {
+  if (!w || !wt) return MDHS_ERR_ARG;
+  g_mdhs_launches++;
+  conv_weight_pack_dgrad_kernel<<<grid_for((int64_t)O * I * R * S, 256), 256, 0, ST(stream)>>>(w, (bf16*)wt, O, I, R, S);
+  MDHS_RETURN_LAST();
+}
+
+extern "C" int mdhs_conv_wgrad_unpack(const float* gp, float* g, int O, int I, int R, int S, int ldk, void* stream) {
+  if (!gp || !g || ldk < R * S * I) return MDHS_ERR_ARG;
+  g_mdhs_launches++;
+  conv_wgrad_unpack_kernel<<<grid_for((int64_t)O * I * R * S, 256), 256, 0, ST(stream)>>>(gp, g, O, I, R, S, ldk);
+  MDHS_RETURN_LAST();
+}
+
+extern "C" int mdhs_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream) {
+  if (!x || !y || n <= 0 || ((uintptr_t)x & 15) || ((uintptr_t)y & 15)) return MDHS_ERR_ARG;
+  g_mdhs_launches++;
+  cast_f32_bf16_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, ST(stream)>>>(x, (bf16*)y, n);
+  MDHS_RETURN_LAST();
+}
+
+extern "C" int mdhs_cast_bf16_f32(const void* x, float* y, int64_t n, void* stream) {
+  if (!x || !y || n <= 0) return MDHS_ERR_ARG;
+  g_mdhs_launches++;
+  cast_bf16_f32_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>((const bf16*)x, y, n);
+  MDHS_RETURN_LAST();
+}
+
+extern "C" int mdhs_nhwc_bf16_to_nchw_f32(const void* x, float* y, int B, int H, int W, int C, void* stream) {
+  if (!x || !y) return MDHS_ERR_ARG;
+  g_mdhs_launches++;
+  nhwc_bf16_to_nchw_f32_kernel<<<grid_for((int64_t)B * H * W * C, 256), 256, 0, ST(stream)>>>((const bf16*)x, y, B, H, W, C);
+  MDHS_RETURN_LAST();
+}
+
+extern "C" int mdhs_nchw_f32_to_nhwc_bf16(const float* x, void* y, int B, int H, int W, int C, void* stream) {
+  if (!x || !y) return MDHS_ERR_ARG;
+  g_mdhs_launches++;
+  nchw_f32_to_nhwc_bf16_kernel<<<grid_for((int64_t)B * H * W * C, 256), 256, 0, ST(stream)>>>(x, (bf16*)y, B, H, W, C);
+  MDHS_RETURN_LAST();
+}

@@ -4,8 +4,8 @@
 //   warp 0      : TMA producer (one elected lane) -> smem ring of STAGES {A tile, B tile}
 //   warp 1      : MMA issuer (one lane) -> tcgen05.mma into one of two TMEM accumulator stages
 //   warp 2      : TMEM allocator / deallocator
-//   warps 4..7  : epilogue: tcgen05.ld -> registers -> per-warp smem transpose -> fused
-//                 bias / activation / act' / residual / BN column statistics -> coalesced stores
+//   warps 4..11 : epilogue: tcgen05.ld -> registers (thread = row) -> fused bias / activation / act' /
+//                 dropout / residual / BN column statistics -> 16-byte row-contiguous global stores
 //
 // Tiles are 128 x BN x 64 (BN in {64,128,256}); operands are staged with the 128-byte TMA/UMMA
 // swizzle; both operands may be K-major or MN-major so forward, dgrad and wgrad need no transposes.
@@ -17,20 +17,18 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;  // 4 control warps + 8 epilogue warps
 constexpr int EPI_WARP0 = 4;
-constexpr int STAGE_ROW = 66;                                // padded fp32 row of the transpose buffer
-constexpr int STAGING_BYTES = 4 * 32 * STAGE_ROW * 4;        // one 32x64 fp32 tile per epilogue warp
 constexpr int A_TILE_BYTES = BM * BK * 2;                    // 16 KiB
 constexpr int SMEM_LIMIT = 232448;                           // 227 KiB opt-in maximum
 
 template <int BN> struct Cfg {
   static constexpr int B_TILE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 7 : 8);
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES;
   static_assert(SMEM_BYTES <= SMEM_LIMIT, "shared memory budget exceeded");
 };
 
@@ -44,6 +42,7 @@ struct Params {
   int act, dact;
   const void* residual; int64_t ldr; int r_f32;
   double* colsum; double* colsumsq;
+  float drop_p; uint64_t drop_seed;
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -126,8 +125,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t tiles_base = smem_base;
-  float* staging = reinterpret_cast<float*>(smem_gen + C::STAGES * C::STAGE_BYTES);
-  const uint32_t bars = smem_base + C::STAGES * C::STAGE_BYTES + STAGING_BYTES;
+  const uint32_t bars = smem_base + C::STAGES * C::STAGE_BYTES;
   // barrier layout: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem base address
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
@@ -135,7 +133,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * C::STAGES + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * C::STAGES + 4);
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + C::STAGES * C::STAGE_BYTES + STAGING_BYTES + 8 * (2 * C::STAGES + 4));
+      reinterpret_cast<volatile uint32_t*>(smem_gen + C::STAGES * C::STAGE_BYTES + 8 * (2 * C::STAGES + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -151,7 +149,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -243,120 +241,174 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= EPI_WARP0) {
     // ------------------------------------------------------------ epilogue
-    const int wq = warp - EPI_WARP0;  // TMEM lane quarter owned by this warp
-    float* buf = staging + wq * 32 * STAGE_ROW;
+    // 8 warps: warp (4+q) and (8+q) share TMEM lane quarter q and split the tile's columns in halves.
+    // Thread = accumulator row; every global access is a 16-byte vector on the thread's own row, so all
+    // sectors are fully used without a shared-memory transpose.
+    const int wq = (warp - EPI_WARP0) & 3;     // TMEM lane quarter
+    const int half = (warp - EPI_WARP0) >> 2;  // column half of the tile
+    constexpr int HALF_COLS = BN / 2;
+    constexpr int GROUPS = HALF_COLS / 32;     // 32-column groups per warp (1, 2 or 4)
+    const float inv_keep = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int split = t % p.splits;
       const int mn = t / p.splits;
       const int n_blk = mn % p.num_n, m_blk = mn / p.num_n;
-      const int n_tile0 = n_blk * BN;
-      const int m_row0 = m_blk * BM + wq * 32;
-      const int n_valid = min(BN, p.N - n_tile0);
-      const int chunks = (n_valid + 63) / 64;
-      const bool add_bias = (p.bias != nullptr) && (split == 0);
+      const int n_half0 = n_blk * BN + half * HALF_COLS;
+      const int64_t m = (int64_t)m_blk * BM + wq * 32 + lane;
+      const bool row_ok = m < p.M;
+      const bool first_split = (split == 0);
 
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN);
+      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN + half * HALF_COLS);
 
-      for (int c = 0; c < chunks; c++) {
-        uint32_t r[64];
-        tmem_ld32(taddr + c * 64, r);
-        tmem_ld32(taddr + c * 64 + 32, r + 32);
+#pragma unroll
+      for (int g = 0; g < GROUPS; g++) {
+        uint32_t r[32];
+        tmem_ld32(taddr + g * 32, r);
         tmem_ld_wait();
-        if (c == chunks - 1) {
-          // accumulator fully read: hand the TMEM stage back to the MMA warp
+        if (g == GROUPS - 1) {
+          // this warp has read its whole slice: hand the TMEM stage back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(acc));
         }
-        // transpose through shared memory: thread = row  ->  lane = column pair
+        const int n0 = n_half0 + g * 32;
+        if (n0 >= p.N) continue;
+        float x[32];
 #pragma unroll
-        for (int j = 0; j < 32; j++) {
-          *reinterpret_cast<float2*>(&buf[lane * STAGE_ROW + 2 * j]) =
-              make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-        }
-        __syncwarp();
-        const int n = n_tile0 + c * 64 + 2 * lane;
-        const bool ncol_ok = n < p.N;
-        float b0 = 0.f, b1 = 0.f;
-        if (add_bias && ncol_ok) {
-          const float2 bb = *reinterpret_cast<const float2*>(p.bias + n);
-          b0 = bb.x;
-          b1 = bb.y;
-        }
-        float cs0 = 0.f, cs1 = 0.f, cq0 = 0.f, cq1 = 0.f;
-        const int rows = min(32, p.M - m_row0);
-        for (int i = 0; i < rows; i++) {
-          const float2 v = *reinterpret_cast<const float2*>(&buf[i * STAGE_ROW + 2 * lane]);
-          if (!ncol_ok) continue;
-          const int64_t m = m_row0 + i;
-          float x0 = v.x + b0, x1 = v.y + b1;
-          if (p.aux_out) {
-            *reinterpret_cast<bf162*>(p.aux_out + m * p.ld_aux_out + n) = __floats2bfloat162_rn(x0, x1);
-          }
-          if (p.act == MDHS_ACT_RELU) {
-            x0 = fmaxf(x0, 0.f);
-            x1 = fmaxf(x1, 0.f);
-          } else if (p.act == MDHS_ACT_GELU) {
-            x0 = gelu_erf(x0);
-            x1 = gelu_erf(x1);
-          }
-          if (p.dact != MDHS_ACT_NONE) {
-            const float2 a = __bfloat1622float2(*reinterpret_cast<const bf162*>(p.aux_in + m * p.ld_aux_in + n));
-            if (p.dact == MDHS_ACT_RELU) {
-              x0 = a.x > 0.f ? x0 : 0.f;
-              x1 = a.y > 0.f ? x1 : 0.f;
-            } else {
-              x0 *= gelu_erf_grad(a.x);
-              x1 *= gelu_erf_grad(a.y);
+        for (int j = 0; j < 32; j++) x[j] = __uint_as_float(r[j]);
+        // ---- bias (same address in every lane: one broadcast transaction per vector)
+        if (p.bias != nullptr && first_split) {
+#pragma unroll
+          for (int v = 0; v < 8; v++) {
+            if (n0 + v * 4 < p.N) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + v * 4));
+              x[v * 4 + 0] += b.x; x[v * 4 + 1] += b.y; x[v * 4 + 2] += b.z; x[v * 4 + 3] += b.w;
             }
           }
-          if (p.residual && split == 0) {
-            if (p.r_f32) {
-              const float2 rr = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(p.residual) + m * p.ldr + n);
-              x0 += rr.x;
-              x1 += rr.y;
-            } else {
-              const float2 rr =
-                  __bfloat1622float2(*reinterpret_cast<const bf162*>(reinterpret_cast<const bf16*>(p.residual) + m * p.ldr + n));
-              x0 += rr.x;
-              x1 += rr.y;
+        }
+        // ---- pre-activation copy
+        if (p.aux_out != nullptr && row_ok) {
+          bf16* ap = p.aux_out + m * p.ld_aux_out + n0;
+#pragma unroll
+          for (int v = 0; v < 4; v++)
+            if (n0 + v * 8 < p.N) store8(ap + v * 8, x + v * 8);
+        }
+        // ---- activation
+        if (p.act == MDHS_ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) x[j] = fmaxf(x[j], 0.f);
+        } else if (p.act == MDHS_ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) x[j] = gelu_erf(x[j]);
+        }
+        // ---- multiply by act'(aux_in) (backward through the activation)
+        if (p.dact != MDHS_ACT_NONE && row_ok) {
+          const bf16* ap = p.aux_in + m * p.ld_aux_in + n0;
+#pragma unroll
+          for (int v = 0; v < 4; v++) {
+            if (n0 + v * 8 < p.N) {
+              float a[8];
+              load8(ap + v * 8, a);
+#pragma unroll
+              for (int k = 0; k < 8; k++) {
+                if (p.dact == MDHS_ACT_RELU) x[v * 8 + k] = a[k] > 0.f ? x[v * 8 + k] : 0.f;
+                else x[v * 8 + k] *= gelu_erf_grad(a[k]);
+              }
             }
           }
-          if (p.d_f32) {
-            float* dp = reinterpret_cast<float*>(p.D) + m * p.ldd + n;
-            if (p.accumulate) {
-              atomicAdd(dp, x0);
-              atomicAdd(dp + 1, x1);
-            } else {
-              *reinterpret_cast<float2*>(dp) = make_float2(x0, x1);
+        }
+        // ---- dropout (stateless: recomputed from (seed, element index) in the backward pass)
+        if (p.drop_p > 0.f) {
+#pragma unroll
+          for (int j = 0; j < 32; j++)
+            x[j] *= dropout_scale(p.drop_seed, (uint64_t)m * (uint64_t)p.N + (uint64_t)(n0 + j), p.drop_p, inv_keep);
+        }
+        // ---- residual
+        if (p.residual != nullptr && first_split && row_ok) {
+          if (p.r_f32) {
+            const float* rp = reinterpret_cast<const float*>(p.residual) + m * p.ldr + n0;
+#pragma unroll
+            for (int v = 0; v < 8; v++) {
+              if (n0 + v * 4 < p.N) {
+                const float4 rr = *reinterpret_cast<const float4*>(rp + v * 4);
+                x[v * 4 + 0] += rr.x; x[v * 4 + 1] += rr.y; x[v * 4 + 2] += rr.z; x[v * 4 + 3] += rr.w;
+              }
             }
           } else {
-            const bf162 o = __floats2bfloat162_rn(x0, x1);
-            *reinterpret_cast<bf162*>(reinterpret_cast<bf16*>(p.D) + m * p.ldd + n) = o;
-            if (p.colsum) {  // statistics of exactly what the next kernel will read back
-              const float2 q = __bfloat1622float2(o);
-              x0 = q.x;
-              x1 = q.y;
+            const bf16* rp = reinterpret_cast<const bf16*>(p.residual) + m * p.ldr + n0;
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+              if (n0 + v * 8 < p.N) {
+                float a[8];
+                load8(rp + v * 8, a);
+#pragma unroll
+                for (int k = 0; k < 8; k++) x[v * 8 + k] += a[k];
+              }
             }
           }
-          if (p.colsum) {
-            cs0 += x0;
-            cs1 += x1;
-            cq0 += x0 * x0;
-            cq1 += x1 * x1;
+        }
+        // ---- store
+        if (p.d_f32) {
+          if (row_ok) {
+            float* dp = reinterpret_cast<float*>(p.D) + m * p.ldd + n0;
+            if (p.accumulate) {
+#pragma unroll
+              for (int j = 0; j < 32; j++)
+                if (n0 + j < p.N) atomicAdd(dp + j, x[j]);
+            } else {
+#pragma unroll
+              for (int v = 0; v < 8; v++)
+                if (n0 + v * 4 < p.N)
+                  *reinterpret_cast<float4*>(dp + v * 4) = make_float4(x[v * 4], x[v * 4 + 1], x[v * 4 + 2], x[v * 4 + 3]);
+            }
+          }
+        } else {
+          // round to bf16 first so that the statistics below describe exactly what was stored
+#pragma unroll
+          for (int j = 0; j < 32; j++) x[j] = __bfloat162float(__float2bfloat16_rn(x[j]));
+          if (row_ok) {
+            bf16* dp = reinterpret_cast<bf16*>(p.D) + m * p.ldd + n0;
+#pragma unroll
+            for (int v = 0; v < 4; v++)
+              if (n0 + v * 8 < p.N) store8(dp + v * 8, x + v * 8);
           }
         }
-        if (p.colsum && ncol_ok && rows > 0) {
-          atomicAdd(p.colsum + n, (double)cs0);
-          atomicAdd(p.colsum + n + 1, (double)cs1);
-          atomicAdd(p.colsumsq + n, (double)cq0);
-          atomicAdd(p.colsumsq + n + 1, (double)cq1);
+        // ---- per-column sum / sum of squares over the 32 rows of this warp (train-mode BN statistics)
+        if (p.colsum != nullptr) {
+          float s[32], q[32];
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            s[j] = row_ok ? x[j] : 0.f;
+            q[j] = s[j] * s[j];
+          }
+          // transposing butterfly: after 5 steps lane l holds the 32-row total of column l
+#pragma unroll
+          for (int step = 0; step < 5; step++) {
+            const int w = 16 >> step;  // 16, 8, 4, 2, 1 live values per lane after this step
+            const bool upper = (lane & w) != 0;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+              if (j < w) {
+                const float keep_s = upper ? s[j + w] : s[j];
+                const float send_s = upper ? s[j] : s[j + w];
+                const float keep_q = upper ? q[j + w] : q[j];
+                const float send_q = upper ? q[j] : q[j + w];
+                s[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, w);
+                q[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, w);
+              }
+            }
+          }
+          // lane l now owns column bitrev-free index: column = sum over steps of (lane & w) ? w : 0 = lane
+          const int n = n0 + lane;
+          if (n < p.N) {
+            atomicAdd(p.colsum + n, (double)s[0]);
+            atomicAdd(p.colsumsq + n, (double)q[0]);
+          }
         }
-        __syncwarp();
       }
       if (++acc == 2) {
         acc = 0;
@@ -464,7 +516,8 @@ extern "C" int mdhs_gemm_bf16(const mdhs_gemm_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!a || !a->A || !a->B || !a->D) return MDHS_ERR_ARG;
   if (a->M <= 0 || a->N <= 0 || a->K <= 0) return MDHS_ERR_ARG;
-  if ((a->K % 8) || (a->N % 2) || (a->lda % 8) || (a->ldb % 8)) return MDHS_ERR_ARG;
+  // K itself is free (TMA zero-fills the tail); only row strides must keep 16-byte alignment
+  if ((a->N % 8) || (a->lda % 8) || (a->ldb % 8)) return MDHS_ERR_ARG;
   if (a->a_mn_major && (a->M % 8)) return MDHS_ERR_ARG;
   if (a->b_mn_major && (a->N % 8)) return MDHS_ERR_ARG;
   if (((uintptr_t)a->A & 15) || ((uintptr_t)a->B & 15)) return MDHS_ERR_ARG;
@@ -472,7 +525,13 @@ extern "C" int mdhs_gemm_bf16(const mdhs_gemm_args* a, void* stream_) {
   if (a->split_k > 1 && (!a->accumulate || a->act || a->dact || a->aux_out || a->colsum)) return MDHS_ERR_ARG;
   if (a->dact != MDHS_ACT_NONE && !a->aux_in) return MDHS_ERR_ARG;
   if ((a->colsum == nullptr) != (a->colsumsq == nullptr)) return MDHS_ERR_ARG;
-  if ((a->ldd % 2) || (a->residual && (a->ldr % 2))) return MDHS_ERR_ARG;
+  if ((a->ldd % 8) || (a->residual && (a->ldr % 8)) || (a->aux_out && (a->ld_aux_out % 8)) ||
+      (a->aux_in && (a->ld_aux_in % 8)))
+    return MDHS_ERR_ARG;
+  if (((uintptr_t)a->D & 15) || ((uintptr_t)a->residual & 15) || ((uintptr_t)a->aux_out & 15) || ((uintptr_t)a->aux_in & 15) ||
+      ((uintptr_t)a->bias & 15))
+    return MDHS_ERR_ARG;
+  if (a->dropout_p < 0.f || a->dropout_p >= 1.f) return MDHS_ERR_ARG;
 
   Params p;
   p.M = a->M; p.N = a->N; p.K = a->K;
@@ -488,6 +547,7 @@ extern "C" int mdhs_gemm_bf16(const mdhs_gemm_args* a, void* stream_) {
   p.act = a->act; p.dact = a->dact;
   p.residual = a->residual; p.ldr = a->ldr; p.r_f32 = (a->r_dtype == MDHS_DT_F32);
   p.colsum = a->colsum; p.colsumsq = a->colsumsq;
+  p.drop_p = a->dropout_p; p.drop_seed = a->dropout_seed;
   p.num_m = p.num_n = 0;
 
   int bn = a->bn_hint;

@@ -1,0 +1,520 @@
+// LayerNorm and train-mode BatchNorm for the hot path: HBM-bound, 128-bit vectorised, warp-shuffle
+// reductions, fp32 statistics.  Activations are bf16 [rows, C] (tokens x features / NHWC pixels x
+// channels); parameters and their gradients are fp32.
+#include "common.cuh"
+#include "../../include/mdhs_b200.h"
+
+extern int64_t g_mdhs_launches;
+
+namespace {
+
+// ------------------------------------------------------------------ LayerNorm
+constexpr int LN_MAXCH = 8;  // C <= 8 * 256 = 2048
+
+// One warp per row.  x may be bf16 or fp32 (XF32).  y = LN(x) * gamma + beta, optional dropout on y.
+template <bool XF32, int NCH>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const void* __restrict__ x_, int64_t ldx, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, bf16* __restrict__ y, int64_t ldy,
+                                                     float* __restrict__ y32, float* __restrict__ mean_out,
+                                                     float* __restrict__ rstd_out, int rows, int C, float eps, float drop_p,
+                                                     uint64_t seed) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int64_t row = warp;
+  float v[NCH][8];
+  const int nch = C >> 8;  // full 256-wide chunks
+  const int rem = C & 255;
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; c++) {
+    const int col = c * 256 + lane * 8;
+    const bool ok = (c < nch) || (c == nch && lane * 8 < rem);
+    if (ok) {
+      if (XF32) {
+        const float* xp = reinterpret_cast<const float*>(x_) + row * ldx + col;
+        const float4 a = *reinterpret_cast<const float4*>(xp), b = *reinterpret_cast<const float4*>(xp + 4);
+        v[c][0] = a.x; v[c][1] = a.y; v[c][2] = a.z; v[c][3] = a.w;
+        v[c][4] = b.x; v[c][5] = b.y; v[c][6] = b.z; v[c][7] = b.w;
+      } else {
+        load8(reinterpret_cast<const bf16*>(x_) + row * ldx + col, v[c]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; i++) s += v[c][i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; i++) v[c][i] = 0.f;
+    }
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; c++) {
+    const bool ok = (c < nch) || (c == nch && lane * 8 < rem);
+    if (ok) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const float d = v[c][i] - mean;
+        q += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+  const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+#pragma unroll
+  for (int c = 0; c < NCH; c++) {
+    const int col = c * 256 + lane * 8;
+    const bool ok = (c < nch) || (c == nch && lane * 8 < rem);
+    if (ok) {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        o[i] = (v[c][i] - mean) * rstd * gamma[col + i] + beta[col + i];
+        if (drop_p > 0.f) o[i] *= dropout_scale(seed, (uint64_t)row * C + col + i, drop_p, inv_keep);
+      }
+      if (y) store8(y + row * ldy + col, o);
+      if (y32) {
+        float* yp = y32 + row * (int64_t)C + col;
+        *reinterpret_cast<float4*>(yp) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(yp + 4) = make_float4(o[4], o[5], o[6], o[7]);
+      }
+    }
+  }
+}
+
+// Backward.  dy (bf16 or fp32) is first multiplied by the forward output-dropout mask (drop_p/seed), then
+//   dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)),   dgamma += sum dy*xhat,  dbeta += sum dy.
+// dx is written as bf16 (dx) and optionally a second copy multiplied by another dropout mask
+// (dx_drop: gradient of the dense branch whose output dropout used (drop2_p, seed2)).
+template <bool XF32, bool DYF32, int NCH>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy_, int64_t lddy, const void* __restrict__ x_,
+                                                     int64_t ldx, const float* __restrict__ mean_in,
+                                                     const float* __restrict__ rstd_in, const float* __restrict__ gamma,
+                                                     bf16* __restrict__ dx, int64_t lddx, bf16* __restrict__ dx_drop,
+                                                     float* __restrict__ dx32, float* __restrict__ dgamma,
+                                                     float* __restrict__ dbeta, int rows, int C, float drop_p, uint64_t seed,
+                                                     float drop2_p, uint64_t seed2) {
+  __shared__ float red[8][256 + 1];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int nwarps_total = (gridDim.x * blockDim.x) >> 5;
+  const int nch = C >> 8;
+  const int rem = C & 255;
+  float dg[NCH][8], db[NCH][8];
+#pragma unroll
+  for (int c = 0; c < NCH; c++)
+#pragma unroll
+    for (int i = 0; i < 8; i++) dg[c][i] = db[c][i] = 0.f;
+  const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const float inv_keep2 = drop2_p > 0.f ? 1.f / (1.f - drop2_p) : 1.f;
+
+  for (int64_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += nwarps_total) {
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float xh[NCH][8], g[NCH][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+      const int col = c * 256 + lane * 8;
+      const bool ok = (c < nch) || (c == nch && lane * 8 < rem);
+      if (ok) {
+        float xv[8], dyv[8];
+        if (XF32) {
+          const float* xp = reinterpret_cast<const float*>(x_) + row * ldx + col;
+          const float4 a = *reinterpret_cast<const float4*>(xp), b = *reinterpret_cast<const float4*>(xp + 4);
+          xv[0] = a.x; xv[1] = a.y; xv[2] = a.z; xv[3] = a.w; xv[4] = b.x; xv[5] = b.y; xv[6] = b.z; xv[7] = b.w;
+        } else {
+          load8(reinterpret_cast<const bf16*>(x_) + row * ldx + col, xv);
+        }
+        if (DYF32) {
+          const float* dp = reinterpret_cast<const float*>(dy_) + row * lddy + col;
+          const float4 a = *reinterpret_cast<const float4*>(dp), b = *reinterpret_cast<const float4*>(dp + 4);
+          dyv[0] = a.x; dyv[1] = a.y; dyv[2] = a.z; dyv[3] = a.w; dyv[4] = b.x; dyv[5] = b.y; dyv[6] = b.z; dyv[7] = b.w;
+        } else {
+          load8(reinterpret_cast<const bf16*>(dy_) + row * lddy + col, dyv);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          float d = dyv[i];
+          if (drop_p > 0.f) d *= dropout_scale(seed, (uint64_t)row * C + col + i, drop_p, inv_keep);
+          const float h = (xv[i] - mean) * rstd;
+          xh[c][i] = h;
+          dg[c][i] += d * h;
+          db[c][i] += d;
+          const float gd = d * gamma[col + i];
+          g[c][i] = gd;
+          s1 += gd;
+          s2 += gd * h;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) xh[c][i] = g[c][i] = 0.f;
+      }
+    }
+    s1 = warp_sum(s1) / (float)C;
+    s2 = warp_sum(s2) / (float)C;
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+      const int col = c * 256 + lane * 8;
+      const bool ok = (c < nch) || (c == nch && lane * 8 < rem);
+      if (ok) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) o[i] = rstd * (g[c][i] - s1 - xh[c][i] * s2);
+        if (dx) store8(dx + row * lddx + col, o);
+        if (dx32) {
+          float* p = dx32 + row * (int64_t)C + col;
+          *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<float4*>(p + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        }
+        if (dx_drop) {
+#pragma unroll
+          for (int i = 0; i < 8; i++) o[i] *= dropout_scale(seed2, (uint64_t)row * C + col + i, drop2_p, inv_keep2);
+          store8(dx_drop + row * lddx + col, o);
+        }
+      }
+    }
+  }
+  // cross-warp reduction of the parameter gradients, one 256-column chunk at a time
+  if (dgamma == nullptr && dbeta == nullptr) return;
+  const int nw = blockDim.x >> 5;
+  for (int pass = 0; pass < 2; pass++) {
+    for (int c = 0; c < NCH; c++) {
+      if (c * 256 >= C) break;
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 8; i++) red[wib][lane * 8 + i] = pass == 0 ? dg[c][i] : db[c][i];
+      __syncthreads();
+      const int col = c * 256 + threadIdx.x;
+      if (threadIdx.x < 256 && col < C) {
+        float s = 0.f;
+        for (int w = 0; w < nw; w++) s += red[w][threadIdx.x];
+        float* dst = pass == 0 ? dgamma : dbeta;
+        if (dst) atomicAdd(dst + col, s);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ BatchNorm (NHWC, train mode)
+// Finalise batch statistics from fp64 column sums (written by the GEMM epilogue or col_stats):
+// mean / invstd, running-stat update (momentum, unbiased variance) and the fused scale/shift pair.
+__global__ void bn_finalize_kernel(const double* __restrict__ colsum, const double* __restrict__ colsumsq, int64_t count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
+                                   float eps, float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ scale,
+                                   float* __restrict__ shift, int C, int training) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mu, var;
+  if (training) {
+    const double m = colsum[c] / (double)count;
+    double v = colsumsq[c] / (double)count - m * m;
+    if (v < 0.0) v = 0.0;
+    mu = (float)m;
+    var = (float)v;
+    if (running_mean) {
+      const double unbiased = count > 1 ? v * (double)count / (double)(count - 1) : v;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mu;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+  } else {
+    mu = running_mean[c];
+    var = running_var[c];
+  }
+  const float is = rsqrtf(var + eps);
+  if (mean) mean[c] = mu;
+  if (invstd) invstd[c] = is;
+  const float sc = gamma[c] * is;
+  scale[c] = sc;
+  shift[c] = beta[c] - mu * sc;
+}
+
+// y = act(x * scale[c] + shift[c] (+ residual)); 8 channels per thread, grid-stride over rows*C/8.
+__global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ scale,
+                                                       const float* __restrict__ shift, const bf16* __restrict__ residual,
+                                                       bf16* __restrict__ y, int64_t total_vec, int C, int relu) {
+  const int cvec = C >> 3;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cvec) * 8;
+    float v[8], r[8];
+    load8(x + i * 8, v);
+    const float4 s0 = *reinterpret_cast<const float4*>(scale + c0), s1 = *reinterpret_cast<const float4*>(scale + c0 + 4);
+    const float4 h0 = *reinterpret_cast<const float4*>(shift + c0), h1 = *reinterpret_cast<const float4*>(shift + c0 + 4);
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+    if (residual) load8(residual + i * 8, r);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      float o = v[k] * sc[k] + sh[k];
+      if (residual) o += r[k];
+      if (relu) o = fmaxf(o, 0.f);
+      v[k] = o;
+    }
+    store8(y + i * 8, v);
+  }
+}
+
+// Per-channel reductions for BN backward: sum(dy') and sum(dy' * xhat), dy' = dy * [y > 0] when relu.
+// Block = 256 threads = 32 channel-vectors(8) x 8 row lanes; grid = (C/256 ceil, row blocks).
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                            const bf16* __restrict__ y, const float* __restrict__ mean,
+                                                            const float* __restrict__ invstd, double* __restrict__ sum_dy,
+                                                            double* __restrict__ sum_dy_xhat, int64_t rows, int C,
+                                                            int rows_per_block, int relu) {
+  __shared__ float sh[2][8][256 + 8];
+  const int cv = threadIdx.x & 31;   // which 8-channel vector inside the 256-channel slab
+  const int rl = threadIdx.x >> 5;   // row lane 0..7
+  const int c0 = blockIdx.x * 256 + cv * 8;
+  const bool ok = c0 < C;
+  float a[8], b[8], mu[8], is[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    a[k] = b[k] = 0.f;
+    mu[k] = ok ? mean[c0 + k] : 0.f;
+    is[k] = ok ? invstd[c0 + k] : 0.f;
+  }
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = min(rows, r0 + rows_per_block);
+  if (ok) {
+    for (int64_t r = r0 + rl; r < r1; r += 8) {
+      float d[8], xv[8], yv[8];
+      load8(dy + r * C + c0, d);
+      load8(x + r * C + c0, xv);
+      if (relu) load8(y + r * C + c0, yv);
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const float dd = (relu && !(yv[k] > 0.f)) ? 0.f : d[k];
+        a[k] += dd;
+        b[k] += dd * (xv[k] - mu[k]) * is[k];
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    sh[0][rl][cv * 8 + k] = a[k];
+    sh[1][rl][cv * 8 + k] = b[k];
+  }
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < C) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+      s0 += sh[0][w][threadIdx.x];
+      s1 += sh[1][w][threadIdx.x];
+    }
+    atomicAdd(sum_dy + c, (double)s0);
+    atomicAdd(sum_dy_xhat + c, (double)s1);
+  }
+}
+
+// dx = gamma*invstd * (dy' - sum_dy/M - xhat * sum_dy_xhat/M); optionally also writes dy' (the
+// ReLU-masked incoming gradient) for the identity branch; accumulates dgamma/dbeta once (block 0).
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                           const bf16* __restrict__ y, const float* __restrict__ mean,
+                                                           const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                           const double* __restrict__ sum_dy,
+                                                           const double* __restrict__ sum_dy_xhat, bf16* __restrict__ dx,
+                                                           bf16* __restrict__ dz, float* __restrict__ dgamma,
+                                                           float* __restrict__ dbeta, int64_t rows, int C, int relu) {
+  const int cvec = C >> 3;
+  const int64_t total_vec = rows * cvec;
+  const float inv_m = 1.f / (float)rows;
+  if (blockIdx.x == 0 && dgamma) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      dgamma[c] += (float)sum_dy_xhat[c];
+      dbeta[c] += (float)sum_dy[c];
+    }
+  }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cvec) * 8;
+    float d[8], xv[8], yv[8], o[8];
+    load8(dy + i * 8, d);
+    load8(x + i * 8, xv);
+    if (relu) load8(y + i * 8, yv);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int c = c0 + k;
+      const float dd = (relu && !(yv[k] > 0.f)) ? 0.f : d[k];
+      d[k] = dd;
+      const float is = invstd[c];
+      const float xh = (xv[k] - mean[c]) * is;
+      o[k] = gamma[c] * is * (dd - (float)sum_dy[c] * inv_m - xh * (float)sum_dy_xhat[c] * inv_m);
+    }
+    store8(dx + i * 8, o);
+    if (dz) store8(dz + i * 8, d);
+  }
+}
+
+// Per-column sum / sum of squares of a bf16 [rows, C] matrix into fp64 (standalone BN statistics) or
+// fp32 (+=, bias gradients).  Same thread layout as bn_bwd_reduce.
+__global__ void __launch_bounds__(256) col_stats_kernel(const bf16* __restrict__ x, int64_t ldx, double* __restrict__ sum64,
+                                                        double* __restrict__ sumsq64, float* __restrict__ sum32,
+                                                        int64_t rows, int C, int rows_per_block) {
+  __shared__ float sh[2][8][256 + 8];
+  const int cv = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 256 + cv * 8;
+  const bool ok = c0 < C;
+  float a[8], b[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) a[k] = b[k] = 0.f;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = min(rows, r0 + rows_per_block);
+  if (ok) {
+    for (int64_t r = r0 + rl; r < r1; r += 8) {
+      float v[8];
+      load8(x + r * ldx + c0, v);
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        a[k] += v[k];
+        b[k] += v[k] * v[k];
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    sh[0][rl][cv * 8 + k] = a[k];
+    sh[1][rl][cv * 8 + k] = b[k];
+  }
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < C) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+      s0 += sh[0][w][threadIdx.x];
+      s1 += sh[1][w][threadIdx.x];
+    }
+    if (sum64) atomicAdd(sum64 + c, (double)s0);
+    if (sumsq64) atomicAdd(sumsq64 + c, (double)s1);
+    if (sum32) atomicAdd(sum32 + c, s0);
+  }
+}
+
+int grid_for(int64_t work_items, int block) {
+  int64_t g = (work_items + block - 1) / block;
+  const int64_t cap = 148 * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+extern "C" int mdhs_layernorm_fwd(const void* x, int x_f32, int64_t ldx, const float* gamma, const float* beta, void* y_bf16,
+                                  int64_t ldy, float* y_f32, float* mean, float* rstd, int rows, int C, float eps,
+                                  float drop_p, uint64_t seed, void* stream) {
+  if (!x || !gamma || !beta || rows <= 0 || C <= 0 || (C % 8) || C > LN_MAXCH * 256) return MDHS_ERR_ARG;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int blocks = ceil_div(rows, 8);
+  g_mdhs_launches++;
+#define LNF(XF, N) ln_fwd_kernel<XF, N><<<blocks, 256, 0, st>>>(x, ldx, gamma, beta, (bf16*)y_bf16, ldy, y_f32, mean, rstd, rows, C, eps, drop_p, seed)
+#define LNF_N(XF)                      \
+  do {                                 \
+    if (C <= 256) LNF(XF, 1);          \
+    else if (C <= 512) LNF(XF, 2);     \
+    else if (C <= 768) LNF(XF, 3);     \
+    else if (C <= 1024) LNF(XF, 4);    \
+    else LNF(XF, 8);                   \
+  } while (0)
+  if (x_f32) LNF_N(true); else LNF_N(false);
+#undef LNF_N
+#undef LNF
+  MDHS_RETURN_LAST();
+}
+
+extern "C" int mdhs_layernorm_bwd(const void* dy, int dy_f32, int64_t lddy, const void* x, int x_f32, int64_t ldx,
+                                  const float* mean, const float* rstd, const float* gamma, void* dx_bf16, int64_t lddx,
+                                  void* dx_drop_bf16, float* dx_f32, float* dgamma, float* dbeta, int rows, int C,
+                                  float drop_p, uint64_t seed, float drop2_p, uint64_t seed2, void* stream) {
+  if (!dy || !x || !mean || !rstd || !gamma || rows <= 0 || (C % 8) || C > LN_MAXCH * 256) return MDHS_ERR_ARG;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int blocks = ceil_div(rows, 8 * 4);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  g_mdhs_launches++;
+#define LNB1(XF, DF, N)                                                                                                       \
+  ln_bwd_kernel<XF, DF, N><<<blocks, 256, 0, st>>>(dy, lddy, x, ldx, mean, rstd, gamma, (bf16*)dx_bf16, lddx,                  \
+                                                   (bf16*)dx_drop_bf16, dx_f32, dgamma, dbeta, rows, C, drop_p, seed, drop2_p, \
+                                                   seed2)
+#define LNB(XF, DF)                     \
+  do {                                  \
+    if (C <= 256) LNB1(XF, DF, 1);      \
+    else if (C <= 512) LNB1(XF, DF, 2); \
+    else if (C <= 768) LNB1(XF, DF, 3); \
+    else if (C <= 1024) LNB1(XF, DF, 4);\
+    else LNB1(XF, DF, 8);               \
+  } while (0)
+  if (x_f32) {
+    if (dy_f32) LNB(true, true); else LNB(true, false);
+  } else {
+    if (dy_f32) LNB(false, true); else LNB(false, false);
+  }
+#undef LNB
+#undef LNB1
+  MDHS_RETURN_LAST();
+}
+
+extern "C" int mdhs_bn_finalize(const double* colsum, const double* colsumsq, int64_t count, const float* gamma,
+                                const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                                float* mean, float* invstd, float* scale, float* shift, int C, int training, void* stream) {
+  if (!gamma || !beta || !scale || !shift || C <= 0) return MDHS_ERR_ARG;
+  if (training && (!colsum || !colsumsq || count <= 0)) return MDHS_ERR_ARG;
+  if (!training && (!running_mean || !running_var)) return MDHS_ERR_ARG;
+  g_mdhs_launches++;
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      colsum, colsumsq, count, gamma, beta, running_mean, running_var, momentum, eps, mean, invstd, scale, shift, C, training);
+  MDHS_RETURN_LAST();
+}
+
+extern "C" int mdhs_bn_apply(const void* x, const float* scale, const float* shift, const void* residual, void* y,
+                             int64_t rows, int C, int relu, void* stream) {
+  if (!x || !scale || !shift || !y || rows <= 0 || (C % 8)) return MDHS_ERR_ARG;
+  const int64_t total_vec = rows * (C / 8);
+  g_mdhs_launches++;
+  bn_apply_kernel<<<grid_for(total_vec, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      (const bf16*)x, scale, shift, (const bf16*)residual, (bf16*)y, total_vec, C, relu);
+  MDHS_RETURN_LAST();
+}
+
+extern "C" int mdhs_bn_bwd(const void* dy, const void* x, const void* y, const float* mean, const float* invstd,
+                           const float* gamma, double* sum_dy, double* sum_dy_xhat, void* dx, void* dz, float* dgamma,
+                           float* dbeta, int64_t rows, int C, int relu, void* stream) {
+  if (!dy || !x || !mean || !invstd || !gamma || !sum_dy || !sum_dy_xhat || !dx || rows <= 0 || (C % 8)) return MDHS_ERR_ARG;
+  if (relu && !y) return MDHS_ERR_ARG;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(sum_dy, 0, sizeof(double) * C, st);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemsetAsync(sum_dy_xhat, 0, sizeof(double) * C, st);
+  if (e != cudaSuccess) return (int)e;
+  const int cslabs = ceil_div(C, 256);
+  int row_blocks = (148 * 8) / cslabs;
+  if (row_blocks < 1) row_blocks = 1;
+  int rpb = ceil_div(rows, row_blocks);
+  rpb = ((rpb + 7) / 8) * 8;
+  row_blocks = ceil_div(rows, rpb);
+  g_mdhs_launches += 2;
+  bn_bwd_reduce_kernel<<<dim3(cslabs, row_blocks), 256, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, mean, invstd,
+                                                                 sum_dy, sum_dy_xhat, rows, C, rpb, relu);
+  const int64_t total_vec = rows * (C / 8);
+  bn_bwd_apply_kernel<<<grid_for(total_vec, 256), 256, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, mean, invstd,
+                                                                gamma, sum_dy, sum_dy_xhat, (bf16*)dx, (bf16*)dz, dgamma, dbeta,
+                                                                rows, C, relu);
+  MDHS_RETURN_LAST();
+}
+
+extern "C" int mdhs_col_stats(const void* x, int64_t ldx, double* sum64, double* sumsq64, float* sum32, int64_t rows, int C,
+                              void* stream) {
+  if (!x || rows <= 0 || (C % 8) || (ldx % 8)) return MDHS_ERR_ARG;
+  const int cslabs = ceil_div(C, 256);
+  int row_blocks = (148 * 8) / cslabs;
+  if (row_blocks < 1) row_blocks = 1;
+  int rpb = ceil_div(rows, row_blocks);
+  rpb = ((rpb + 7) / 8) * 8;
+  row_blocks = ceil_div(rows, rpb);
+  g_mdhs_launches++;
+  col_stats_kernel<<<dim3(cslabs, row_blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      (const bf16*)x, ldx, sum64, sumsq64, sum32, rows, C, rpb);
+  MDHS_RETURN_LAST();
+}

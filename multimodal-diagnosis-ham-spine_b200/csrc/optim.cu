@@ -1,0 +1,108 @@
+// Fused optimizer step over the flat parameter buffer (scripts/train.py:257-309 Adam/AdamW/SGD;
+// mibf_net/train_resnet.py:136-139).  One launch updates every parameter: reads the (all-reduced) fp32
+// gradient, updates fp32 master weights and moments, refreshes the bf16 shadow copy consumed by the
+// tensor-core kernels and zeroes the gradient for the next step.  HBM-bound: 4 x float4 per thread.
+#include "common.cuh"
+#include "../../include/mdhs_b200.h"
+
+extern int64_t g_mdhs_launches;
+
+namespace {
+
+// mode 0: AdamW (decoupled decay), 1: Adam (L2 decay folded into the gradient)
+__global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                                        float* __restrict__ v, bf16* __restrict__ shadow, int64_t n, float lr,
+                                                        float beta1, float beta2, float eps, float wd, float bc1, float bc2,
+                                                        float grad_scale, int mode, int zero_grad) {
+  const int64_t nv = n >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    float4 gg = reinterpret_cast<float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float* P = reinterpret_cast<float*>(&pp);
+    float* G = reinterpret_cast<float*>(&gg);
+    float* M = reinterpret_cast<float*>(&mm);
+    float* V = reinterpret_cast<float*>(&vv);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      float gr = G[k] * grad_scale;
+      if (mode == 1) gr += wd * P[k];
+      else P[k] *= (1.f - lr * wd);
+      M[k] = beta1 * M[k] + (1.f - beta1) * gr;
+      V[k] = beta2 * V[k] + (1.f - beta2) * gr * gr;
+      const float denom = sqrtf(V[k]) / sqrtf(bc2) + eps;
+      P[k] -= (lr / bc1) * (M[k] / denom);
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (shadow) {
+      bf162* s = reinterpret_cast<bf162*>(shadow) + i * 2;
+      s[0] = __floats2bfloat162_rn(P[0], P[1]);
+      s[1] = __floats2bfloat162_rn(P[2], P[3]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) sgd_flat_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ mom,
+                                                       bf16* __restrict__ shadow, int64_t n, float lr, float momentum, float wd,
+                                                       float grad_scale, int first_step, int zero_grad) {
+  const int64_t nv = n >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    float4 gg = reinterpret_cast<float4*>(g)[i];
+    float4 bb = mom ? reinterpret_cast<float4*>(mom)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float* P = reinterpret_cast<float*>(&pp);
+    float* G = reinterpret_cast<float*>(&gg);
+    float* Bf = reinterpret_cast<float*>(&bb);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      float gr = G[k] * grad_scale + wd * P[k];
+      if (mom) {
+        Bf[k] = first_step ? gr : momentum * Bf[k] + gr;  // torch.optim.SGD: buffer initialised with the gradient
+        gr = Bf[k];
+      }
+      P[k] -= lr * gr;
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    if (mom) reinterpret_cast<float4*>(mom)[i] = bb;
+    if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (shadow) {
+      bf162* s = reinterpret_cast<bf162*>(shadow) + i * 2;
+      s[0] = __floats2bfloat162_rn(P[0], P[1]);
+      s[1] = __floats2bfloat162_rn(P[2], P[3]);
+    }
+  }
+}
+
+int grid_for(int64_t items) {
+  int64_t g = (items + 255) / 256;
+  const int64_t cap = 148 * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+// n must be a multiple of 4 (the flat buffer is padded); all pointers 16-byte aligned.
+extern "C" int mdhs_adam_flat(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, int64_t n,
+                              float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                              int adamw, int zero_grad, void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq || n <= 0 || (n % 4) || step < 1) return MDHS_ERR_ARG;
+  const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+  g_mdhs_launches++;
+  adam_flat_kernel<<<grid_for(n / 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      params, grads, exp_avg, exp_avg_sq, (bf16*)shadow_bf16, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale,
+      adamw ? 0 : 1, zero_grad);
+  MDHS_RETURN_LAST();
+}
+
+extern "C" int mdhs_sgd_flat(float* params, float* grads, float* momentum_buf, void* shadow_bf16, int64_t n, float lr,
+                             float momentum, float weight_decay, float grad_scale, int first_step, int zero_grad, void* stream) {
+  if (!params || !grads || n <= 0 || (n % 4)) return MDHS_ERR_ARG;
+  g_mdhs_launches++;
+  sgd_flat_kernel<<<grid_for(n / 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      params, grads, momentum_buf, (bf16*)shadow_bf16, n, lr, momentum, weight_decay, grad_scale, first_step, zero_grad);
+  MDHS_RETURN_LAST();
+}

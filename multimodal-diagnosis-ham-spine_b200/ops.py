@@ -29,7 +29,7 @@ def _require_cuda(*ts):
 
 def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bias=None, act=ACT_NONE,
          aux_out=None, aux_in=None, dact=ACT_NONE, residual=None, accumulate=False, split_k=1,
-         bn_hint=0, colsum=None, colsumsq=None, M=None, N=None, K=None):
+         bn_hint=0, colsum=None, colsumsq=None, M=None, N=None, K=None, dropout_p=0.0, dropout_seed=0):
     """D[M,N] (+)= epi(A . B^T).  `a` is [M,K] (K-major) or [K,M] when a_mn; `b` is [N,K] or [K,N] when b_mn.
     2-D bf16 tensors with unit inner stride (row stride may exceed the row length)."""
     _require_cuda(a, b)
@@ -71,8 +71,262 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bi
         args.residual, args.ldr = residual.data_ptr(), residual.stride(0)
         args.r_dtype = DT_F32 if residual.dtype == torch.float32 else DT_BF16
     args.split_k, args.bn_hint = split_k, bn_hint
+    args.dropout_p, args.dropout_seed = float(dropout_p), int(dropout_seed)
     if colsum is not None:
         assert colsum.dtype == torch.float64 and colsumsq.dtype == torch.float64
         args.colsum, args.colsumsq = colsum.data_ptr(), colsumsq.data_ptr()
     check(_lib.lib().mdhs_gemm_bf16(ctypes.byref(args), _stream()), "mdhs_gemm_bf16")
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# thin wrappers for the remaining entry points (argument order = include/mdhs_b200.h)
+# --------------------------------------------------------------------------------------------
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def layernorm_fwd(x, gamma, beta, eps, *, out_bf16=True, out_f32=False, drop_p=0.0, seed=0, save_stats=True):
+    """x: [rows, C] bf16 or fp32 (row stride may exceed C).  Returns (y_bf16|None, y_f32|None, mean, rstd)."""
+    _require_cuda(x, gamma, beta)
+    rows, C = x.shape
+    y = torch.empty((rows, C), device=x.device, dtype=torch.bfloat16) if out_bf16 else None
+    y32 = torch.empty((rows, C), device=x.device, dtype=torch.float32) if out_f32 else None
+    mean = torch.empty(rows, device=x.device, dtype=torch.float32) if save_stats else None
+    rstd = torch.empty(rows, device=x.device, dtype=torch.float32) if save_stats else None
+    _lib.call("mdhs_layernorm_fwd", _p(x), int(x.dtype == torch.float32), x.stride(0), _p(gamma), _p(beta), _p(y), C,
+              _p(y32), _p(mean), _p(rstd), rows, C, float(eps), float(drop_p), int(seed), _s())
+    return y, y32, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, *, dx_bf16=True, dx_f32=False, drop_p=0.0, seed=0,
+                  drop2_p=0.0, seed2=0, want_dx_drop=False):
+    rows, C = x.shape
+    dx = torch.empty((rows, C), device=x.device, dtype=torch.bfloat16) if dx_bf16 else None
+    dxd = torch.empty((rows, C), device=x.device, dtype=torch.bfloat16) if want_dx_drop else None
+    dx32 = torch.empty((rows, C), device=x.device, dtype=torch.float32) if dx_f32 else None
+    _lib.call("mdhs_layernorm_bwd", _p(dy), int(dy.dtype == torch.float32), dy.stride(0), _p(x),
+              int(x.dtype == torch.float32), x.stride(0), _p(mean), _p(rstd), _p(gamma), _p(dx), C, _p(dxd), _p(dx32),
+              _p(dgamma), _p(dbeta), rows, C, float(drop_p), int(seed), float(drop2_p), int(seed2), _s())
+    return dx, dxd, dx32
+
+
+def bn_finalize(colsum, colsumsq, count, gamma, beta, running_mean, running_var, momentum, eps, training=True):
+    C = gamma.numel()
+    dev = gamma.device
+    mean = torch.empty(C, device=dev, dtype=torch.float32)
+    invstd = torch.empty(C, device=dev, dtype=torch.float32)
+    scale = torch.empty(C, device=dev, dtype=torch.float32)
+    shift = torch.empty(C, device=dev, dtype=torch.float32)
+    _lib.call("mdhs_bn_finalize", _p(colsum), _p(colsumsq), int(count), _p(gamma), _p(beta), _p(running_mean),
+              _p(running_var), float(momentum), float(eps), _p(mean), _p(invstd), _p(scale), _p(shift), C, int(training), _s())
+    return mean, invstd, scale, shift
+
+
+def bn_apply(x, scale, shift, residual=None, relu=True, out=None):
+    rows, C = x.shape
+    y = torch.empty_like(x) if out is None else out
+    _lib.call("mdhs_bn_apply", _p(x), _p(scale), _p(shift), _p(residual), _p(y), rows, C, int(relu), _s())
+    return y
+
+
+def bn_bwd(dy, x, y, mean, invstd, gamma, dgamma, dbeta, relu=True, want_dz=False):
+    rows, C = x.shape
+    ws = torch.empty((2, C), device=x.device, dtype=torch.float64)
+    dx = torch.empty_like(x)
+    dz = torch.empty_like(x) if want_dz else None
+    _lib.call("mdhs_bn_bwd", _p(dy), _p(x), _p(y), _p(mean), _p(invstd), _p(gamma), ws[0].data_ptr(), ws[1].data_ptr(),
+              _p(dx), _p(dz), _p(dgamma), _p(dbeta), rows, C, int(relu), _s())
+    return dx, dz
+
+
+def col_stats(x, sum64=None, sumsq64=None, sum32=None):
+    rows, C = x.shape
+    _lib.call("mdhs_col_stats", _p(x), x.stride(0), _p(sum64), _p(sumsq64), _p(sum32), rows, C, _s())
+
+
+def im2col_nchw_f32(x, R, S, stride, pad, ldc):
+    B, C, H, W = x.shape
+    Ho, Wo = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
+    col = torch.empty((B * Ho * Wo, ldc), device=x.device, dtype=torch.bfloat16)
+    _lib.call("mdhs_im2col_nchw_f32", _p(x), _p(col), B, C, H, W, R, S, stride, pad, ldc, _s())
+    return col, Ho, Wo
+
+
+def im2col_nhwc(x, B, H, W, C, R, S, stride, pad):
+    Ho, Wo = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
+    col = torch.empty((B * Ho * Wo, R * S * C), device=x.device, dtype=torch.bfloat16)
+    _lib.call("mdhs_im2col_nhwc", _p(x), _p(col), B, H, W, C, R, S, stride, pad, _s())
+    return col, Ho, Wo
+
+
+def col2im_nhwc(dcol, B, H, W, C, R, S, stride, pad, add=None):
+    dx = torch.empty((B * H * W, C), device=dcol.device, dtype=torch.bfloat16)
+    _lib.call("mdhs_col2im_nhwc", _p(dcol), _p(add), _p(dx), B, H, W, C, R, S, stride, pad, _s())
+    return dx
+
+
+def maxpool_fwd(x, B, H, W, C):
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y = torch.empty((B * Ho * Wo, C), device=x.device, dtype=torch.bfloat16)
+    idx = torch.empty((B * Ho * Wo, C), device=x.device, dtype=torch.uint8)
+    _lib.call("mdhs_maxpool3x3s2_fwd", _p(x), _p(y), _p(idx), B, H, W, C, _s())
+    return y, idx, Ho, Wo
+
+
+def maxpool_bwd(dy, idx, B, H, W, C):
+    dx = torch.empty((B * H * W, C), device=dy.device, dtype=torch.bfloat16)
+    _lib.call("mdhs_maxpool3x3s2_bwd", _p(dy), _p(idx), _p(dx), B, H, W, C, _s())
+    return dx
+
+
+def mean_tokens_fwd(x, B, T, C, scale=None, out32=None, accumulate=False, want_bf16=False):
+    scale = 1.0 / T if scale is None else scale
+    if out32 is None and not want_bf16:
+        out32 = torch.empty((B, C), device=x.device, dtype=torch.float32)
+    y16 = torch.empty((B, C), device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    _lib.call("mdhs_mean_tokens_fwd", _p(x), _p(out32), _p(y16), B, T, C, float(scale), int(accumulate), _s())
+    return out32, y16
+
+
+def mean_tokens_bwd(dy, B, T, C, scale=None):
+    scale = 1.0 / T if scale is None else scale
+    dx = torch.empty((B * T, C), device=dy.device, dtype=torch.bfloat16)
+    if dy.dtype == torch.float32:
+        _lib.call("mdhs_mean_tokens_bwd", _p(dy), None, _p(dx), B, T, C, float(scale), _s())
+    else:
+        _lib.call("mdhs_mean_tokens_bwd", None, _p(dy), _p(dx), B, T, C, float(scale), _s())
+    return dx
+
+
+def conv_weight_pack(w, ldk=None, out=None):
+    O, I, R, S = w.shape
+    ldk = R * S * I if ldk is None else ldk
+    wp = torch.empty((O, ldk), device=w.device, dtype=torch.bfloat16) if out is None else out
+    _lib.call("mdhs_conv_weight_pack", _p(w), _p(wp), O, I, R, S, ldk, _s())
+    return wp
+
+
+def conv_wgrad_unpack(gp, g):
+    O, I, R, S = g.shape
+    _lib.call("mdhs_conv_wgrad_unpack", _p(gp), _p(g), O, I, R, S, gp.stride(0), _s())
+
+
+def cast_f32_bf16(x, out=None):
+    y = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if out is None else out
+    _lib.call("mdhs_cast_f32_bf16", _p(x), _p(y), x.numel(), _s())
+    return y
+
+
+def cast_bf16_f32(x, out=None):
+    y = torch.empty(x.shape, device=x.device, dtype=torch.float32) if out is None else out
+    _lib.call("mdhs_cast_bf16_f32", _p(x), _p(y), x.numel(), _s())
+    return y
+
+
+def nhwc_bf16_to_nchw_f32(x, B, H, W, C):
+    y = torch.empty((B, C, H, W), device=x.device, dtype=torch.float32)
+    _lib.call("mdhs_nhwc_bf16_to_nchw_f32", _p(x), _p(y), B, H, W, C, _s())
+    return y
+
+
+def nchw_f32_to_nhwc_bf16(x):
+    B, C, H, W = x.shape
+    y = torch.empty((B * H * W, C), device=x.device, dtype=torch.bfloat16)
+    _lib.call("mdhs_nchw_f32_to_nhwc_bf16", _p(x), _p(y), B, H, W, C, _s())
+    return y
+
+
+def attention_fwd(q, k, v, B, H, Sq, Sk, D, scale, key_mask=None, drop_p=0.0, seed=0, out=None):
+    """q/k/v: 2-D token-major bf16 views [B*S, >= H*D] (row stride free)."""
+    o = torch.empty((B * Sq, H * D), device=q.device, dtype=torch.bfloat16) if out is None else out
+    lse = torch.empty((B * H * Sq,), device=q.device, dtype=torch.float32)
+    _lib.call("mdhs_attention_fwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0),
+              _p(key_mask), _p(lse), B, H, Sq, Sk, D, float(scale), float(drop_p), int(seed), _s())
+    return o, lse
+
+
+def attention_bwd(q, k, v, o, d_o, lse, B, H, Sq, Sk, D, scale, key_mask=None, drop_p=0.0, seed=0, dq=None, dk=None, dv=None):
+    """dq/dk/dv: optional pre-allocated bf16 views with the same row strides as q/k/v."""
+    if dq is None:
+        dq = torch.empty((B * Sq, H * D), device=q.device, dtype=torch.bfloat16)
+        assert q.stride(0) == H * D
+    if dk is None:
+        dk = torch.empty((B * Sk, H * D), device=q.device, dtype=torch.bfloat16)
+        dv = torch.empty((B * Sk, H * D), device=q.device, dtype=torch.bfloat16)
+        assert k.stride(0) == H * D and v.stride(0) == H * D
+    assert dq.stride(0) == q.stride(0) and dk.stride(0) == k.stride(0) and dv.stride(0) == v.stride(0)
+    assert d_o.stride(0) == o.stride(0)
+    dk32 = dv32 = None
+    if Sq > 64:
+        dk32 = torch.zeros((B * Sk, k.stride(0)), device=q.device, dtype=torch.float32)
+        dv32 = torch.zeros((B * Sk, v.stride(0)), device=q.device, dtype=torch.float32)
+    _lib.call("mdhs_attention_bwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), _p(d_o), o.stride(0),
+              _p(key_mask), _p(lse), _p(dq), _p(dk), _p(dv), _p(dk32), _p(dv32), B, H, Sq, Sk, D, float(scale),
+              float(drop_p), int(seed), _s())
+    if dk32 is not None:
+        # fp32 accumulators cover the full row stride; copy the head columns back as bf16
+        dk.copy_(cast_f32_bf16(dk32)[:, :dk.shape[1]])
+        dv.copy_(cast_f32_bf16(dv32)[:, :dv.shape[1]])
+    return dq, dk, dv
+
+
+def embed_gather(ids, type_ids, word, pos, type_emb, S):
+    rows = ids.numel()
+    C = word.shape[1]
+    e = torch.empty((rows, C), device=word.device, dtype=torch.float32)
+    _lib.call("mdhs_embed_gather", _p(ids), _p(type_ids), _p(word), _p(pos), _p(type_emb), _p(e), rows, S, C, word.shape[0], _s())
+    return e
+
+
+def embed_scatter(de, ids, type_ids, gword, gpos, gtype, S):
+    rows, C = de.shape
+    vocab = gword.shape[0] if gword is not None else 1 << 30
+    _lib.call("mdhs_embed_scatter", _p(de), _p(ids), _p(type_ids), _p(gword), _p(gpos), _p(gtype), rows, S, C, vocab, _s())
+
+
+def linear_f32_fwd(x, w, bias=None, act=ACT_NONE):
+    M, K = x.shape
+    N = w.shape[0]
+    y = torch.empty((M, N), device=x.device, dtype=torch.float32)
+    _lib.call("mdhs_linear_f32_fwd", _p(x), x.stride(0), _p(w), _p(bias), _p(y), N, M, N, K, act, _s())
+    return y
+
+
+def linear_f32_bwd(dy, x, w, dw=None, db=None, need_dx=True):
+    M, N = dy.shape
+    K = w.shape[1]
+    dx = torch.empty((M, K), device=dy.device, dtype=torch.float32) if need_dx else None
+    _lib.call("mdhs_linear_f32_bwd", _p(dy), dy.stride(0), _p(x), x.stride(0) if x is not None else 0, _p(w), _p(dx), K, 0,
+              _p(dw), _p(db), M, N, K, _s())
+    return dx
+
+
+def ce_loss(logits, labels, class_weights=None, label_smoothing=0.0, focal=False, gamma=2.0, want_grad=True):
+    B, C = logits.shape
+    loss = torch.empty(1, device=logits.device, dtype=torch.float32)
+    dl = torch.empty((B, C), device=logits.device, dtype=torch.float32) if want_grad else None
+    _lib.call("mdhs_ce_loss", _p(logits), logits.stride(0), _p(labels), _p(class_weights), _p(loss), _p(dl), B, C,
+              float(label_smoothing), int(focal), float(gamma), _s())
+    return loss, dl
+
+
+def axpby(x, y, a=1.0, b=0.0, a_dev=None):
+    _lib.call("mdhs_axpby_f32", _p(x), _p(y), x.numel(), _p(a_dev), float(a), float(b), _s())
+    return y
+
+
+def adam_flat(params, grads, exp_avg, exp_avg_sq, shadow, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0,
+              adamw=True, zero_grad=True):
+    _lib.call("mdhs_adam_flat", _p(params), _p(grads), _p(exp_avg), _p(exp_avg_sq), _p(shadow), params.numel(), float(lr),
+              float(beta1), float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale), int(adamw),
+              int(zero_grad), _s())
+
+
+def sgd_flat(params, grads, mom, shadow, lr, momentum, weight_decay, grad_scale=1.0, first_step=False, zero_grad=True):
+    _lib.call("mdhs_sgd_flat", _p(params), _p(grads), _p(mom), _p(shadow), params.numel(), float(lr), float(momentum),
+              float(weight_decay), float(grad_scale), int(first_step), int(zero_grad), _s())

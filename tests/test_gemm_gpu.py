@@ -102,3 +102,19 @@ def test_gemm_rejects_bad_args(mdhs):
     b = torch.randn(64, 60, device="cuda").bfloat16()
     with pytest.raises(_lib.MdhsError):
         ops.gemm(a, b)
+
+
+def test_gemm_dropout_epilogue(mdhs):
+    """Epilogue dropout: stateless mask hash(seed, m*N+n); forward and act'-backward use the same mask."""
+    from mdhs_b200 import ops
+    torch.manual_seed(3)
+    M, N, K, p = 256, 256, 128, 0.1
+    a = torch.randn(M, K, device="cuda").bfloat16()
+    w = torch.randn(N, K, device="cuda").bfloat16()
+    y0 = ops.gemm(a, w, out_dtype=torch.float32)
+    y1 = ops.gemm(a, w, out_dtype=torch.float32, dropout_p=p, dropout_seed=99)
+    y2 = ops.gemm(a, w, out_dtype=torch.float32, dropout_p=p, dropout_seed=99)
+    assert torch.equal(y1, y2)
+    kept = y1 != 0
+    assert abs((~kept).float().mean().item() - p) < 0.01
+    assert torch.allclose(y1[kept], y0[kept] / (1 - p), rtol=1e-5, atol=1e-5)

@@ -1,0 +1,311 @@
+"""Per-kernel parity (GPU): every C-ABI entry point against the same op in plain PyTorch fp32 on
+identical (bf16-rounded where the kernel takes bf16) inputs.  Tolerances: bf16 outputs <= 1e-2 of the
+tensor's max-norm (one bf16 rounding, 2^-8), fp32 outputs <= 1e-4 relative unless noted."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def relerr(a, b):
+    return (a.float() - b.float()).abs().max().item() / (b.float().abs().max().item() + 1e-12)
+
+
+@pytest.fixture(scope="module")
+def ops(mdhs):
+    from mdhs_b200 import ops as o
+    return o
+
+
+@pytest.mark.parametrize("rows,C,xf32", [(100, 256, False), (257, 768, False), (64, 768, True), (33, 1024, False), (16, 2048, False), (50, 136, False)])
+def test_layernorm(ops, rows, C, xf32):
+    torch.manual_seed(0)
+    x = torch.randn(rows, C, device="cuda") * 2 + 0.5
+    x = x if xf32 else x.bfloat16()
+    g = torch.randn(C, device="cuda")
+    b = torch.randn(C, device="cuda")
+    y, y32, mean, rstd = ops.layernorm_fwd(x, g, b, 1e-12, out_bf16=True, out_f32=True)
+    xr = x.float().requires_grad_(True)
+    gr, br = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = F.layer_norm(xr, (C,), gr, br, 1e-12)
+    assert relerr(y32, ref) < 1e-5
+    assert relerr(y, ref) < 1e-2
+    dy = torch.randn(rows, C, device="cuda").bfloat16()
+    ref.backward(dy.float())
+    dg = torch.zeros(C, device="cuda")
+    db = torch.zeros(C, device="cuda")
+    dx, _, dx32 = ops.layernorm_bwd(dy, x, mean, rstd, g, dg, db, dx_bf16=True, dx_f32=True)
+    assert relerr(dx32, xr.grad) < 1e-4
+    assert relerr(dx, xr.grad) < 1e-2
+    assert relerr(dg, gr.grad) < 1e-4
+    assert relerr(db, br.grad) < 1e-4
+
+
+def test_layernorm_dropout_consistency(ops):
+    """Forward output dropout and the backward mask come from the same stateless hash."""
+    torch.manual_seed(1)
+    rows, C, p = 64, 768, 0.1
+    x = torch.randn(rows, C, device="cuda")
+    g = torch.ones(C, device="cuda")
+    b = torch.zeros(C, device="cuda")
+    y0, _, mean, rstd = ops.layernorm_fwd(x, g, b, 1e-12)
+    y1, _, _, _ = ops.layernorm_fwd(x, g, b, 1e-12, drop_p=p, seed=1234)
+    keep = (y1.float() != 0) | (y0.float() == 0)
+    frac = 1.0 - keep.float().mean().item()
+    assert abs(frac - p) < 0.02
+    assert relerr(y1.float()[keep], (y0.float() / (1 - p))[keep]) < 1e-2
+    dy = torch.ones(rows, C, device="cuda").bfloat16()
+    dg = torch.zeros(C, device="cuda")
+    db = torch.zeros(C, device="cuda")
+    ops.layernorm_bwd(dy, x, mean, rstd, g, dg, db, drop_p=p, seed=1234)
+    # dbeta = sum over rows of the masked dy = keep-count / (1-p)
+    assert relerr(db, keep.float().sum(0) / (1 - p)) < 1e-3
+
+
+@pytest.mark.parametrize("rows,C", [(4 * 56 * 56, 64), (2 * 14 * 14, 1024), (1000, 256)])
+def test_batchnorm_train(ops, rows, C):
+    torch.manual_seed(0)
+    x = (torch.randn(rows, C, device="cuda") * 1.5 + 0.3).bfloat16()
+    gamma = torch.rand(C, device="cuda") + 0.5
+    beta = torch.randn(C, device="cuda")
+    res = torch.randn(rows, C, device="cuda").bfloat16()
+    rm = torch.zeros(C, device="cuda")
+    rv = torch.ones(C, device="cuda")
+    cs = torch.zeros(C, device="cuda", dtype=torch.float64)
+    cq = torch.zeros(C, device="cuda", dtype=torch.float64)
+    ops.col_stats(x, cs, cq)
+    mean, invstd, scale, shift = ops.bn_finalize(cs, cq, rows, gamma, beta, rm, rv, 0.1, 1e-5)
+    y = ops.bn_apply(x, scale, shift, residual=res, relu=True)
+    # reference: NCHW-free formulation on [rows, C]
+    xr = x.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm_ref, rv_ref = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    bn = F.batch_norm(xr, rm_ref, rv_ref, gr, br, True, 0.1, 1e-5)
+    resr = res.float().requires_grad_(True)
+    ref = torch.relu(bn + resr)
+    assert relerr(y, ref) < 1e-2
+    assert relerr(rm, rm_ref) < 1e-4 and relerr(rv, rv_ref) < 1e-4
+    dy = torch.randn(rows, C, device="cuda").bfloat16()
+    # reference backward with the mask of OUR (bf16-rounded) output to avoid boundary flips
+    (bn + resr).backward(dy.float() * (y.float() > 0))
+    dg = torch.zeros(C, device="cuda")
+    db = torch.zeros(C, device="cuda")
+    dx, dz = ops.bn_bwd(dy, x, y, mean, invstd, gamma, dg, db, relu=True, want_dz=True)
+    assert relerr(dx, xr.grad) < 1.5e-2
+    assert relerr(dz, resr.grad) < 1e-2
+    assert relerr(dg, gr.grad) < 2e-3
+    assert relerr(db, br.grad) < 2e-3
+
+
+@pytest.mark.parametrize("Cin,Cout,R,stride,pad,H", [(64, 64, 3, 1, 1, 14), (128, 128, 3, 2, 1, 14), (256, 512, 1, 2, 0, 14), (64, 256, 1, 1, 0, 8)])
+def test_conv_via_im2col_gemm(ops, Cin, Cout, R, stride, pad, H):
+    """conv fprop / dgrad / wgrad = im2col + tcgen05 GEMM + col2im, against F.conv2d autograd."""
+    torch.manual_seed(0)
+    B = 3
+    x = torch.randn(B, Cin, H, H, device="cuda").bfloat16().float()
+    w = (torch.randn(Cout, Cin, R, R, device="cuda") / math.sqrt(Cin * R * R)).bfloat16().float()
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    ref = F.conv2d(xr, wr, stride=stride, padding=pad)
+    x_nhwc = ops.nchw_f32_to_nhwc_bf16(x)
+    col, Ho, Wo = ops.im2col_nhwc(x_nhwc, B, H, H, Cin, R, R, stride, pad)
+    wp = ops.conv_weight_pack(w)
+    y = ops.gemm(col, wp)  # [B*Ho*Wo, Cout]
+    y_nchw = ops.nhwc_bf16_to_nchw_f32(y, B, Ho, Wo, Cout)
+    assert relerr(y_nchw, ref) < 1e-2
+    dy = torch.randn_like(ref).bfloat16().float()
+    ref.backward(dy)
+    dy_nhwc = ops.nchw_f32_to_nhwc_bf16(dy)
+    dcol = ops.gemm(dy_nhwc, wp, b_mn=True)  # [M, R*S*Cin] = dY . Wp
+    dx = ops.col2im_nhwc(dcol, B, H, H, Cin, R, R, stride, pad)
+    assert relerr(ops.nhwc_bf16_to_nchw_f32(dx, B, H, H, Cin), xr.grad) < 1.5e-2
+    gp = torch.zeros(Cout, R * R * Cin, device="cuda")
+    ops.gemm(dy_nhwc, col, a_mn=True, b_mn=True, out=gp, accumulate=True, split_k=4)
+    gw = torch.zeros_like(w)
+    ops.conv_wgrad_unpack(gp, gw)
+    assert relerr(gw, wr.grad) < 5e-3
+
+
+def test_stem_im2col(ops):
+    torch.manual_seed(0)
+    B, H = 2, 64
+    x = torch.randn(B, 3, H, H, device="cuda")
+    w = torch.randn(64, 3, 7, 7, device="cuda") * 0.05
+    ldk = 152
+    col, Ho, Wo = ops.im2col_nchw_f32(x, 7, 7, 2, 3, ldk)
+    wp = ops.conv_weight_pack(w, ldk=ldk)
+    y = ops.gemm(col, wp)
+    ref = F.conv2d(x.bfloat16().float(), w.bfloat16().float(), stride=2, padding=3)
+    assert relerr(ops.nhwc_bf16_to_nchw_f32(y, B, Ho, Wo, 64), ref) < 1e-2
+
+
+def test_maxpool(ops):
+    torch.manual_seed(0)
+    B, H, C = 3, 30, 64
+    x = torch.randn(B, C, H, H, device="cuda").bfloat16().float()
+    xr = x.clone().requires_grad_(True)
+    ref = F.max_pool2d(xr, 3, 2, 1)
+    xn = ops.nchw_f32_to_nhwc_bf16(x)
+    y, idx, Ho, Wo = ops.maxpool_fwd(xn, B, H, H, C)
+    assert relerr(ops.nhwc_bf16_to_nchw_f32(y, B, Ho, Wo, C), ref) == 0
+    dy = torch.randn_like(ref).bfloat16().float()
+    ref.backward(dy)
+    dx = ops.maxpool_bwd(ops.nchw_f32_to_nhwc_bf16(dy), idx, B, H, H, C)
+    assert relerr(ops.nhwc_bf16_to_nchw_f32(dx, B, H, H, C), xr.grad) < 1e-2
+
+
+def test_mean_tokens(ops):
+    torch.manual_seed(0)
+    B, T, C = 5, 49, 256
+    x = torch.randn(B * T, C, device="cuda").bfloat16()
+    y, _ = ops.mean_tokens_fwd(x, B, T, C)
+    assert relerr(y, x.float().view(B, T, C).mean(1)) < 1e-5
+    dy = torch.randn(B, C, device="cuda")
+    dx = ops.mean_tokens_bwd(dy, B, T, C)
+    assert relerr(dx.view(B, T, C), (dy / T).unsqueeze(1).expand(B, T, C)) < 1e-2
+
+
+def _attn_ref(q, k, v, mask, scale):
+    s = torch.einsum("bhqd,bhkd->bhqk", q, k) * scale
+    if mask is not None:
+        s = s.masked_fill(~mask[:, None, None, :].bool(), float("-inf"))
+    p = torch.softmax(s, -1)
+    return torch.einsum("bhqk,bhkd->bhqd", p, v)
+
+
+@pytest.mark.parametrize("B,H,Sq,Sk,D,masked", [(3, 12, 64, 64, 64, True), (2, 8, 49, 49, 32, False), (2, 8, 49, 64, 32, True),
+                                                 (2, 8, 196, 40, 32, True), (1, 12, 130, 130, 64, True), (1, 12, 256, 256, 64, False)])
+def test_attention(ops, B, H, Sq, Sk, D, masked):
+    torch.manual_seed(0)
+    q = torch.randn(B * Sq, H * D, device="cuda").bfloat16()
+    kv = torch.randn(B * Sk, 2 * H * D, device="cuda").bfloat16()  # K and V as column slices of one buffer
+    k, v = kv[:, :H * D], kv[:, H * D:]
+    mask = None
+    if masked:
+        lens = torch.randint(Sk // 2, Sk + 1, (B,), device="cuda")
+        mask = (torch.arange(Sk, device="cuda")[None, :] < lens[:, None]).to(torch.uint8)
+    scale = 1.0 / math.sqrt(D)
+    o, lse = ops.attention_fwd(q, k, v, B, H, Sq, Sk, D, scale, key_mask=mask)
+
+    def heads(t, S):
+        return t.float().reshape(B, S, H, D).permute(0, 2, 1, 3).contiguous().requires_grad_(True)
+    qr, kr, vr = heads(q, Sq), heads(k, Sk), heads(v, Sk)
+    ref = _attn_ref(qr, kr, vr, mask, scale)
+    ref_tok = ref.permute(0, 2, 1, 3).reshape(B * Sq, H * D)
+    assert relerr(o, ref_tok) < 1e-2
+    do = torch.randn(B * Sq, H * D, device="cuda").bfloat16()
+    ref_tok.backward(do.float())
+    dkv = torch.empty_like(kv)
+    dq, dk, dv = ops.attention_bwd(q, k, v, o, do, lse, B, H, Sq, Sk, D, scale, key_mask=mask,
+                                   dk=dkv[:, :H * D], dv=dkv[:, H * D:])
+
+    def tok(t, S):
+        return t.permute(0, 2, 1, 3).reshape(B * S, H * D)
+    assert relerr(dq, tok(qr.grad, Sq)) < 2e-2
+    assert relerr(dk, tok(kr.grad, Sk)) < 2e-2
+    assert relerr(dv, tok(vr.grad, Sk)) < 2e-2
+
+
+def test_attention_dropout_statistics(ops):
+    torch.manual_seed(0)
+    B, H, S, D, p = 2, 4, 64, 32, 0.25
+    q = torch.randn(B * S, H * D, device="cuda").bfloat16()
+    k = torch.randn(B * S, H * D, device="cuda").bfloat16()
+    v = torch.ones(B * S, H * D, device="cuda").bfloat16()
+    # with V == 1 the output equals sum_j P_ij m_ij, whose expectation is 1
+    o, _ = ops.attention_fwd(q, k, v, B, H, S, S, D, 0.1, drop_p=p, seed=7)
+    assert abs(o.float().mean().item() - 1.0) < 0.05
+    o2, _ = ops.attention_fwd(q, k, v, B, H, S, S, D, 0.1, drop_p=p, seed=7)
+    assert torch.equal(o, o2)
+
+
+def test_embedding(ops):
+    torch.manual_seed(0)
+    B, S, C, V = 4, 16, 768, 1000
+    word = torch.randn(V, C, device="cuda")
+    pos = torch.randn(512, C, device="cuda")
+    typ = torch.randn(2, C, device="cuda")
+    ids = torch.randint(0, V, (B, S), device="cuda")
+    e = ops.embed_gather(ids, None, word, pos, typ, S)
+    ref = word[ids] + pos[:S][None] + typ[0]
+    assert relerr(e, ref.reshape(B * S, C)) < 1e-6
+    de = torch.randn(B * S, C, device="cuda")
+    gw, gp, gt = torch.zeros_like(word), torch.zeros_like(pos), torch.zeros_like(typ)
+    ops.embed_scatter(de, ids, None, gw, gp, gt, S)
+    gw_ref = torch.zeros_like(word).index_add_(0, ids.reshape(-1), de)
+    assert relerr(gw, gw_ref) < 1e-5
+    assert relerr(gp[:S], de.view(B, S, C).sum(0)) < 1e-5
+    assert relerr(gt[0], de.sum(0)) < 1e-5
+
+
+def test_linear_f32_and_ce(ops):
+    torch.manual_seed(0)
+    M, K, N = 37, 256, 7
+    x = torch.randn(M, K, device="cuda", requires_grad=True)
+    w = (torch.randn(N, K, device="cuda") * 0.1).requires_grad_(True)
+    b = torch.randn(N, device="cuda", requires_grad=True)
+    labels = torch.randint(0, N, (M,), device="cuda")
+    cw = torch.rand(N, device="cuda") + 0.5
+    for kwargs, ref_fn in [
+        (dict(label_smoothing=0.02), lambda z: F.cross_entropy(z, labels, label_smoothing=0.02)),
+        (dict(label_smoothing=0.1, class_weights=cw), lambda z: F.cross_entropy(z, labels, weight=cw, label_smoothing=0.1)),
+        (dict(), lambda z: F.cross_entropy(z, labels)),
+    ]:
+        for t in (x, w, b):
+            t.grad = None
+        z_ref = F.linear(x, w, b)
+        loss_ref = ref_fn(z_ref)
+        loss_ref.backward()
+        z = ops.linear_f32_fwd(x.detach(), w.detach(), b.detach())
+        assert relerr(z, z_ref) < 1e-5
+        loss, dl = ops.ce_loss(z, labels, **kwargs)
+        assert abs(loss.item() - loss_ref.item()) < 1e-5 * max(1.0, abs(loss_ref.item()))
+        dw, db = torch.zeros_like(w), torch.zeros_like(b)
+        dx = ops.linear_f32_bwd(dl, x.detach(), w.detach(), dw, db)
+        assert relerr(dx, x.grad) < 1e-4
+        assert relerr(dw, w.grad) < 1e-4
+        assert relerr(db, b.grad) < 1e-4
+
+
+def test_focal_loss(ops):
+    torch.manual_seed(0)
+    B, C, gamma = 64, 7, 2.0
+    z = torch.randn(B, C, device="cuda", requires_grad=True)
+    y = torch.randint(0, C, (B,), device="cuda")
+    ce = F.cross_entropy(z, y, reduction="none")
+    ref = ((1 - torch.exp(-ce)) ** gamma * ce).mean()
+    ref.backward()
+    loss, dl = ops.ce_loss(z.detach(), y, focal=True, gamma=gamma)
+    assert abs(loss.item() - ref.item()) < 1e-5
+    assert relerr(dl, z.grad) < 1e-4
+
+
+def test_adamw_and_sgd_flat(ops):
+    torch.manual_seed(0)
+    n = 4096 + 8
+    p = torch.randn(n, device="cuda")
+    ref = p.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([ref], lr=2e-4, weight_decay=1e-2)
+    m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    shadow = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+    for step in range(1, 4):
+        g = torch.randn(n, device="cuda")
+        ref.grad = g.clone()
+        opt.step()
+        gg = g.clone()
+        ops.adam_flat(p, gg, m, v, shadow, 2e-4, 0.9, 0.999, 1e-8, 1e-2, step)
+        assert gg.abs().max().item() == 0
+    assert relerr(p, ref.detach()) < 1e-6
+    assert relerr(shadow, p) < 1e-2
+    p2 = torch.randn(n, device="cuda")
+    ref2 = p2.clone().requires_grad_(True)
+    opt2 = torch.optim.SGD([ref2], lr=0.01, momentum=0.9)
+    mom = torch.zeros(n, device="cuda")
+    for step in range(3):
+        g = torch.randn(n, device="cuda")
+        ref2.grad = g.clone()
+        opt2.step()
+        ops.sgd_flat(p2, g.clone(), mom, None, 0.01, 0.9, 0.0, first_step=(step == 0))
+    assert relerr(p2, ref2.detach()) < 1e-6
