@@ -157,6 +157,13 @@ int mdhs_ce_loss(const float* logits, int64_t ld, const int64_t* labels, const f
                  float* dlogits, int B, int C, float label_smoothing, int focal, float gamma, void* stream);
 int mdhs_axpby_f32(const float* x, float* y, int64_t n, const float* a_dev, float a, float b, void* stream);
 
+/* elementwise helpers between fused ops: g = dy * dropout_mask * act'(aux) (bf16), ReLU backward, product (fp32) */
+int mdhs_act_dropout_bwd(const void* dy, const void* aux, void* g, int64_t n, int act, float drop_p, uint64_t seed,
+                         void* stream);
+int mdhs_relu_bwd_f32(const float* dy, const float* y, float* dx, int64_t n, void* stream);
+int mdhs_mul_f32(const float* a, const float* b, float* c, int64_t n, void* stream);
+int mdhs_dropout_f32(const float* x, float* y, int64_t n, float p, uint64_t seed, void* stream);
+
 /* Fused optimizer step on the flat parameter buffer (scripts/train.py:257-309) */
 int mdhs_adam_flat(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, int64_t n,
                    float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,

@@ -1,0 +1,160 @@
+"""MultimodalBaselineModel with the reference's constructor (same 38 keyword arguments read from
+config.yml by scripts/train.py:179-211) and call surface (model.py:21-345): forward(), forward_features(),
+classifier, freeze_encoders(), ablation modes, optional dual-expert gate.
+
+Everything numeric runs on the sm_100a kernels; this file only wires modules together the way the
+reference does.  Side branches that are outside the hot-path scope (tabular MLP,
+LSTM/GRU sequence encoder, global/local crop) are accepted by the constructor for config compatibility
+and raise NotImplementedError when enabled.
+"""
+import torch
+import torch.nn as nn
+
+from . import functional as Fm
+from .encoder import ImageEncoder, MdhsModule, TextEncoder
+from .modules.fusion_blocks import (BilinearFusionModule, ConcatFusionModule, FusionModule, HadamardFusionModule,
+                                    MultiScaleFusionModule, SSMFusionModule, VMambaFusionModule,
+                                    WeightedConcatFusionModule, _pool_image)
+from .modules.gating import DualExpertGate
+from .modules.heads import AttentionPoolingClassifier, MLPHead, ResidualClassifier, build_kan_head
+
+
+class MultimodalBaselineModel(MdhsModule):
+    def __init__(
+        self,
+        num_classes,
+        image_feature_dim=512,
+        text_feature_dim=768,
+        hidden_dim=256,
+        dropout=0.2,
+        pretrained_image=True,
+        image_weights_path="/home/medteam/.cache/torch/hub/checkpoints/resnet18-f37072fd.pth",
+        text_model_name="bert-base-uncased",
+        num_heads=8,
+        image_backbone="resnet18",
+        classifier_type="mlp",
+        fusion_type="basic",
+        text_pool="cls",
+        kan_num_groups=8,
+        kan_act_mode="gelu",
+        tabular_enabled=False,
+        tabular_input_dim=0,
+        tabular_hidden_dim=128,
+        tabular_dropout=0.1,
+        gate_enabled=False,
+        gate_hidden_dim=128,
+        gate_use_entropy=True,
+        gate_local_mode="image_only",
+        gate_context_mode="full",
+        sequence_enabled=False,
+        sequence_type="lstm",
+        sequence_hidden_dim=256,
+        sequence_num_layers=1,
+        sequence_bidirectional=True,
+        sequence_dropout=0.1,
+        sequence_num_heads=4,
+        global_local_enabled=False,
+        global_local_crop_ratio=0.6,
+        global_local_combine="avg",
+    ):
+        super().__init__()
+        fusion_dropout = min(dropout, 0.1)   # model.py:62-63
+        head_dropout = min(dropout, 0.1)
+        self.fusion_type = fusion_type
+        self.tabular_enabled = tabular_enabled
+        self.sequence_enabled = sequence_enabled
+        self.global_local_enabled = global_local_enabled
+        self.global_local_crop_ratio = global_local_crop_ratio
+        self.global_local_combine = global_local_combine
+        if tabular_enabled or sequence_enabled or global_local_enabled:
+            raise NotImplementedError(
+                "tabular / sequence / global-local branches are outside the B200 hot-path scope (SURVEY.md 8f)")
+
+        self.image_encoder = ImageEncoder(feature_dim=hidden_dim, pretrained=pretrained_image,
+                                          weights_path=image_weights_path, backbone=image_backbone,
+                                          multi_scale=(fusion_type == "multiscale"))
+        self.global_local_proj = None
+        self.text_encoder = TextEncoder(model_path=text_model_name, feature_dim=text_feature_dim)
+
+        if fusion_type == "multiscale":
+            self.fusion = MultiScaleFusionModule(text_dim=text_feature_dim, hidden_dim=hidden_dim, num_heads=num_heads,
+                                                 dropout=fusion_dropout)
+        elif fusion_type == "hadamard":
+            self.fusion = HadamardFusionModule(text_dim=text_feature_dim, hidden_dim=hidden_dim, text_pool=text_pool)
+        elif fusion_type == "bilinear":
+            self.fusion = BilinearFusionModule(text_dim=text_feature_dim, hidden_dim=hidden_dim, text_pool=text_pool)
+        elif fusion_type == "mamba":
+            self.fusion = SSMFusionModule(text_dim=text_feature_dim, hidden_dim=hidden_dim, text_pool=text_pool)
+        elif fusion_type == "vmamba":
+            self.fusion = VMambaFusionModule(text_dim=text_feature_dim, hidden_dim=hidden_dim, text_pool=text_pool)
+        elif fusion_type == "weighted_concat":
+            self.fusion = WeightedConcatFusionModule(text_dim=text_feature_dim, hidden_dim=hidden_dim, text_pool=text_pool)
+        elif fusion_type == "concat":
+            self.fusion = ConcatFusionModule(text_dim=text_feature_dim, hidden_dim=hidden_dim, text_pool=text_pool)
+        else:
+            self.fusion = FusionModule(text_dim=text_feature_dim, hidden_dim=hidden_dim, num_heads=num_heads,
+                                       dropout=fusion_dropout)
+
+        self.gate_enabled = gate_enabled
+        self.gate_local_mode = gate_local_mode
+        self.gate_context_mode = gate_context_mode
+        if self.gate_enabled:
+            self.gate = DualExpertGate(lesion_dim=hidden_dim, context_dim=hidden_dim, hidden_dim=gate_hidden_dim,
+                                       use_entropy=gate_use_entropy)
+
+        self.classifier_type = classifier_type
+        if classifier_type == "kan":
+            self.classifier = build_kan_head(hidden_dim=hidden_dim, num_classes=num_classes, dropout=head_dropout,
+                                             num_groups=kan_num_groups, act_mode=kan_act_mode)
+        elif classifier_type == "residual":
+            self.classifier = ResidualClassifier(hidden_dim, hidden_dim, num_classes, head_dropout)
+        elif classifier_type == "attention_pooling":
+            self.classifier = AttentionPoolingClassifier(hidden_dim, hidden_dim, num_classes, num_heads, head_dropout)
+        else:
+            self.classifier = MLPHead(hidden_dim, num_classes, head_dropout)
+
+    # ------------------------------------------------------------------ reference call surface
+    def forward_features(self, image_input, text_input_ids, text_attention_mask, tabular_input=None, ablation_mode=None):
+        self.store(image_input.device)
+        image_tokens, pooled_image = self._encode_image_tokens(image_input, want_pooled=(ablation_mode == "image_only"))
+        if ablation_mode == "image_only":
+            return pooled_image
+        text_tokens = self.text_encoder(text_input_ids, text_attention_mask)
+        if ablation_mode == "text_off":
+            text_tokens = torch.zeros_like(text_tokens)
+        return self.fusion(image_tokens, text_tokens, text_attention_mask)
+
+    def forward(self, image_input, text_input_ids, text_attention_mask, tabular_input=None, ablation_mode=None):
+        if ablation_mode is not None or not self.gate_enabled:
+            fused = self.forward_features(image_input, text_input_ids, text_attention_mask, tabular_input=tabular_input,
+                                          ablation_mode=ablation_mode)
+            return self.classifier(fused)
+        context_mode = None if self.gate_context_mode == "full" else self.gate_context_mode
+        context_feat = self.forward_features(image_input, text_input_ids, text_attention_mask, tabular_input=tabular_input,
+                                             ablation_mode=context_mode)
+        local_feat = self.forward_features(image_input, text_input_ids, text_attention_mask, tabular_input=tabular_input,
+                                           ablation_mode=self.gate_local_mode)
+        logits_context = self.classifier(context_feat)
+        logits_local = self.classifier(local_feat)
+        entropy = None
+        if self.gate.use_entropy:
+            probs = torch.softmax(logits_local, dim=1)
+            entropy = -(probs * (probs + 1e-8).log()).sum(dim=1, keepdim=True)
+        alpha = self.gate(local_feat, context_feat, entropy)
+        return alpha * logits_local + (1 - alpha) * logits_context
+
+    def _pool_image_tokens(self, image_tokens):
+        return _pool_image(image_tokens)
+
+    def _encode_image_tokens(self, image_input, want_pooled=True):
+        if image_input.dim() == 5:
+            raise ValueError("Sequence input provided but sequence encoder is disabled.")
+        tokens = self.image_encoder(image_input)
+        pooled = self._pool_image_tokens(tokens) if want_pooled else None
+        return tokens, pooled
+
+    def freeze_encoders(self):
+        for param in self.image_encoder.parameters():
+            param.requires_grad = False
+        for param in self.text_encoder.parameters():
+            param.requires_grad = False

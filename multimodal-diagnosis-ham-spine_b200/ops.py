@@ -330,3 +330,27 @@ def adam_flat(params, grads, exp_avg, exp_avg_sq, shadow, lr, beta1, beta2, eps,
 def sgd_flat(params, grads, mom, shadow, lr, momentum, weight_decay, grad_scale=1.0, first_step=False, zero_grad=True):
     _lib.call("mdhs_sgd_flat", _p(params), _p(grads), _p(mom), _p(shadow), params.numel(), float(lr), float(momentum),
               float(weight_decay), float(grad_scale), int(first_step), int(zero_grad), _s())
+
+
+def act_dropout_bwd(dy, aux, act, drop_p, seed):
+    g = torch.empty_like(dy)
+    _lib.call("mdhs_act_dropout_bwd", _p(dy), _p(aux), _p(g), dy.numel(), act, float(drop_p), int(seed), _s())
+    return g
+
+
+def relu_bwd_f32(dy, y):
+    dx = torch.empty_like(dy)
+    _lib.call("mdhs_relu_bwd_f32", _p(dy), _p(y), _p(dx), dy.numel(), _s())
+    return dx
+
+
+def mul_f32(a, b):
+    c = torch.empty_like(a)
+    _lib.call("mdhs_mul_f32", _p(a), _p(b), _p(c), a.numel(), _s())
+    return c
+
+
+def dropout_f32(x, p, seed):
+    y = torch.empty_like(x)
+    _lib.call("mdhs_dropout_f32", _p(x), _p(y), x.numel(), float(p), int(seed), _s())
+    return y

@@ -1,0 +1,190 @@
+"""ResNet trunk (torchvision topology: BasicBlock for resnet18/34, Bottleneck for resnet50) on the B200
+kernels: NHWC bf16 activations, every convolution an (im2col +) tcgen05 GEMM whose epilogue also
+produces the train-mode BatchNorm statistics, BN-apply + residual + ReLU fused in one pass, and a
+hand-scheduled backward (BN reduce/apply, dgrad GEMM, split-K wgrad GEMM accumulating in fp32).
+
+Reference path: encoder.py:61-72,88-99 (ImageEncoder stem/layer1-4) and mibf_net/model_resnet.py:15-16,40
+(torchvision resnet50 incl. avg-pool + fc).  The nn.Module objects only hold parameters / buffers with
+the reference's state_dict keys; all arithmetic happens here.
+"""
+import torch
+
+from . import ops
+
+
+def _out_hw(h, k, s, p):
+    return (h + 2 * p - k) // s + 1
+
+
+class _Conv:
+    """One Conv2d(bias=False) + its BatchNorm2d."""
+
+    def __init__(self, store, conv, bn, stem=False):
+        self.store, self.conv, self.bn, self.stem = store, conv, bn, stem
+        self.O, self.I, self.R, self.S = conv.weight.shape
+        self.stride, self.pad = conv.stride[0], conv.padding[0]
+        self.K = self.R * self.S * self.I
+        self.ldk = (self.K + 7) // 8 * 8
+        self.direct = (self.R == 1 and self.stride == 1)  # NHWC activation matrix is already the GEMM operand
+        self.plain = (self.R == 1)                        # packed layout == OIHW layout
+        dev = store.device
+        if self.plain:
+            self.wp = store.w16(conv.weight).view(self.O, self.I)
+            self.gp = None
+        else:
+            self.wp = torch.zeros((self.O, self.ldk), device=dev, dtype=torch.bfloat16)
+            self.gp = torch.zeros((self.O, self.ldk), device=dev, dtype=torch.float32)
+            store.add_packer(self.repack)
+
+    def repack(self):
+        ops.conv_weight_pack(self.conv.weight.data, ldk=self.ldk, out=self.wp)
+
+    def wgrad_splits(self, rows):
+        tiles = ((self.O + 127) // 128) * ((self.ldk + 255) // 256)
+        kb = (rows + 63) // 64
+        return max(1, min(kb // 4 if kb >= 8 else 1, (148 * 2 + tiles - 1) // tiles))
+
+
+class ResNetEngine:
+    def __init__(self, store, net):
+        """net: a torchvision.models.ResNet instance used as the parameter container."""
+        self.store = store
+        self.net = net
+        self.stem = _Conv(store, net.conv1, net.bn1, stem=True)
+        self.layers = []
+        for layer in (net.layer1, net.layer2, net.layer3, net.layer4):
+            blocks = []
+            for blk in layer:
+                convs = [_Conv(store, blk.conv1, blk.bn1), _Conv(store, blk.conv2, blk.bn2)]
+                if hasattr(blk, "conv3"):
+                    convs.append(_Conv(store, blk.conv3, blk.bn3))
+                down = None
+                if blk.downsample is not None:
+                    down = _Conv(store, blk.downsample[0], blk.downsample[1])
+                blocks.append((convs, down))
+            self.layers.append(blocks)
+        self._stats = None
+
+    # ------------------------------------------------------------------ forward pieces
+    def _conv_bn(self, c, x, B, H, W, relu, residual, training, saved):
+        """x: [B*H*W, Cin] bf16 (or the NCHW fp32 image for the stem).  Returns y, Ho, Wo."""
+        if c.stem:
+            A, Ho, Wo = ops.im2col_nchw_f32(x, c.R, c.S, c.stride, c.pad, c.ldk)
+        elif c.direct:
+            A, Ho, Wo = x, H, W
+        else:
+            A, Ho, Wo = ops.im2col_nhwc(x, B, H, W, c.I, c.R, c.S, c.stride, c.pad)
+        rows = B * Ho * Wo
+        bn = c.bn
+        if training:
+            st = torch.zeros((2, c.O), device=A.device, dtype=torch.float64)
+            raw = ops.gemm(A, c.wp, colsum=st[0], colsumsq=st[1], N=c.O)
+            mom = bn.momentum if bn.momentum is not None else 0.1
+            track = bn.track_running_stats and bn.running_mean is not None
+            mean, invstd, scale, shift = ops.bn_finalize(
+                st[0], st[1], rows, bn.weight.data, bn.bias.data, bn.running_mean if track else None,
+                bn.running_var if track else None, mom, bn.eps, training=True)
+            if track and bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += 1
+        else:
+            raw = ops.gemm(A, c.wp, N=c.O)
+            mean, invstd, scale, shift = ops.bn_finalize(None, None, rows, bn.weight.data, bn.bias.data, bn.running_mean,
+                                                         bn.running_var, 0.0, bn.eps, training=False)
+        y = ops.bn_apply(raw, scale, shift, residual=residual, relu=relu)
+        if saved is not None:
+            saved.append(dict(c=c, A=A, raw=raw, y=y if relu else None, mean=mean, invstd=invstd, relu=relu,
+                              B=B, H=H, W=W, Ho=Ho, Wo=Wo, has_res=residual is not None))
+        return y, Ho, Wo
+
+    def forward(self, images, training, need_grad):
+        """images: [B,3,H,W] fp32 CUDA.  Returns ({name: (feat2d bf16, h, w, C)}, ctx)."""
+        B, _, H, W = images.shape
+        saved = [] if need_grad else None
+        ctx = dict(saved=saved, B=B)
+        x, H1, W1 = self._conv_bn(self.stem, images.contiguous(), B, H, W, True, None, training, saved)
+        y, idx, H2, W2 = ops.maxpool_fwd(x, B, H1, W1, self.stem.O)
+        ctx["pool"] = (idx, H1, W1, self.stem.O)
+        x, H, W = y, H2, W2
+        feats = {}
+        for li, blocks in enumerate(self.layers):
+            for convs, down in blocks:
+                inp, Hi, Wi = x, H, W
+                t = inp
+                for ci, c in enumerate(convs[:-1]):
+                    t, H, W = self._conv_bn(c, t, B, H, W, True, None, training, saved)
+                if down is not None:
+                    idn, _, _ = self._conv_bn(down, inp, B, Hi, Wi, False, None, training, saved)
+                else:
+                    idn = inp
+                x, H, W = self._conv_bn(convs[-1], t, B, H, W, True, idn, training, saved)
+                if saved is not None:
+                    saved.append(dict(block_end=True, n_main=len(convs), has_down=down is not None))
+            feats[f"layer{li + 1}"] = (x, H, W, convs[-1].O)
+        return feats, ctx
+
+    # ------------------------------------------------------------------ backward pieces
+    def _conv_bn_bwd(self, rec, dy, add_to_dx, need_dx=True):
+        """dy: grad wrt the BN(+res)(+relu) output.  Returns (dx, dz) where dz is the masked dy (identity branch)."""
+        c = rec["c"]
+        st = self.store
+        train_w = c.conv.weight.requires_grad
+        bnw = c.bn.weight
+        dgamma = st.g32(bnw) if bnw.requires_grad else None
+        dbeta = st.g32(c.bn.bias) if bnw.requires_grad else None
+        draw, dz = ops.bn_bwd(dy, rec["raw"], rec["y"], rec["mean"], rec["invstd"], bnw.data, dgamma, dbeta,
+                              relu=rec["relu"], want_dz=rec["has_res"])
+        A = rec["A"]
+        rows = A.shape[0]
+        if train_w:
+            if c.plain:
+                gw = st.g32(c.conv.weight).view(c.O, c.I)
+                ops.gemm(draw, A, a_mn=True, b_mn=True, out=gw, accumulate=True, split_k=c.wgrad_splits(rows),
+                         M=c.O, N=c.I, K=rows)
+            else:
+                c.gp.zero_()
+                ops.gemm(draw, A, a_mn=True, b_mn=True, out=c.gp, accumulate=True, split_k=c.wgrad_splits(rows),
+                         M=c.O, N=c.ldk, K=rows)
+                ops.conv_wgrad_unpack(c.gp, st.g32(c.conv.weight))
+        dx = None
+        if need_dx:
+            if c.direct:
+                dx = ops.gemm(draw, c.wp, b_mn=True, residual=add_to_dx, M=rows, N=c.I, K=c.O)
+            else:
+                dcol = ops.gemm(draw, c.wp[:, :c.K], b_mn=True, M=rows, N=c.K, K=c.O)
+                dx = ops.col2im_nhwc(dcol, rec["B"], rec["H"], rec["W"], c.I, c.R, c.S, c.stride, c.pad, add=add_to_dx)
+        return dx, dz
+
+    def backward(self, ctx, dfeats):
+        """dfeats: {name: grad 2-D bf16 or None}.  Accumulates parameter gradients; images get no gradient."""
+        saved = ctx["saved"]
+        B = ctx["B"]
+        i = len(saved) - 1
+        dx = None
+        for li in range(3, -1, -1):
+            g = dfeats.get(f"layer{li + 1}")
+            if g is not None:
+                dx = g if dx is None else dx + g
+            for _ in self.layers[li]:
+                end = saved[i]
+                assert end.get("block_end")
+                n_main, has_down = end["n_main"], end["has_down"]
+                recs = saved[i - n_main - (1 if has_down else 0):i]
+                i -= n_main + (1 if has_down else 0) + 1
+                main = recs[:n_main - 1]
+                last = recs[-1]
+                down = recs[n_main - 1] if has_down else None
+                if dx is None:
+                    continue  # nothing downstream needs this block
+                d, dz = self._conv_bn_bwd(last, dx, None)
+                for rec in reversed(main[1:]):
+                    d, _ = self._conv_bn_bwd(rec, d, None)
+                if has_down:
+                    d_idn, _ = self._conv_bn_bwd(down, dz, None)
+                else:
+                    d_idn = dz
+                dx, _ = self._conv_bn_bwd(main[0], d, d_idn)
+        if dx is None:
+            return
+        idx, H1, W1, C = ctx["pool"]
+        d = ops.maxpool_bwd(dx, idx, B, H1, W1, C)
+        self._conv_bn_bwd(saved[0], d, None, need_dx=False)

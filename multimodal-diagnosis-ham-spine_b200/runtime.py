@@ -1,0 +1,131 @@
+"""Flat parameter storage for one model on one GPU.
+
+All parameters of a model live in ONE fp32 buffer (master weights), with a same-shaped fp32 gradient
+buffer and a bf16 shadow copy that the tensor-core kernels read.  `nn.Parameter.data` / `.grad` become
+views into these buffers, so state_dict()/load_state_dict() and torch.optim keep working unchanged
+(the state_dict key set is the drop-in contract), while
+  * the optimizer step is one fused kernel over the flat buffer (csrc/optim.cu),
+  * data-parallel gradient buckets are plain contiguous slices (parallel.py),
+  * groups of parameters that one GEMM wants to see as a single operand (BERT q/k/v) are laid out
+    back to back and exposed as one fused view without any copy.
+Gradients are written by our backward kernels straight into the flat gradient buffer (they do not
+travel through autograd's AccumulateGrad).
+"""
+import torch
+
+from . import ops
+
+_ALIGN = 64  # elements; keeps every view 256-byte aligned in fp32 and 128-byte aligned in bf16
+
+
+class ParamStore:
+    def __init__(self, module, device, groups=()):
+        """groups: iterable of lists of parameters that must be contiguous (in that order)."""
+        self.device = torch.device(device)
+        params = []
+        seen = set()
+        order = []
+        grouped = {}
+        for grp in groups:
+            for p in grp:
+                grouped[id(p)] = grp
+        for p in module.parameters():
+            if id(p) in seen:
+                continue
+            if id(p) in grouped:
+                for q in grouped[id(p)]:
+                    if id(q) not in seen:
+                        seen.add(id(q))
+                        order.append((q, False))
+                # the next group member must directly follow: mark packing (no alignment gap)
+            else:
+                seen.add(id(p))
+                order.append((p, True))
+        # members of a group after the first are packed without alignment padding
+        packed = set()
+        for grp in groups:
+            for q in grp[1:]:
+                packed.add(id(q))
+        offsets = {}
+        off = 0
+        for p, _ in order:
+            if id(p) not in packed:
+                off = (off + _ALIGN - 1) // _ALIGN * _ALIGN
+            offsets[id(p)] = off
+            off += p.numel()
+            params.append(p)
+        self.total = (off + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.params = params
+        self.offsets = offsets
+        self.flat = torch.zeros(self.total, device=self.device, dtype=torch.float32)
+        self.grad = torch.zeros(self.total, device=self.device, dtype=torch.float32)
+        self.shadow = torch.zeros(self.total, device=self.device, dtype=torch.bfloat16)
+        with torch.no_grad():
+            for p in params:
+                o = offsets[id(p)]
+                view = self.flat[o:o + p.numel()].view(p.shape)
+                view.copy_(p.data.to(self.device, torch.float32))
+                p.data = view
+                p.grad = self.grad[o:o + p.numel()].view(p.shape)
+        self._versions = None
+        self._packers = []  # callables run after every shadow refresh (conv weight re-layout)
+        # dummy differentiable leaf: makes autograd call the backward of Functions whose real
+        # parameters do not pass through autograd
+        self.anchor = torch.zeros(1, device=self.device, dtype=torch.float32, requires_grad=True)
+        self.refresh(force=True)
+
+    # ------------------------------------------------------------------ views
+    def owns(self, p):
+        o = self.offsets.get(id(p))
+        return o is not None and p.data.data_ptr() == self.flat.data_ptr() + 4 * o
+
+    def valid(self):
+        return all(self.owns(p) for p in self.params)
+
+    def w16(self, p):
+        o = self.offsets[id(p)]
+        return self.shadow[o:o + p.numel()].view(p.shape)
+
+    def g32(self, p):
+        o = self.offsets[id(p)]
+        return self.grad[o:o + p.numel()].view(p.shape)
+
+    def fused(self, plist, shape):
+        """One view over parameters declared as a contiguous group: (master fp32, shadow bf16, grad fp32)."""
+        o = self.offsets[id(plist[0])]
+        n = sum(p.numel() for p in plist)
+        oo = o
+        for p in plist:
+            assert self.offsets[id(p)] == oo, "parameters are not contiguous in the flat buffer"
+            oo += p.numel()
+        return (self.flat[o:o + n].view(shape), self.shadow[o:o + n].view(shape), self.grad[o:o + n].view(shape))
+
+    # ------------------------------------------------------------------ freshness of the bf16 copies
+    def add_packer(self, fn):
+        self._packers.append(fn)
+        fn()
+
+    def mark_fresh(self):
+        """Called by the fused optimizer, which rewrites the shadow itself."""
+        for fn in self._packers:
+            fn()
+        self._versions = [p._version for p in self.params]
+
+    def refresh(self, force=False):
+        """Recast master -> bf16 when any parameter changed through torch (load_state_dict, torch.optim)."""
+        versions = [p._version for p in self.params]
+        if force or versions != self._versions:
+            ops.cast_f32_bf16(self.flat, out=self.shadow)
+            for fn in self._packers:
+                fn()
+            self._versions = versions
+
+    def attach_grads(self):
+        """Re-point .grad at the flat gradient buffer (torch.optim.zero_grad(set_to_none=True) drops it)."""
+        for p in self.params:
+            if p.requires_grad and p.grad is None:
+                o = self.offsets[id(p)]
+                p.grad = self.grad[o:o + p.numel()].view(p.shape)
+
+    def zero_grad(self):
+        self.grad.zero_()

@@ -1,0 +1,66 @@
+"""Helpers shared by the oracle tests and the golden-fixture generator (dev container only parts are guarded)."""
+import contextlib
+import io
+import os
+import sys
+
+import torch
+
+REF_ROOT = "/root/reference"
+BERT_DIR = os.environ.get("MDHS_BERT_DIR", "/tmp/mdhs_bert_base")
+
+
+def have_reference():
+    return os.path.isdir(REF_ROOT) and os.path.exists(os.path.join(REF_ROOT, "model.py"))
+
+
+def bert_dir():
+    """A local HF directory holding a randomly initialised bert-base-uncased (config defaults), built once."""
+    if not os.path.exists(os.path.join(BERT_DIR, "config.json")):
+        from transformers import BertConfig, BertModel
+        torch.manual_seed(0)
+        os.makedirs(BERT_DIR, exist_ok=True)
+        BertModel(BertConfig()).save_pretrained(BERT_DIR)
+    return BERT_DIR
+
+
+@contextlib.contextmanager
+def quiet():
+    with contextlib.redirect_stdout(io.StringIO()):
+        yield
+
+
+def build_reference_model(fusion="basic", head="mlp", num_classes=7, backbone="resnet50", gate=False, **kw):
+    """The reference's MultimodalBaselineModel, with the ResNet-50 shim of SURVEY.md section 8c step 3
+    (encoder.py:31-33 only admits resnet18/34)."""
+    import torch.nn as nn
+    import torchvision
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    with quiet():
+        from model import MultimodalBaselineModel as RefModel
+        ref_backbone = "resnet18" if backbone == "resnet50" else backbone
+        m = RefModel(num_classes=num_classes, hidden_dim=256, dropout=0.2, pretrained_image=False, image_weights_path=None,
+                     text_model_name=bert_dir(), num_heads=8, image_backbone=ref_backbone, classifier_type=head,
+                     fusion_type=fusion, gate_enabled=gate, **kw)
+    if backbone == "resnet50":
+        enc = m.image_encoder
+        net = torchvision.models.resnet50(weights=None)
+        net.fc = nn.Identity()
+        enc.model = net
+        enc.stem = nn.Sequential(net.conv1, net.bn1, net.relu, net.maxpool)
+        enc.layer1, enc.layer2, enc.layer3, enc.layer4 = net.layer1, net.layer2, net.layer3, net.layer4
+        if enc.multi_scale:
+            enc.proj2 = nn.Linear(512, 256)
+            enc.proj3 = nn.Linear(1024, 256)
+        enc.proj4 = nn.Linear(2048, 256)
+    return m
+
+
+def build_ours(fusion="basic", head="mlp", num_classes=7, backbone="resnet50", gate=False, **kw):
+    import mdhs_b200
+    with quiet():
+        return mdhs_b200.MultimodalBaselineModel(
+            num_classes=num_classes, hidden_dim=256, dropout=0.2, pretrained_image=False, image_weights_path=None,
+            text_model_name=bert_dir(), num_heads=8, image_backbone=backbone, classifier_type=head, fusion_type=fusion,
+            gate_enabled=gate, **kw)

@@ -1,0 +1,125 @@
+"""Pins the oracle (oracle/port.py) against the REAL reference modules imported from /root/reference.
+Runs only where the reference checkout exists (the dev container); the GPU box relies on tests/golden/.
+Tolerance: fp32 CPU, identical weights and inputs -> max-norm relative error <= 1e-5 (observed ~1e-6)."""
+import os
+import sys
+
+import pytest
+import torch
+
+from refutil import REF_ROOT, build_reference_model, have_reference, quiet
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import port, weights  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not have_reference(), reason="reference checkout not present (GPU box)")
+
+
+def rel(a, b):
+    return (a - b).abs().max().item() / (b.abs().max().item() + 1e-12)
+
+
+@pytest.mark.parametrize("fusion,head,gate", [("basic", "mlp", False), ("multiscale", "residual", False),
+                                              ("concat", "attention_pooling", False), ("weighted_concat", "mlp", True),
+                                              ("hadamard", "mlp", False), ("bilinear", "mlp", False)])
+def test_model_forward_matches_reference(fusion, head, gate):
+    ref = build_reference_model(fusion=fusion, head=head, gate=gate).eval()
+    sd = weights.synth_state_dict(ref.state_dict(), seed=1)
+    ref.load_state_dict(sd)
+    images, ids, mask, _ = weights.synthetic_batch(2, 16, 7, image_hw=64)
+    with torch.no_grad():
+        want = ref(images, ids, mask)
+        got = port.model_forward(sd, images, ids, mask, fusion=fusion, head=head, gate=gate)
+    assert rel(got, want) < 1e-5
+
+
+def test_train_mode_bn_and_grads_match_reference():
+    ref = build_reference_model(fusion="concat", head="mlp").train()
+    for m in ref.modules():  # dropout off, BatchNorm in train mode
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    ref.text_encoder.model.eval()
+    sd = weights.synth_state_dict(ref.state_dict(), seed=2)
+    ref.load_state_dict(sd)
+    images, ids, mask, labels = weights.synthetic_batch(4, 8, 7, image_hw=64)
+    loss_ref = torch.nn.functional.cross_entropy(ref(images, ids, mask), labels, label_smoothing=0.02)
+    loss_ref.backward()
+    sd_g = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    loss = port.ce_label_smoothing(port.model_forward(sd_g, images, ids, mask, fusion="concat", training_bn=True), labels)
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) < 1e-5
+    named = dict(ref.named_parameters())
+    for key in ("classifier.3.weight", "fusion.proj.weight", "text_encoder.model.encoder.layer.5.intermediate.dense.weight",
+                "image_encoder.model.layer3.2.conv2.weight", "image_encoder.model.bn1.weight"):
+        g_ref, g = named[key].grad, sd_g[key].grad
+        assert rel(g, g_ref) < 1e-3, key  # conv grads are ill-conditioned even between fp32 runs
+
+
+def test_losses_match_reference():
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    torch.manual_seed(0)
+    logits = torch.randn(16, 7)
+    labels = torch.randint(0, 7, (16,))
+    feats = torch.randn(16, 32)
+    import importlib.util
+    # scripts/train.py pulls in tensorboard / data loaders; load only the two loss classes from its source text
+    src = open(os.path.join(REF_ROOT, "scripts", "train.py")).read()
+    start, end = src.index("class SupConLoss"), src.index("def _compute_class_weights")
+    ns = {}
+    exec("import torch\nimport torch.nn as nn\nimport torch.nn.functional as F\n" + src[start:end], ns)  # reference code, run as-is
+    assert abs(ns["SupConLoss"]()(feats, labels).item() - port.supcon_loss(feats, labels).item()) < 1e-5
+    assert abs(ns["FocalLoss"]()(logits, labels).item() - port.focal_loss(logits, labels).item()) < 1e-6
+
+
+def test_mibf_matches_reference(tmp_path, monkeypatch):
+    import torchvision
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    from refutil import bert_dir
+    # models.resnet50(pretrained=True) is satisfied offline by a seeded checkpoint in TORCH_HOME
+    hub = tmp_path / "hub" / "checkpoints"
+    hub.mkdir(parents=True)
+    torch.manual_seed(0)
+    torch.save(torchvision.models.resnet50(weights=None).state_dict(), hub / "resnet50-0676ba61.pth")
+    monkeypatch.setenv("TORCH_HOME", str(tmp_path))
+    torch.hub.set_dir(str(tmp_path / "hub"))
+    with quiet():
+        from mibf_net.model_resnet import Resnet50WithOurs
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref = Resnet50WithOurs(num_labels=6, bert_path=bert_dir()).eval()
+    sd = weights.synth_state_dict(ref.state_dict(), seed=3)
+    ref.load_state_dict(sd)
+    images, ids, mask, labels = weights.synthetic_batch(2, 16, 6, image_hw=64, unit_range=True)
+    batch = {"transformed_image": images, "input_ids": ids, "attention_mask": mask}
+    with torch.no_grad():
+        want = ref(batch)
+        got = port.mibf_forward(sd, images, ids, mask)
+    for k in ("image_text", "text", "image"):
+        assert rel(got[k], want[k]) < 1e-5, k
+    l_ref = ref.cal_loss(want, labels).item()
+    assert abs(l_ref - port.mp_loss(got["image"], got["text"], got["image_text"], labels).item()) < 1e-5 * max(1.0, abs(l_ref))
+
+
+def test_kan_and_moe_match_reference():
+    sys.path.insert(0, os.path.join(REF_ROOT, "ConNexT"))
+    from models.block.kan1 import KAN1
+    from models.block.moe import MoE
+    torch.manual_seed(0)
+    kan = KAN1([64, 32, 7]).eval()
+    sd = weights.synth_state_dict(kan.state_dict(), seed=4)
+    kan.load_state_dict(sd)
+    x = torch.randn(9, 64) * 1.5  # includes values outside the [-2.2, 2.2) knot range
+    x[0, :4] = torch.tensor([-2.2, 2.2, 3.0, -5.0])
+    with torch.no_grad():
+        assert rel(port.kan_net(sd, "", x), kan(x)) < 1e-5
+    moe = MoE(input_size=64, output_size=7, num_experts=4, hidden_size=32, k=2, layers_hidden=[64, 32, 7]).eval()
+    sd = weights.synth_state_dict(moe.state_dict(), seed=5)
+    moe.load_state_dict(sd)
+    with torch.no_grad():
+        y_ref, l_ref = moe(x)
+        y, l = port.moe_forward_eval(sd, "", x, 4, 2)
+    assert rel(y, y_ref) < 1e-5
+    assert abs(l.item() - l_ref.item()) < 1e-6
