@@ -167,9 +167,14 @@ int mdhs_dropout_f32(const float* x, float* y, int64_t n, float p, uint64_t seed
 /* Fused optimizer step on the flat parameter buffer (scripts/train.py:257-309) */
 int mdhs_adam_flat(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, int64_t n,
                    float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
-                   int adamw, int zero_grad, void* stream);
+                   int adamw, int zero_grad, const float* lr_dev, const int* step_dev, void* stream);
 int mdhs_sgd_flat(float* params, float* grads, float* momentum_buf, void* shadow_bf16, int64_t n, float lr,
-                  float momentum, float weight_decay, float grad_scale, int first_step, int zero_grad, void* stream);
+                  float momentum, float weight_decay, float grad_scale, int first_step, int zero_grad,
+                  const float* lr_dev, const int* step_dev, void* stream);
+/* lr_dev / step_dev (optional device scalars) override lr / step so a captured CUDA graph of the step can be
+ * replayed with a changing learning rate and step count.  mdhs_step_begin: once per step before the forward:
+ * ++*step_dev and advance the dropout seed tick folded into every stateless dropout mask. */
+int mdhs_step_begin(int* step_dev, void* stream);
 
 #ifdef __cplusplus
 }

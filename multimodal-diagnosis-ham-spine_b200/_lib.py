@@ -69,8 +69,9 @@ SIGNATURES = {
     "mdhs_relu_bwd_f32": "ppplp",
     "mdhs_mul_f32": "ppplp",
     "mdhs_dropout_f32": "pplfup",
-    "mdhs_adam_flat": "ppppplfffffifiip",
-    "mdhs_sgd_flat": "pppplffffiip",
+    "mdhs_adam_flat": "ppppplfffffifiippp",
+    "mdhs_sgd_flat": "pppplffffiippp",
+    "mdhs_step_begin": "pp",
 }
 _CT = {"p": ctypes.c_void_p, "i": ctypes.c_int32, "l": ctypes.c_int64, "f": ctypes.c_float, "u": ctypes.c_uint64}
 

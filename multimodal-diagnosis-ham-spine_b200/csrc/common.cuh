@@ -88,10 +88,18 @@ __device__ __forceinline__ uint32_t hash_u32(uint64_t seed, uint64_t idx) {
   z = z ^ (z >> 31);
   return (uint32_t)(z >> 32);
 }
+// Per-translation-unit copy of the training-step counter folded into every dropout seed, so that a CUDA
+// graph replay (which bakes the seed arguments) still draws fresh masks each step.  mdhs_seed_tick()
+// advances all copies by the same amount once per step; forward and backward of one step agree.
+static __device__ uint64_t g_seed_tick = 0;
+#define MDHS_DEFINE_SEED_TICK(tu)                                                       \
+  static __global__ void seed_tick_kernel_##tu(uint64_t inc) { g_seed_tick += inc; }    \
+  void mdhs_seed_tick_##tu(uint64_t inc, cudaStream_t st) { seed_tick_kernel_##tu<<<1, 1, 0, st>>>(inc); }
+
 // keep-mask scale: returns 0 or 1/(1-p). p == 0 -> always 1.
 __device__ __forceinline__ float dropout_scale(uint64_t seed, uint64_t idx, float p, float inv_keep) {
   if (p <= 0.f) return 1.f;
-  float u = (float)(hash_u32(seed, idx) >> 8) * (1.0f / 16777216.0f);
+  float u = (float)(hash_u32(seed + g_seed_tick * 0x2545F4914F6CDD1Dull, idx) >> 8) * (1.0f / 16777216.0f);
   return u < p ? 0.f : inv_keep;
 }
 

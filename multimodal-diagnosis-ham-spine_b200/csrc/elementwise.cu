@@ -2,6 +2,8 @@
 #include "common.cuh"
 #include "../../include/mdhs_b200.h"
 
+MDHS_DEFINE_SEED_TICK(elementwise)
+
 extern int64_t g_mdhs_launches;
 
 namespace {

@@ -13,6 +13,8 @@
 #include "common.cuh"
 #include "../../include/mdhs_b200.h"
 
+MDHS_DEFINE_SEED_TICK(gemm_tc)
+
 namespace {
 
 constexpr int BM = 128;

@@ -6,6 +6,10 @@
 #include "../../include/mdhs_b200.h"
 
 extern int64_t g_mdhs_launches;
+void mdhs_seed_tick_gemm_tc(uint64_t, cudaStream_t);
+void mdhs_seed_tick_norm(uint64_t, cudaStream_t);
+void mdhs_seed_tick_attention(uint64_t, cudaStream_t);
+void mdhs_seed_tick_elementwise(uint64_t, cudaStream_t);
 
 namespace {
 
@@ -13,8 +17,15 @@ namespace {
 __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                                                         float* __restrict__ v, bf16* __restrict__ shadow, int64_t n, float lr,
                                                         float beta1, float beta2, float eps, float wd, float bc1, float bc2,
-                                                        float grad_scale, int mode, int zero_grad) {
+                                                        float grad_scale, int mode, int zero_grad,
+                                                        const float* __restrict__ lr_dev, const int* __restrict__ step_dev) {
   const int64_t nv = n >> 2;
+  if (lr_dev) lr = lr_dev[0];
+  if (step_dev) {  // graph-replay safe: the step count lives in device memory
+    const float t = (float)step_dev[0];
+    bc1 = 1.f - powf(beta1, t);
+    bc2 = 1.f - powf(beta2, t);
+  }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
     float4 pp = reinterpret_cast<float4*>(p)[i];
     float4 gg = reinterpret_cast<float4*>(g)[i];
@@ -48,8 +59,11 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, f
 
 __global__ void __launch_bounds__(256) sgd_flat_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ mom,
                                                        bf16* __restrict__ shadow, int64_t n, float lr, float momentum, float wd,
-                                                       float grad_scale, int first_step, int zero_grad) {
+                                                       float grad_scale, int first_step, int zero_grad,
+                                                       const float* __restrict__ lr_dev, const int* __restrict__ step_dev) {
   const int64_t nv = n >> 2;
+  if (lr_dev) lr = lr_dev[0];
+  if (step_dev) first_step = step_dev[0] <= 1;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
     float4 pp = reinterpret_cast<float4*>(p)[i];
     float4 gg = reinterpret_cast<float4*>(g)[i];
@@ -88,21 +102,43 @@ int grid_for(int64_t items) {
 // n must be a multiple of 4 (the flat buffer is padded); all pointers 16-byte aligned.
 extern "C" int mdhs_adam_flat(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, int64_t n,
                               float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
-                              int adamw, int zero_grad, void* stream) {
-  if (!params || !grads || !exp_avg || !exp_avg_sq || n <= 0 || (n % 4) || step < 1) return MDHS_ERR_ARG;
+                              int adamw, int zero_grad, const float* lr_dev, const int* step_dev, void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq || n <= 0 || (n % 4) || (step < 1 && !step_dev)) return MDHS_ERR_ARG;
   const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
   g_mdhs_launches++;
   adam_flat_kernel<<<grid_for(n / 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       params, grads, exp_avg, exp_avg_sq, (bf16*)shadow_bf16, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale,
-      adamw ? 0 : 1, zero_grad);
+      adamw ? 0 : 1, zero_grad, lr_dev, step_dev);
   MDHS_RETURN_LAST();
 }
 
 extern "C" int mdhs_sgd_flat(float* params, float* grads, float* momentum_buf, void* shadow_bf16, int64_t n, float lr,
-                             float momentum, float weight_decay, float grad_scale, int first_step, int zero_grad, void* stream) {
+                             float momentum, float weight_decay, float grad_scale, int first_step, int zero_grad,
+                             const float* lr_dev, const int* step_dev, void* stream) {
   if (!params || !grads || n <= 0 || (n % 4)) return MDHS_ERR_ARG;
   g_mdhs_launches++;
   sgd_flat_kernel<<<grid_for(n / 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      params, grads, momentum_buf, (bf16*)shadow_bf16, n, lr, momentum, weight_decay, grad_scale, first_step, zero_grad);
+      params, grads, momentum_buf, (bf16*)shadow_bf16, n, lr, momentum, weight_decay, grad_scale, first_step, zero_grad, lr_dev,
+      step_dev);
+  MDHS_RETURN_LAST();
+}
+
+namespace {
+__global__ void step_begin_kernel(int* step_dev) {
+  if (step_dev) step_dev[0] += 1;
+}
+}  // namespace
+
+// Once per training step, before the forward pass: advances the device-side step counter (optimizer bias
+// correction) and the dropout seed tick of every translation unit.  Both live in device memory so that a
+// captured CUDA graph of the whole step stays correct when replayed.
+extern "C" int mdhs_step_begin(int* step_dev, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  g_mdhs_launches += 5;
+  step_begin_kernel<<<1, 1, 0, st>>>(step_dev);
+  mdhs_seed_tick_gemm_tc(1, st);
+  mdhs_seed_tick_norm(1, st);
+  mdhs_seed_tick_attention(1, st);
+  mdhs_seed_tick_elementwise(1, st);
   MDHS_RETURN_LAST();
 }

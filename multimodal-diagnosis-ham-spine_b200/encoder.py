@@ -81,32 +81,32 @@ class MdhsModule(nn.Module):
 
 class _TrunkFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, anchor, images, engine, training, names):
-        need = anchor is not None and torch.is_grad_enabled()
+    def forward(ctx, anchor, images, engine, training, names, need):
         feats, c = engine.forward(images, training, need)
         ctx.engine, ctx.c, ctx.names = engine, c, names
         return tuple(feats[n][0] for n in names)
 
     @staticmethod
     def backward(ctx, *grads):
-        ctx.engine.backward(ctx.c, {n: (g.contiguous() if g is not None else None) for n, g in zip(ctx.names, grads)})
+        if ctx.c is not None:  # frozen trunk: outputs still carry grad so that downstream Functions run backward
+            ctx.engine.backward(ctx.c, {n: (g.contiguous() if g is not None else None) for n, g in zip(ctx.names, grads)})
         ctx.c = None
-        return None, None, None, None, None
+        return None, None, None, None, None, None
 
 
 class _BertFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, anchor, input_ids, attention_mask, engine, training):
-        need = anchor is not None and torch.is_grad_enabled()
+    def forward(ctx, anchor, input_ids, attention_mask, engine, training, need):
         h, c = engine.forward(input_ids, attention_mask, training, need)
         ctx.engine, ctx.c = engine, c
         return h
 
     @staticmethod
     def backward(ctx, dh):
-        ctx.engine.backward(ctx.c, dh.contiguous())
+        if ctx.c is not None:
+            ctx.engine.backward(ctx.c, dh.contiguous())
         ctx.c = None
-        return None, None, None, None, None
+        return None, None, None, None, None, None
 
 
 _CHANNELS = {
@@ -160,8 +160,8 @@ class ImageEncoder(MdhsModule):
         st = self.store(x.device)
         B = x.shape[0]
         names = ("layer2", "layer3", "layer4") if self.multi_scale else ("layer4",)
-        anchor = st.anchor if self._trainable() else None
-        feats = _TrunkFn.apply(anchor, x.float(), self._engine, self.training, names)
+        need = self._trainable() and torch.is_grad_enabled()
+        feats = _TrunkFn.apply(st.anchor, x.float(), self._engine, self.training, names, need)
         if self.multi_scale:
             out = {}
             for name, f, proj in zip(names, feats, (self.proj2, self.proj3, self.proj4)):
@@ -191,5 +191,6 @@ class TextEncoder(MdhsModule):
         st = self.store(input_ids.device)
         B, S = input_ids.shape
         trainable = any(p.requires_grad for p in self.model.encoder.parameters())
-        h = _BertFn.apply(st.anchor if trainable else None, input_ids, attention_mask, self._engine, self.training)
+        need = trainable and torch.is_grad_enabled()
+        h = _BertFn.apply(st.anchor, input_ids, attention_mask, self._engine, self.training, need)
         return h.view(B, S, h.shape[1])

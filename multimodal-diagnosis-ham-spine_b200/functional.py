@@ -20,11 +20,10 @@ class LinearFn(torch.autograd.Function):
     """y = act(x W^T + b) (+ residual), bf16 [T,K] -> bf16 [T,N] on the tcgen05 GEMM."""
 
     @staticmethod
-    def forward(ctx, x, residual, w16, gw, bias, gb, act, drop_p, seed):
+    def forward(ctx, x, residual, w16, gw, bias, gb, act, drop_p, seed, need):
         x = x.contiguous() if x.stride(1) != 1 else x
         T, K = x.shape
         N = w16.shape[0]
-        need = torch.is_grad_enabled()
         aux = None
         if act == ops.ACT_GELU and need:
             aux = torch.empty((T, N), device=x.device, dtype=torch.bfloat16)
@@ -53,7 +52,7 @@ class LinearFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = ops.gemm(g, ctx.w16, b_mn=True, M=T, N=K, K=N)
-        return dx, dres, None, None, None, None, None, None, None
+        return dx, dres, None, None, None, None, None, None, None, None
 
 
 def linear(x, store, weight, bias=None, act=ops.ACT_NONE, residual=None, drop_p=0.0, seed=0, w16=None, gw=None, b32=None, gb=None):
@@ -64,15 +63,14 @@ def linear(x, store, weight, bias=None, act=ops.ACT_NONE, residual=None, drop_p=
         if bias is not None:
             b32 = bias.data
             gb = store.g32(bias) if bias.requires_grad else None
-    return LinearFn.apply(x, residual, w16, gw, b32, gb, act, float(drop_p), int(seed))
+    return LinearFn.apply(x, residual, w16, gw, b32, gb, act, float(drop_p), int(seed), torch.is_grad_enabled())
 
 
 class LayerNormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, gg, gb, eps):
         x = x.contiguous()
-        need = torch.is_grad_enabled()
-        y, _, mean, rstd = ops.layernorm_fwd(x, gamma, beta, eps, save_stats=need)
+        y, _, mean, rstd = ops.layernorm_fwd(x, gamma, beta, eps, save_stats=True)
         ctx.gg, ctx.gb, ctx.gamma = gg, gb, gamma
         ctx.save_for_backward(x, mean, rstd)
         return y

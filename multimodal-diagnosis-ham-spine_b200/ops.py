@@ -321,15 +321,20 @@ def axpby(x, y, a=1.0, b=0.0, a_dev=None):
 
 
 def adam_flat(params, grads, exp_avg, exp_avg_sq, shadow, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0,
-              adamw=True, zero_grad=True):
+              adamw=True, zero_grad=True, lr_dev=None, step_dev=None):
     _lib.call("mdhs_adam_flat", _p(params), _p(grads), _p(exp_avg), _p(exp_avg_sq), _p(shadow), params.numel(), float(lr),
               float(beta1), float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale), int(adamw),
-              int(zero_grad), _s())
+              int(zero_grad), _p(lr_dev), _p(step_dev), _s())
 
 
-def sgd_flat(params, grads, mom, shadow, lr, momentum, weight_decay, grad_scale=1.0, first_step=False, zero_grad=True):
+def sgd_flat(params, grads, mom, shadow, lr, momentum, weight_decay, grad_scale=1.0, first_step=False, zero_grad=True,
+             lr_dev=None, step_dev=None):
     _lib.call("mdhs_sgd_flat", _p(params), _p(grads), _p(mom), _p(shadow), params.numel(), float(lr), float(momentum),
-              float(weight_decay), float(grad_scale), int(first_step), int(zero_grad), _s())
+              float(weight_decay), float(grad_scale), int(first_step), int(zero_grad), _p(lr_dev), _p(step_dev), _s())
+
+
+def step_begin(step_dev=None):
+    _lib.call("mdhs_step_begin", _p(step_dev), _s())
 
 
 def act_dropout_bwd(dy, aux, act, drop_p, seed):

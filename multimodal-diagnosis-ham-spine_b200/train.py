@@ -1,0 +1,158 @@
+"""Training step for the multimodal model on one B200 per process (the caller of the hot path:
+scripts/train.py:349-394 in the reference): forward_features -> classifier -> loss -> backward -> gradient
+all-reduce (data parallel) -> fused optimizer step over the flat parameter buffer.
+
+* The whole step can be captured into ONE CUDA graph (`capture=True`): learning rate, step count and the
+  dropout seed tick live in device memory, so replays stay correct.
+* Data parallel = one process per GPU; gradients are averaged with NCCL over NVLink in two contiguous
+  slices of the flat gradient buffer: [text encoder | fusion | head] is reduced on the communication
+  stream while the ResNet trunk is still back-propagating, the image-encoder slice afterwards.
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import functional as Fm
+from . import ops
+
+
+class Trainer:
+    def __init__(self, model, optimizer="adamw", lr=2e-4, weight_decay=None, betas=(0.9, 0.999), eps=1e-8, momentum=0.9,
+                 loss="ce", label_smoothing=0.02, focal_gamma=2.0, class_weights=None, process_group=None,
+                 overlap_comm=True):
+        self.model = model
+        self.opt = optimizer.lower()
+        if self.opt not in ("adamw", "adam", "sgd"):
+            raise ValueError(f"Unsupported optimizer: {optimizer}")
+        if weight_decay is None:
+            weight_decay = 1e-2 if self.opt == "adamw" else 0.0   # torch defaults used by scripts/train.py:283-309
+        self.lr, self.wd, self.betas, self.eps, self.momentum = lr, weight_decay, betas, eps, momentum
+        self.loss_type, self.label_smoothing, self.focal_gamma = loss, label_smoothing, focal_gamma
+        self.class_weights = class_weights
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.overlap = overlap_comm and self.world > 1
+        self.store = None
+        self._graph = None
+        self._static = None
+        self._comm_works = []
+
+    # ------------------------------------------------------------------ setup
+    def _ensure(self, device):
+        if self.store is not None:
+            return
+        st = self.model.store(device)
+        self.store = st
+        n = st.total
+        self.m = torch.zeros(n, device=device)
+        self.v = torch.zeros(n, device=device) if self.opt != "sgd" else None
+        self.lr_dev = torch.full((1,), float(self.lr), device=device)
+        self.step_dev = torch.zeros(1, device=device, dtype=torch.int32)
+        # slice boundary for the overlapped all-reduce: everything from the text encoder on
+        self.split = 0
+        te = getattr(self.model, "text_encoder", None)
+        if te is not None:
+            offs = [st.offsets[id(p)] for p in te.parameters()]
+            self.split = min(offs) if offs else 0
+        if self.world > 1:
+            # same initial weights everywhere (rank 0 wins), like DistributedDataParallel's constructor
+            dist.broadcast(st.flat, src=0, group=self.pg)
+            st.refresh(force=True)
+
+    def set_lr(self, lr):
+        self.lr = lr
+        if self.store is not None:
+            self.lr_dev.fill_(float(lr))
+
+    # ------------------------------------------------------------------ one step (eager)
+    def _loss(self, logits, labels):
+        if self.loss_type == "focal":
+            return Fm.cross_entropy(logits, labels, self.class_weights, 0.0, True, self.focal_gamma)
+        return Fm.cross_entropy(logits, labels, self.class_weights, self.label_smoothing, False, 2.0)
+
+    def _allreduce(self, lo, hi, async_op):
+        if hi <= lo:
+            return None
+        return dist.all_reduce(self.store.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.pg, async_op=async_op)
+
+    def _step_impl(self, images, ids, mask, labels):
+        st = self.store
+        ops.step_begin(self.step_dev)
+        hook = None
+        works = []
+        if self.overlap and self.split > 0:
+            eng = self.model.text_encoder._engine
+            orig = eng.backward
+
+            def bert_backward_then_reduce(ctx, dh):
+                orig(ctx, dh)
+                works.append(self._allreduce(self.split, st.total, True))
+
+            eng.backward = bert_backward_then_reduce
+            hook = (eng, orig)
+        try:
+            feats = self.model.forward_features(images, ids, mask)
+            logits = self.model.classifier(feats)
+            loss = self._loss(logits, labels)
+            loss.backward()
+        finally:
+            if hook is not None:
+                hook[0].backward = hook[1]
+        if self.world > 1:
+            if works:
+                works.append(self._allreduce(0, self.split, True))
+            else:
+                works.append(self._allreduce(0, st.total, True))
+            for w in works:
+                if w is not None:
+                    w.wait()
+        scale = 1.0 / self.world
+        if self.opt == "sgd":
+            ops.sgd_flat(st.flat, st.grad, self.m if self.momentum > 0 else None, st.shadow, self.lr, self.momentum, self.wd,
+                         grad_scale=scale, lr_dev=self.lr_dev, step_dev=self.step_dev)
+        else:
+            ops.adam_flat(st.flat, st.grad, self.m, self.v, st.shadow, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
+                          1, grad_scale=scale, adamw=(self.opt == "adamw"), lr_dev=self.lr_dev, step_dev=self.step_dev)
+        st.mark_fresh()
+        return loss.detach(), logits.detach()
+
+    def step(self, images, ids, mask, labels):
+        """Eager step on device tensors.  Returns (loss, logits) device tensors (no host sync)."""
+        self._ensure(images.device)
+        self.model.train()
+        return self._step_impl(images, ids, mask, labels)
+
+    # ------------------------------------------------------------------ CUDA-graph step
+    def capture(self, images, ids, mask, labels, warmup=3):
+        """Capture the whole step for fixed shapes.  Afterwards `replay(images, ids, mask, labels)` copies the new
+        batch into the static input buffers and launches the graph."""
+        self._ensure(images.device)
+        self.model.train()
+        self._static = [t.clone() for t in (images, ids, mask, labels)]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._step_impl(*self._static)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._static_out = self._step_impl(*self._static)
+        return self._static_out
+
+    def replay(self, images=None, ids=None, mask=None, labels=None):
+        if images is not None:
+            for dst, src in zip(self._static, (images, ids, mask, labels)):
+                dst.copy_(src, non_blocking=True)
+        self._graph.replay()
+        return self._static_out
+
+
+def warmup_cosine_lr(base_lr, epoch, warmup_epochs, total_epochs):
+    """LambdaLR factor of scripts/train.py:321-334 (linear warm-up then cosine decay)."""
+    if warmup_epochs > 0 and epoch < warmup_epochs:
+        return base_lr * float(epoch + 1) / float(warmup_epochs)
+    progress = (epoch - warmup_epochs) / max(1, total_epochs - warmup_epochs)
+    return base_lr * 0.5 * (1.0 + math.cos(math.pi * progress))
