@@ -27,10 +27,13 @@ constexpr int SMEM_LIMIT = 232448;                           // 227 KiB opt-in m
 template <int BN> struct Cfg {
   static constexpr int B_TILE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 7 : 8);
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES;
+  // two 16 KiB output staging boxes (128 rows x 128 bytes, 128B-swizzled) feeding the TMA store / reduce-add
+  static constexpr int STAGING_BYTES = 2 * 16384;
+  static constexpr int EPI_GROUPS = (BN == 64) ? 1 : 2;   // warp groups (4 warps each) that drain the accumulator
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES;
   static_assert(SMEM_BYTES <= SMEM_LIMIT, "shared memory budget exceeded");
 };
 
@@ -107,6 +110,33 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  bf162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
 // UMMA shared-memory matrix descriptor, 128-byte swizzle, sm_100 version bit set.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -121,13 +151,15 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 // ------------------------------------------------------------------ kernel
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmD, const Params p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t tiles_base = smem_base;
-  const uint32_t bars = smem_base + C::STAGES * C::STAGE_BYTES;
+  const uint32_t staging_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  const uint32_t bars = staging_base + C::STAGING_BYTES;
   // barrier layout: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem base address
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
@@ -135,7 +167,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * C::STAGES + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * C::STAGES + 4);
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + C::STAGES * C::STAGE_BYTES + 8 * (2 * C::STAGES + 4));
+      reinterpret_cast<volatile uint32_t*>(smem_gen + C::STAGES * C::STAGE_BYTES + C::STAGING_BYTES + 8 * (2 * C::STAGES + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -143,6 +175,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmD)) : "memory");
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; s++) {
@@ -151,7 +184,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 8);
+      mbar_init(tempty_bar(a), 4 * C::EPI_GROUPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -241,15 +274,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         acc_phase ^= 1u;
       }
     }
-  } else if (warp >= EPI_WARP0) {
+  } else if (warp >= EPI_WARP0 && (warp - EPI_WARP0) < 4 * C::EPI_GROUPS) {
     // ------------------------------------------------------------ epilogue
-    // 8 warps: warp (4+q) and (8+q) share TMEM lane quarter q and split the tile's columns in halves.
-    // Thread = accumulator row; every global access is a 16-byte vector on the thread's own row, so all
-    // sectors are fully used without a shared-memory transpose.
+    // Warp (4+q) [and (8+q) when BN >= 128] owns TMEM lane quarter q; two groups split the tile's columns in
+    // halves.  Thread = accumulator row.  The result is written into a 128B-swizzled shared-memory box
+    // (128 rows x 128 bytes) and leaves through one TMA store (bf16 / fp32) or TMA reduce-add (fp32 gradient
+    // accumulation, split-K) per box: full-line writes, no per-thread global stores.
     const int wq = (warp - EPI_WARP0) & 3;     // TMEM lane quarter
     const int half = (warp - EPI_WARP0) >> 2;  // column half of the tile
-    constexpr int HALF_COLS = BN / 2;
-    constexpr int GROUPS = HALF_COLS / 32;     // 32-column groups per warp (1, 2 or 4)
+    constexpr int HALF_COLS = BN / C::EPI_GROUPS;
+    constexpr int GROUPS = HALF_COLS / 32;     // 32-column groups per warp (2 or 4)
+    const uint32_t stage_box = staging_base + half * 16384;
+    const int row_in_box = wq * 32 + lane;
+    const uint32_t stage_row = stage_box + row_in_box * 128;
+    const int swz = row_in_box & 7;
+    const bool issuer = (wq == 0 && lane == 0);
+    const int bar_id = 1 + half;               // named barrier of this warp group (128 threads)
     const float inv_keep = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -278,7 +318,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (lane == 0) mbar_arrive(tempty_bar(acc));
         }
         const int n0 = n_half0 + g * 32;
-        if (n0 >= p.N) continue;
+        // NOTE: no early exit for column groups beyond N: the whole warp group must reach the named barriers;
+        // TMA clips out-of-range columns / rows and every global access below is bounds-checked.
         float x[32];
 #pragma unroll
         for (int j = 0; j < 32; j++) x[j] = __uint_as_float(r[j]);
@@ -353,30 +394,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
-        // ---- store
+        // ---- store through the staging box + TMA
         if (p.d_f32) {
-          if (row_ok) {
-            float* dp = reinterpret_cast<float*>(p.D) + m * p.ldd + n0;
-            if (p.accumulate) {
+          // one 32-column fp32 group == one full box (128 bytes per row)
+          if (issuer) bulk_wait_read0();        // previous box has been read out of shared memory
+          named_bar(bar_id, 128);
 #pragma unroll
-              for (int j = 0; j < 32; j++)
-                if (n0 + j < p.N) atomicAdd(dp + j, x[j]);
-            } else {
-#pragma unroll
-              for (int v = 0; v < 8; v++)
-                if (n0 + v * 4 < p.N)
-                  *reinterpret_cast<float4*>(dp + v * 4) = make_float4(x[v * 4], x[v * 4 + 1], x[v * 4 + 2], x[v * 4 + 3]);
-            }
+          for (int c = 0; c < 8; c++)
+            st_shared_v4(stage_row + ((c ^ swz) << 4), __float_as_uint(x[4 * c]), __float_as_uint(x[4 * c + 1]),
+                         __float_as_uint(x[4 * c + 2]), __float_as_uint(x[4 * c + 3]));
+          fence_async_smem();
+          named_bar(bar_id, 128);
+          if (issuer) {
+            if (p.accumulate) tma_reduce_add_2d(&tmD, stage_box, n0, m_blk * BM);
+            else tma_store_2d(&tmD, stage_box, n0, m_blk * BM);
+            bulk_commit();
           }
         } else {
           // round to bf16 first so that the statistics below describe exactly what was stored
+          uint32_t pk[16];
 #pragma unroll
-          for (int j = 0; j < 32; j++) x[j] = __bfloat162float(__float2bfloat16_rn(x[j]));
-          if (row_ok) {
-            bf16* dp = reinterpret_cast<bf16*>(p.D) + m * p.ldd + n0;
+          for (int j = 0; j < 16; j++) {
+            pk[j] = pack_bf16(x[2 * j], x[2 * j + 1]);
+            const float2 q = __bfloat1622float2(*reinterpret_cast<bf162*>(&pk[j]));
+            x[2 * j] = q.x;
+            x[2 * j + 1] = q.y;
+          }
+          const int sub = g & 1;                // which 32-column half of the 64-column bf16 box
+          if (sub == 0) {
+            if (issuer) bulk_wait_read0();
+            named_bar(bar_id, 128);
+          }
 #pragma unroll
-            for (int v = 0; v < 4; v++)
-              if (n0 + v * 8 < p.N) store8(dp + v * 8, x + v * 8);
+          for (int c = 0; c < 4; c++)
+            st_shared_v4(stage_row + (((sub * 4 + c) ^ swz) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+          if (sub == 1) {
+            fence_async_smem();
+            named_bar(bar_id, 128);
+            if (issuer) {
+              tma_store_2d(&tmD, stage_box, n0 - 32, m_blk * BM);
+              bulk_commit();
+            }
           }
         }
         // ---- per-column sum / sum of squares over the 32 rows of this warp (train-mode BN statistics)
@@ -417,6 +475,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         acc_phase ^= 1u;
       }
     }
+    if (issuer) bulk_wait0();   // all TMA stores of this CTA have completed before the CTA exits
   }
 
   tc_fence_before();
@@ -447,15 +506,17 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2-D bf16 tensor map: `inner` contiguous elements per row, `outer` rows `ld` elements apart.
-int make_map(CUtensorMap* map, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_inner, int box_outer) {
+// 2-D tensor map (bf16, or fp32 when f32): `inner` contiguous elements per row, `outer` rows `ld` elements apart.
+int make_map(CUtensorMap* map, const void* ptr, int64_t inner, int64_t outer, int64_t ld, int box_inner, int box_outer,
+             bool f32 = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return MDHS_ERR_DRIVER;
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * (f32 ? 4 : 2)};
   cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims,
+                   strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? MDHS_OK : MDHS_ERR_ARG;
@@ -478,8 +539,10 @@ int launch(const mdhs_gemm_args* a, const Params& p0, cudaStream_t stream) {
   Params p = p0;
   p.num_m = ceil_div(a->M, BM);
   p.num_n = ceil_div(a->N, BN);
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmD;
   int rc;
+  rc = make_map(&tmD, a->D, a->N, a->M, a->ldd, p.d_f32 ? 32 : 64, BM, p.d_f32 != 0);
+  if (rc) return rc;
   if (!A_MN) rc = make_map(&tmA, a->A, a->K, a->M, a->lda, BK, BM);
   else       rc = make_map(&tmA, a->A, a->M, a->K, a->lda, 64, BK);
   if (rc) return rc;
@@ -495,7 +558,7 @@ int launch(const mdhs_gemm_args* a, const Params& p0, cudaStream_t stream) {
   }
   const int total = p.num_m * p.num_n * p.splits;
   const int grid = total < num_sms() ? total : num_sms();
-  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmD, p);
   MDHS_RETURN_LAST();
 }
 
@@ -527,7 +590,7 @@ extern "C" int mdhs_gemm_bf16(const mdhs_gemm_args* a, void* stream_) {
   if (a->split_k > 1 && (!a->accumulate || a->act || a->dact || a->aux_out || a->colsum)) return MDHS_ERR_ARG;
   if (a->dact != MDHS_ACT_NONE && !a->aux_in) return MDHS_ERR_ARG;
   if ((a->colsum == nullptr) != (a->colsumsq == nullptr)) return MDHS_ERR_ARG;
-  if ((a->ldd % 8) || (a->residual && (a->ldr % 8)) || (a->aux_out && (a->ld_aux_out % 8)) ||
+  if ((a->ldd % (a->d_dtype == MDHS_DT_F32 ? 4 : 8)) || (a->residual && (a->ldr % 8)) || (a->aux_out && (a->ld_aux_out % 8)) ||
       (a->aux_in && (a->ld_aux_in % 8)))
     return MDHS_ERR_ARG;
   if (((uintptr_t)a->D & 15) || ((uintptr_t)a->residual & 15) || ((uintptr_t)a->aux_out & 15) || ((uintptr_t)a->aux_in & 15) ||
