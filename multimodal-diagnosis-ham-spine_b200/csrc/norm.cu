@@ -314,38 +314,54 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restri
   }
 }
 
-// dx = gamma*invstd * (dy' - sum_dy/M - xhat * sum_dy_xhat/M); optionally also writes dy' (the
-// ReLU-masked incoming gradient) for the identity branch; accumulates dgamma/dbeta once (block 0).
+// Per-channel coefficients of the BN input gradient, from the fp64 reductions:
+//   dx = gamma*invstd * (dy' - sum_dy/M - xhat * sum_dy_xhat/M) = ca * dy' + cb * x + cc
+// Also accumulates dgamma / dbeta (one thread per channel).
+__global__ void bn_bwd_coeff_kernel(const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ gamma, const double* __restrict__ sum_dy,
+                                    const double* __restrict__ sum_dy_xhat, float* __restrict__ coef, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta, int64_t rows, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double inv_m = 1.0 / (double)rows;
+  const double is = invstd[c], mu = mean[c], g = gamma[c];
+  const double s1 = sum_dy[c], s2 = sum_dy_xhat[c];
+  const double ca = g * is;
+  const double cb = -g * is * is * s2 * inv_m;
+  coef[c] = (float)ca;
+  coef[C + c] = (float)cb;
+  coef[2 * C + c] = (float)(-ca * s1 * inv_m - cb * mu);
+  if (dgamma) {
+    dgamma[c] += (float)s2;
+    dbeta[c] += (float)s1;
+  }
+}
+
+// dx = ca[c] * dy' + cb[c] * x + cc[c]; optionally also writes dy' (the ReLU-masked incoming gradient) for the
+// identity branch.  Pure streaming: 8 channels per thread, coefficient vectors read as float4.
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
-                                                           const bf16* __restrict__ y, const float* __restrict__ mean,
-                                                           const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                                           const double* __restrict__ sum_dy,
-                                                           const double* __restrict__ sum_dy_xhat, bf16* __restrict__ dx,
-                                                           bf16* __restrict__ dz, float* __restrict__ dgamma,
-                                                           float* __restrict__ dbeta, int64_t rows, int C, int relu) {
+                                                           const bf16* __restrict__ y, const float* __restrict__ coef,
+                                                           bf16* __restrict__ dx, bf16* __restrict__ dz, int64_t rows, int C,
+                                                           int relu) {
   const int cvec = C >> 3;
   const int64_t total_vec = rows * cvec;
-  const float inv_m = 1.f / (float)rows;
-  if (blockIdx.x == 0 && dgamma) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      dgamma[c] += (float)sum_dy_xhat[c];
-      dbeta[c] += (float)sum_dy[c];
-    }
-  }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
     const int c0 = (int)(i % cvec) * 8;
-    float d[8], xv[8], yv[8], o[8];
+    float d[8], xv[8], yv[8], o[8], ca[8], cb[8], cc[8];
     load8(dy + i * 8, d);
     load8(x + i * 8, xv);
     if (relu) load8(y + i * 8, yv);
+    *reinterpret_cast<float4*>(ca) = *reinterpret_cast<const float4*>(coef + c0);
+    *reinterpret_cast<float4*>(ca + 4) = *reinterpret_cast<const float4*>(coef + c0 + 4);
+    *reinterpret_cast<float4*>(cb) = *reinterpret_cast<const float4*>(coef + C + c0);
+    *reinterpret_cast<float4*>(cb + 4) = *reinterpret_cast<const float4*>(coef + C + c0 + 4);
+    *reinterpret_cast<float4*>(cc) = *reinterpret_cast<const float4*>(coef + 2 * C + c0);
+    *reinterpret_cast<float4*>(cc + 4) = *reinterpret_cast<const float4*>(coef + 2 * C + c0 + 4);
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      const int c = c0 + k;
       const float dd = (relu && !(yv[k] > 0.f)) ? 0.f : d[k];
       d[k] = dd;
-      const float is = invstd[c];
-      const float xh = (xv[k] - mean[c]) * is;
-      o[k] = gamma[c] * is * (dd - (float)sum_dy[c] * inv_m - xh * (float)sum_dy_xhat[c] * inv_m);
+      o[k] = fmaf(ca[k], dd, fmaf(cb[k], xv[k], cc[k]));
     }
     store8(dx + i * 8, o);
     if (dz) store8(dz + i * 8, d);
@@ -481,9 +497,9 @@ extern "C" int mdhs_bn_apply(const void* x, const float* scale, const float* shi
 }
 
 extern "C" int mdhs_bn_bwd(const void* dy, const void* x, const void* y, const float* mean, const float* invstd,
-                           const float* gamma, double* sum_dy, double* sum_dy_xhat, void* dx, void* dz, float* dgamma,
-                           float* dbeta, int64_t rows, int C, int relu, void* stream) {
-  if (!dy || !x || !mean || !invstd || !gamma || !sum_dy || !sum_dy_xhat || !dx || rows <= 0 || (C % 8)) return MDHS_ERR_ARG;
+                           const float* gamma, double* sum_dy, double* sum_dy_xhat, float* coef, void* dx, void* dz,
+                           float* dgamma, float* dbeta, int64_t rows, int C, int relu, void* stream) {
+  if (!dy || !x || !mean || !invstd || !gamma || !sum_dy || !sum_dy_xhat || !coef || !dx || rows <= 0 || (C % 8)) return MDHS_ERR_ARG;
   if (relu && !y) return MDHS_ERR_ARG;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaError_t e = cudaMemsetAsync(sum_dy, 0, sizeof(double) * C, st);
@@ -496,13 +512,13 @@ extern "C" int mdhs_bn_bwd(const void* dy, const void* x, const void* y, const f
   int rpb = ceil_div(rows, row_blocks);
   rpb = ((rpb + 7) / 8) * 8;
   row_blocks = ceil_div(rows, rpb);
-  g_mdhs_launches += 2;
+  g_mdhs_launches += 3;
   bn_bwd_reduce_kernel<<<dim3(cslabs, row_blocks), 256, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, mean, invstd,
                                                                  sum_dy, sum_dy_xhat, rows, C, rpb, relu);
+  bn_bwd_coeff_kernel<<<ceil_div(C, 128), 128, 0, st>>>(mean, invstd, gamma, sum_dy, sum_dy_xhat, coef, dgamma, dbeta, rows, C);
   const int64_t total_vec = rows * (C / 8);
-  bn_bwd_apply_kernel<<<grid_for(total_vec, 256), 256, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, mean, invstd,
-                                                                gamma, sum_dy, sum_dy_xhat, (bf16*)dx, (bf16*)dz, dgamma, dbeta,
-                                                                rows, C, relu);
+  bn_bwd_apply_kernel<<<grid_for(total_vec, 256), 256, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, coef, (bf16*)dx,
+                                                                (bf16*)dz, rows, C, relu);
   MDHS_RETURN_LAST();
 }
 

@@ -137,10 +137,11 @@ def bn_apply(x, scale, shift, residual=None, relu=True, out=None):
 def bn_bwd(dy, x, y, mean, invstd, gamma, dgamma, dbeta, relu=True, want_dz=False):
     rows, C = x.shape
     ws = torch.empty((2, C), device=x.device, dtype=torch.float64)
+    coef = torch.empty((3, C), device=x.device, dtype=torch.float32)
     dx = torch.empty_like(x)
     dz = torch.empty_like(x) if want_dz else None
     _lib.call("mdhs_bn_bwd", _p(dy), _p(x), _p(y), _p(mean), _p(invstd), _p(gamma), ws[0].data_ptr(), ws[1].data_ptr(),
-              _p(dx), _p(dz), _p(dgamma), _p(dbeta), rows, C, int(relu), _s())
+              _p(coef), _p(dx), _p(dz), _p(dgamma), _p(dbeta), rows, C, int(relu), _s())
     return dx, dz
 
 

@@ -118,3 +118,20 @@ def test_gemm_dropout_epilogue(mdhs):
     kept = y1 != 0
     assert abs((~kept).float().mean().item() - p) < 0.01
     assert torch.allclose(y1[kept], y0[kept] / (1 - p), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("bn", [64, 128, 256])
+@pytest.mark.parametrize("M,N,K,split", [(512, 768, 128, 1), (64, 576, 3000, 5), (2304, 768, 1024, 2), (136, 72, 264, 1)])
+def test_gemm_wgrad_accumulate_all_tiles(mdhs, bn, M, N, K, split):
+    """fp32 TMA reduce-add path (gradient accumulation) for every tile width."""
+    from mdhs_b200 import ops
+    torch.manual_seed(5)
+    dy = torch.randn(K, M, device="cuda").bfloat16()
+    x = torch.randn(K, N, device="cuda").bfloat16()
+    acc = torch.full((M, N), 0.5, device="cuda")
+    ops.gemm(dy, x, a_mn=True, b_mn=True, out=acc, accumulate=True, split_k=split, bn_hint=bn)
+    ops.gemm(dy, x, a_mn=True, b_mn=True, out=acc, accumulate=True, split_k=split, bn_hint=bn)
+    ref = 2 * (dy.float().t() @ x.float()) + 0.5
+    assert (acc - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
+    out = ops.gemm(dy, x, a_mn=True, b_mn=True, out_dtype=torch.float32, bn_hint=bn)
+    assert (out - (ref - 0.5) / 2).abs().max().item() <= 2e-3 * ref.abs().max().item()
