@@ -256,7 +256,7 @@ def run_ours(args):
             M = kw.get("M") or (a.shape[1] if a_mn else a.shape[0])
             N = kw.get("N") or (b.shape[1] if b_mn else b.shape[0])
             K = kw.get("K") or (a.shape[0] if a_mn else a.shape[1])
-            recs.append((2.0 * M * N * K, s_, e_))
+            recs.append((2.0 * M * N * K, s_, e_, (M, N, K, int(a_mn), int(b_mn), int(bool(kw.get("accumulate"))), kw.get("split_k", 1))))
             return out
         ops.gemm = timed_gemm
         try:
@@ -278,6 +278,19 @@ def run_ours(args):
             gms = sum(r[1].elapsed_time(r[2]) for r in recs)
             peak, hbm, src = _peaks()
             ach = gflop / gms  # GFLOP/ms == TFLOP/s
+            if args.dump_gemms:
+                import collections
+                agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
+                for r in recs:
+                    a_ = agg[r[3]]
+                    a_[0] += 1
+                    a_[1] += r[1].elapsed_time(r[2])
+                    a_[2] += r[0]
+                os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+                with open(os.path.join(ROOT, "gpurun_out", "gemm_shapes.txt"), "w") as fh:
+                    fh.write("M N K a_mn b_mn acc split | count total_ms TFLOP/s\n")
+                    for k_, (c_, ms_, fl_) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                        fh.write(f"{k_} | {c_} {ms_:.3f} {fl_ / ms_ / 1e9:.1f}\n")
             roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM: all Linear / conv contractions)",
                     "achieved": round(ach, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": None,
                     "peak_source": f"{src} bf16_tflops_sustained", "launches_per_step": len(recs),
@@ -321,6 +334,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=8, help="samples per CPU step of the reference arm")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-gemms", action="store_true", help="write per-shape GEMM timings to gpurun_out/gemm_shapes.txt")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -54,7 +54,7 @@ typedef struct {
   int32_t act;                                /* MDHS_ACT_* applied in the epilogue */
   int32_t dact;                               /* MDHS_ACT_*: multiply by act'(aux_in) */
   const void* residual; int64_t ldr; int32_t r_dtype;
-  int32_t split_k;                            /* 0/1 = none; >1 needs accumulate=1 */
+  int32_t split_k;                            /* 0/1 = none; >1 needs accumulate=1; <0 = auto (with accumulate) */
   int32_t bn_hint;                            /* 0 = auto; else 64/128/256 tile width */
   double* colsum; double* colsumsq;           /* optional fp64 [N] atomics: per-column sum / sum of
                                                  squares of the stored value (train-mode BN stats) */

@@ -106,7 +106,7 @@ class BertEngine:
             gb = (st.g32(lin.bias) if gb is None else gb)
             tiles = ((N + 127) // 128) * ((K + 255) // 256)
             splits = max(1, min((T + 63) // 64 // 4, (148 + tiles - 1) // tiles))
-            ops.gemm(dy, x_in, a_mn=True, b_mn=True, out=gw, accumulate=True, split_k=splits, M=N, N=K, K=T)
+            ops.gemm(dy, x_in, a_mn=True, b_mn=True, out=gw, accumulate=True, split_k=-1, M=N, N=K, K=T)
             ops.col_stats(dy, sum32=gb)
         if not need_dx:
             return None

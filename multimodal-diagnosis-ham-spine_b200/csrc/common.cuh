@@ -96,11 +96,25 @@ static __device__ uint64_t g_seed_tick = 0;
   static __global__ void seed_tick_kernel_##tu(uint64_t inc) { g_seed_tick += inc; }    \
   void mdhs_seed_tick_##tu(uint64_t inc, cudaStream_t st) { seed_tick_kernel_##tu<<<1, 1, 0, st>>>(inc); }
 
-// keep-mask scale: returns 0 or 1/(1-p). p == 0 -> always 1.
+// keep-mask scale: returns 0 or 1/(1-p). p == 0 -> always 1.  One 64-bit hash serves the 4 consecutive element
+// indices idx & ~3 .. idx | 3 (16 random bits each), so vectorised callers pay one hash per 4 elements.
+__device__ __forceinline__ uint64_t dropout_bits4(uint64_t seed, uint64_t idx4) {
+  uint64_t z = seed + g_seed_tick * 0x2545F4914F6CDD1Dull + idx4 * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
 __device__ __forceinline__ float dropout_scale(uint64_t seed, uint64_t idx, float p, float inv_keep) {
   if (p <= 0.f) return 1.f;
-  float u = (float)(hash_u32(seed + g_seed_tick * 0x2545F4914F6CDD1Dull, idx) >> 8) * (1.0f / 16777216.0f);
-  return u < p ? 0.f : inv_keep;
+  const uint32_t r16 = (uint32_t)(dropout_bits4(seed, idx >> 2) >> ((idx & 3) * 16)) & 0xffffu;
+  return (float)r16 < p * 65536.f ? 0.f : inv_keep;
+}
+// 4 consecutive elements starting at idx (idx % 4 == 0): out[k] *= mask
+__device__ __forceinline__ void dropout_apply4(uint64_t seed, uint64_t idx, float p, float inv_keep, float* v) {
+  const uint64_t bits = dropout_bits4(seed, idx >> 2);
+  const float thr = p * 65536.f;
+#pragma unroll
+  for (int k = 0; k < 4; k++) v[k] *= ((float)((uint32_t)(bits >> (16 * k)) & 0xffffu) < thr) ? 0.f : inv_keep;
 }
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

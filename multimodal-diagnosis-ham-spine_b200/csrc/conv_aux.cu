@@ -19,21 +19,30 @@ int grid_for(int64_t items, int block) {
 __global__ void __launch_bounds__(256) im2col_nchw_f32_kernel(const float* __restrict__ x, bf16* __restrict__ col, int B, int C,
                                                               int H, int W, int R, int S, int stride, int pad, int Ho, int Wo,
                                                               int ldc) {
-  const int64_t total = (int64_t)B * Ho * Wo * ldc;
+  // one thread = 8 consecutive k of one output pixel = one 16-byte store (ldc % 8 == 0)
+  const int kvec = ldc >> 3;
+  const int64_t total = (int64_t)B * Ho * Wo * kvec;
   const int K = R * S * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int k = (int)(i % ldc);
-    const int64_t row = i / ldc;
-    float v = 0.f;
-    if (k < K) {
-      const int c = k % C, rs = k / C, s = rs % S, r = rs / S;
-      const int wo = (int)(row % Wo);
-      const int ho = (int)((row / Wo) % Ho);
-      const int b = (int)(row / ((int64_t)Wo * Ho));
-      const int h = ho * stride - pad + r, w = wo * stride - pad + s;
-      if (h >= 0 && h < H && w >= 0 && w < W) v = x[(((int64_t)b * C + c) * H + h) * W + w];
+    const int kv = (int)(i % kvec);
+    const int64_t row = i / kvec;
+    const int wo = (int)(row % Wo);
+    const int ho = (int)((row / Wo) % Ho);
+    const int b = (int)(row / ((int64_t)Wo * Ho));
+    const float* xb = x + (int64_t)b * C * H * W;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int k = kv * 8 + j;
+      float val = 0.f;
+      if (k < K) {
+        const int c = k % C, rs = k / C, s = rs % S, r = rs / S;
+        const int h = ho * stride - pad + r, w = wo * stride - pad + s;
+        if (h >= 0 && h < H && w >= 0 && w < W) val = __ldg(xb + ((int64_t)c * H + h) * W + w);
+      }
+      v[j] = val;
     }
-    col[i] = __float2bfloat16_rn(v);
+    store8(col + row * ldc + kv * 8, v);
   }
 }
 
@@ -328,10 +337,10 @@ __global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, bf16* 
 
 extern "C" int mdhs_im2col_nchw_f32(const float* x, void* col, int B, int C, int H, int W, int R, int S, int stride, int pad,
                                     int ldc, void* stream) {
-  if (!x || !col || ldc < R * S * C) return MDHS_ERR_ARG;
+  if (!x || !col || ldc < R * S * C || (ldc % 8)) return MDHS_ERR_ARG;
   const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
   g_mdhs_launches++;
-  im2col_nchw_f32_kernel<<<grid_for((int64_t)B * Ho * Wo * ldc, 256), 256, 0, ST(stream)>>>(x, (bf16*)col, B, C, H, W, R, S, stride,
+  im2col_nchw_f32_kernel<<<grid_for((int64_t)B * Ho * Wo * (ldc / 8), 256), 256, 0, ST(stream)>>>(x, (bf16*)col, B, C, H, W, R, S, stride,
                                                                                             pad, Ho, Wo, ldc);
   MDHS_RETURN_LAST();
 }

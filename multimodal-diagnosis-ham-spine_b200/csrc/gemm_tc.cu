@@ -152,7 +152,8 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmD, const Params p) {
+               const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmAux,
+               const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmAuxIn, const Params p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -166,6 +167,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * C::STAGES + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * C::STAGES + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * C::STAGES + 4);
+  auto lbar = [&](int h) { return bars + 8u * (2 * C::STAGES + 6 + h); };  // epilogue box-load barriers
   volatile uint32_t* tmem_slot_gen =
       reinterpret_cast<volatile uint32_t*>(smem_gen + C::STAGES * C::STAGE_BYTES + C::STAGING_BYTES + 8 * (2 * C::STAGES + 4));
 
@@ -183,6 +185,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; a++) {
+      mbar_init(lbar(a), 1);
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 4 * C::EPI_GROUPS);
     }
@@ -277,13 +280,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp >= EPI_WARP0 && (warp - EPI_WARP0) < 4 * C::EPI_GROUPS) {
     // ------------------------------------------------------------ epilogue
     // Warp (4+q) [and (8+q) when BN >= 128] owns TMEM lane quarter q; two groups split the tile's columns in
-    // halves.  Thread = accumulator row.  The result is written into a 128B-swizzled shared-memory box
-    // (128 rows x 128 bytes) and leaves through one TMA store (bf16 / fp32) or TMA reduce-add (fp32 gradient
-    // accumulation, split-K) per box: full-line writes, no per-thread global stores.
+    // halves and walk them 64 columns at a time.  Thread = accumulator row.  Results are written into a
+    // 128B-swizzled shared-memory box (128 rows x 128 bytes) and leave through one TMA store (bf16 / fp32) or
+    // TMA reduce-add (fp32 gradient accumulation, split-K) per box: full-line writes, no per-thread stores.
     const int wq = (warp - EPI_WARP0) & 3;     // TMEM lane quarter
     const int half = (warp - EPI_WARP0) >> 2;  // column half of the tile
     constexpr int HALF_COLS = BN / C::EPI_GROUPS;
-    constexpr int GROUPS = HALF_COLS / 32;     // 32-column groups per warp (2 or 4)
+    constexpr int PAIRS = HALF_COLS / 64;      // 64-column steps per warp (1 or 2)
     const uint32_t stage_box = staging_base + half * 16384;
     const int row_in_box = wq * 32 + lane;
     const uint32_t stage_row = stage_box + row_in_box * 128;
@@ -293,6 +296,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const float inv_keep = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
     int acc = 0;
     uint32_t acc_phase = 0;
+
+    // stage 64 bf16 columns (one box) from packed registers and hand the box to the TMA engine
+    auto emit_bf16_box = [&](const CUtensorMap* map, const uint32_t* pk, int col0, int row0) {
+      if (issuer) bulk_wait_read0();            // previous box has been read out of shared memory
+      named_bar(bar_id, 128);
+#pragma unroll
+      for (int c = 0; c < 8; c++)
+        st_shared_v4(stage_row + ((c ^ swz) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      fence_async_smem();
+      named_bar(bar_id, 128);
+      if (issuer) {
+        tma_store_2d(map, stage_box, col0, row0);
+        bulk_commit();
+      }
+    };
+
+    // TMA-load one bf16 box (128 rows x 64 columns) of a residual / activation tensor into the staging buffer and
+    // return this thread's row as 64 floats.  Replaces 8 row-strided 16-byte global loads per thread.
+    uint32_t lphase = 0;
+    auto load_box_row = [&](const CUtensorMap* map, int col0, int row0, float* out) {
+      named_bar(bar_id, 128);                   // every thread is done with the previous contents of the box
+      if (issuer) {
+        bulk_wait_read0();                      // ... and so is the TMA engine (previous store)
+        mbar_expect_tx(lbar(half), 16384);
+        tma_load_2d(stage_box, map, lbar(half), col0, row0);
+      }
+      mbar_wait(lbar(half), lphase);
+      lphase ^= 1u;
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        uint32_t w0, w1, w2, w3;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                     : "r"(stage_row + ((c ^ swz) << 4)));
+        const uint32_t w[4] = {w0, w1, w2, w3};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const bf162*>(&w[k]));
+          out[c * 8 + 2 * k] = f.x;
+          out[c * 8 + 2 * k + 1] = f.y;
+        }
+      }
+    };
+
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int split = t % p.splits;
       const int mn = t / p.splits;
@@ -307,166 +354,147 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN + half * HALF_COLS);
 
 #pragma unroll
-      for (int g = 0; g < GROUPS; g++) {
-        uint32_t r[32];
-        tmem_ld32(taddr + g * 32, r);
+      for (int pr = 0; pr < PAIRS; pr++) {
+        uint32_t r[64];
+        tmem_ld32(taddr + pr * 64, r);
+        tmem_ld32(taddr + pr * 64 + 32, r + 32);
         tmem_ld_wait();
-        if (g == GROUPS - 1) {
+        if (pr == PAIRS - 1) {
           // this warp has read its whole slice: hand the TMEM stage back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(acc));
         }
-        const int n0 = n_half0 + g * 32;
-        // NOTE: no early exit for column groups beyond N: the whole warp group must reach the named barriers;
-        // TMA clips out-of-range columns / rows and every global access below is bounds-checked.
-        float x[32];
+        const int n0 = n_half0 + pr * 64;
+        // NOTE: no early exit for columns beyond N: the whole warp group must reach the named barriers; TMA clips
+        // out-of-range columns / rows and every direct global access below is bounds-checked.
+        float x[64];
 #pragma unroll
-        for (int j = 0; j < 32; j++) x[j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 64; j++) x[j] = __uint_as_float(r[j]);
         // ---- bias (same address in every lane: one broadcast transaction per vector)
         if (p.bias != nullptr && first_split) {
 #pragma unroll
-          for (int v = 0; v < 8; v++) {
+          for (int v = 0; v < 16; v++) {
             if (n0 + v * 4 < p.N) {
               const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + v * 4));
               x[v * 4 + 0] += b.x; x[v * 4 + 1] += b.y; x[v * 4 + 2] += b.z; x[v * 4 + 3] += b.w;
             }
           }
         }
-        // ---- pre-activation copy
-        if (p.aux_out != nullptr && row_ok) {
-          bf16* ap = p.aux_out + m * p.ld_aux_out + n0;
+        // ---- pre-activation copy (second TMA store through the same staging box)
+        if (p.aux_out != nullptr) {
+          uint32_t pk[32];
 #pragma unroll
-          for (int v = 0; v < 4; v++)
-            if (n0 + v * 8 < p.N) store8(ap + v * 8, x + v * 8);
+          for (int j = 0; j < 32; j++) pk[j] = pack_bf16(x[2 * j], x[2 * j + 1]);
+          emit_bf16_box(&tmAux, pk, n0, m_blk * BM);
         }
         // ---- activation
         if (p.act == MDHS_ACT_RELU) {
 #pragma unroll
-          for (int j = 0; j < 32; j++) x[j] = fmaxf(x[j], 0.f);
+          for (int j = 0; j < 64; j++) x[j] = fmaxf(x[j], 0.f);
         } else if (p.act == MDHS_ACT_GELU) {
 #pragma unroll
-          for (int j = 0; j < 32; j++) x[j] = gelu_erf(x[j]);
+          for (int j = 0; j < 64; j++) x[j] = gelu_erf(x[j]);
         }
-        // ---- multiply by act'(aux_in) (backward through the activation)
-        if (p.dact != MDHS_ACT_NONE && row_ok) {
-          const bf16* ap = p.aux_in + m * p.ld_aux_in + n0;
+        // ---- multiply by act'(aux_in) (backward through the activation); aux_in arrives by TMA
+        if (p.dact != MDHS_ACT_NONE) {
+          float a[64];
+          load_box_row(&tmAuxIn, n0, m_blk * BM, a);
 #pragma unroll
-          for (int v = 0; v < 4; v++) {
-            if (n0 + v * 8 < p.N) {
-              float a[8];
-              load8(ap + v * 8, a);
-#pragma unroll
-              for (int k = 0; k < 8; k++) {
-                if (p.dact == MDHS_ACT_RELU) x[v * 8 + k] = a[k] > 0.f ? x[v * 8 + k] : 0.f;
-                else x[v * 8 + k] *= gelu_erf_grad(a[k]);
-              }
-            }
+          for (int j = 0; j < 64; j++) {
+            if (p.dact == MDHS_ACT_RELU) x[j] = a[j] > 0.f ? x[j] : 0.f;
+            else x[j] *= gelu_erf_grad(a[j]);
           }
         }
         // ---- dropout (stateless: recomputed from (seed, element index) in the backward pass)
-        if (p.drop_p > 0.f) {
+        if (p.drop_p > 0.f) {   // N % 8 == 0 and n0 % 64 == 0: groups of 4 columns share one hash
 #pragma unroll
-          for (int j = 0; j < 32; j++)
-            x[j] *= dropout_scale(p.drop_seed, (uint64_t)m * (uint64_t)p.N + (uint64_t)(n0 + j), p.drop_p, inv_keep);
+          for (int j = 0; j < 64; j += 4)
+            dropout_apply4(p.drop_seed, (uint64_t)m * (uint64_t)p.N + (uint64_t)(n0 + j), p.drop_p, inv_keep, x + j);
         }
-        // ---- residual
-        if (p.residual != nullptr && first_split && row_ok) {
+        // ---- residual (bf16: TMA box load; fp32: direct row loads)
+        if (p.residual != nullptr && first_split) {
           if (p.r_f32) {
-            const float* rp = reinterpret_cast<const float*>(p.residual) + m * p.ldr + n0;
+            if (row_ok) {
+              const float* rp = reinterpret_cast<const float*>(p.residual) + m * p.ldr + n0;
 #pragma unroll
-            for (int v = 0; v < 8; v++) {
-              if (n0 + v * 4 < p.N) {
-                const float4 rr = *reinterpret_cast<const float4*>(rp + v * 4);
-                x[v * 4 + 0] += rr.x; x[v * 4 + 1] += rr.y; x[v * 4 + 2] += rr.z; x[v * 4 + 3] += rr.w;
+              for (int v = 0; v < 16; v++) {
+                if (n0 + v * 4 < p.N) {
+                  const float4 rr = *reinterpret_cast<const float4*>(rp + v * 4);
+                  x[v * 4 + 0] += rr.x; x[v * 4 + 1] += rr.y; x[v * 4 + 2] += rr.z; x[v * 4 + 3] += rr.w;
+                }
               }
             }
           } else {
-            const bf16* rp = reinterpret_cast<const bf16*>(p.residual) + m * p.ldr + n0;
+            float a[64];
+            load_box_row(&tmRes, n0, m_blk * BM, a);
 #pragma unroll
-            for (int v = 0; v < 4; v++) {
-              if (n0 + v * 8 < p.N) {
-                float a[8];
-                load8(rp + v * 8, a);
-#pragma unroll
-                for (int k = 0; k < 8; k++) x[v * 8 + k] += a[k];
-              }
-            }
+            for (int j = 0; j < 64; j++) x[j] += a[j];
           }
         }
         // ---- store through the staging box + TMA
         if (p.d_f32) {
-          // one 32-column fp32 group == one full box (128 bytes per row)
-          if (issuer) bulk_wait_read0();        // previous box has been read out of shared memory
-          named_bar(bar_id, 128);
+          // 32 fp32 columns == one full box (128 bytes per row): two boxes per 64-column step
 #pragma unroll
-          for (int c = 0; c < 8; c++)
-            st_shared_v4(stage_row + ((c ^ swz) << 4), __float_as_uint(x[4 * c]), __float_as_uint(x[4 * c + 1]),
-                         __float_as_uint(x[4 * c + 2]), __float_as_uint(x[4 * c + 3]));
-          fence_async_smem();
-          named_bar(bar_id, 128);
-          if (issuer) {
-            if (p.accumulate) tma_reduce_add_2d(&tmD, stage_box, n0, m_blk * BM);
-            else tma_store_2d(&tmD, stage_box, n0, m_blk * BM);
-            bulk_commit();
+          for (int hb = 0; hb < 2; hb++) {
+            if (issuer) bulk_wait_read0();
+            named_bar(bar_id, 128);
+#pragma unroll
+            for (int c = 0; c < 8; c++)
+              st_shared_v4(stage_row + ((c ^ swz) << 4), __float_as_uint(x[hb * 32 + 4 * c]), __float_as_uint(x[hb * 32 + 4 * c + 1]),
+                           __float_as_uint(x[hb * 32 + 4 * c + 2]), __float_as_uint(x[hb * 32 + 4 * c + 3]));
+            fence_async_smem();
+            named_bar(bar_id, 128);
+            if (issuer) {
+              if (p.accumulate) tma_reduce_add_2d(&tmD, stage_box, n0 + hb * 32, m_blk * BM);
+              else tma_store_2d(&tmD, stage_box, n0 + hb * 32, m_blk * BM);
+              bulk_commit();
+            }
           }
         } else {
           // round to bf16 first so that the statistics below describe exactly what was stored
-          uint32_t pk[16];
+          uint32_t pk[32];
 #pragma unroll
-          for (int j = 0; j < 16; j++) {
+          for (int j = 0; j < 32; j++) {
             pk[j] = pack_bf16(x[2 * j], x[2 * j + 1]);
             const float2 q = __bfloat1622float2(*reinterpret_cast<bf162*>(&pk[j]));
             x[2 * j] = q.x;
             x[2 * j + 1] = q.y;
           }
-          const int sub = g & 1;                // which 32-column half of the 64-column bf16 box
-          if (sub == 0) {
-            if (issuer) bulk_wait_read0();
-            named_bar(bar_id, 128);
-          }
-#pragma unroll
-          for (int c = 0; c < 4; c++)
-            st_shared_v4(stage_row + (((sub * 4 + c) ^ swz) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-          if (sub == 1) {
-            fence_async_smem();
-            named_bar(bar_id, 128);
-            if (issuer) {
-              tma_store_2d(&tmD, stage_box, n0 - 32, m_blk * BM);
-              bulk_commit();
-            }
-          }
+          emit_bf16_box(&tmD, pk, n0, m_blk * BM);
         }
         // ---- per-column sum / sum of squares over the 32 rows of this warp (train-mode BN statistics)
         if (p.colsum != nullptr) {
-          float s[32], q[32];
 #pragma unroll
-          for (int j = 0; j < 32; j++) {
-            s[j] = row_ok ? x[j] : 0.f;
-            q[j] = s[j] * s[j];
-          }
-          // transposing butterfly: after 5 steps lane l holds the 32-row total of column l
+          for (int hb = 0; hb < 2; hb++) {
+            float s[32], q[32];
 #pragma unroll
-          for (int step = 0; step < 5; step++) {
-            const int w = 16 >> step;  // 16, 8, 4, 2, 1 live values per lane after this step
-            const bool upper = (lane & w) != 0;
+            for (int j = 0; j < 32; j++) {
+              s[j] = row_ok ? x[hb * 32 + j] : 0.f;
+              q[j] = s[j] * s[j];
+            }
+            // transposing butterfly: after 5 steps lane l holds the 32-row total of column l
 #pragma unroll
-            for (int j = 0; j < 16; j++) {
-              if (j < w) {
-                const float keep_s = upper ? s[j + w] : s[j];
-                const float send_s = upper ? s[j] : s[j + w];
-                const float keep_q = upper ? q[j + w] : q[j];
-                const float send_q = upper ? q[j] : q[j + w];
-                s[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, w);
-                q[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, w);
+            for (int step = 0; step < 5; step++) {
+              const int w = 16 >> step;  // 16, 8, 4, 2, 1 live values per lane after this step
+              const bool upper = (lane & w) != 0;
+#pragma unroll
+              for (int j = 0; j < 16; j++) {
+                if (j < w) {
+                  const float keep_s = upper ? s[j + w] : s[j];
+                  const float send_s = upper ? s[j] : s[j + w];
+                  const float keep_q = upper ? q[j + w] : q[j];
+                  const float send_q = upper ? q[j] : q[j + w];
+                  s[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, w);
+                  q[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, w);
+                }
               }
             }
-          }
-          // lane l now owns column bitrev-free index: column = sum over steps of (lane & w) ? w : 0 = lane
-          const int n = n0 + lane;
-          if (n < p.N) {
-            atomicAdd(p.colsum + n, (double)s[0]);
-            atomicAdd(p.colsumsq + n, (double)q[0]);
+            const int n = n0 + hb * 32 + lane;
+            if (n < p.N) {
+              atomicAdd(p.colsum + n, (double)s[0]);
+              atomicAdd(p.colsumsq + n, (double)q[0]);
+            }
           }
         }
       }
@@ -539,9 +567,19 @@ int launch(const mdhs_gemm_args* a, const Params& p0, cudaStream_t stream) {
   Params p = p0;
   p.num_m = ceil_div(a->M, BM);
   p.num_n = ceil_div(a->N, BN);
-  CUtensorMap tmA, tmB, tmD;
+  CUtensorMap tmA, tmB, tmD, tmAux;
   int rc;
   rc = make_map(&tmD, a->D, a->N, a->M, a->ldd, p.d_f32 ? 32 : 64, BM, p.d_f32 != 0);
+  if (rc) return rc;
+  if (a->aux_out) rc = make_map(&tmAux, a->aux_out, a->N, a->M, a->ld_aux_out, 64, BM, false);
+  else tmAux = tmD;
+  if (rc) return rc;
+  CUtensorMap tmRes, tmAuxIn;
+  if (a->residual && a->r_dtype == MDHS_DT_BF16) rc = make_map(&tmRes, a->residual, a->N, a->M, a->ldr, 64, BM, false);
+  else tmRes = tmD;
+  if (rc) return rc;
+  if (a->aux_in) rc = make_map(&tmAuxIn, a->aux_in, a->N, a->M, a->ld_aux_in, 64, BM, false);
+  else tmAuxIn = tmD;
   if (rc) return rc;
   if (!A_MN) rc = make_map(&tmA, a->A, a->K, a->M, a->lda, BK, BM);
   else       rc = make_map(&tmA, a->A, a->M, a->K, a->lda, 64, BK);
@@ -558,7 +596,7 @@ int launch(const mdhs_gemm_args* a, const Params& p0, cudaStream_t stream) {
   }
   const int total = p.num_m * p.num_n * p.splits;
   const int grid = total < num_sms() ? total : num_sms();
-  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmD, p);
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmD, tmAux, tmRes, tmAuxIn, p);
   MDHS_RETURN_LAST();
 }
 
@@ -602,6 +640,32 @@ extern "C" int mdhs_gemm_bf16(const mdhs_gemm_args* a, void* stream_) {
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.kb_total = ceil_div(a->K, BK);
   int splits = a->split_k > 1 ? a->split_k : 1;
+  int auto_bn = 0;
+  if (a->split_k < 0 && a->accumulate && !a->act && !a->dact && !a->aux_out && !a->colsum) {
+    // auto: pick (tile width, split count) that fills whole waves of the persistent grid
+    const int sms = num_sms();
+    const int cand[3] = {256, 128, 64};
+    double best = -1.0;
+    const int max_s = p.kb_total / 4 > 1 ? (p.kb_total / 4 < 32 ? p.kb_total / 4 : 32) : 1;
+    for (int i = 0; i < 3; i++) {
+      const int c = cand[i];
+      if (c > 64 && a->N <= c / 2) continue;
+      const int64_t mn = (int64_t)ceil_div(a->M, BM) * ceil_div(a->N, c);
+      for (int sp = 1; sp <= max_s; sp++) {
+        const int64_t tiles = mn * sp;
+        const int64_t waves = (tiles + sms - 1) / sms;
+        double eff = (double)tiles / (double)(waves * sms);
+        eff *= (c == 256 ? 1.0 : (c == 128 ? 0.93 : 0.80));
+        eff *= (double)a->N / (double)((int64_t)ceil_div(a->N, c) * c);
+        eff *= 1.0 - 0.004 * sp;   // every extra split re-reduces the whole output
+        if (eff > best) {
+          best = eff;
+          splits = sp;
+          auto_bn = c;
+        }
+      }
+    }
+  }
   if (splits > p.kb_total) splits = p.kb_total;
   p.kb_per_split = ceil_div(p.kb_total, splits);
   p.splits = ceil_div(p.kb_total, p.kb_per_split);
@@ -616,6 +680,7 @@ extern "C" int mdhs_gemm_bf16(const mdhs_gemm_args* a, void* stream_) {
   p.num_m = p.num_n = 0;
 
   int bn = a->bn_hint;
+  if (bn != 64 && bn != 128 && bn != 256 && auto_bn) bn = auto_bn;
   if (bn != 64 && bn != 128 && bn != 256) {
     // pick the tile width with the best wave efficiency on this GPU; prefer wider tiles on ties
     const int sms = num_sms();

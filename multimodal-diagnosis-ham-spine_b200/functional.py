@@ -46,7 +46,7 @@ class LinearFn(torch.autograd.Function):
             # gradient at the pre-activation (both GEMMs below consume it as a TMA operand)
             g = ops.act_dropout_bwd(dy, aux, ctx.act, ctx.drop_p, ctx.seed)
         if ctx.gw is not None:
-            ops.gemm(g, x, a_mn=True, b_mn=True, out=ctx.gw, accumulate=True, split_k=_wgrad_splits(T, N, K), M=N, N=K, K=T)
+            ops.gemm(g, x, a_mn=True, b_mn=True, out=ctx.gw, accumulate=True, split_k=-1, M=N, N=K, K=T)
             if ctx.gb is not None:
                 ops.col_stats(g, sum32=ctx.gb)
         dx = None

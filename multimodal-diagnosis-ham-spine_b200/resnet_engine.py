@@ -12,6 +12,11 @@ import torch
 from . import ops
 
 
+# Train-mode BN statistics: fused into the conv GEMM epilogue (register butterfly) or one extra column pass over
+# the raw conv output.  Measured on B200 (round 1): the extra pass is cheaper than the butterfly for small-K convs.
+FUSE_BN_STATS_IN_GEMM = False
+
+
 def _out_hw(h, k, s, p):
     return (h + 2 * p - k) // s + 1
 
@@ -78,7 +83,11 @@ class ResNetEngine:
         bn = c.bn
         if training:
             st = torch.zeros((2, c.O), device=A.device, dtype=torch.float64)
-            raw = ops.gemm(A, c.wp, colsum=st[0], colsumsq=st[1], N=c.O)
+            if FUSE_BN_STATS_IN_GEMM:
+                raw = ops.gemm(A, c.wp, colsum=st[0], colsumsq=st[1], N=c.O)
+            else:
+                raw = ops.gemm(A, c.wp, N=c.O)
+                ops.col_stats(raw, st[0], st[1])
             mom = bn.momentum if bn.momentum is not None else 0.1
             track = bn.track_running_stats and bn.running_mean is not None
             mean, invstd, scale, shift = ops.bn_finalize(
@@ -138,11 +147,11 @@ class ResNetEngine:
         if train_w:
             if c.plain:
                 gw = st.g32(c.conv.weight).view(c.O, c.I)
-                ops.gemm(draw, A, a_mn=True, b_mn=True, out=gw, accumulate=True, split_k=c.wgrad_splits(rows),
+                ops.gemm(draw, A, a_mn=True, b_mn=True, out=gw, accumulate=True, split_k=-1,
                          M=c.O, N=c.I, K=rows)
             else:
                 c.gp.zero_()
-                ops.gemm(draw, A, a_mn=True, b_mn=True, out=c.gp, accumulate=True, split_k=c.wgrad_splits(rows),
+                ops.gemm(draw, A, a_mn=True, b_mn=True, out=c.gp, accumulate=True, split_k=-1,
                          M=c.O, N=c.ldk, K=rows)
                 ops.conv_wgrad_unpack(c.gp, st.g32(c.conv.weight))
         dx = None
