@@ -127,6 +127,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # collectives are captured into the step's CUDA graph: the NCCL watchdog's async error handling must not
+        # poll events of a capturing stream (torch CUDA-graphs notes)
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
         dist.init_process_group("nccl", device_id=dev)
     import mdhs_b200
     from mdhs_b200 import _lib, ops
@@ -151,7 +154,11 @@ def run_ours(args):
     d_in = [t.to(dev, non_blocking=True) for t in h_in]
     torch.cuda.synchronize()
 
-    use_graph = not args.no_graph
+    use_graph = not args.no_graph and (world == 1 or args.graph_multi_gpu)
+    def _mark(msg):
+        if args.verbose:
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+    _mark("model built")
     launches_per_step = None
     if use_graph:
         try:
@@ -174,9 +181,11 @@ def run_ours(args):
             return trainer.replay()
         return trainer.step(*d_in)
 
+    _mark(f"first step done (graph={use_graph})")
     for _ in range(max(args.warmup, 3)):
         one_step()
     torch.cuda.synchronize()
+    _mark("warm-up done")
     if world > 1:
         dist.barrier()
     sampler = ClockSampler(local) if rank == 0 else None
@@ -192,6 +201,7 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     ms = e0.elapsed_time(e1)
+    _mark(f"timed region done: {ms / args.steps:.2f} ms/step")
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([ms], device=dev)
     if world > 1:
@@ -334,6 +344,8 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=8, help="samples per CPU step of the reference arm")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph-multi-gpu", action="store_true", help="capture the step (incl. NCCL) into a CUDA graph for N>1")
+    ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--dump-gemms", action="store_true", help="write per-shape GEMM timings to gpurun_out/gemm_shapes.txt")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -15,6 +15,7 @@ import torch.distributed as dist
 
 from . import functional as Fm
 from . import ops
+from .parallel import GradSync, split_offset
 
 
 class Trainer:
@@ -50,11 +51,8 @@ class Trainer:
         self.lr_dev = torch.full((1,), float(self.lr), device=device)
         self.step_dev = torch.zeros(1, device=device, dtype=torch.int32)
         # slice boundary for the overlapped all-reduce: everything from the text encoder on
-        self.split = 0
-        te = getattr(self.model, "text_encoder", None)
-        if te is not None:
-            offs = [st.offsets[id(p)] for p in te.parameters()]
-            self.split = min(offs) if offs else 0
+        self.split = split_offset(st, getattr(self.model, "text_encoder", None))
+        self.sync = GradSync(st.grad, self.split if self.overlap else 0, self.pg)
         if self.world > 1:
             # same initial weights everywhere (rank 0 wins), like DistributedDataParallel's constructor
             dist.broadcast(st.flat, src=0, group=self.pg)
@@ -71,23 +69,17 @@ class Trainer:
             return Fm.cross_entropy(logits, labels, self.class_weights, 0.0, True, self.focal_gamma)
         return Fm.cross_entropy(logits, labels, self.class_weights, self.label_smoothing, False, 2.0)
 
-    def _allreduce(self, lo, hi, async_op):
-        if hi <= lo:
-            return None
-        return dist.all_reduce(self.store.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.pg, async_op=async_op)
-
     def _step_impl(self, images, ids, mask, labels):
         st = self.store
         ops.step_begin(self.step_dev)
         hook = None
-        works = []
         if self.overlap and self.split > 0:
             eng = self.model.text_encoder._engine
             orig = eng.backward
 
             def bert_backward_then_reduce(ctx, dh):
                 orig(ctx, dh)
-                works.append(self._allreduce(self.split, st.total, True))
+                self.sync.reduce_tail()
 
             eng.backward = bert_backward_then_reduce
             hook = (eng, orig)
@@ -99,15 +91,7 @@ class Trainer:
         finally:
             if hook is not None:
                 hook[0].backward = hook[1]
-        if self.world > 1:
-            if works:
-                works.append(self._allreduce(0, self.split, True))
-            else:
-                works.append(self._allreduce(0, st.total, True))
-            for w in works:
-                if w is not None:
-                    w.wait()
-        scale = 1.0 / self.world
+        scale = self.sync.finish()
         if self.opt == "sgd":
             ops.sgd_flat(st.flat, st.grad, self.m if self.momentum > 0 else None, st.shadow, self.lr, self.momentum, self.wd,
                          grad_scale=scale, lr_dev=self.lr_dev, step_dev=self.step_dev)

@@ -1,0 +1,73 @@
+"""Host-side data-parallel logic on CPU: world_size-2 gloo run of GradSync (the same code path NCCL uses on the
+GPUs), plus the flat-buffer bucket boundary."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import mdhs_b200  # noqa: F401
+    from mdhs_b200.parallel import GradSync
+    n, split = 1000, 300
+    torch.manual_seed(rank)
+    g = torch.randn(n)
+    mine = g.clone()
+    sync = GradSync(g, split)
+    sync.reduce_tail()                      # tail slice first (overlapped with the rest of backward on the GPUs)
+    scale = sync.finish()
+    others = []
+    for r in range(world):
+        torch.manual_seed(r)
+        others.append(torch.randn(n))
+    want = sum(others)
+    ok = torch.allclose(g, want, atol=1e-6) and abs(scale - 1.0 / world) < 1e-12
+    # without the early call everything goes out in finish()
+    g2 = mine.clone()
+    sync2 = GradSync(g2, split)
+    sync2.finish()
+    ok = ok and torch.allclose(g2, want, atol=1e-6)
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_gradsync_gloo_world2():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29600 + (os.getpid() % 200)
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert all(ret[r] for r in range(world))
+
+
+def test_split_offset_orders_text_encoder_after_image_encoder():
+    import torch.nn as nn
+    import mdhs_b200  # noqa: F401
+    from mdhs_b200.parallel import split_offset
+
+    class FakeStore:
+        def __init__(self, mod):
+            self.offsets, off = {}, 0
+            for p in mod.parameters():
+                self.offsets[id(p)] = off
+                off += p.numel()
+
+    class M(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.image_encoder = nn.Linear(4, 4)
+            self.text_encoder = nn.Linear(4, 2)
+            self.head = nn.Linear(2, 2)
+
+    m = M()
+    st = FakeStore(m)
+    assert split_offset(st, m.text_encoder) == 4 * 4 + 4
+    assert split_offset(st, None) == 0
