@@ -165,6 +165,18 @@ int mdhs_relu_bwd_f32(const float* dy, const float* y, float* dx, int64_t n, voi
 int mdhs_mul_f32(const float* a, const float* b, float* c, int64_t n, void* stream);
 int mdhs_dropout_f32(const float* x, float* y, int64_t n, float p, uint64_t seed, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * MIBF-Net: IBFA cross-attention with one token per modality (mibf_net/attention.py:47-70; keys/values of x and
+ * y concatenated -> softmax over 2 keys per head) on the fused projections [K_x|Q_x|V_x] and [K_y|V_y];
+ * MP-Loss forward + backward (mibf_net/model_resnet.py:76-94, attention.py:25-28).
+ */
+int mdhs_ibfa_fwd(const void* kqv_x, int64_t ldx, const void* kv_y, int64_t ldy, void* out, float* probs, int B, int H,
+                  int D, void* stream);
+int mdhs_ibfa_bwd(const void* kqv_x, int64_t ldx, const void* kv_y, int64_t ldy, const void* dout, const float* probs,
+                  void* dkqv_x, void* dkv_y, int B, int H, int D, void* stream);
+int mdhs_mp_loss(const float* img_logits, const float* txt_logits, const float* fused_logits, const int64_t* labels,
+                 float* loss, float* g_img, float* g_txt, float* g_fused, int B, int C, void* stream);
+
 /* Fused optimizer step on the flat parameter buffer (scripts/train.py:257-309) */
 int mdhs_adam_flat(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, int64_t n,
                    float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,

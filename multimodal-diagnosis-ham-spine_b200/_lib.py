@@ -69,6 +69,9 @@ SIGNATURES = {
     "mdhs_relu_bwd_f32": "ppplp",
     "mdhs_mul_f32": "ppplp",
     "mdhs_dropout_f32": "pplfup",
+    "mdhs_ibfa_fwd": "plplppiiip",
+    "mdhs_ibfa_bwd": "plplppppiiip",
+    "mdhs_mp_loss": "ppppppppiip",
     "mdhs_adam_flat": "ppppplfffffifiippp",
     "mdhs_sgd_flat": "pppplffffiippp",
     "mdhs_step_begin": "pp",

@@ -360,3 +360,25 @@ def dropout_f32(x, p, seed):
     y = torch.empty_like(x)
     _lib.call("mdhs_dropout_f32", _p(x), _p(y), x.numel(), float(p), int(seed), _s())
     return y
+
+
+def ibfa_fwd(kqv_x, kv_y, B, H, D):
+    out = torch.empty((B, H * D), device=kqv_x.device, dtype=torch.bfloat16)
+    probs = torch.empty((B * H, 2), device=kqv_x.device, dtype=torch.float32)
+    _lib.call("mdhs_ibfa_fwd", _p(kqv_x), kqv_x.stride(0), _p(kv_y), kv_y.stride(0), _p(out), _p(probs), B, H, D, _s())
+    return out, probs
+
+
+def ibfa_bwd(kqv_x, kv_y, dout, probs, B, H, D):
+    dx = torch.empty_like(kqv_x)
+    dy = torch.empty_like(kv_y)
+    _lib.call("mdhs_ibfa_bwd", _p(kqv_x), kqv_x.stride(0), _p(kv_y), kv_y.stride(0), _p(dout), _p(probs), _p(dx), _p(dy), B, H, D, _s())
+    return dx, dy
+
+
+def mp_loss(zi, zt, zf, labels, want_grad=True):
+    B, C = zi.shape
+    loss = torch.empty(1, device=zi.device, dtype=torch.float32)
+    g = [torch.empty_like(zi) for _ in range(3)] if want_grad else [None, None, None]
+    _lib.call("mdhs_mp_loss", _p(zi), _p(zt), _p(zf), _p(labels), _p(loss), _p(g[0]), _p(g[1]), _p(g[2]), B, C, _s())
+    return loss, g

@@ -92,3 +92,47 @@ def test_cuda_matches_reference_logits(name):
     top2 = want.topk(2, dim=1).values
     safe = (top2[:, 0] - top2[:, 1]) > 2 * (got.float().cpu() - want).abs().max()
     assert torch.equal(got.float().cpu().argmax(1)[safe], want.argmax(1)[safe])
+
+
+@pytest.mark.gpu
+def test_cuda_mibf_matches_reference_and_oracle():
+    """MIBF-Net (ResNet-50 + BERT CLS + IBFA x2 + 3 heads + MP-Loss): eval logits vs the real reference's golden
+    outputs (<= 3e-2 max-norm: 768-wide single-head attention over two keys in bf16), MP-loss within 2e-2, and a
+    train-mode backward whose head gradients match the fp32 oracle (cosine >= 0.98)."""
+    import mdhs_b200
+    from mdhs_b200.mibf_net import Resnet50WithOurs
+    from refutil import bert_dir, quiet
+    with quiet():
+        model = Resnet50WithOurs(num_labels=6, bert_path=bert_dir(), pretrained=False)
+    sd = weights.synth_state_dict(model.state_dict(), seed=3)
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    im, ii, mm, ll = weights.synthetic_batch(4, 16, 6, image_hw=64, unit_range=True)
+    batch = {"transformed_image": im.cuda(), "input_ids": ii.cuda(), "attention_mask": mm.cuda()}
+    with torch.no_grad():
+        out = model(batch)
+        loss = model.cal_loss(out, ll.cuda())
+    gold = GOLD["mibf"]
+    for k in ("image_text", "text", "image"):
+        assert rel(out[k], gold[k]) < 3e-2, (k, rel(out[k], gold[k]))
+    assert abs(loss.item() - gold["mp_loss"].item()) < 2e-2 * max(1.0, abs(gold["mp_loss"].item()))
+    # backward (train-mode BN, BERT dropout off)
+    model.text_encoder.bert.config.hidden_dropout_prob = 0.0
+    model.text_encoder._engine.p_hidden = model.text_encoder._engine.p_attn = 0.0
+    model.train()
+    out = model(batch)
+    loss = model.cal_loss(out, ll.cuda())
+    loss.backward()
+    sd_g = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+    o = port.mibf_forward(sd_g, im, ii, mm, training_bn=True)
+    lref = port.mp_loss(o["image"], o["text"], o["image_text"], ll)
+    lref.backward()
+    assert abs(loss.item() - lref.item()) < 3e-2 * max(1.0, abs(lref.item()))
+    named = dict(model.named_parameters())
+    for key in ("fc.weight", "fc_text.3.weight", "fc_image.1.weight", "textbased_cross_attention.to_out.weight",
+                "imagbased_cross_attention.toV_y.weight", "image_encoder.fc.weight"):
+        g, r = named[key].grad.float().cpu().flatten(), sd_g[key].grad.flatten()
+        c = (g @ r / (g.norm() * r.norm() + 1e-30)).item()
+        assert c > 0.98, (key, c)
+    # parameters that never receive a gradient in the reference (BERT pooler, I2Iattention) stay untouched here too
+    assert named["I2Iattention.query.weight"].grad.abs().sum().item() == 0

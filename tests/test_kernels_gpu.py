@@ -309,3 +309,20 @@ def test_adamw_and_sgd_flat(ops):
         opt2.step()
         ops.sgd_flat(p2, g.clone(), mom, None, 0.01, 0.9, 0.0, first_step=(step == 0))
     assert relerr(p2, ref2.detach()) < 1e-6
+
+
+def test_mp_loss_kernel(ops):
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import port
+    torch.manual_seed(0)
+    B, C = 33, 6
+    zs = [(torch.randn(B, C, device="cuda") * s).requires_grad_(True) for s in (1.0, 2.0, 0.5)]
+    y = torch.randint(0, C, (B,), device="cuda")
+    cpu = [z.detach().cpu().requires_grad_(True) for z in zs]
+    ref = port.mp_loss(cpu[0], cpu[1], cpu[2], y.cpu())
+    ref.backward()
+    loss, g = ops.mp_loss(zs[0].detach(), zs[1].detach(), zs[2].detach(), y)
+    assert abs(loss.item() - ref.item()) < 1e-4 * max(1.0, abs(ref.item()))
+    for a, b in zip(g, cpu):
+        assert relerr(a.cpu(), b.grad) < 1e-3
