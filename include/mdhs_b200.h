@@ -177,6 +177,35 @@ int mdhs_ibfa_bwd(const void* kqv_x, int64_t ldx, const void* kv_y, int64_t ldy,
 int mdhs_mp_loss(const float* img_logits, const float* txt_logits, const float* fused_logits, const int64_t* labels,
                  float* loss, float* g_img, float* g_txt, float* g_fused, int B, int C, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * KAN (ConNexT/models/block/kan1.py:77-165, grid_size 5 / spline_order 3) and sparsely-gated MoE
+ * (ConNexT/models/block/moe.py:171-291).  kan_basis_*: x -> bf16 GEMM operand [SiLU(x) | 8 cubic B-spline bases per
+ * input] and its derivative; weight pack/unpack between (base_weight, spline_weight, spline_scaler) and the fused
+ * operand; MoE noisy top-k gating forward/backward, cv^2 balance loss and gate-weighted expert combination.
+ */
+int mdhs_kan_basis_fwd(const float* x, int64_t ldx, const float* grid, void* op, int64_t rows, int in, int ld_op,
+                       void* stream);
+int mdhs_kan_basis_bwd(const float* x, int64_t ldx, const float* grid, const void* dop, float* dx, int64_t rows, int in,
+                       int ld_op, int accumulate, void* stream);
+int mdhs_kan_weight_pack(const float* base_w, const float* spline_w, const float* scaler, void* wcat, int out, int out_pad,
+                         int in, int ld, void* stream);
+int mdhs_kan_wgrad_unpack(const float* gcat, const float* spline_w, const float* scaler, float* g_base, float* g_spline,
+                          float* g_scaler, int out, int in, int ld, void* stream);
+int mdhs_moe_gate_fwd(const float* x, const float* wg, const float* wn, const float* noise, float* gates, float* clean,
+                      float* raw, float* probs, int* topidx, float* importance, float* load, const float* normal_mean,
+                      const float* normal_std, int B, int in, int E, int k, int noisy, void* stream);
+int mdhs_moe_loss(const float* importance, const float* load, float* loss, float* d_imp, float* d_load, int E, float coef,
+                  void* stream);
+int mdhs_moe_gate_bwd(const float* x, const float* wg, const float* wn, const float* noise, const float* dgates,
+                      const float* d_imp, const float* d_load, float dloss, const float* dloss_dev, const float* clean,
+                      const float* raw, const float* probs, const int* topidx, float* dx, float* dwg, float* dwn,
+                      const float* normal_mean, const float* normal_std, int B, int in, int E, int k, int noisy, void* stream);
+/* standard-normal noise (moe.py:246 randn_like) from the counter-based generator shared with dropout */
+int mdhs_randn_f32(float* out, int64_t n, uint64_t seed, void* stream);
+int mdhs_moe_combine_fwd(const float* gates, const float* Y, float* y, int B, int E, int C, int ldy, void* stream);
+int mdhs_moe_combine_bwd(const float* gates, const float* Y, const float* dy, float* dgates, float* dY, int B, int E, int C,
+                         int ldy, void* stream);
+
 /* Fused optimizer step on the flat parameter buffer (scripts/train.py:257-309) */
 int mdhs_adam_flat(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, int64_t n,
                    float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,

@@ -72,6 +72,16 @@ SIGNATURES = {
     "mdhs_ibfa_fwd": "plplppiiip",
     "mdhs_ibfa_bwd": "plplppppiiip",
     "mdhs_mp_loss": "ppppppppiip",
+    "mdhs_kan_basis_fwd": "plpplii" "p",
+    "mdhs_kan_basis_bwd": "plppplii" "i" "p",
+    "mdhs_kan_weight_pack": "ppppiiii" "p",
+    "mdhs_kan_wgrad_unpack": "ppppppiii" "p",
+    "mdhs_moe_gate_fwd": "ppppppppppp" "pp" "iiiii" "p",
+    "mdhs_moe_loss": "pppppif" "p",
+    "mdhs_moe_gate_bwd": "ppppppp" "f" "pppppppp" "pp" "iiiii" "p",
+    "mdhs_randn_f32": "plup",
+    "mdhs_moe_combine_fwd": "pppiiii" "p",
+    "mdhs_moe_combine_bwd": "pppppiiii" "p",
     "mdhs_adam_flat": "ppppplfffffifiippp",
     "mdhs_sgd_flat": "pppplffffiippp",
     "mdhs_step_begin": "pp",

@@ -10,6 +10,7 @@ void mdhs_seed_tick_gemm_tc(uint64_t, cudaStream_t);
 void mdhs_seed_tick_norm(uint64_t, cudaStream_t);
 void mdhs_seed_tick_attention(uint64_t, cudaStream_t);
 void mdhs_seed_tick_elementwise(uint64_t, cudaStream_t);
+void mdhs_seed_tick_kan_moe(uint64_t, cudaStream_t);
 
 namespace {
 
@@ -140,5 +141,6 @@ extern "C" int mdhs_step_begin(int* step_dev, void* stream) {
   mdhs_seed_tick_norm(1, st);
   mdhs_seed_tick_attention(1, st);
   mdhs_seed_tick_elementwise(1, st);
+  mdhs_seed_tick_kan_moe(1, st);
   MDHS_RETURN_LAST();
 }

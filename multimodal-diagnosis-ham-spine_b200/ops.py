@@ -382,3 +382,91 @@ def mp_loss(zi, zt, zf, labels, want_grad=True):
     g = [torch.empty_like(zi) for _ in range(3)] if want_grad else [None, None, None]
     _lib.call("mdhs_mp_loss", _p(zi), _p(zt), _p(zf), _p(labels), _p(loss), _p(g[0]), _p(g[1]), _p(g[2]), B, C, _s())
     return loss, g
+
+
+# ---------------------------------------------------------------- KAN / MoE (csrc/kan_moe.cu)
+KAN_NB = 8  # grid_size 5 + spline_order 3 bases per input
+
+
+def kan_basis_fwd(x, grid, ld_op=None):
+    """x fp32 [rows, in] (row stride free) -> bf16 [rows, ld_op] = [SiLU(x) | B_0..7(x_0) | B_0..7(x_1) ...]."""
+    rows, n_in = x.shape
+    ld_op = n_in * (1 + KAN_NB) if ld_op is None else ld_op
+    op = torch.empty((rows, ld_op), device=x.device, dtype=torch.bfloat16)
+    _lib.call("mdhs_kan_basis_fwd", _p(x), x.stride(0), _p(grid), _p(op), rows, n_in, ld_op, _s())
+    return op
+
+
+def kan_basis_bwd(x, grid, dop, dx=None, accumulate=False):
+    rows, n_in = x.shape
+    if dx is None:
+        dx = torch.empty((rows, n_in), device=x.device, dtype=torch.float32)
+        accumulate = False
+    _lib.call("mdhs_kan_basis_bwd", _p(x), x.stride(0), _p(grid), _p(dop), _p(dx), rows, n_in, dop.stride(0), int(accumulate), _s())
+    return dx
+
+
+def kan_weight_pack(base_w, spline_w, scaler, wcat):
+    out, n_in = base_w.shape
+    _lib.call("mdhs_kan_weight_pack", _p(base_w), _p(spline_w), _p(scaler), _p(wcat), out, wcat.shape[0], n_in, wcat.stride(0), _s())
+    return wcat
+
+
+def kan_wgrad_unpack(gcat, spline_w, scaler, g_base, g_spline, g_scaler):
+    out, n_in = spline_w.shape[0], spline_w.shape[1]
+    _lib.call("mdhs_kan_wgrad_unpack", _p(gcat), _p(spline_w), _p(scaler), _p(g_base), _p(g_spline), _p(g_scaler), out, n_in,
+              gcat.stride(0), _s())
+
+
+def randn_f32(shape, device, seed):
+    out = torch.empty(shape, device=device, dtype=torch.float32)
+    _lib.call("mdhs_randn_f32", _p(out), out.numel(), int(seed), _s())
+    return out
+
+
+def moe_gate_fwd(x, wg, wn, noise, k, noisy, nmean=None, nstd=None):
+    B, n_in = x.shape
+    E = wg.shape[1]
+    dev = x.device
+    f = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
+    gates, clean, probs = f(B, E), f(B, E), f(B, E)
+    raw = f(B, E) if noisy else None
+    topidx = torch.empty((B, k + 1), device=dev, dtype=torch.int32)
+    importance, load = f(E), f(E)
+    _lib.call("mdhs_moe_gate_fwd", _p(x), _p(wg), _p(wn), _p(noise), _p(gates), _p(clean), _p(raw), _p(probs), _p(topidx),
+              _p(importance), _p(load), _p(nmean), _p(nstd), B, n_in, E, k, int(noisy), _s())
+    return gates, clean, raw, probs, topidx, importance, load
+
+
+def moe_loss(importance, load, coef):
+    E = importance.numel()
+    loss = torch.empty(1, device=importance.device, dtype=torch.float32)
+    d_imp = torch.empty_like(importance)
+    d_load = torch.empty_like(load)
+    _lib.call("mdhs_moe_loss", _p(importance), _p(load), _p(loss), _p(d_imp), _p(d_load), E, float(coef), _s())
+    return loss, d_imp, d_load
+
+
+def moe_gate_bwd(x, wg, wn, noise, dgates, d_imp, d_load, dloss_dev, clean, raw, probs, topidx, dx, dwg, dwn, k, noisy,
+                 nmean=None, nstd=None):
+    B, n_in = x.shape
+    E = wg.shape[1]
+    _lib.call("mdhs_moe_gate_bwd", _p(x), _p(wg), _p(wn), _p(noise), _p(dgates), _p(d_imp), _p(d_load), 1.0, _p(dloss_dev),
+              _p(clean), _p(raw), _p(probs), _p(topidx), _p(dx), _p(dwg), _p(dwn), _p(nmean), _p(nstd), B, n_in, E, k, int(noisy), _s())
+
+
+def moe_combine_fwd(gates, Y, C):
+    """Y fp32 [E, B, ldy] -> y fp32 [B, C] = sum_e gates[b, e] * Y[e, b, :C]."""
+    E, B, ldy = Y.shape
+    y = torch.empty((B, C), device=Y.device, dtype=torch.float32)
+    _lib.call("mdhs_moe_combine_fwd", _p(gates), _p(Y), _p(y), B, E, C, ldy, _s())
+    return y
+
+
+def moe_combine_bwd(gates, Y, dy):
+    E, B, ldy = Y.shape
+    C = dy.shape[1]
+    dgates = torch.empty_like(gates)
+    dY = torch.empty_like(Y)
+    _lib.call("mdhs_moe_combine_bwd", _p(gates), _p(Y), _p(dy), _p(dgates), _p(dY), B, E, C, ldy, _s())
+    return dgates, dY

@@ -96,6 +96,26 @@ def main():
         y, l = moe(x)
         out["kan_moe"] = {"x": x, "kan_out": kan(x).clone(), "moe_out": y.clone(), "moe_loss": l.clone(),
                           "kan_grid": sdk["layers.0.grid"].clone()}
+    # MoE in training mode: noisy gating with the Gaussian noise injected (torch.randn_like patched), loss + gradients
+    moe_t = MoE(input_size=64, output_size=7, num_experts=4, hidden_size=32, k=2, layers_hidden=[64, 32, 7]).train()
+    sdt = weights.synth_state_dict(moe_t.state_dict(), seed=6)
+    moe_t.load_state_dict(sdt)
+    g2 = torch.Generator().manual_seed(5)
+    xt = torch.randn(12, 64, generator=g2)
+    noise = torch.randn(12, 4, generator=g2)
+    orig_randn_like = torch.randn_like
+    torch.randn_like = lambda t: noise.to(t.dtype)
+    try:
+        xr = xt.clone().requires_grad_(True)
+        yt, lt = moe_t(xr)
+        (yt.square().sum() + lt.sum()).backward()
+    finally:
+        torch.randn_like = orig_randn_like
+    named = dict(moe_t.named_parameters())
+    keep = ["w_gate", "w_noise", "experts.1.layers.0.spline_weight", "experts.2.layers.1.base_weight",
+            "experts.0.layers.0.spline_scaler", "experts.3.layers.0.base_weight"]
+    out["moe_train"] = {"x": xt, "noise": noise, "y": yt.detach().clone(), "loss": lt.detach().clone(), "dx": xr.grad.clone(),
+                        "grads": {k: named[k].grad.clone() for k in keep}, "mean": sdt["mean"].clone(), "std": sdt["std"].clone()}
     path = os.path.join(HERE, "reference_outputs.pt")
     torch.save(out, path)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -13,7 +13,7 @@ from oracle import port, weights  # noqa: E402
 from refutil import build_ours  # noqa: E402
 
 GOLD = torch.load(os.path.join(ROOT, "tests", "golden", "reference_outputs.pt"), weights_only=False)
-CASES = [k for k in GOLD if k not in ("meta", "train_basic_mlp", "mibf", "kan_moe")]
+CASES = [k for k in GOLD if k not in ("meta", "train_basic_mlp", "mibf", "kan_moe", "moe_train")]
 
 
 def rel(a, b):
@@ -136,3 +136,98 @@ def test_cuda_mibf_matches_reference_and_oracle():
         assert c > 0.98, (key, c)
     # parameters that never receive a gradient in the reference (BERT pooler, I2Iattention) stay untouched here too
     assert named["I2Iattention.query.weight"].grad.abs().sum().item() == 0
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# KAN / MoE (ConNexT/models/block/kan1.py, moe.py)
+# ----------------------------------------------------------------------------------------------------------------
+def _moe_template(prefix_sizes=(64, 32, 7), E=4):
+    case = GOLD["kan_moe"]
+    tm = {}
+    for e in range(E):
+        for i, (a, b) in enumerate(zip(prefix_sizes, prefix_sizes[1:])):
+            p = f"experts.{e}.layers.{i}."
+            tm[p + "grid"] = case["kan_grid"][:1].expand(a, -1).contiguous()
+            tm[p + "base_weight"] = torch.empty(b, a)
+            tm[p + "spline_weight"] = torch.empty(b, a, 8)
+            tm[p + "spline_scaler"] = torch.empty(b, a)
+    tm["w_gate"] = torch.empty(prefix_sizes[0], E)
+    tm["w_noise"] = torch.empty(prefix_sizes[0], E)
+    tm["mean"] = torch.tensor([0.0])
+    tm["std"] = torch.tensor([1.0])
+    return tm
+
+
+def test_oracle_reproduces_reference_moe_training():
+    """oracle/port.py::moe_forward_train against the real reference's training-mode MoE (noise injected): output,
+    balance loss and gradients."""
+    case = GOLD["moe_train"]
+    sd = weights.synth_state_dict(_moe_template(), seed=6)
+    assert torch.equal(sd["mean"], case["mean"]) and torch.equal(sd["std"], case["std"])
+    sd_g = {k: v.clone().requires_grad_(v.is_floating_point() and k not in ("mean", "std") and not k.endswith("grid"))
+            for k, v in sd.items()}
+    x = case["x"].clone().requires_grad_(True)
+    y, l = port.moe_forward_train(sd_g, "", x, case["noise"], 4, 2)
+    (y.square().sum() + l).backward()
+    assert rel(y, case["y"]) < 1e-5
+    assert abs(l.item() - case["loss"].item()) < 1e-6
+    assert rel(x.grad, case["dx"]) < 1e-4
+    for k, g in case["grads"].items():
+        assert rel(sd_g[k].grad, g) < 1e-4, k
+
+
+@pytest.mark.gpu
+def test_cuda_kan_matches_reference():
+    """KAN1 [64, 32, 7] on the tcgen05 GEMM (bf16 basis operand, fp32 accumulate) vs the real reference's output on
+    inputs that include the knot-range edges (-2.2, 2.2) and values outside it.  Tolerance 1e-2 max-norm."""
+    import mdhs_b200  # noqa: F401
+    from mdhs_b200.connext import KAN1
+    case = GOLD["kan_moe"]
+    kan = KAN1([64, 32, 7])
+    sdk = weights.synth_state_dict(kan.state_dict(), seed=4)
+    kan.load_state_dict(sdk)
+    kan = kan.cuda().eval()
+    with torch.no_grad():
+        y = kan(case["x"].cuda())
+    assert y.shape == case["kan_out"].shape
+    assert rel(y, case["kan_out"]) < 1e-2, rel(y, case["kan_out"])
+
+
+@pytest.mark.gpu
+def test_cuda_moe_eval_matches_reference():
+    import mdhs_b200  # noqa: F401
+    from mdhs_b200.connext import MoE
+    case = GOLD["kan_moe"]
+    moe = MoE(input_size=64, output_size=7, num_experts=4, hidden_size=32, k=2, layers_hidden=[64, 32, 7])
+    sdm = weights.synth_state_dict(moe.state_dict(), seed=5)
+    sdm["mean"], sdm["std"] = torch.tensor([0.0]), torch.tensor([1.0])
+    moe.load_state_dict(sdm)
+    moe = moe.cuda().eval()
+    with torch.no_grad():
+        y, l = moe(case["x"].cuda())
+    assert rel(y, case["moe_out"]) < 1e-2, rel(y, case["moe_out"])
+    assert abs(l.item() - case["moe_loss"].item()) < 1e-5
+
+
+@pytest.mark.gpu
+def test_cuda_moe_training_matches_reference():
+    """Noisy top-k gating, smooth load estimator, balance loss and every gradient (experts through the bf16 GEMMs:
+    <= 2e-2 max-norm; gating / loss path is fp32: <= 1e-3) vs the golden outputs of the real reference."""
+    import mdhs_b200  # noqa: F401
+    from mdhs_b200.connext import MoE
+    case = GOLD["moe_train"]
+    moe = MoE(input_size=64, output_size=7, num_experts=4, hidden_size=32, k=2, layers_hidden=[64, 32, 7])
+    sd = weights.synth_state_dict(moe.state_dict(), seed=6)
+    moe.load_state_dict(sd)
+    moe = moe.cuda().train()
+    object.__setattr__(moe, "_noise_override", case["noise"].cuda())
+    x = case["x"].cuda().requires_grad_(True)
+    y, l = moe(x)
+    (y.square().sum() + l).backward()
+    assert rel(y, case["y"]) < 1e-2, rel(y, case["y"])
+    assert abs(l.item() - case["loss"].item()) < 1e-5 * max(1.0, abs(case["loss"].item()))
+    assert rel(x.grad, case["dx"]) < 2e-2, rel(x.grad, case["dx"])
+    named = dict(moe.named_parameters())
+    for k, g in case["grads"].items():
+        tol = 1e-3 if k in ("w_noise",) else 2e-2
+        assert rel(named[k].grad, g) < tol, (k, rel(named[k].grad, g))

@@ -123,3 +123,31 @@ def test_kan_and_moe_match_reference():
         y, l = port.moe_forward_eval(sd, "", x, 4, 2)
     assert rel(y, y_ref) < 1e-5
     assert abs(l.item() - l_ref.item()) < 1e-6
+
+
+def test_moe_training_mode_matches_reference(monkeypatch):
+    """Noisy top-k gating + smooth load estimator + gradients, with the Gaussian noise injected on both sides."""
+    sys.path.insert(0, os.path.join(REF_ROOT, "ConNexT"))
+    from models.block import moe as ref_moe
+    torch.manual_seed(0)
+    moe = ref_moe.MoE(input_size=64, output_size=7, num_experts=4, hidden_size=32, k=2, layers_hidden=[64, 32, 7]).train()
+    sd = weights.synth_state_dict(moe.state_dict(), seed=6)
+    moe.load_state_dict(sd)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(12, 64, generator=g)
+    noise = torch.randn(12, 4, generator=g)
+    monkeypatch.setattr(torch, "randn_like", lambda t: noise.to(t.dtype))
+    xr = x.clone().requires_grad_(True)
+    y_ref, l_ref = moe(xr)
+    (y_ref.square().sum() + l_ref.sum()).backward()
+    sd_g = {k: v.clone().requires_grad_(v.is_floating_point() and k not in ("mean", "std")) for k, v in sd.items()}
+    xo = x.clone().requires_grad_(True)
+    y, l = port.moe_forward_train(sd_g, "", xo, noise, 4, 2)
+    (y.square().sum() + l).backward()
+    assert rel(y, y_ref) < 1e-5
+    assert abs(l.item() - l_ref.item()) < 1e-6
+    assert rel(xo.grad, xr.grad) < 1e-4
+    named = dict(moe.named_parameters())
+    for key in ("w_gate", "w_noise", "experts.1.layers.0.spline_weight", "experts.2.layers.1.base_weight",
+                "experts.0.layers.0.spline_scaler"):
+        assert rel(sd_g[key].grad, named[key].grad) < 1e-4, key
