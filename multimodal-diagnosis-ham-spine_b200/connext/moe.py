@@ -20,13 +20,12 @@ from .kan1 import KAN1, _KanChain
 
 class _MoEFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, anchor, moe, noisy, noise, coef):
+    def forward(ctx, x, anchor, moe, noisy, noise, coef, need):
         st = moe._store
         E, k = moe.num_experts, moe.k
         wg, wn = moe.w_gate.data, moe.w_noise.data
         gates, clean, raw, probs, topidx, importance, load = ops.moe_gate_fwd(x, wg, wn, noise, k, noisy, moe.mean, moe.std)
         loss, d_imp, d_load = ops.moe_loss(importance, load, coef)
-        need = torch.is_grad_enabled()
         B = x.shape[0]
         chains = moe._chains
         l0 = chains[0].layers[0]
@@ -87,7 +86,7 @@ class _MoEFn(torch.autograd.Function):
         ops.moe_gate_bwd(x, moe.w_gate.data, moe.w_noise.data, ctx.noise, dgates, d_imp, d_load, dloss.contiguous().view(1),
                          clean, raw, probs, topidx, dx, st.g32(moe.w_gate) if trg else None,
                          st.g32(moe.w_noise) if (trg and ctx.noisy) else None, k, ctx.noisy, moe.mean, moe.std)
-        return dx, None, None, None, None, None
+        return dx, None, None, None, None, None, None
 
 
 class MoE(MdhsModule):
@@ -142,5 +141,5 @@ class MoE(MdhsModule):
             if noise is None:
                 object.__setattr__(self, "_calls", self._calls + 1)
                 noise = ops.randn_f32((x.shape[0], self.num_experts), x.device, seed=0x6d6f65 + self._calls * 7919)
-        y, loss = _MoEFn.apply(x, st.anchor, self, noisy, noise, float(loss_coef))
+        y, loss = _MoEFn.apply(x, st.anchor, self, noisy, noise, float(loss_coef), torch.is_grad_enabled())
         return y, loss

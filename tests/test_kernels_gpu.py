@@ -176,7 +176,8 @@ def _attn_ref(q, k, v, mask, scale):
 
 
 @pytest.mark.parametrize("B,H,Sq,Sk,D,masked", [(3, 12, 64, 64, 64, True), (2, 8, 49, 49, 32, False), (2, 8, 49, 64, 32, True),
-                                                 (2, 8, 196, 40, 32, True), (1, 12, 130, 130, 64, True), (1, 12, 256, 256, 64, False)])
+                                                 (2, 8, 196, 40, 32, True), (1, 12, 130, 130, 64, True), (1, 12, 256, 256, 64, False),
+                                                 (1, 2, 512, 512, 64, True), (2, 8, 784, 64, 32, True)])
 def test_attention(ops, B, H, Sq, Sk, D, masked):
     torch.manual_seed(0)
     q = torch.randn(B * Sq, H * D, device="cuda").bfloat16()
@@ -219,6 +220,40 @@ def test_attention_dropout_statistics(ops):
     assert abs(o.float().mean().item() - 1.0) < 0.05
     o2, _ = ops.attention_fwd(q, k, v, B, H, S, S, D, 0.1, drop_p=p, seed=7)
     assert torch.equal(o, o2)
+
+
+def test_attention_dropout_backward_matches_autograd(ops):
+    """The dropout mask is a pure function of (seed, element index): recover it from a forward pass with V = I, then
+    check forward and backward of a random-V problem against autograd with that explicit mask."""
+    torch.manual_seed(0)
+    B, H, S, D, p, seed = 2, 3, 64, 64, 0.2, 99
+    q = torch.randn(B * S, H * D, device="cuda").bfloat16()
+    k = torch.randn(B * S, H * D, device="cuda").bfloat16()
+    scale = 1.0 / math.sqrt(D)
+    eye = torch.eye(S, device="cuda").repeat(B, H).bfloat16()            # [B*S, H*D] with V_bh = I
+    o_eye, _ = ops.attention_fwd(q, k, eye, B, H, S, S, D, scale, drop_p=p, seed=seed)
+
+    def heads(t):
+        return t.float().reshape(B, S, H, D).permute(0, 2, 1, 3).contiguous()
+    qh, kh = heads(q).requires_grad_(True), heads(k).requires_grad_(True)
+    probs = torch.softmax(qh @ kh.transpose(-1, -2) * scale, dim=-1)
+    pm = heads(o_eye)                                                    # = probs * mask (bf16-rounded)
+    mask = torch.where(pm > 0.5 * probs.detach() / (1 - p), torch.full_like(pm, 1.0 / (1 - p)), torch.zeros_like(pm))
+    assert abs((mask == 0).float().mean().item() - p) < 0.02
+    v = torch.randn(B * S, H * D, device="cuda").bfloat16()
+    vh = heads(v).requires_grad_(True)
+    ref = ((probs * mask) @ vh).permute(0, 2, 1, 3).reshape(B * S, H * D)
+    o, lse = ops.attention_fwd(q, k, v, B, H, S, S, D, scale, drop_p=p, seed=seed)
+    assert relerr(o, ref) < 1e-2
+    do = torch.randn(B * S, H * D, device="cuda").bfloat16()
+    ref.backward(do.float())
+    dq, dk, dv = ops.attention_bwd(q, k, v, o, do, lse, B, H, S, S, D, scale, drop_p=p, seed=seed)
+
+    def tok(t):
+        return t.permute(0, 2, 1, 3).reshape(B * S, H * D)
+    assert relerr(dq, tok(qh.grad)) < 2e-2
+    assert relerr(dk, tok(kh.grad)) < 2e-2
+    assert relerr(dv, tok(vh.grad)) < 2e-2
 
 
 def test_embedding(ops):
