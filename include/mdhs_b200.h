@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define MDHS_ABI_VERSION 1
+#define MDHS_ABI_VERSION 2
 int mdhs_abi_version(void);
 /* Number of kernels launched through this library since load (for bench.py's gpu_launches). */
 int64_t mdhs_launch_count(void);
@@ -59,6 +59,15 @@ typedef struct {
   double* colsum; double* colsumsq;           /* optional fp64 [N] atomics: per-column sum / sum of
                                                  squares of the stored value (train-mode BN stats) */
   float dropout_p; uint64_t dropout_seed;     /* inverted dropout after act/act' (mask = hash(seed, m*N+n)) */
+  /* Implicit-GEMM convolution (torchvision Conv2d 3x3 / strided 1x1 of the ResNet trunk, encoder.py:61-72): one operand
+   * is the NHWC bf16 activation X[cN, cH, cW, cC] read through a TMA im2col descriptor, no patch matrix in HBM.
+   *   conv_mode 1: A(m, k) = X[n, p*stride - pad + r, q*stride - pad + s, c], m = (n, p, q) output pixel, k = (r, s, c)
+   *                (A = X, lda ignored, M = cN*Ho*Wo, K = cR*cS*cC): fprop with B = packed weights [O, (r,s,c)], and
+   *                stride-1 dgrad with X = dY, pad' = R-1-pad and B = mdhs_conv_weight_pack_dgrad weights;
+   *   conv_mode 2: B(n, k) = the same matrix with n = (r, s, c), k = pixel (B = X, b_mn_major = 1, ldb ignored): wgrad
+   *                dW[o, (r,s,c)] = sum_pixels dY[pixel, o] * im2col(X)[pixel, (r,s,c)] with A = dY (a_mn_major = 1).
+   * cC % 64 == 0, cR == cS, 1 <= c_stride <= 8. */
+  int32_t conv_mode; int32_t cN, cH, cW, cC, cR, cS, c_stride, c_pad;
 } mdhs_gemm_args;
 int mdhs_gemm_bf16(const mdhs_gemm_args* args, void* stream);
 

@@ -30,6 +30,9 @@ class GemmArgs(ctypes.Structure):
         ("split_k", ctypes.c_int32), ("bn_hint", ctypes.c_int32),
         ("colsum", ctypes.c_void_p), ("colsumsq", ctypes.c_void_p),
         ("dropout_p", ctypes.c_float), ("dropout_seed", ctypes.c_uint64),
+        ("conv_mode", ctypes.c_int32), ("cN", ctypes.c_int32), ("cH", ctypes.c_int32), ("cW", ctypes.c_int32),
+        ("cC", ctypes.c_int32), ("cR", ctypes.c_int32), ("cS", ctypes.c_int32), ("c_stride", ctypes.c_int32),
+        ("c_pad", ctypes.c_int32),
     ]
 
 

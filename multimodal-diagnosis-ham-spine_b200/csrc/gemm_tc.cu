@@ -48,6 +48,9 @@ struct Params {
   const void* residual; int64_t ldr; int r_f32;
   double* colsum; double* colsumsq;
   float drop_p; uint64_t drop_seed;
+  // implicit-GEMM convolution: one operand is read straight from the NHWC activation through a TMA im2col map
+  int conv_mode;                       // 0 none, 1 = A is im2col(X) (fprop / dgrad), 2 = B is im2col(X), MN-major (wgrad)
+  int cHo, cWo, cS, c_stride, c_pad, c_cblk;   // output extent, filter width, stride, padding, C / 64
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -82,6 +85,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+// im2col-mode TMA: the box is `pixelsPerColumn` consecutive output pixels (traversed W -> H -> N inside the padded
+// bounding box of the tensor map, with the convolution stride) x 64 channels starting at c; (off_w, off_h) select the
+// filter tap.  Out-of-image taps are zero-filled by the TMA unit, so no halo handling is needed in the kernel.
+__device__ __forceinline__ void tma_load_im2col(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w, int h, int n,
+                                                uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], "
+      "{%7, %8};" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
       : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -219,7 +233,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_expect_tx(fb, C::STAGE_BYTES);
         const uint32_t sA = tiles_base + stage * C::STAGE_BYTES;
         const uint32_t sB = sA + A_TILE_BYTES;
-        if (!A_MN) {
+        if (!A_MN && p.conv_mode == 1) {
+          // k-block = (filter tap, 64-channel block); the tile's first output pixel fixes the base coordinates
+          const int tap = kb / p.c_cblk, cb = kb - tap * p.c_cblk;
+          const int r = tap / p.cS, sx = tap - r * p.cS;
+          const int pix = m_blk * BM;
+          const int img = pix / (p.cHo * p.cWo), rem = pix - img * (p.cHo * p.cWo);
+          const int ph = rem / p.cWo, pw = rem - ph * p.cWo;
+          tma_load_im2col(sA, &tmA, fb, cb * 64, pw * p.c_stride - p.c_pad, ph * p.c_stride - p.c_pad, img, (uint16_t)sx,
+                          (uint16_t)r);
+        } else if (!A_MN) {
           tma_load_2d(sA, &tmA, fb, kb * BK, m_blk * BM);
         } else {
           tma_load_2d(sA, &tmA, fb, m_blk * BM, kb * BK);
@@ -227,6 +250,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (!B_MN) {
           tma_load_2d(sB, &tmB, fb, kb * BK, n_blk * BN);
+        } else if (p.conv_mode == 2) {
+          // wgrad: B(n, k) = im2col(X)[pixel k, column n]: 64 pixels x 64 channels per (tap, channel block) sub-tile
+          const int pix = kb * BK;
+          const int img = pix / (p.cHo * p.cWo), rem = pix - img * (p.cHo * p.cWo);
+          const int ph = rem / p.cWo, pw = rem - ph * p.cWo;
+#pragma unroll
+          for (int j = 0; j < BN / 64; j++) {
+            const int nb = n_blk * (BN / 64) + j;
+            const int tap = nb / p.c_cblk, cb = nb - tap * p.c_cblk;
+            const int r = tap / p.cS, sx = tap - r * p.cS;
+            tma_load_im2col(sB + j * 8192, &tmB, fb, cb * 64, pw * p.c_stride - p.c_pad, ph * p.c_stride - p.c_pad, img,
+                            (uint16_t)sx, (uint16_t)r);
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < BN / 64; j++) tma_load_2d(sB + j * 8192, &tmB, fb, n_blk * BN + j * 64, kb * BK);
@@ -550,6 +586,40 @@ int make_map(CUtensorMap* map, const void* ptr, int64_t inner, int64_t outer, in
   return r == CUDA_SUCCESS ? MDHS_OK : MDHS_ERR_ARG;
 }
 
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeIm2colFn get_encode_im2col() {
+  static EncodeIm2colFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeIm2colFn>(f);
+    }
+  }
+  return fn;
+}
+
+// NHWC bf16 activation [N, H, W, C] seen through the R x S / stride / pad convolution window: boxes of `pixels` output
+// pixels x 64 channels, 128B-swizzled (the same shared-memory image as a K-major [pixels, 64] tile).
+int make_im2col_map(CUtensorMap* map, const void* x, int N, int H, int W, int C, int R, int S, int stride, int pad, int pixels) {
+  EncodeIm2colFn enc = get_encode_im2col();
+  if (!enc) return MDHS_ERR_DRIVER;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  int lower[2] = {-pad, -pad};
+  int upper[2] = {pad - (S - 1), pad - (R - 1)};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, lower, upper, 64,
+                   (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MDHS_OK : MDHS_ERR_ARG;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -581,10 +651,12 @@ int launch(const mdhs_gemm_args* a, const Params& p0, cudaStream_t stream) {
   if (a->aux_in) rc = make_map(&tmAuxIn, a->aux_in, a->N, a->M, a->ld_aux_in, 64, BM, false);
   else tmAuxIn = tmD;
   if (rc) return rc;
-  if (!A_MN) rc = make_map(&tmA, a->A, a->K, a->M, a->lda, BK, BM);
+  if (a->conv_mode == 1) rc = make_im2col_map(&tmA, a->A, a->cN, a->cH, a->cW, a->cC, a->cR, a->cS, a->c_stride, a->c_pad, BM);
+  else if (!A_MN) rc = make_map(&tmA, a->A, a->K, a->M, a->lda, BK, BM);
   else       rc = make_map(&tmA, a->A, a->M, a->K, a->lda, 64, BK);
   if (rc) return rc;
-  if (!B_MN) rc = make_map(&tmB, a->B, a->K, a->N, a->ldb, BK, BN);
+  if (a->conv_mode == 2) rc = make_im2col_map(&tmB, a->B, a->cN, a->cH, a->cW, a->cC, a->cR, a->cS, a->c_stride, a->c_pad, BK);
+  else if (!B_MN) rc = make_map(&tmB, a->B, a->K, a->N, a->ldb, BK, BN);
   else       rc = make_map(&tmB, a->B, a->N, a->K, a->ldb, 64, BK);
   if (rc) return rc;
   static bool attr_set = false;
@@ -620,7 +692,19 @@ extern "C" int mdhs_gemm_bf16(const mdhs_gemm_args* a, void* stream_) {
   if (!a || !a->A || !a->B || !a->D) return MDHS_ERR_ARG;
   if (a->M <= 0 || a->N <= 0 || a->K <= 0) return MDHS_ERR_ARG;
   // K itself is free (TMA zero-fills the tail); only row strides must keep 16-byte alignment
-  if ((a->N % 8) || (a->lda % 8) || (a->ldb % 8)) return MDHS_ERR_ARG;
+  if ((a->N % 8) || (a->conv_mode != 1 && (a->lda % 8)) || (a->conv_mode != 2 && (a->ldb % 8))) return MDHS_ERR_ARG;
+  int cHo = 0, cWo = 0;
+  if (a->conv_mode) {
+    if (a->conv_mode != 1 && a->conv_mode != 2) return MDHS_ERR_ARG;
+    if (a->cN <= 0 || a->cH <= 0 || a->cW <= 0 || a->cC <= 0 || (a->cC % 64) || a->cR <= 0 || a->cS <= 0 || a->cR != a->cS ||
+        a->c_stride < 1 || a->c_stride > 8 || a->c_pad < 0 || a->c_pad >= a->cR + 120)
+      return MDHS_ERR_ARG;
+    cHo = (a->cH + 2 * a->c_pad - a->cR) / a->c_stride + 1;
+    cWo = (a->cW + 2 * a->c_pad - a->cS) / a->c_stride + 1;
+    const int64_t pixels = (int64_t)a->cN * cHo * cWo, kdim = (int64_t)a->cR * a->cS * a->cC;
+    if (a->conv_mode == 1 && (a->a_mn_major || a->M != pixels || a->K != kdim)) return MDHS_ERR_ARG;
+    if (a->conv_mode == 2 && (!a->b_mn_major || a->K != pixels || a->N != kdim)) return MDHS_ERR_ARG;
+  }
   if (a->a_mn_major && (a->M % 8)) return MDHS_ERR_ARG;
   if (a->b_mn_major && (a->N % 8)) return MDHS_ERR_ARG;
   if (((uintptr_t)a->A & 15) || ((uintptr_t)a->B & 15)) return MDHS_ERR_ARG;
@@ -677,6 +761,8 @@ extern "C" int mdhs_gemm_bf16(const mdhs_gemm_args* a, void* stream_) {
   p.residual = a->residual; p.ldr = a->ldr; p.r_f32 = (a->r_dtype == MDHS_DT_F32);
   p.colsum = a->colsum; p.colsumsq = a->colsumsq;
   p.drop_p = a->dropout_p; p.drop_seed = a->dropout_seed;
+  p.conv_mode = a->conv_mode; p.cHo = cHo; p.cWo = cWo; p.cS = a->cS; p.c_stride = a->c_stride; p.c_pad = a->c_pad;
+  p.c_cblk = a->conv_mode ? a->cC / 64 : 1;
   p.num_m = p.num_n = 0;
 
   int bn = a->bn_hint;

@@ -29,17 +29,26 @@ def _require_cuda(*ts):
 
 def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bias=None, act=ACT_NONE,
          aux_out=None, aux_in=None, dact=ACT_NONE, residual=None, accumulate=False, split_k=1,
-         bn_hint=0, colsum=None, colsumsq=None, M=None, N=None, K=None, dropout_p=0.0, dropout_seed=0):
+         bn_hint=0, colsum=None, colsumsq=None, M=None, N=None, K=None, dropout_p=0.0, dropout_seed=0, conv=None):
     """D[M,N] (+)= epi(A . B^T).  `a` is [M,K] (K-major) or [K,M] when a_mn; `b` is [N,K] or [K,N] when b_mn.
-    2-D bf16 tensors with unit inner stride (row stride may exceed the row length)."""
+    2-D bf16 tensors with unit inner stride (row stride may exceed the row length).
+    conv = (mode, N, H, W, C, R, S, stride, pad): implicit-GEMM convolution, the NHWC activation [N*H*W, C] is passed as
+    `a` (mode 1: fprop / dgrad) or as `b` (mode 2: wgrad, with a_mn = b_mn = True) and M, N, K must be given."""
     _require_cuda(a, b)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
-    if a_mn:
+    if conv is not None:
+        assert M is not None and N is not None and K is not None
+        x = a if conv[0] == 1 else b
+        assert x.is_contiguous() and x.shape[0] == conv[1] * conv[2] * conv[3] and x.shape[1] == conv[4]
+        m = k_a = k_b = n = None
+    elif a_mn:
         k_a, m = a.shape
     else:
         m, k_a = a.shape
-    if b_mn:
+    if conv is not None:
+        pass
+    elif b_mn:
         k_b, n = b.shape
     else:
         n, k_b = b.shape
@@ -71,6 +80,8 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bi
         args.residual, args.ldr = residual.data_ptr(), residual.stride(0)
         args.r_dtype = DT_F32 if residual.dtype == torch.float32 else DT_BF16
     args.split_k, args.bn_hint = split_k, bn_hint
+    if conv is not None:
+        (args.conv_mode, args.cN, args.cH, args.cW, args.cC, args.cR, args.cS, args.c_stride, args.c_pad) = [int(v) for v in conv]
     args.dropout_p, args.dropout_seed = float(dropout_p), int(dropout_seed)
     if colsum is not None:
         assert colsum.dtype == torch.float64 and colsumsq.dtype == torch.float64
@@ -210,6 +221,14 @@ def conv_weight_pack(w, ldk=None, out=None):
     wp = torch.empty((O, ldk), device=w.device, dtype=torch.bfloat16) if out is None else out
     _lib.call("mdhs_conv_weight_pack", _p(w), _p(wp), O, I, R, S, ldk, _s())
     return wp
+
+
+def conv_weight_pack_dgrad(w, out=None):
+    """OIHW fp32 -> bf16 [I, (R-1-r, S-1-s, o)]: the B operand of the stride-1 implicit-GEMM dgrad."""
+    O, I, R, S = w.shape
+    wt = torch.empty((I, R * S * O), device=w.device, dtype=torch.bfloat16) if out is None else out
+    _lib.call("mdhs_conv_weight_pack_dgrad", _p(w), _p(wt), O, I, R, S, _s())
+    return wt
 
 
 def conv_wgrad_unpack(gp, g):

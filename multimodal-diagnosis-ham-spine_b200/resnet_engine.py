@@ -32,17 +32,28 @@ class _Conv:
         self.ldk = (self.K + 7) // 8 * 8
         self.direct = (self.R == 1 and self.stride == 1)  # NHWC activation matrix is already the GEMM operand
         self.plain = (self.R == 1)                        # packed layout == OIHW layout
+        # implicit GEMM: the activation is read through a TMA im2col descriptor (no patch matrix in HBM)
+        self.implicit = (not stem) and (not self.direct) and self.I % 64 == 0
+        self.implicit_dgrad = self.implicit and self.stride == 1 and self.O % 64 == 0
         dev = store.device
+        self.wt = None
         if self.plain:
             self.wp = store.w16(conv.weight).view(self.O, self.I)
             self.gp = None
         else:
             self.wp = torch.zeros((self.O, self.ldk), device=dev, dtype=torch.bfloat16)
             self.gp = torch.zeros((self.O, self.ldk), device=dev, dtype=torch.float32)
+            self.wt = (torch.zeros((self.I, self.R * self.S * self.O), device=dev, dtype=torch.bfloat16)
+                       if self.implicit_dgrad else None)
             store.add_packer(self.repack)
 
     def repack(self):
         ops.conv_weight_pack(self.conv.weight.data, ldk=self.ldk, out=self.wp)
+        if self.wt is not None:
+            ops.conv_weight_pack_dgrad(self.conv.weight.data, out=self.wt)
+
+    def conv_desc(self, mode, B, H, W):
+        return (mode, B, H, W, self.I, self.R, self.S, self.stride, self.pad)
 
     def wgrad_splits(self, rows):
         tiles = ((self.O + 127) // 128) * ((self.ldk + 255) // 256)
@@ -77,16 +88,19 @@ class ResNetEngine:
             A, Ho, Wo = ops.im2col_nchw_f32(x, c.R, c.S, c.stride, c.pad, c.ldk)
         elif c.direct:
             A, Ho, Wo = x, H, W
+        elif c.implicit:
+            A, Ho, Wo = x, _out_hw(H, c.R, c.stride, c.pad), _out_hw(W, c.S, c.stride, c.pad)
         else:
             A, Ho, Wo = ops.im2col_nhwc(x, B, H, W, c.I, c.R, c.S, c.stride, c.pad)
         rows = B * Ho * Wo
         bn = c.bn
+        gkw = dict(conv=c.conv_desc(1, B, H, W), M=rows, K=c.K) if c.implicit else {}
         if training:
             st = torch.zeros((2, c.O), device=A.device, dtype=torch.float64)
             if FUSE_BN_STATS_IN_GEMM:
-                raw = ops.gemm(A, c.wp, colsum=st[0], colsumsq=st[1], N=c.O)
+                raw = ops.gemm(A, c.wp, colsum=st[0], colsumsq=st[1], N=c.O, **gkw)
             else:
-                raw = ops.gemm(A, c.wp, N=c.O)
+                raw = ops.gemm(A, c.wp, N=c.O, **gkw)
                 ops.col_stats(raw, st[0], st[1])
             mom = bn.momentum if bn.momentum is not None else 0.1
             track = bn.track_running_stats and bn.running_mean is not None
@@ -96,7 +110,7 @@ class ResNetEngine:
             if track and bn.num_batches_tracked is not None:
                 bn.num_batches_tracked += 1
         else:
-            raw = ops.gemm(A, c.wp, N=c.O)
+            raw = ops.gemm(A, c.wp, N=c.O, **gkw)
             mean, invstd, scale, shift = ops.bn_finalize(None, None, rows, bn.weight.data, bn.bias.data, bn.running_mean,
                                                          bn.running_var, 0.0, bn.eps, training=False)
         y = ops.bn_apply(raw, scale, shift, residual=residual, relu=relu)
@@ -143,9 +157,20 @@ class ResNetEngine:
         draw, dz = ops.bn_bwd(dy, rec["raw"], rec["y"], rec["mean"], rec["invstd"], bnw.data, dgamma, dbeta,
                               relu=rec["relu"], want_dz=rec["has_res"])
         A = rec["A"]
-        rows = A.shape[0]
+        rows = rec["B"] * rec["Ho"] * rec["Wo"]
         if train_w:
-            if c.plain:
+            if c.implicit:
+                # wgrad as an implicit GEMM: B operand = im2col(x) through TMA; plain 1x1 (strided) convs accumulate
+                # straight into the flat gradient buffer, k x k ones into the packed buffer
+                cd = c.conv_desc(2, rec["B"], rec["H"], rec["W"])
+                if c.plain:
+                    gw = st.g32(c.conv.weight).view(c.O, c.I)
+                    ops.gemm(draw, A, a_mn=True, b_mn=True, out=gw, accumulate=True, split_k=-1, M=c.O, N=c.K, K=rows, conv=cd)
+                else:
+                    c.gp.zero_()
+                    ops.gemm(draw, A, a_mn=True, b_mn=True, out=c.gp, accumulate=True, split_k=-1, M=c.O, N=c.K, K=rows, conv=cd)
+                    ops.conv_wgrad_unpack(c.gp, st.g32(c.conv.weight))
+            elif c.plain:
                 gw = st.g32(c.conv.weight).view(c.O, c.I)
                 ops.gemm(draw, A, a_mn=True, b_mn=True, out=gw, accumulate=True, split_k=-1,
                          M=c.O, N=c.I, K=rows)
@@ -158,6 +183,10 @@ class ResNetEngine:
         if need_dx:
             if c.direct:
                 dx = ops.gemm(draw, c.wp, b_mn=True, residual=add_to_dx, M=rows, N=c.I, K=c.O)
+            elif c.implicit_dgrad:
+                # stride-1 k x k dgrad = the same implicit GEMM over dY with the flipped / transposed filter
+                dx = ops.gemm(draw, c.wt, residual=add_to_dx, M=rec["B"] * rec["H"] * rec["W"], N=c.I, K=c.R * c.S * c.O,
+                              conv=(1, rec["B"], rec["Ho"], rec["Wo"], c.O, c.R, c.S, 1, c.R - 1 - c.pad))
             else:
                 dcol = ops.gemm(draw, c.wp[:, :c.K], b_mn=True, M=rows, N=c.K, K=c.O)
                 dx = ops.col2im_nhwc(dcol, rec["B"], rec["H"], rec["W"], c.I, c.R, c.S, c.stride, c.pad, add=add_to_dx)

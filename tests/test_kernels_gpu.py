@@ -167,6 +167,35 @@ def test_mean_tokens(ops):
     assert relerr(dx.view(B, T, C), (dy / T).unsqueeze(1).expand(B, T, C)) < 1e-2
 
 
+@pytest.mark.parametrize("B,H,W,C,O,R,stride,pad", [(4, 56, 56, 64, 64, 3, 1, 1), (2, 28, 28, 128, 128, 3, 2, 1),
+                                                    (2, 14, 14, 256, 512, 1, 2, 0), (2, 7, 7, 512, 512, 3, 1, 1),
+                                                    (3, 9, 9, 64, 64, 3, 2, 1), (16, 14, 14, 256, 256, 3, 1, 1)])
+def test_implicit_gemm_conv(ops, B, H, W, C, O, R, stride, pad):
+    """TMA-im2col implicit GEMM (fprop, wgrad, stride-1 dgrad) vs torch conv2d autograd on bf16-rounded operands.
+    Tolerance 1e-2 of the max-norm (bf16 outputs) / 2e-3 (fp32 wgrad accumulators)."""
+    torch.manual_seed(0)
+    x = torch.randn(B, C, H, W, device="cuda").bfloat16()
+    w = (torch.randn(O, C, R, R, device="cuda") / math.sqrt(C * R * R)).bfloat16().float()
+    x_rows = x.permute(0, 2, 3, 1).reshape(B * H * W, C).contiguous()
+    Ho, Wo = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - R) // stride + 1
+    rows, K = B * Ho * Wo, R * R * C
+    wp = ops.conv_weight_pack(w)
+    y = ops.gemm(x_rows, wp, conv=(1, B, H, W, C, R, R, stride, pad), M=rows, N=O, K=K)
+    xr, wr = x.float().requires_grad_(True), w.clone().requires_grad_(True)
+    ref = F.conv2d(xr, wr, stride=stride, padding=pad)
+    assert relerr(y, ref.permute(0, 2, 3, 1).reshape(rows, O)) < 1e-2
+    dy = torch.randn(rows, O, device="cuda").bfloat16()
+    ref.backward(dy.float().view(B, Ho, Wo, O).permute(0, 3, 1, 2))
+    gp = torch.zeros(O, K, device="cuda")
+    ops.gemm(dy, x_rows, a_mn=True, b_mn=True, out=gp, accumulate=True, split_k=-1, M=O, N=K, K=rows,
+             conv=(2, B, H, W, C, R, R, stride, pad))
+    assert relerr(gp, wr.grad.permute(0, 2, 3, 1).reshape(O, K)) < 2e-3
+    if stride == 1:
+        wt = ops.conv_weight_pack_dgrad(w)
+        dx = ops.gemm(dy, wt, conv=(1, B, Ho, Wo, O, R, R, 1, R - 1 - pad), M=B * H * W, N=C, K=R * R * O)
+        assert relerr(dx, xr.grad.permute(0, 2, 3, 1).reshape(B * H * W, C)) < 1e-2
+
+
 def _attn_ref(q, k, v, mask, scale):
     s = torch.einsum("bhqd,bhkd->bhqk", q, k) * scale
     if mask is not None:
