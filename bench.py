@@ -154,7 +154,7 @@ def run_ours(args):
     d_in = [t.to(dev, non_blocking=True) for t in h_in]
     torch.cuda.synchronize()
 
-    use_graph = not args.no_graph and (world == 1 or args.graph_multi_gpu)
+    use_graph = not args.no_graph
     def _mark(msg):
         if args.verbose:
             print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
@@ -330,7 +330,14 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # the captured step holds NCCL work inside a CUDA graph; tearing the communicator down under it can block, so
+        # drop the graph first, drain the device, and leave without the (optional) communicator destruction
+        trainer.release_graph()
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
@@ -344,7 +351,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=8, help="samples per CPU step of the reference arm")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--graph-multi-gpu", action="store_true", help="capture the step (incl. NCCL) into a CUDA graph for N>1")
+    ap.add_argument("--graph-multi-gpu", action="store_true", help="(default now; kept for old command lines)")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--dump-gemms", action="store_true", help="write per-shape GEMM timings to gpurun_out/gemm_shapes.txt")
     args = ap.parse_args()

@@ -51,13 +51,29 @@ __device__ __forceinline__ float block_max(float v, float* red) {
   return r;
 }
 
+// erf-GELU through the complementary error function Q(|x|) = erfc(|x|/sqrt(2)) = poly5(t) * exp(-x^2/2),
+// t = 1/(1 + p|x|/sqrt(2))  (Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7): one ex2 + one rcp + 7 FMAs, branch-free, and
+// exact in the tails because Phi(x) = Q/2 for x < 0 is formed without cancellation.  The same exponential serves the
+// density term of the derivative.  (erff + expf cost ~4x as many issue slots; the GEMM epilogues are issue-bound.)
+__device__ __forceinline__ float gelu_q_(float ax, float& e) {
+  const float t = __frcp_rn(fmaf(0.3275911f * 0.70710678118654752440f, ax, 1.f));
+  e = __expf(-0.5f * ax * ax);
+  float q = fmaf(1.061405429f, t, -1.453152027f);
+  q = fmaf(q, t, 1.421413741f);
+  q = fmaf(q, t, -0.284496736f);
+  q = fmaf(q, t, 0.254829592f);
+  return q * t * e;
+}
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+  float e;
+  const float hq = 0.5f * gelu_q_(fabsf(x), e);
+  return x * (x >= 0.f ? 1.f - hq : hq);
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
-  float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float e;
+  const float hq = 0.5f * gelu_q_(fabsf(x), e);
+  const float cdf = x >= 0.f ? 1.f - hq : hq;
+  return fmaf(x * 0.39894228040143267794f, e, cdf);
 }
 
 // 8 x bf16 <-> 8 x float through one 128-bit access.

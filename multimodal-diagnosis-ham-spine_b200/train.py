@@ -122,9 +122,17 @@ class Trainer:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
+        # with NCCL in the step, other threads (the process-group watchdog) keep issuing CUDA calls while this thread
+        # captures: only this thread's unsafe calls may invalidate the capture
+        mode = "thread_local" if self.world > 1 else "global"
+        with torch.cuda.graph(self._graph, capture_error_mode=mode):
             self._static_out = self._step_impl(*self._static)
         return self._static_out
+
+    def release_graph(self):
+        """Drop the captured graph (and its private memory pool); `step()` keeps working."""
+        self._graph = None
+        self._static_out = None
 
     def replay(self, images=None, ids=None, mask=None, labels=None):
         if images is not None:

@@ -1,0 +1,107 @@
+"""Micro-benchmark of mdhs_gemm_bf16 with the SAME epilogue options the training step uses (BERT / ResNet shapes).
+
+Each case is captured into a CUDA graph of REP back-to-back launches over ROT rotating buffer sets (so big operands
+come from HBM like in the step) and timed with CUDA events.  Output: one JSON line per case.
+  python tools/bench_gemm_step.py [filter-substring] [bn_hint]
+"""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import mdhs_b200  # noqa
+from mdhs_b200 import ops
+
+REP, ROT = 12, 3
+T, C, F = 8192, 768, 3072
+
+# name, M, N, K, a_mn, b_mn, options
+CASES = [
+    ("plain_8192_768_768", T, C, C, 0, 0, {}),
+    ("plain_8192_3072_768", T, F, C, 0, 0, {}),
+    ("plain_8192_768_3072", T, C, F, 0, 0, {}),
+    ("qkv_fwd", T, 3 * C, C, 0, 0, dict(bias=1)),
+    ("out_fwd", T, C, C, 0, 0, dict(bias=1, residual=1, drop=0.1)),
+    ("out_fwd_nodrop", T, C, C, 0, 0, dict(bias=1, residual=1)),
+    ("ffn1_fwd", T, F, C, 0, 0, dict(bias=1, act=ops.ACT_GELU, aux_out=1)),
+    ("ffn1_fwd_noaux", T, F, C, 0, 0, dict(bias=1, act=ops.ACT_GELU)),
+    ("ffn2_fwd", T, C, F, 0, 0, dict(bias=1, residual=1, drop=0.1)),
+    ("ffn2_dgrad", T, F, C, 0, 1, dict(dact=ops.ACT_GELU, aux_in=1)),
+    ("ffn2_dgrad_plain", T, F, C, 0, 1, {}),
+    ("ffn1_dgrad", T, C, F, 0, 1, dict(residual=1)),
+    ("out_dgrad", T, C, C, 0, 1, {}),
+    ("qkv_dgrad", T, C, 3 * C, 0, 1, dict(residual=1)),
+    ("ffn2_wgrad", C, F, T, 1, 1, dict(acc=1)),
+    ("ffn1_wgrad", F, C, T, 1, 1, dict(acc=1)),
+    ("qkv_wgrad", 3 * C, C, T, 1, 1, dict(acc=1)),
+    ("out_wgrad", C, C, T, 1, 1, dict(acc=1)),
+    ("l1_1x1_64_256", 401408, 256, 64, 0, 0, {}),
+    ("l1_1x1_256_64", 401408, 64, 256, 0, 0, {}),
+    ("l1_dgrad_256_64", 401408, 64, 256, 0, 1, {}),
+    ("l1_dgrad_64_256", 401408, 256, 64, 0, 1, dict(residual=1)),
+    ("l2_1x1_128_512", 100352, 512, 128, 0, 0, {}),
+    ("l3_1x1_256_1024", 25088, 1024, 256, 0, 0, {}),
+    ("l3_1x1_1024_256", 25088, 256, 1024, 0, 0, {}),
+    ("l4_1x1_2048_512", 6272, 512, 2048, 0, 0, {}),
+    ("l3_wgrad_1024_256", 1024, 256, 25088, 1, 1, dict(acc=1)),
+    ("l1_wgrad_256_64", 256, 64, 401408, 1, 1, dict(acc=1)),
+]
+
+
+def main():
+    filt = sys.argv[1] if len(sys.argv) > 1 else ""
+    bn_hint = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    dev = "cuda"
+    for name, M, N, K, a_mn, b_mn, o in CASES:
+        if filt and filt not in name:
+            continue
+        sets = []
+        for _ in range(ROT):
+            a = torch.randn((K, M) if a_mn else (M, K), device=dev).mul_(0.5).bfloat16()
+            b = torch.randn((K, N) if b_mn else (N, K), device=dev).mul_(0.05).bfloat16()
+            kw = dict(a_mn=bool(a_mn), b_mn=bool(b_mn), bn_hint=bn_hint)
+            if o.get("acc"):
+                kw.update(out=torch.zeros(M, N, device=dev), accumulate=True, split_k=-1)
+            else:
+                kw.update(out=torch.empty(M, N, device=dev, dtype=torch.bfloat16))
+            if o.get("bias"):
+                kw["bias"] = torch.randn(N, device=dev)
+            if o.get("act"):
+                kw["act"] = o["act"]
+            if o.get("aux_out"):
+                kw["aux_out"] = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+            if o.get("dact"):
+                kw["dact"] = o["dact"]
+                kw["aux_in"] = torch.randn(M, N, device=dev).bfloat16()
+            if o.get("residual"):
+                kw["residual"] = torch.randn(M, N, device=dev).bfloat16()
+            if o.get("drop"):
+                kw.update(dropout_p=o["drop"], dropout_seed=1234)
+            sets.append((a, b, kw))
+        for a, b, kw in sets:
+            ops.gemm(a, b, **kw)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for i in range(REP):
+                a, b, kw = sets[i % ROT]
+                ops.gemm(a, b, **kw)
+        g.replay()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) / REP)
+        t = sorted(ts)[len(ts) // 2]
+        fl = 2.0 * M * N * K
+        print(json.dumps({"name": name, "M": M, "N": N, "K": K, "us": round(t * 1e3, 2), "tflops": round(fl / t / 1e9, 1)}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
