@@ -93,7 +93,9 @@ int mdhs_layernorm_bwd(const void* dy, int dy_f32, int64_t lddy, const void* x, 
  * running statistics and emits scale/shift; apply fuses normalise + residual add + ReLU.
  * mdhs_bn_bwd = two passes (reduce, apply); relu != 0 masks dy with (y > 0); dz optionally receives the
  * masked dy (gradient of the identity branch); dgamma/dbeta accumulate (+=).  Workspaces: sum_dy, sum_dy_xhat
- * (fp64 [C]) and coef (fp32 [3*C]).
+ * (fp64 [C]) and coef (fp32 [5*C]).  With relu != 0 and y == NULL the mask is recomputed from x as
+ * fmaf(x, scale, shift) > 0 (bit-identical to what mdhs_bn_apply evaluated; only valid for layers without a
+ * residual input), which saves one full read of y in both passes.
  */
 int mdhs_bn_finalize(const double* colsum, const double* colsumsq, int64_t count, const float* gamma,
                      const float* beta, float* running_mean, float* running_var, float momentum, float eps,
@@ -101,8 +103,8 @@ int mdhs_bn_finalize(const double* colsum, const double* colsumsq, int64_t count
 int mdhs_bn_apply(const void* x, const float* scale, const float* shift, const void* residual, void* y,
                   int64_t rows, int C, int relu, void* stream);
 int mdhs_bn_bwd(const void* dy, const void* x, const void* y, const float* mean, const float* invstd,
-                const float* gamma, double* sum_dy, double* sum_dy_xhat, float* coef, void* dx, void* dz,
-                float* dgamma, float* dbeta, int64_t rows, int C, int relu, void* stream);
+                const float* gamma, const float* scale, const float* shift, double* sum_dy, double* sum_dy_xhat,
+                float* coef, void* dx, void* dz, float* dgamma, float* dbeta, int64_t rows, int C, int relu, void* stream);
 /* column sums of a bf16 [rows, C] matrix: fp64 sum / sum of squares (BN statistics) and/or fp32 += (bias grads) */
 int mdhs_col_stats(const void* x, int64_t ldx, double* sum64, double* sumsq64, float* sum32, int64_t rows, int C,
                    void* stream);

@@ -44,7 +44,7 @@ SIGNATURES = {
     "mdhs_layernorm_bwd": "pilpilppp" "plpppp" "iifufup",
     "mdhs_bn_finalize": "pplppppffppppiip",
     "mdhs_bn_apply": "pppppliip",
-    "mdhs_bn_bwd": "ppppppppppppp" "liip",
+    "mdhs_bn_bwd": "ppppppppppppppp" "liip",
     "mdhs_col_stats": "plppplip",
     "mdhs_im2col_nchw_f32": "ppiiiiiiiiip",
     "mdhs_im2col_nhwc": "ppiiiiiiiip",

@@ -55,9 +55,19 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 // t = 1/(1 + p|x|/sqrt(2))  (Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7): one ex2 + one rcp + 7 FMAs, branch-free, and
 // exact in the tails because Phi(x) = Q/2 for x < 0 is formed without cancellation.  The same exponential serves the
 // density term of the derivative.  (erff + expf cost ~4x as many issue slots; the GEMM epilogues are issue-bound.)
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float gelu_q_(float ax, float& e) {
-  const float t = __frcp_rn(fmaf(0.3275911f * 0.70710678118654752440f, ax, 1.f));
-  e = __expf(-0.5f * ax * ax);
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752440f, ax, 1.f));
+  e = ex2_approx(-0.72134752044448170368f * ax * ax);   // exp(-x^2/2) = 2^(-x^2 * log2(e) / 2)
   float q = fmaf(1.061405429f, t, -1.453152027f);
   q = fmaf(q, t, 1.421413741f);
   q = fmaf(q, t, -0.284496736f);

@@ -24,16 +24,21 @@ constexpr int EPI_WARP0 = 4;
 constexpr int A_TILE_BYTES = BM * BK * 2;                    // 16 KiB
 constexpr int SMEM_LIMIT = 232448;                           // 227 KiB opt-in maximum
 
-template <int BN> struct Cfg {
+// LD = the epilogue reads bf16 operand boxes (act'(aux_in) and / or a bf16 residual): they are prefetched by TMA into a
+// dedicated shared-memory box per epilogue warp group, one tile ahead of the accumulator, so their HBM latency is
+// hidden under the main loop (one pipeline stage is traded for the boxes).  Only BN <= 128 (one 64-column box per group).
+template <int BN, bool LD> struct Cfg {
+  static_assert(!(LD && BN == 256), "operand prefetch needs BN <= 128");
   static constexpr int B_TILE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? (LD ? 5 : 6) : (LD ? 7 : 8));
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int BAR_BYTES = 256;
   // two 16 KiB output staging boxes (128 rows x 128 bytes, 128B-swizzled) feeding the TMA store / reduce-add
   static constexpr int STAGING_BYTES = 2 * 16384;
   static constexpr int EPI_GROUPS = (BN == 64) ? 1 : 2;   // warp groups (4 warps each) that drain the accumulator
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES;
+  static constexpr int IN_BYTES = LD ? EPI_GROUPS * 16384 : 0;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + IN_BYTES + BAR_BYTES;
   static_assert(SMEM_BYTES <= SMEM_LIMIT, "shared memory budget exceeded");
 };
 
@@ -163,18 +168,19 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 
 // ------------------------------------------------------------------ kernel
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool LD>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmAux,
                const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmAuxIn, const Params p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, LD>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t tiles_base = smem_base;
   const uint32_t staging_base = smem_base + C::STAGES * C::STAGE_BYTES;
-  const uint32_t bars = staging_base + C::STAGING_BYTES;
+  const uint32_t in_base = staging_base + C::STAGING_BYTES;
+  const uint32_t bars = in_base + C::IN_BYTES;
   // barrier layout: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem base address
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
@@ -183,7 +189,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_slot = bars + 8u * (2 * C::STAGES + 4);
   auto lbar = [&](int h) { return bars + 8u * (2 * C::STAGES + 6 + h); };  // epilogue box-load barriers
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + C::STAGES * C::STAGE_BYTES + C::STAGING_BYTES + 8 * (2 * C::STAGES + 4));
+      reinterpret_cast<volatile uint32_t*>(smem_gen + C::STAGES * C::STAGE_BYTES + C::STAGING_BYTES + C::IN_BYTES +
+                                           8 * (2 * C::STAGES + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -332,6 +339,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const float inv_keep = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
     int acc = 0;
     uint32_t acc_phase = 0;
+    float cacc[PAIRS][4];
+#pragma unroll
+    for (int i = 0; i < PAIRS; i++) cacc[i][0] = cacc[i][1] = cacc[i][2] = cacc[i][3] = 0.f;
 
     // stage 64 bf16 columns (one box) from packed registers and hand the box to the TMA engine
     auto emit_bf16_box = [&](const CUtensorMap* map, const uint32_t* pk, int col0, int row0) {
@@ -375,6 +385,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     };
+
+    // ---- LD: operand boxes run one item ahead.  Items of a tile, in consumption order: [aux_in] [bf16 residual].
+    const uint32_t in_box = in_base + half * 16384;
+    const uint32_t in_row = in_box + row_in_box * 128;
+    const bool has_aux_in = p.dact != MDHS_ACT_NONE;
+    const int n_items = (has_aux_in ? 1 : 0) + ((p.residual != nullptr && !p.r_f32) ? 1 : 0);
+    auto issue_item = [&](int t, int q) {       // issuer thread only; splits == 1 in LD mode
+      const int n_blk = t % p.num_n, m_blk = t / p.num_n;
+      const CUtensorMap* map = (has_aux_in && q == 0) ? &tmAuxIn : &tmRes;
+      mbar_expect_tx(lbar(half), 16384);
+      tma_load_2d(in_box, map, lbar(half), n_blk * BN + half * HALF_COLS, m_blk * BM);
+    };
+    auto consume_item = [&](int t, int q, float* out) {
+      mbar_wait(lbar(half), lphase);
+      lphase ^= 1u;
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        uint32_t w0, w1, w2, w3;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                     : "r"(in_row + ((c ^ swz) << 4)));
+        const uint32_t w[4] = {w0, w1, w2, w3};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const bf162*>(&w[k]));
+          out[c * 8 + 2 * k] = f.x;
+          out[c * 8 + 2 * k + 1] = f.y;
+        }
+      }
+      named_bar(bar_id, 128);                   // every thread of the group has copied its row out of the box
+      if (issuer) {
+        if (q + 1 < n_items) issue_item(t, q + 1);
+        else if (t + (int)gridDim.x < total_tiles) issue_item(t + (int)gridDim.x, 0);
+      }
+    };
+    if (LD && issuer && n_items > 0 && (int)blockIdx.x < total_tiles) issue_item(blockIdx.x, 0);
 
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int split = t % p.splits;
@@ -435,7 +481,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ---- multiply by act'(aux_in) (backward through the activation); aux_in arrives by TMA
         if (p.dact != MDHS_ACT_NONE) {
           float a[64];
-          load_box_row(&tmAuxIn, n0, m_blk * BM, a);
+          if (LD) consume_item(t, 0, a);
+          else load_box_row(&tmAuxIn, n0, m_blk * BM, a);
 #pragma unroll
           for (int j = 0; j < 64; j++) {
             if (p.dact == MDHS_ACT_RELU) x[j] = a[j] > 0.f ? x[j] : 0.f;
@@ -463,7 +510,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           } else {
             float a[64];
-            load_box_row(&tmRes, n0, m_blk * BM, a);
+            if (LD) consume_item(t, n_items - 1, a);
+            else load_box_row(&tmRes, n0, m_blk * BM, a);
 #pragma unroll
             for (int j = 0; j < 64; j++) x[j] += a[j];
           }
@@ -490,53 +538,52 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         } else {
           // round to bf16 first so that the statistics below describe exactly what was stored
           uint32_t pk[32];
+          const bool zero_row = (p.colsum != nullptr) && !row_ok;   // rows beyond M must not reach the statistics
 #pragma unroll
-          for (int j = 0; j < 32; j++) {
-            pk[j] = pack_bf16(x[2 * j], x[2 * j + 1]);
-            const float2 q = __bfloat1622float2(*reinterpret_cast<bf162*>(&pk[j]));
-            x[2 * j] = q.x;
-            x[2 * j + 1] = q.y;
-          }
+          for (int j = 0; j < 32; j++) pk[j] = zero_row ? 0u : pack_bf16(x[2 * j], x[2 * j + 1]);
           emit_bf16_box(&tmD, pk, n0, m_blk * BM);
         }
-        // ---- per-column sum / sum of squares over the 32 rows of this warp (train-mode BN statistics)
+        // ---- per-column sum / sum of squares (train-mode BN statistics) of exactly what was stored: the staged bf16 box
+        // is re-read column-wise (lane = column pair, warp = 32-row quarter; one conflict-free 4-byte word per lane and
+        // row) into register accumulators that persist across this CTA's tiles (the grid is a multiple of num_n, so a
+        // CTA always sees the same column block); one fp64 atomic per column and warp when the CTA is done.
         if (p.colsum != nullptr) {
-#pragma unroll
-          for (int hb = 0; hb < 2; hb++) {
-            float s[32], q[32];
-#pragma unroll
-            for (int j = 0; j < 32; j++) {
-              s[j] = row_ok ? x[hb * 32 + j] : 0.f;
-              q[j] = s[j] * s[j];
-            }
-            // transposing butterfly: after 5 steps lane l holds the 32-row total of column l
-#pragma unroll
-            for (int step = 0; step < 5; step++) {
-              const int w = 16 >> step;  // 16, 8, 4, 2, 1 live values per lane after this step
-              const bool upper = (lane & w) != 0;
-#pragma unroll
-              for (int j = 0; j < 16; j++) {
-                if (j < w) {
-                  const float keep_s = upper ? s[j + w] : s[j];
-                  const float send_s = upper ? s[j] : s[j + w];
-                  const float keep_q = upper ? q[j + w] : q[j];
-                  const float send_q = upper ? q[j] : q[j + w];
-                  s[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, w);
-                  q[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, w);
-                }
-              }
-            }
-            const int n = n0 + hb * 32 + lane;
-            if (n < p.N) {
-              atomicAdd(p.colsum + n, (double)s[0]);
-              atomicAdd(p.colsumsq + n, (double)q[0]);
-            }
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+          for (int r = 0; r < 32; r++) {
+            const int row = wq * 32 + r;
+            uint32_t w;
+            asm volatile("ld.shared.b32 %0, [%1];"
+                         : "=r"(w)
+                         : "r"(stage_box + row * 128 + ((((lane >> 2) ^ (row & 7))) << 4) + ((lane & 3) << 2)));
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const bf162*>(&w));
+            s0 += f.x;
+            s1 += f.y;
+            q0 = fmaf(f.x, f.x, q0);
+            q1 = fmaf(f.y, f.y, q1);
           }
+          cacc[pr][0] += s0;
+          cacc[pr][1] += s1;
+          cacc[pr][2] += q0;
+          cacc[pr][3] += q1;
         }
       }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1u;
+      }
+    }
+    if (p.colsum != nullptr && (int)blockIdx.x < total_tiles) {
+      const int n_blk = blockIdx.x % p.num_n;
+#pragma unroll
+      for (int pr = 0; pr < PAIRS; pr++) {
+        const int n = n_blk * BN + half * HALF_COLS + pr * 64 + 2 * lane;
+        if (n < p.N) {       // N % 8 == 0, so n + 1 < N as well
+          atomicAdd(p.colsum + n, (double)cacc[pr][0]);
+          atomicAdd(p.colsum + n + 1, (double)cacc[pr][1]);
+          atomicAdd(p.colsumsq + n, (double)cacc[pr][2]);
+          atomicAdd(p.colsumsq + n + 1, (double)cacc[pr][3]);
+        }
       }
     }
     if (issuer) bulk_wait0();   // all TMA stores of this CTA have completed before the CTA exits
@@ -631,9 +678,9 @@ int num_sms() {
   return n;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool LD>
 int launch(const mdhs_gemm_args* a, const Params& p0, cudaStream_t stream) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, LD>;
   Params p = p0;
   p.num_m = ceil_div(a->M, BM);
   p.num_n = ceil_div(a->N, BN);
@@ -660,24 +707,31 @@ int launch(const mdhs_gemm_args* a, const Params& p0, cudaStream_t stream) {
   else       rc = make_map(&tmB, a->B, a->N, a->K, a->ldb, 64, BK);
   if (rc) return rc;
   static bool attr_set = false;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, LD>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   const int total = p.num_m * p.num_n * p.splits;
-  const int grid = total < num_sms() ? total : num_sms();
+  int grid = total < num_sms() ? total : num_sms();
+  if (a->colsum) {
+    // column statistics are accumulated in registers across a CTA's tiles: every CTA must keep one column block
+    if (p.num_n > grid) return MDHS_ERR_ARG;
+    grid = (grid / p.num_n) * p.num_n;
+  }
   kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmD, tmAux, tmRes, tmAuxIn, p);
   MDHS_RETURN_LAST();
 }
 
-template <int BN>
+template <int BN, bool LD>
 int dispatch_major(const mdhs_gemm_args* a, const Params& p, cudaStream_t s) {
   if (a->a_mn_major) {
-    return a->b_mn_major ? launch<BN, true, true>(a, p, s) : launch<BN, true, false>(a, p, s);
+    // MN-major A only occurs in weight-gradient GEMMs, which never read epilogue operand boxes
+    if (LD) return MDHS_ERR_ARG;
+    return a->b_mn_major ? launch<BN, true, true, false>(a, p, s) : launch<BN, true, false, false>(a, p, s);
   }
-  return a->b_mn_major ? launch<BN, false, true>(a, p, s) : launch<BN, false, false>(a, p, s);
+  return a->b_mn_major ? launch<BN, false, true, LD>(a, p, s) : launch<BN, false, false, LD>(a, p, s);
 }
 
 }  // namespace
@@ -712,6 +766,7 @@ extern "C" int mdhs_gemm_bf16(const mdhs_gemm_args* a, void* stream_) {
   if (a->split_k > 1 && (!a->accumulate || a->act || a->dact || a->aux_out || a->colsum)) return MDHS_ERR_ARG;
   if (a->dact != MDHS_ACT_NONE && !a->aux_in) return MDHS_ERR_ARG;
   if ((a->colsum == nullptr) != (a->colsumsq == nullptr)) return MDHS_ERR_ARG;
+  if (a->colsum && a->d_dtype != MDHS_DT_BF16) return MDHS_ERR_ARG;   // statistics are taken from the staged bf16 box
   if ((a->ldd % (a->d_dtype == MDHS_DT_F32 ? 4 : 8)) || (a->residual && (a->ldr % 8)) || (a->aux_out && (a->ld_aux_out % 8)) ||
       (a->aux_in && (a->ld_aux_in % 8)))
     return MDHS_ERR_ARG;
@@ -765,6 +820,9 @@ extern "C" int mdhs_gemm_bf16(const mdhs_gemm_args* a, void* stream_) {
   p.c_cblk = a->conv_mode ? a->cC / 64 : 1;
   p.num_m = p.num_n = 0;
 
+  // epilogue operand boxes (act'(aux_in), bf16 residual) are prefetched one tile ahead when the tile is <= 128 wide
+  const bool wants_ld = (a->aux_in != nullptr || (a->residual != nullptr && a->r_dtype == MDHS_DT_BF16)) && p.splits == 1 &&
+                        !a->a_mn_major;
   int bn = a->bn_hint;
   if (bn != 64 && bn != 128 && bn != 256 && auto_bn) bn = auto_bn;
   if (bn != 64 && bn != 128 && bn != 256) {
@@ -776,6 +834,7 @@ extern "C" int mdhs_gemm_bf16(const mdhs_gemm_args* a, void* stream_) {
     for (int i = 0; i < 3; i++) {
       const int c = cand[i];
       if (c > 64 && a->N <= c / 2) continue;
+      if (c == 256 && wants_ld) continue;
       const int64_t tiles = (int64_t)ceil_div(a->M, BM) * ceil_div(a->N, c) * p.splits;
       const int64_t waves = (tiles + sms - 1) / sms;
       double eff = (double)tiles / (double)(waves * sms);
@@ -790,9 +849,10 @@ extern "C" int mdhs_gemm_bf16(const mdhs_gemm_args* a, void* stream_) {
     }
   }
   g_mdhs_launches++;
+  const bool ld = wants_ld && bn != 256;
   switch (bn) {
-    case 256: return dispatch_major<256>(a, p, stream);
-    case 128: return dispatch_major<128>(a, p, stream);
-    default:  return dispatch_major<64>(a, p, stream);
+    case 256: return dispatch_major<256, false>(a, p, stream);
+    case 128: return ld ? dispatch_major<128, true>(a, p, stream) : dispatch_major<128, false>(a, p, stream);
+    default:  return ld ? dispatch_major<64, true>(a, p, stream) : dispatch_major<64, false>(a, p, stream);
   }
 }

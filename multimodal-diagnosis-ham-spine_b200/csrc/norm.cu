@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ 
     if (residual) load8(residual + i * 8, r);
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      float o = v[k] * sc[k] + sh[k];
+      float o = fmaf(v[k], sc[k], sh[k]);   // the backward recomputes the ReLU mask from exactly this expression
       if (residual) o += r[k];
       if (relu) o = fmaxf(o, 0.f);
       v[k] = o;
@@ -260,38 +260,58 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ 
   }
 }
 
-// Per-channel reductions for BN backward: sum(dy') and sum(dy' * xhat), dy' = dy * [y > 0] when relu.
-// Block = 256 threads = 32 channel-vectors(8) x 8 row lanes; grid = (C/256 ceil, row blocks).
+// Per-channel reductions for BN backward: sum(dy') and sum(dy' * xhat), dy' = dy * [y > 0] when relu.  The ReLU mask
+// comes from y when the layer had a residual input, otherwise it is recomputed from x (fmaf(x, scale, shift) > 0 is
+// exactly what bn_apply evaluated), which saves one full read of y.
+// Block = 256 threads = 32 channel-vectors(8) x 8 row lanes over a `Cw`-wide view of the matrix: Cw = C, or 256 when
+// C in {64, 128} (the contiguous [rows, C] matrix re-read as [rows*C/256, 256]; column j holds channel j % C), so
+// narrow layers keep all 32 vector lanes busy.  grid = (Cw/256 ceil, row blocks).
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                             const bf16* __restrict__ y, const float* __restrict__ mean,
-                                                            const float* __restrict__ invstd, double* __restrict__ sum_dy,
-                                                            double* __restrict__ sum_dy_xhat, int64_t rows, int C,
+                                                            const float* __restrict__ invstd, const float* __restrict__ scale,
+                                                            const float* __restrict__ shift, double* __restrict__ sum_dy,
+                                                            double* __restrict__ sum_dy_xhat, int64_t rows, int C, int Cw,
                                                             int rows_per_block, int relu) {
   __shared__ float sh[2][8][256 + 8];
-  const int cv = threadIdx.x & 31;   // which 8-channel vector inside the 256-channel slab
+  const int cv = threadIdx.x & 31;   // which 8-channel vector inside the 256-column slab
   const int rl = threadIdx.x >> 5;   // row lane 0..7
   const int c0 = blockIdx.x * 256 + cv * 8;
-  const bool ok = c0 < C;
-  float a[8], b[8], mu[8], is[8];
+  const bool ok = c0 < Cw;
+  const int ch0 = c0 % C;
+  const bool remask = relu && (y == nullptr);
+  float a[8], b[8], mu[8], is[8], sc[8], sf[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) {
     a[k] = b[k] = 0.f;
-    mu[k] = ok ? mean[c0 + k] : 0.f;
-    is[k] = ok ? invstd[c0 + k] : 0.f;
+    mu[k] = ok ? mean[ch0 + k] : 0.f;
+    is[k] = ok ? invstd[ch0 + k] : 0.f;
+    sc[k] = (ok && remask) ? scale[ch0 + k] : 0.f;
+    sf[k] = (ok && remask) ? shift[ch0 + k] : 0.f;
   }
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
   const int64_t r1 = min(rows, r0 + rows_per_block);
   if (ok) {
-    for (int64_t r = r0 + rl; r < r1; r += 8) {
-      float d[8], xv[8], yv[8];
-      load8(dy + r * C + c0, d);
-      load8(x + r * C + c0, xv);
-      if (relu) load8(y + r * C + c0, yv);
+    for (int64_t r = r0 + rl; r < r1; r += 16) {
+      const bool two = r + 8 < r1;
+      float d[2][8], xv[2][8], yv[2][8];
+      load8(dy + r * Cw + c0, d[0]);
+      load8(x + r * Cw + c0, xv[0]);
+      if (relu && !remask) load8(y + r * Cw + c0, yv[0]);
+      if (two) {
+        load8(dy + (r + 8) * Cw + c0, d[1]);
+        load8(x + (r + 8) * Cw + c0, xv[1]);
+        if (relu && !remask) load8(y + (r + 8) * Cw + c0, yv[1]);
+      }
 #pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const float dd = (relu && !(yv[k] > 0.f)) ? 0.f : d[k];
-        a[k] += dd;
-        b[k] += dd * (xv[k] - mu[k]) * is[k];
+      for (int u = 0; u < 2; u++) {
+        if (u == 1 && !two) break;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const float act = remask ? fmaf(xv[u][k], sc[k], sf[k]) : yv[u][k];
+          const float dd = (relu && !(act > 0.f)) ? 0.f : d[u][k];
+          a[k] += dd;
+          b[k] += dd * (xv[u][k] - mu[k]) * is[k];
+        }
       }
     }
   }
@@ -301,14 +321,27 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restri
     sh[1][rl][cv * 8 + k] = b[k];
   }
   __syncthreads();
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; w++) {
+    s0 += sh[0][w][threadIdx.x];
+    s1 += sh[1][w][threadIdx.x];
+  }
+  if (Cw != C) {   // folded view: columns t, t + C, t + 2C, ... belong to channel t
+    __syncthreads();
+    sh[0][0][threadIdx.x] = s0;
+    sh[1][0][threadIdx.x] = s1;
+    __syncthreads();
+    if (threadIdx.x < C) {
+      s0 = s1 = 0.f;
+      for (int j = threadIdx.x; j < 256; j += C) {
+        s0 += sh[0][0][j];
+        s1 += sh[1][0][j];
+      }
+    }
+  }
   const int c = blockIdx.x * 256 + threadIdx.x;
   if (c < C) {
-    float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; w++) {
-      s0 += sh[0][w][threadIdx.x];
-      s1 += sh[1][w][threadIdx.x];
-    }
     atomicAdd(sum_dy + c, (double)s0);
     atomicAdd(sum_dy_xhat + c, (double)s1);
   }
@@ -319,7 +352,8 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restri
 // Also accumulates dgamma / dbeta (one thread per channel).
 __global__ void bn_bwd_coeff_kernel(const float* __restrict__ mean, const float* __restrict__ invstd,
                                     const float* __restrict__ gamma, const double* __restrict__ sum_dy,
-                                    const double* __restrict__ sum_dy_xhat, float* __restrict__ coef, float* __restrict__ dgamma,
+                                    const double* __restrict__ sum_dy_xhat, const float* __restrict__ scale,
+                                    const float* __restrict__ shift, float* __restrict__ coef, float* __restrict__ dgamma,
                                     float* __restrict__ dbeta, int64_t rows, int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -331,6 +365,10 @@ __global__ void bn_bwd_coeff_kernel(const float* __restrict__ mean, const float*
   coef[c] = (float)ca;
   coef[C + c] = (float)cb;
   coef[2 * C + c] = (float)(-ca * s1 * inv_m - cb * mu);
+  if (scale) {
+    coef[3 * C + c] = scale[c];
+    coef[4 * C + c] = shift[c];
+  }
   if (dgamma) {
     dgamma[c] += (float)s2;
     dbeta[c] += (float)s1;
@@ -338,25 +376,36 @@ __global__ void bn_bwd_coeff_kernel(const float* __restrict__ mean, const float*
 }
 
 // dx = ca[c] * dy' + cb[c] * x + cc[c]; optionally also writes dy' (the ReLU-masked incoming gradient) for the
-// identity branch.  Pure streaming: 8 channels per thread, coefficient vectors read as float4.
+// identity branch.  Pure streaming: 8 channels per thread, coefficient vectors read as float4.  coef rows 3 and 4 hold
+// the forward scale / shift when the ReLU mask is recomputed from x (y == nullptr).
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                            const bf16* __restrict__ y, const float* __restrict__ coef,
                                                            bf16* __restrict__ dx, bf16* __restrict__ dz, int64_t rows, int C,
                                                            int relu) {
   const int cvec = C >> 3;
   const int64_t total_vec = rows * cvec;
+  const bool remask = relu && (y == nullptr);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
     const int c0 = (int)(i % cvec) * 8;
     float d[8], xv[8], yv[8], o[8], ca[8], cb[8], cc[8];
     load8(dy + i * 8, d);
     load8(x + i * 8, xv);
-    if (relu) load8(y + i * 8, yv);
+    if (relu && !remask) load8(y + i * 8, yv);
     *reinterpret_cast<float4*>(ca) = *reinterpret_cast<const float4*>(coef + c0);
     *reinterpret_cast<float4*>(ca + 4) = *reinterpret_cast<const float4*>(coef + c0 + 4);
     *reinterpret_cast<float4*>(cb) = *reinterpret_cast<const float4*>(coef + C + c0);
     *reinterpret_cast<float4*>(cb + 4) = *reinterpret_cast<const float4*>(coef + C + c0 + 4);
     *reinterpret_cast<float4*>(cc) = *reinterpret_cast<const float4*>(coef + 2 * C + c0);
     *reinterpret_cast<float4*>(cc + 4) = *reinterpret_cast<const float4*>(coef + 2 * C + c0 + 4);
+    if (remask) {
+      float sc[8], sf[8];
+      *reinterpret_cast<float4*>(sc) = *reinterpret_cast<const float4*>(coef + 3 * C + c0);
+      *reinterpret_cast<float4*>(sc + 4) = *reinterpret_cast<const float4*>(coef + 3 * C + c0 + 4);
+      *reinterpret_cast<float4*>(sf) = *reinterpret_cast<const float4*>(coef + 4 * C + c0);
+      *reinterpret_cast<float4*>(sf + 4) = *reinterpret_cast<const float4*>(coef + 4 * C + c0 + 4);
+#pragma unroll
+      for (int k = 0; k < 8; k++) yv[k] = fmaf(xv[k], sc[k], sf[k]);
+    }
 #pragma unroll
     for (int k = 0; k < 8; k++) {
       const float dd = (relu && !(yv[k] > 0.f)) ? 0.f : d[k];
@@ -369,27 +418,40 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restric
 }
 
 // Per-column sum / sum of squares of a bf16 [rows, C] matrix into fp64 (standalone BN statistics) or
-// fp32 (+=, bias gradients).  Same thread layout as bn_bwd_reduce.
+// fp32 (+=, bias gradients).  Same thread layout (and the same folded Cw-wide view for C in {64, 128}) as bn_bwd_reduce.
 __global__ void __launch_bounds__(256) col_stats_kernel(const bf16* __restrict__ x, int64_t ldx, double* __restrict__ sum64,
                                                         double* __restrict__ sumsq64, float* __restrict__ sum32,
-                                                        int64_t rows, int C, int rows_per_block) {
+                                                        int64_t rows, int C, int Cw, int rows_per_block) {
   __shared__ float sh[2][8][256 + 8];
   const int cv = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c0 = blockIdx.x * 256 + cv * 8;
-  const bool ok = c0 < C;
+  const bool ok = c0 < Cw;
   float a[8], b[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) a[k] = b[k] = 0.f;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
   const int64_t r1 = min(rows, r0 + rows_per_block);
   if (ok) {
-    for (int64_t r = r0 + rl; r < r1; r += 8) {
+    int64_t r = r0 + rl;
+    for (; r + 24 < r1; r += 32) {
+      float v[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; u++) load8(x + (r + 8 * u) * ldx + c0, v[u]);
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          a[k] += v[u][k];
+          b[k] = fmaf(v[u][k], v[u][k], b[k]);
+        }
+    }
+    for (; r < r1; r += 8) {
       float v[8];
       load8(x + r * ldx + c0, v);
 #pragma unroll
       for (int k = 0; k < 8; k++) {
         a[k] += v[k];
-        b[k] += v[k] * v[k];
+        b[k] = fmaf(v[k], v[k], b[k]);
       }
     }
   }
@@ -399,18 +461,43 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const bf16* __restrict__
     sh[1][rl][cv * 8 + k] = b[k];
   }
   __syncthreads();
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; w++) {
+    s0 += sh[0][w][threadIdx.x];
+    s1 += sh[1][w][threadIdx.x];
+  }
+  if (Cw != C) {
+    __syncthreads();
+    sh[0][0][threadIdx.x] = s0;
+    sh[1][0][threadIdx.x] = s1;
+    __syncthreads();
+    if (threadIdx.x < C) {
+      s0 = s1 = 0.f;
+      for (int j = threadIdx.x; j < 256; j += C) {
+        s0 += sh[0][0][j];
+        s1 += sh[1][0][j];
+      }
+    }
+  }
   const int c = blockIdx.x * 256 + threadIdx.x;
   if (c < C) {
-    float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; w++) {
-      s0 += sh[0][w][threadIdx.x];
-      s1 += sh[1][w][threadIdx.x];
-    }
     if (sum64) atomicAdd(sum64 + c, (double)s0);
     if (sumsq64) atomicAdd(sumsq64 + c, (double)s1);
     if (sum32) atomicAdd(sum32 + c, s0);
   }
+}
+
+// Folded view for narrow matrices: [rows, C] contiguous with 256 % C == 0 is re-read as [rows*C/256, 256].
+static inline bool fold_view(int64_t rows, int C, int64_t ld, int64_t* rows_w, int* Cw) {
+  if (C < 256 && (256 % C) == 0 && ld == C && (rows % (256 / C)) == 0) {
+    *rows_w = rows / (256 / C);
+    *Cw = 256;
+    return true;
+  }
+  *rows_w = rows;
+  *Cw = C;
+  return false;
 }
 
 int grid_for(int64_t work_items, int block) {
@@ -497,25 +584,31 @@ extern "C" int mdhs_bn_apply(const void* x, const float* scale, const float* shi
 }
 
 extern "C" int mdhs_bn_bwd(const void* dy, const void* x, const void* y, const float* mean, const float* invstd,
-                           const float* gamma, double* sum_dy, double* sum_dy_xhat, float* coef, void* dx, void* dz,
-                           float* dgamma, float* dbeta, int64_t rows, int C, int relu, void* stream) {
+                           const float* gamma, const float* scale, const float* shift, double* sum_dy, double* sum_dy_xhat,
+                           float* coef, void* dx, void* dz, float* dgamma, float* dbeta, int64_t rows, int C, int relu,
+                           void* stream) {
   if (!dy || !x || !mean || !invstd || !gamma || !sum_dy || !sum_dy_xhat || !coef || !dx || rows <= 0 || (C % 8)) return MDHS_ERR_ARG;
-  if (relu && !y) return MDHS_ERR_ARG;
+  if (relu && !y && (!scale || !shift)) return MDHS_ERR_ARG;   // the mask comes from y or is recomputed from scale / shift
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaError_t e = cudaMemsetAsync(sum_dy, 0, sizeof(double) * C, st);
   if (e != cudaSuccess) return (int)e;
   e = cudaMemsetAsync(sum_dy_xhat, 0, sizeof(double) * C, st);
   if (e != cudaSuccess) return (int)e;
-  const int cslabs = ceil_div(C, 256);
+  int64_t rows_w;
+  int Cw;
+  fold_view(rows, C, C, &rows_w, &Cw);
+  const int cslabs = ceil_div(Cw, 256);
   int row_blocks = (148 * 8) / cslabs;
   if (row_blocks < 1) row_blocks = 1;
-  int rpb = ceil_div(rows, row_blocks);
-  rpb = ((rpb + 7) / 8) * 8;
-  row_blocks = ceil_div(rows, rpb);
+  int rpb = ceil_div(rows_w, row_blocks);
+  rpb = ((rpb + 15) / 16) * 16;
+  row_blocks = ceil_div(rows_w, rpb);
   g_mdhs_launches += 3;
+  const bool remask = relu && !y;
   bn_bwd_reduce_kernel<<<dim3(cslabs, row_blocks), 256, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, mean, invstd,
-                                                                 sum_dy, sum_dy_xhat, rows, C, rpb, relu);
-  bn_bwd_coeff_kernel<<<ceil_div(C, 128), 128, 0, st>>>(mean, invstd, gamma, sum_dy, sum_dy_xhat, coef, dgamma, dbeta, rows, C);
+                                                                 scale, shift, sum_dy, sum_dy_xhat, rows_w, C, Cw, rpb, relu);
+  bn_bwd_coeff_kernel<<<ceil_div(C, 128), 128, 0, st>>>(mean, invstd, gamma, sum_dy, sum_dy_xhat, remask ? scale : nullptr,
+                                                        remask ? shift : nullptr, coef, dgamma, dbeta, rows, C);
   const int64_t total_vec = rows * (C / 8);
   bn_bwd_apply_kernel<<<grid_for(total_vec, 256), 256, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, coef, (bf16*)dx,
                                                                 (bf16*)dz, rows, C, relu);
@@ -525,14 +618,17 @@ extern "C" int mdhs_bn_bwd(const void* dy, const void* x, const void* y, const f
 extern "C" int mdhs_col_stats(const void* x, int64_t ldx, double* sum64, double* sumsq64, float* sum32, int64_t rows, int C,
                               void* stream) {
   if (!x || rows <= 0 || (C % 8) || (ldx % 8)) return MDHS_ERR_ARG;
-  const int cslabs = ceil_div(C, 256);
+  int64_t rows_w;
+  int Cw;
+  if (fold_view(rows, C, ldx, &rows_w, &Cw)) ldx = Cw;
+  const int cslabs = ceil_div(Cw, 256);
   int row_blocks = (148 * 8) / cslabs;
   if (row_blocks < 1) row_blocks = 1;
-  int rpb = ceil_div(rows, row_blocks);
-  rpb = ((rpb + 7) / 8) * 8;
-  row_blocks = ceil_div(rows, rpb);
+  int rpb = ceil_div(rows_w, row_blocks);
+  rpb = ((rpb + 31) / 32) * 32;
+  row_blocks = ceil_div(rows_w, rpb);
   g_mdhs_launches++;
   col_stats_kernel<<<dim3(cslabs, row_blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      (const bf16*)x, ldx, sum64, sumsq64, sum32, rows, C, rpb);
+      (const bf16*)x, ldx, sum64, sumsq64, sum32, rows_w, C, Cw, rpb);
   MDHS_RETURN_LAST();
 }

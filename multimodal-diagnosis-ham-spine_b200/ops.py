@@ -145,14 +145,15 @@ def bn_apply(x, scale, shift, residual=None, relu=True, out=None):
     return y
 
 
-def bn_bwd(dy, x, y, mean, invstd, gamma, dgamma, dbeta, relu=True, want_dz=False):
+def bn_bwd(dy, x, y, mean, invstd, gamma, dgamma, dbeta, relu=True, want_dz=False, scale=None, shift=None):
+    """y may be None when relu and the layer had no residual input: the mask is recomputed from (x, scale, shift)."""
     rows, C = x.shape
     ws = torch.empty((2, C), device=x.device, dtype=torch.float64)
-    coef = torch.empty((3, C), device=x.device, dtype=torch.float32)
+    coef = torch.empty((5, C), device=x.device, dtype=torch.float32)
     dx = torch.empty_like(x)
     dz = torch.empty_like(x) if want_dz else None
-    _lib.call("mdhs_bn_bwd", _p(dy), _p(x), _p(y), _p(mean), _p(invstd), _p(gamma), ws[0].data_ptr(), ws[1].data_ptr(),
-              _p(coef), _p(dx), _p(dz), _p(dgamma), _p(dbeta), rows, C, int(relu), _s())
+    _lib.call("mdhs_bn_bwd", _p(dy), _p(x), _p(y), _p(mean), _p(invstd), _p(gamma), _p(scale), _p(shift), ws[0].data_ptr(),
+              ws[1].data_ptr(), _p(coef), _p(dx), _p(dz), _p(dgamma), _p(dbeta), rows, C, int(relu), _s())
     return dx, dz
 
 

@@ -12,9 +12,9 @@ import torch
 from . import ops
 
 
-# Train-mode BN statistics: fused into the conv GEMM epilogue (register butterfly) or one extra column pass over
-# the raw conv output.  Measured on B200 (round 1): the extra pass is cheaper than the butterfly for small-K convs.
-FUSE_BN_STATS_IN_GEMM = False
+# Train-mode BN statistics: fused into the conv GEMM epilogue (column sums of the staged bf16 output box, accumulated in
+# registers across the persistent CTA's tiles) or, when False, one extra column pass (col_stats) over the raw conv output.
+FUSE_BN_STATS_IN_GEMM = True
 
 
 def _out_hw(h, k, s, p):
@@ -115,8 +115,10 @@ class ResNetEngine:
                                                          bn.running_var, 0.0, bn.eps, training=False)
         y = ops.bn_apply(raw, scale, shift, residual=residual, relu=relu)
         if saved is not None:
-            saved.append(dict(c=c, A=A, raw=raw, y=y if relu else None, mean=mean, invstd=invstd, relu=relu,
-                              B=B, H=H, W=W, Ho=Ho, Wo=Wo, has_res=residual is not None))
+            # y is only kept for the backward ReLU mask when a residual entered the activation; otherwise the mask is
+            # recomputed from (raw, scale, shift)
+            saved.append(dict(c=c, A=A, raw=raw, y=y if (relu and residual is not None) else None, mean=mean, invstd=invstd,
+                              scale=scale, shift=shift, relu=relu, B=B, H=H, W=W, Ho=Ho, Wo=Wo, has_res=residual is not None))
         return y, Ho, Wo
 
     def forward(self, images, training, need_grad):
@@ -155,7 +157,7 @@ class ResNetEngine:
         dgamma = st.g32(bnw) if bnw.requires_grad else None
         dbeta = st.g32(c.bn.bias) if bnw.requires_grad else None
         draw, dz = ops.bn_bwd(dy, rec["raw"], rec["y"], rec["mean"], rec["invstd"], bnw.data, dgamma, dbeta,
-                              relu=rec["relu"], want_dz=rec["has_res"])
+                              relu=rec["relu"], want_dz=rec["has_res"], scale=rec["scale"], shift=rec["shift"])
         A = rec["A"]
         rows = rec["B"] * rec["Ho"] * rec["Wo"]
         if train_w:

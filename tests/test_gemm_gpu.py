@@ -69,6 +69,23 @@ def test_gemm_epilogues(mdhs):
     assert (g - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("M,N,K,bn", [(50000, 64, 72, 0), (50000, 256, 64, 0), (50000, 256, 64, 128), (30000, 512, 128, 64),
+                                      (9000, 2048, 64, 128), (20000, 1024, 64, 256)])
+def test_gemm_column_statistics_persistent(mdhs, M, N, K, bn):
+    """Train-mode BN statistics fused into the conv GEMM: many tiles per persistent CTA, every tile width."""
+    from mdhs_b200 import ops
+    torch.manual_seed(2)
+    a = torch.randn(M, K, device="cuda").bfloat16()
+    w = (torch.randn(N, K, device="cuda") * 0.2).bfloat16()
+    cs = torch.zeros(N, device="cuda", dtype=torch.float64)
+    cq = torch.zeros(N, device="cuda", dtype=torch.float64)
+    out = ops.gemm(a, w, colsum=cs, colsumsq=cq, bn_hint=bn)
+    ref = a.float() @ w.float().t()
+    assert (out.float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+    assert torch.allclose(cs, out.double().sum(0), rtol=1e-5, atol=2e-2)
+    assert torch.allclose(cq, (out.double() ** 2).sum(0), rtol=1e-5, atol=2e-2)
+
+
 def test_gemm_splitk_accumulate(mdhs):
     from mdhs_b200 import ops
     torch.manual_seed(1)

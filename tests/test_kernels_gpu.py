@@ -100,6 +100,35 @@ def test_batchnorm_train(ops, rows, C):
     assert relerr(db, br.grad) < 2e-3
 
 
+@pytest.mark.parametrize("rows,C", [(4 * 56 * 56, 64), (3 * 28 * 28, 128), (2 * 14 * 14, 1024), (1001, 256), (1004, 64)])
+def test_batchnorm_bwd_mask_recomputed(ops, rows, C):
+    """No residual input: the backward gets y=None and rebuilds the ReLU mask from (x, scale, shift); must equal the
+    y-based path bit for bit (narrow C exercises the folded 256-wide view of the reductions)."""
+    torch.manual_seed(1)
+    x = (torch.randn(rows, C, device="cuda") * 1.5 + 0.3).bfloat16()
+    gamma = torch.rand(C, device="cuda") + 0.5
+    beta = torch.randn(C, device="cuda") * 0.3
+    cs = torch.zeros(C, device="cuda", dtype=torch.float64)
+    cq = torch.zeros(C, device="cuda", dtype=torch.float64)
+    ops.col_stats(x, cs, cq)
+    assert relerr(cs.float(), x.float().sum(0)) < 1e-5 and relerr(cq.float(), (x.float() ** 2).sum(0)) < 1e-5
+    mean, invstd, scale, shift = ops.bn_finalize(cs, cq, rows, gamma, beta, None, None, 0.1, 1e-5)
+    y = ops.bn_apply(x, scale, shift, residual=None, relu=True)
+    dy = torch.randn(rows, C, device="cuda").bfloat16()
+    dg0, db0 = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dg1, db1 = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dx0, _ = ops.bn_bwd(dy, x, y, mean, invstd, gamma, dg0, db0, relu=True)
+    dx1, _ = ops.bn_bwd(dy, x, None, mean, invstd, gamma, dg1, db1, relu=True, scale=scale, shift=shift)
+    assert torch.equal(dx0, dx1)
+    assert relerr(dg1, dg0) < 1e-5 and relerr(db1, db0) < 1e-5
+    xr = x.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    bn = F.batch_norm(xr, None, None, gr, br, True, 0.1, 1e-5)
+    bn.backward(dy.float() * (y.float() > 0))
+    assert relerr(dx1, xr.grad) < 1.5e-2
+    assert relerr(dg1, gr.grad) < 2e-3 and relerr(db1, br.grad) < 2e-3
+
+
 @pytest.mark.parametrize("Cin,Cout,R,stride,pad,H", [(64, 64, 3, 1, 1, 14), (128, 128, 3, 2, 1, 14), (256, 512, 1, 2, 0, 14), (64, 256, 1, 1, 0, 8)])
 def test_conv_via_im2col_gemm(ops, Cin, Cout, R, stride, pad, H):
     """conv fprop / dgrad / wgrad = im2col + tcgen05 GEMM + col2im, against F.conv2d autograd."""
