@@ -16,34 +16,52 @@ int grid_for(int64_t items, int block) {
 
 // NCHW fp32 image -> im2col rows for the stem (C_in = 3 is too narrow for channel vectors).
 // col[(b,ho,wo), (r*S+s)*C + c] ; columns >= R*S*C are zero padding up to ldc.
+// A block assembles IM2COL_PIX consecutive patch rows in shared memory -- one task per (pixel, filter row, channel)
+// reads the S consecutive input floats of that filter row and scatters them as bf16 -- and then streams the finished
+// rows (one contiguous IM2COL_PIX * ldc * 2-byte chunk of the patch matrix) out with 16-byte stores.  The previous
+// one-thread-per-8-columns form spent ~60 integer instructions per element on index arithmetic (ncu: 79 % issue-bound,
+// 0.9 ms for the ResNet stem at B = 128).
+constexpr int IM2COL_PIX = 32;
 __global__ void __launch_bounds__(256) im2col_nchw_f32_kernel(const float* __restrict__ x, bf16* __restrict__ col, int B, int C,
                                                               int H, int W, int R, int S, int stride, int pad, int Ho, int Wo,
                                                               int ldc) {
-  // one thread = 8 consecutive k of one output pixel = one 16-byte store (ldc % 8 == 0)
-  const int kvec = ldc >> 3;
-  const int64_t total = (int64_t)B * Ho * Wo * kvec;
+  extern __shared__ __align__(16) uint8_t im2col_smem[];
+  bf16* tile = reinterpret_cast<bf16*>(im2col_smem);
+  const int64_t total_rows = (int64_t)B * Ho * Wo;
+  const int64_t row0 = (int64_t)blockIdx.x * IM2COL_PIX;
   const int K = R * S * C;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int kv = (int)(i % kvec);
-    const int64_t row = i / kvec;
+  // zero the padding columns once (they are never written by the tasks)
+  for (int i = threadIdx.x; i < IM2COL_PIX * (ldc - K); i += blockDim.x) {
+    const int p = i / (ldc - K), k = K + i % (ldc - K);
+    tile[p * ldc + k] = __float2bfloat16(0.f);
+  }
+  const int tasks = IM2COL_PIX * R * C;
+  for (int t = threadIdx.x; t < tasks; t += blockDim.x) {
+    const int p = t % IM2COL_PIX;          // consecutive threads -> consecutive output pixels (coalesced-ish reads)
+    const int rc = t / IM2COL_PIX;
+    const int c = rc % C, r = rc / C;
+    const int64_t row = row0 + p;
+    bf16* dst = tile + p * ldc + (r * S) * C + c;
+    if (row >= total_rows) continue;
     const int wo = (int)(row % Wo);
     const int ho = (int)((row / Wo) % Ho);
     const int b = (int)(row / ((int64_t)Wo * Ho));
-    const float* xb = x + (int64_t)b * C * H * W;
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const int k = kv * 8 + j;
-      float val = 0.f;
-      if (k < K) {
-        const int c = k % C, rs = k / C, s = rs % S, r = rs / S;
-        const int h = ho * stride - pad + r, w = wo * stride - pad + s;
-        if (h >= 0 && h < H && w >= 0 && w < W) val = __ldg(xb + ((int64_t)c * H + h) * W + w);
-      }
-      v[j] = val;
+    const int h = ho * stride - pad + r;
+    const int w0 = wo * stride - pad;
+    const bool h_ok = (h >= 0 && h < H);
+    const float* src = x + (((int64_t)b * C + c) * H + (h_ok ? h : 0)) * W;
+    for (int sx = 0; sx < S; sx++) {
+      const int w = w0 + sx;
+      const float v = (h_ok && w >= 0 && w < W) ? __ldg(src + w) : 0.f;
+      dst[sx * C] = __float2bfloat16(v);
     }
-    store8(col + row * ldc + kv * 8, v);
   }
+  __syncthreads();
+  const int64_t rows_here = total_rows - row0 < IM2COL_PIX ? total_rows - row0 : IM2COL_PIX;
+  const int nvec = (int)(rows_here * ldc / 8);       // ldc % 8 == 0: the block's rows are one contiguous chunk
+  const uint4* tv = reinterpret_cast<const uint4*>(tile);
+  uint4* gv = reinterpret_cast<uint4*>(col + row0 * ldc);
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) gv[i] = tv[i];
 }
 
 // NHWC bf16 -> im2col rows, 8 channels per thread.  col[(b,ho,wo), (r*S+s)*C + c].
@@ -340,8 +358,11 @@ extern "C" int mdhs_im2col_nchw_f32(const float* x, void* col, int B, int C, int
   if (!x || !col || ldc < R * S * C || (ldc % 8)) return MDHS_ERR_ARG;
   const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
   g_mdhs_launches++;
-  im2col_nchw_f32_kernel<<<grid_for((int64_t)B * Ho * Wo * (ldc / 8), 256), 256, 0, ST(stream)>>>(x, (bf16*)col, B, C, H, W, R, S, stride,
-                                                                                            pad, Ho, Wo, ldc);
+  const int64_t rows = (int64_t)B * Ho * Wo;
+  const size_t smem = (size_t)IM2COL_PIX * ldc * sizeof(bf16);
+  if (smem > 48 * 1024 || ((uintptr_t)col & 15)) return MDHS_ERR_ARG;
+  im2col_nchw_f32_kernel<<<(unsigned)((rows + IM2COL_PIX - 1) / IM2COL_PIX), 256, smem, ST(stream)>>>(x, (bf16*)col, B, C, H, W, R, S,
+                                                                                                  stride, pad, Ho, Wo, ldc);
   MDHS_RETURN_LAST();
 }
 

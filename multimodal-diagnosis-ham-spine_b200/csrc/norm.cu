@@ -72,11 +72,16 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const void* __restrict__ x_
     const int col = c * 256 + lane * 8;
     const bool ok = (c < nch) || (c == nch && lane * 8 < rem);
     if (ok) {
-      float o[8];
+      float o[8], gm[8], bt[8];
+      *reinterpret_cast<float4*>(gm) = *reinterpret_cast<const float4*>(gamma + col);
+      *reinterpret_cast<float4*>(gm + 4) = *reinterpret_cast<const float4*>(gamma + col + 4);
+      *reinterpret_cast<float4*>(bt) = *reinterpret_cast<const float4*>(beta + col);
+      *reinterpret_cast<float4*>(bt + 4) = *reinterpret_cast<const float4*>(beta + col + 4);
 #pragma unroll
-      for (int i = 0; i < 8; i++) {
-        o[i] = (v[c][i] - mean) * rstd * gamma[col + i] + beta[col + i];
-        if (drop_p > 0.f) o[i] *= dropout_scale(seed, (uint64_t)row * C + col + i, drop_p, inv_keep);
+      for (int i = 0; i < 8; i++) o[i] = (v[c][i] - mean) * rstd * gm[i] + bt[i];
+      if (drop_p > 0.f) {
+        dropout_apply4(seed, (uint64_t)row * C + col, drop_p, inv_keep, o);
+        dropout_apply4(seed, (uint64_t)row * C + col + 4, drop_p, inv_keep, o + 4);
       }
       if (y) store8(y + row * ldy + col, o);
       if (y32) {
@@ -88,116 +93,158 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const void* __restrict__ x_
   }
 }
 
-// Backward.  dy (bf16 or fp32) is first multiplied by the forward output-dropout mask (drop_p/seed), then
-//   dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)),   dgamma += sum dy*xhat,  dbeta += sum dy.
+// Backward, input gradient.  dy (bf16 or fp32) is first multiplied by the forward output-dropout mask (drop_p/seed), then
+//   dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)).
 // dx is written as bf16 (dx) and optionally a second copy multiplied by another dropout mask
-// (dx_drop: gradient of the dense branch whose output dropout used (drop2_p, seed2)).
+// (dx_drop: gradient of the dense branch whose output dropout used (drop2_p, seed2)).  One warp per row, no state
+// carried across rows, so the kernel runs at full occupancy; the parameter gradients are a separate column reduction
+// (ln_bwd_param_kernel) -- the previous single-kernel form held 4 x 24 floats per thread and ran at 12 % occupancy.
 template <bool XF32, bool DYF32, int NCH>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const void* __restrict__ dy_, int64_t lddy, const void* __restrict__ x_,
-                                                     int64_t ldx, const float* __restrict__ mean_in,
-                                                     const float* __restrict__ rstd_in, const float* __restrict__ gamma,
-                                                     bf16* __restrict__ dx, int64_t lddx, bf16* __restrict__ dx_drop,
-                                                     float* __restrict__ dx32, float* __restrict__ dgamma,
-                                                     float* __restrict__ dbeta, int rows, int C, float drop_p, uint64_t seed,
-                                                     float drop2_p, uint64_t seed2) {
-  __shared__ float red[8][256 + 1];
+__global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const void* __restrict__ dy_, int64_t lddy, const void* __restrict__ x_,
+                                                        int64_t ldx, const float* __restrict__ mean_in,
+                                                        const float* __restrict__ rstd_in, const float* __restrict__ gamma,
+                                                        bf16* __restrict__ dx, int64_t lddx, bf16* __restrict__ dx_drop,
+                                                        float* __restrict__ dx32, int rows, int C, float drop_p, uint64_t seed,
+                                                        float drop2_p, uint64_t seed2) {
   const int lane = threadIdx.x & 31;
-  const int wib = threadIdx.x >> 5;
-  const int nwarps_total = (gridDim.x * blockDim.x) >> 5;
+  const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
   const int nch = C >> 8;
   const int rem = C & 255;
-  float dg[NCH][8], db[NCH][8];
-#pragma unroll
-  for (int c = 0; c < NCH; c++)
-#pragma unroll
-    for (int i = 0; i < 8; i++) dg[c][i] = db[c][i] = 0.f;
   const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const float inv_keep2 = drop2_p > 0.f ? 1.f / (1.f - drop2_p) : 1.f;
-
-  for (int64_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += nwarps_total) {
-    const float mean = mean_in[row], rstd = rstd_in[row];
-    float xh[NCH][8], g[NCH][8];
-    float s1 = 0.f, s2 = 0.f;
+  const float mean = mean_in[row], rstd = rstd_in[row];
+  float xh[NCH][8], g[NCH][8];
+  float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int c = 0; c < NCH; c++) {
-      const int col = c * 256 + lane * 8;
-      const bool ok = (c < nch) || (c == nch && lane * 8 < rem);
-      if (ok) {
-        float xv[8], dyv[8];
-        if (XF32) {
-          const float* xp = reinterpret_cast<const float*>(x_) + row * ldx + col;
-          const float4 a = *reinterpret_cast<const float4*>(xp), b = *reinterpret_cast<const float4*>(xp + 4);
-          xv[0] = a.x; xv[1] = a.y; xv[2] = a.z; xv[3] = a.w; xv[4] = b.x; xv[5] = b.y; xv[6] = b.z; xv[7] = b.w;
-        } else {
-          load8(reinterpret_cast<const bf16*>(x_) + row * ldx + col, xv);
-        }
-        if (DYF32) {
-          const float* dp = reinterpret_cast<const float*>(dy_) + row * lddy + col;
-          const float4 a = *reinterpret_cast<const float4*>(dp), b = *reinterpret_cast<const float4*>(dp + 4);
-          dyv[0] = a.x; dyv[1] = a.y; dyv[2] = a.z; dyv[3] = a.w; dyv[4] = b.x; dyv[5] = b.y; dyv[6] = b.z; dyv[7] = b.w;
-        } else {
-          load8(reinterpret_cast<const bf16*>(dy_) + row * lddy + col, dyv);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-          float d = dyv[i];
-          if (drop_p > 0.f) d *= dropout_scale(seed, (uint64_t)row * C + col + i, drop_p, inv_keep);
-          const float h = (xv[i] - mean) * rstd;
-          xh[c][i] = h;
-          dg[c][i] += d * h;
-          db[c][i] += d;
-          const float gd = d * gamma[col + i];
-          g[c][i] = gd;
-          s1 += gd;
-          s2 += gd * h;
-        }
+  for (int c = 0; c < NCH; c++) {
+    const int col = c * 256 + lane * 8;
+    const bool ok = (c < nch) || (c == nch && lane * 8 < rem);
+    if (ok) {
+      float xv[8], dyv[8], gm[8];
+      if (XF32) {
+        const float* xp = reinterpret_cast<const float*>(x_) + row * ldx + col;
+        *reinterpret_cast<float4*>(xv) = *reinterpret_cast<const float4*>(xp);
+        *reinterpret_cast<float4*>(xv + 4) = *reinterpret_cast<const float4*>(xp + 4);
       } else {
-#pragma unroll
-        for (int i = 0; i < 8; i++) xh[c][i] = g[c][i] = 0.f;
+        load8(reinterpret_cast<const bf16*>(x_) + row * ldx + col, xv);
       }
+      if (DYF32) {
+        const float* dp = reinterpret_cast<const float*>(dy_) + row * lddy + col;
+        *reinterpret_cast<float4*>(dyv) = *reinterpret_cast<const float4*>(dp);
+        *reinterpret_cast<float4*>(dyv + 4) = *reinterpret_cast<const float4*>(dp + 4);
+      } else {
+        load8(reinterpret_cast<const bf16*>(dy_) + row * lddy + col, dyv);
+      }
+      *reinterpret_cast<float4*>(gm) = *reinterpret_cast<const float4*>(gamma + col);
+      *reinterpret_cast<float4*>(gm + 4) = *reinterpret_cast<const float4*>(gamma + col + 4);
+      if (drop_p > 0.f) {
+        dropout_apply4(seed, (uint64_t)row * C + col, drop_p, inv_keep, dyv);
+        dropout_apply4(seed, (uint64_t)row * C + col + 4, drop_p, inv_keep, dyv + 4);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const float h = (xv[i] - mean) * rstd;
+        xh[c][i] = h;
+        const float gd = dyv[i] * gm[i];
+        g[c][i] = gd;
+        s1 += gd;
+        s2 = fmaf(gd, h, s2);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; i++) xh[c][i] = g[c][i] = 0.f;
     }
-    s1 = warp_sum(s1) / (float)C;
-    s2 = warp_sum(s2) / (float)C;
+  }
+  s1 = warp_sum(s1) / (float)C;
+  s2 = warp_sum(s2) / (float)C;
 #pragma unroll
-    for (int c = 0; c < NCH; c++) {
-      const int col = c * 256 + lane * 8;
-      const bool ok = (c < nch) || (c == nch && lane * 8 < rem);
-      if (ok) {
-        float o[8];
+  for (int c = 0; c < NCH; c++) {
+    const int col = c * 256 + lane * 8;
+    const bool ok = (c < nch) || (c == nch && lane * 8 < rem);
+    if (ok) {
+      float o[8];
 #pragma unroll
-        for (int i = 0; i < 8; i++) o[i] = rstd * (g[c][i] - s1 - xh[c][i] * s2);
-        if (dx) store8(dx + row * lddx + col, o);
-        if (dx32) {
-          float* p = dx32 + row * (int64_t)C + col;
-          *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
-          *reinterpret_cast<float4*>(p + 4) = make_float4(o[4], o[5], o[6], o[7]);
-        }
-        if (dx_drop) {
-#pragma unroll
-          for (int i = 0; i < 8; i++) o[i] *= dropout_scale(seed2, (uint64_t)row * C + col + i, drop2_p, inv_keep2);
-          store8(dx_drop + row * lddx + col, o);
-        }
+      for (int i = 0; i < 8; i++) o[i] = rstd * (g[c][i] - s1 - xh[c][i] * s2);
+      if (dx) store8(dx + row * lddx + col, o);
+      if (dx32) {
+        float* p = dx32 + row * (int64_t)C + col;
+        *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(p + 4) = make_float4(o[4], o[5], o[6], o[7]);
+      }
+      if (dx_drop) {
+        dropout_apply4(seed2, (uint64_t)row * C + col, drop2_p, inv_keep2, o);
+        dropout_apply4(seed2, (uint64_t)row * C + col + 4, drop2_p, inv_keep2, o + 4);
+        store8(dx_drop + row * lddx + col, o);
       }
     }
   }
-  // cross-warp reduction of the parameter gradients, one 256-column chunk at a time
-  if (dgamma == nullptr && dbeta == nullptr) return;
-  const int nw = blockDim.x >> 5;
-  for (int pass = 0; pass < 2; pass++) {
-    for (int c = 0; c < NCH; c++) {
-      if (c * 256 >= C) break;
-      __syncthreads();
+}
+
+// Backward, parameter gradients: dgamma[c] += sum_r dy'[r,c] * xhat[r,c], dbeta[c] += sum_r dy'[r,c] (dy' = dy times the
+// forward output-dropout mask).  Column reduction with the bn_bwd_reduce thread layout: block = 32 channel vectors(8) x 8
+// row lanes over a 256-column slab, grid = (slabs, row blocks), fp32 atomics at the end.
+template <bool XF32, bool DYF32>
+__global__ void __launch_bounds__(256) ln_bwd_param_kernel(const void* __restrict__ dy_, int64_t lddy, const void* __restrict__ x_,
+                                                           int64_t ldx, const float* __restrict__ mean_in,
+                                                           const float* __restrict__ rstd_in, float* __restrict__ dgamma,
+                                                           float* __restrict__ dbeta, int rows, int C, int rows_per_block,
+                                                           float drop_p, uint64_t seed) {
+  __shared__ float sh[2][8][256 + 8];
+  const int cv = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 256 + cv * 8;
+  const bool ok = c0 < C;
+  const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  float a[8], b[8];
 #pragma unroll
-      for (int i = 0; i < 8; i++) red[wib][lane * 8 + i] = pass == 0 ? dg[c][i] : db[c][i];
-      __syncthreads();
-      const int col = c * 256 + threadIdx.x;
-      if (threadIdx.x < 256 && col < C) {
-        float s = 0.f;
-        for (int w = 0; w < nw; w++) s += red[w][threadIdx.x];
-        float* dst = pass == 0 ? dgamma : dbeta;
-        if (dst) atomicAdd(dst + col, s);
+  for (int k = 0; k < 8; k++) a[k] = b[k] = 0.f;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  if (ok) {
+    for (int r = r0 + rl; r < r1; r += 8) {
+      float xv[8], dyv[8];
+      if (XF32) {
+        const float* xp = reinterpret_cast<const float*>(x_) + (int64_t)r * ldx + c0;
+        *reinterpret_cast<float4*>(xv) = *reinterpret_cast<const float4*>(xp);
+        *reinterpret_cast<float4*>(xv + 4) = *reinterpret_cast<const float4*>(xp + 4);
+      } else {
+        load8(reinterpret_cast<const bf16*>(x_) + (int64_t)r * ldx + c0, xv);
+      }
+      if (DYF32) {
+        const float* dp = reinterpret_cast<const float*>(dy_) + (int64_t)r * lddy + c0;
+        *reinterpret_cast<float4*>(dyv) = *reinterpret_cast<const float4*>(dp);
+        *reinterpret_cast<float4*>(dyv + 4) = *reinterpret_cast<const float4*>(dp + 4);
+      } else {
+        load8(reinterpret_cast<const bf16*>(dy_) + (int64_t)r * lddy + c0, dyv);
+      }
+      if (drop_p > 0.f) {
+        dropout_apply4(seed, (uint64_t)r * C + c0, drop_p, inv_keep, dyv);
+        dropout_apply4(seed, (uint64_t)r * C + c0 + 4, drop_p, inv_keep, dyv + 4);
+      }
+      const float mu = mean_in[r], rs = rstd_in[r];
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        a[k] = fmaf(dyv[k], (xv[k] - mu) * rs, a[k]);
+        b[k] += dyv[k];
       }
     }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    sh[0][rl][cv * 8 + k] = a[k];
+    sh[1][rl][cv * 8 + k] = b[k];
+  }
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < C) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+      s0 += sh[0][w][threadIdx.x];
+      s1 += sh[1][w][threadIdx.x];
+    }
+    if (dgamma) atomicAdd(dgamma + c, s0);
+    if (dbeta) atomicAdd(dbeta + c, s1);
   }
 }
 
@@ -235,23 +282,55 @@ __global__ void bn_finalize_kernel(const double* __restrict__ colsum, const doub
   shift[c] = beta[c] - mu * sc;
 }
 
-// y = act(x * scale[c] + shift[c] (+ residual)); 8 channels per thread, grid-stride over rows*C/8.
+// y = act(x * scale[c] + shift[c] (+ residual)); 8 channels per thread, grid-stride over rows*C/8.  The host sizes the
+// grid so that the stride is a multiple of C/8: a thread then stays on ONE channel vector and its scale / shift live in
+// registers (per-iteration parameter loads made this kernel L1-bound: ncu l1tex 89 % at 65 % of HBM peak).
 __global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ scale,
                                                        const float* __restrict__ shift, const bf16* __restrict__ residual,
                                                        bf16* __restrict__ y, int64_t total_vec, int C, int relu) {
   const int cvec = C >> 3;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % cvec) * 8;
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int c0 = (int)(i0 % cvec) * 8;
+  float sc[8], sh[8];
+  *reinterpret_cast<float4*>(sc) = *reinterpret_cast<const float4*>(scale + c0);
+  *reinterpret_cast<float4*>(sc + 4) = *reinterpret_cast<const float4*>(scale + c0 + 4);
+  *reinterpret_cast<float4*>(sh) = *reinterpret_cast<const float4*>(shift + c0);
+  *reinterpret_cast<float4*>(sh + 4) = *reinterpret_cast<const float4*>(shift + c0 + 4);
+  int64_t i = i0;
+  for (; i + stride < total_vec; i += 2 * stride) {   // two independent 16-byte streams in flight per thread
+    float v0[8], v1[8], r0[8], r1[8];
+    load8(x + i * 8, v0);
+    load8(x + (i + stride) * 8, v1);
+    if (residual) {
+      load8(residual + i * 8, r0);
+      load8(residual + (i + stride) * 8, r1);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      float o0 = fmaf(v0[k], sc[k], sh[k]);   // the backward recomputes the ReLU mask from exactly this expression
+      float o1 = fmaf(v1[k], sc[k], sh[k]);
+      if (residual) {
+        o0 += r0[k];
+        o1 += r1[k];
+      }
+      if (relu) {
+        o0 = fmaxf(o0, 0.f);
+        o1 = fmaxf(o1, 0.f);
+      }
+      v0[k] = o0;
+      v1[k] = o1;
+    }
+    store8(y + i * 8, v0);
+    store8(y + (i + stride) * 8, v1);
+  }
+  if (i < total_vec) {
     float v[8], r[8];
     load8(x + i * 8, v);
-    const float4 s0 = *reinterpret_cast<const float4*>(scale + c0), s1 = *reinterpret_cast<const float4*>(scale + c0 + 4);
-    const float4 h0 = *reinterpret_cast<const float4*>(shift + c0), h1 = *reinterpret_cast<const float4*>(shift + c0 + 4);
-    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
     if (residual) load8(residual + i * 8, r);
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      float o = fmaf(v[k], sc[k], sh[k]);   // the backward recomputes the ReLU mask from exactly this expression
+      float o = fmaf(v[k], sc[k], sh[k]);
       if (residual) o += r[k];
       if (relu) o = fmaxf(o, 0.f);
       v[k] = o;
@@ -266,7 +345,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ 
 // Block = 256 threads = 32 channel-vectors(8) x 8 row lanes over a `Cw`-wide view of the matrix: Cw = C, or 256 when
 // C in {64, 128} (the contiguous [rows, C] matrix re-read as [rows*C/256, 256]; column j holds channel j % C), so
 // narrow layers keep all 32 vector lanes busy.  grid = (Cw/256 ceil, row blocks).
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+__global__ void __launch_bounds__(256, 3) bn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                             const bf16* __restrict__ y, const float* __restrict__ mean,
                                                             const float* __restrict__ invstd, const float* __restrict__ scale,
                                                             const float* __restrict__ shift, double* __restrict__ sum_dy,
@@ -376,8 +455,9 @@ __global__ void bn_bwd_coeff_kernel(const float* __restrict__ mean, const float*
 }
 
 // dx = ca[c] * dy' + cb[c] * x + cc[c]; optionally also writes dy' (the ReLU-masked incoming gradient) for the
-// identity branch.  Pure streaming: 8 channels per thread, coefficient vectors read as float4.  coef rows 3 and 4 hold
-// the forward scale / shift when the ReLU mask is recomputed from x (y == nullptr).
+// identity branch.  Pure streaming, 8 channels per thread; the grid stride is a multiple of C/8 (see bn_apply), so the
+// five coefficient vectors of a thread's channel group are loaded once.  coef rows 3 and 4 hold the forward scale /
+// shift when the ReLU mask is recomputed from x (y == nullptr).
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                            const bf16* __restrict__ y, const float* __restrict__ coef,
                                                            bf16* __restrict__ dx, bf16* __restrict__ dz, int64_t rows, int C,
@@ -385,24 +465,28 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restric
   const int cvec = C >> 3;
   const int64_t total_vec = rows * cvec;
   const bool remask = relu && (y == nullptr);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % cvec) * 8;
-    float d[8], xv[8], yv[8], o[8], ca[8], cb[8], cc[8];
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int c0 = (int)(i0 % cvec) * 8;
+  float ca[8], cb[8], cc[8], sc[8], sf[8];
+  *reinterpret_cast<float4*>(ca) = *reinterpret_cast<const float4*>(coef + c0);
+  *reinterpret_cast<float4*>(ca + 4) = *reinterpret_cast<const float4*>(coef + c0 + 4);
+  *reinterpret_cast<float4*>(cb) = *reinterpret_cast<const float4*>(coef + C + c0);
+  *reinterpret_cast<float4*>(cb + 4) = *reinterpret_cast<const float4*>(coef + C + c0 + 4);
+  *reinterpret_cast<float4*>(cc) = *reinterpret_cast<const float4*>(coef + 2 * C + c0);
+  *reinterpret_cast<float4*>(cc + 4) = *reinterpret_cast<const float4*>(coef + 2 * C + c0 + 4);
+  if (remask) {
+    *reinterpret_cast<float4*>(sc) = *reinterpret_cast<const float4*>(coef + 3 * C + c0);
+    *reinterpret_cast<float4*>(sc + 4) = *reinterpret_cast<const float4*>(coef + 3 * C + c0 + 4);
+    *reinterpret_cast<float4*>(sf) = *reinterpret_cast<const float4*>(coef + 4 * C + c0);
+    *reinterpret_cast<float4*>(sf + 4) = *reinterpret_cast<const float4*>(coef + 4 * C + c0 + 4);
+  }
+  for (int64_t i = i0; i < total_vec; i += stride) {
+    float d[8], xv[8], yv[8], o[8];
     load8(dy + i * 8, d);
     load8(x + i * 8, xv);
     if (relu && !remask) load8(y + i * 8, yv);
-    *reinterpret_cast<float4*>(ca) = *reinterpret_cast<const float4*>(coef + c0);
-    *reinterpret_cast<float4*>(ca + 4) = *reinterpret_cast<const float4*>(coef + c0 + 4);
-    *reinterpret_cast<float4*>(cb) = *reinterpret_cast<const float4*>(coef + C + c0);
-    *reinterpret_cast<float4*>(cb + 4) = *reinterpret_cast<const float4*>(coef + C + c0 + 4);
-    *reinterpret_cast<float4*>(cc) = *reinterpret_cast<const float4*>(coef + 2 * C + c0);
-    *reinterpret_cast<float4*>(cc + 4) = *reinterpret_cast<const float4*>(coef + 2 * C + c0 + 4);
     if (remask) {
-      float sc[8], sf[8];
-      *reinterpret_cast<float4*>(sc) = *reinterpret_cast<const float4*>(coef + 3 * C + c0);
-      *reinterpret_cast<float4*>(sc + 4) = *reinterpret_cast<const float4*>(coef + 3 * C + c0 + 4);
-      *reinterpret_cast<float4*>(sf) = *reinterpret_cast<const float4*>(coef + 4 * C + c0);
-      *reinterpret_cast<float4*>(sf + 4) = *reinterpret_cast<const float4*>(coef + 4 * C + c0 + 4);
 #pragma unroll
       for (int k = 0; k < 8; k++) yv[k] = fmaf(xv[k], sc[k], sf[k]);
     }
@@ -500,6 +584,24 @@ static inline bool fold_view(int64_t rows, int C, int64_t ld, int64_t* rows_w, i
   return false;
 }
 
+// Grid for the channel-vector streaming kernels: (grid * 256) % (C / 8) == 0, close to 16 blocks per SM.
+int grid_for_channels(int64_t total_vec, int C) {
+  const int cvec = C >> 3;
+  int a = cvec, b = 256;
+  while (b) {
+    const int t = a % b;
+    a = b;
+    b = t;
+  }
+  const int unit = cvec / a;                     // grid must be a multiple of cvec / gcd(cvec, 256)
+  int64_t g = (total_vec + 255) / 256;
+  const int64_t cap = 148 * 16;
+  if (g > cap) g = cap;
+  g = (g / unit) * unit;
+  if (g < unit) g = unit;
+  return (int)g;
+}
+
 int grid_for(int64_t work_items, int block) {
   int64_t g = (work_items + block - 1) / block;
   const int64_t cap = 148 * 16;
@@ -536,13 +638,12 @@ extern "C" int mdhs_layernorm_bwd(const void* dy, int dy_f32, int64_t lddy, cons
                                   float drop_p, uint64_t seed, float drop2_p, uint64_t seed2, void* stream) {
   if (!dy || !x || !mean || !rstd || !gamma || rows <= 0 || (C % 8) || C > LN_MAXCH * 256) return MDHS_ERR_ARG;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  int blocks = ceil_div(rows, 8 * 4);
-  if (blocks > 148 * 4) blocks = 148 * 4;
-  g_mdhs_launches++;
+  const int blocks = ceil_div(rows, 8);
+  const bool params = (dgamma != nullptr) || (dbeta != nullptr);
+  g_mdhs_launches += params ? 2 : 1;
 #define LNB1(XF, DF, N)                                                                                                       \
-  ln_bwd_kernel<XF, DF, N><<<blocks, 256, 0, st>>>(dy, lddy, x, ldx, mean, rstd, gamma, (bf16*)dx_bf16, lddx,                  \
-                                                   (bf16*)dx_drop_bf16, dx_f32, dgamma, dbeta, rows, C, drop_p, seed, drop2_p, \
-                                                   seed2)
+  ln_bwd_dx_kernel<XF, DF, N><<<blocks, 256, 0, st>>>(dy, lddy, x, ldx, mean, rstd, gamma, (bf16*)dx_bf16, lddx,               \
+                                                      (bf16*)dx_drop_bf16, dx_f32, rows, C, drop_p, seed, drop2_p, seed2)
 #define LNB(XF, DF)                     \
   do {                                  \
     if (C <= 256) LNB1(XF, DF, 1);      \
@@ -558,6 +659,22 @@ extern "C" int mdhs_layernorm_bwd(const void* dy, int dy_f32, int64_t lddy, cons
   }
 #undef LNB
 #undef LNB1
+  if (params) {
+    const int cslabs = ceil_div(C, 256);
+    int row_blocks = (148 * 4) / cslabs;
+    if (row_blocks < 1) row_blocks = 1;
+    int rpb = ceil_div(rows, row_blocks);
+    rpb = ((rpb + 7) / 8) * 8;
+    row_blocks = ceil_div(rows, rpb);
+    const dim3 grid(cslabs, row_blocks);
+#define LNP(XF, DF) ln_bwd_param_kernel<XF, DF><<<grid, 256, 0, st>>>(dy, lddy, x, ldx, mean, rstd, dgamma, dbeta, rows, C, rpb, drop_p, seed)
+    if (x_f32) {
+      if (dy_f32) LNP(true, true); else LNP(true, false);
+    } else {
+      if (dy_f32) LNP(false, true); else LNP(false, false);
+    }
+#undef LNP
+  }
   MDHS_RETURN_LAST();
 }
 
@@ -578,7 +695,7 @@ extern "C" int mdhs_bn_apply(const void* x, const float* scale, const float* shi
   if (!x || !scale || !shift || !y || rows <= 0 || (C % 8)) return MDHS_ERR_ARG;
   const int64_t total_vec = rows * (C / 8);
   g_mdhs_launches++;
-  bn_apply_kernel<<<grid_for(total_vec, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  bn_apply_kernel<<<grid_for_channels(total_vec, C), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       (const bf16*)x, scale, shift, (const bf16*)residual, (bf16*)y, total_vec, C, relu);
   MDHS_RETURN_LAST();
 }
@@ -610,7 +727,7 @@ extern "C" int mdhs_bn_bwd(const void* dy, const void* x, const void* y, const f
   bn_bwd_coeff_kernel<<<ceil_div(C, 128), 128, 0, st>>>(mean, invstd, gamma, sum_dy, sum_dy_xhat, remask ? scale : nullptr,
                                                         remask ? shift : nullptr, coef, dgamma, dbeta, rows, C);
   const int64_t total_vec = rows * (C / 8);
-  bn_bwd_apply_kernel<<<grid_for(total_vec, 256), 256, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, coef, (bf16*)dx,
+  bn_bwd_apply_kernel<<<grid_for_channels(total_vec, C), 256, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, coef, (bf16*)dx,
                                                                 (bf16*)dz, rows, C, relu);
   MDHS_RETURN_LAST();
 }
