@@ -217,6 +217,27 @@ int mdhs_moe_combine_fwd(const float* gates, const float* Y, float* y, int B, in
 int mdhs_moe_combine_bwd(const float* gates, const float* Y, const float* dy, float* dgates, float* dY, int B, int E, int C,
                          int ldy, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * ConvNeXt (torchvision CNBlock behind ConNexT/models/ourmodel.py:57-62 and ConNexT/models/image_encoder.py): depthwise
+ * 7x7 convolution (pad 3) on NHWC bf16 -- forward (flip = 0, + bias) / input gradient (flip = 1: mirrored taps on dy)
+ * and weight + bias gradient (dw [C][49], db [C]: fp32 +=); layer-scale + row-mode stochastic depth + residual
+ * out = x + ls[c] * keep(sample) * z with keep in {0, 1/(1-p)} drawn per sample, and its backward (dz, dls +=).
+ * Single-query attention of the text -> image CrossAttention (ourmodel.py:17-31, a 1-token query over T image
+ * positions; the reference applies no 1/sqrt(d)): probs = softmax_t(scale * q.k_t), out = sum_t probs_t v_t.
+ */
+int mdhs_dwconv7_fwd(const void* x, const float* w, const float* bias, void* y, int B, int H, int W, int C, int flip,
+                     void* stream);
+int mdhs_dwconv7_wgrad(const void* x, const void* dy, float* dw, float* db, int B, int H, int W, int C, void* stream);
+int mdhs_layer_scale_fwd(const void* x, const void* z, const float* ls, void* out, int64_t rows, int C, int rows_per_sample,
+                         float p, uint64_t seed, void* stream);
+int mdhs_layer_scale_bwd(const void* dy, const void* z, const float* ls, void* dz, float* dls, int64_t rows, int C,
+                         int rows_per_sample, float p, uint64_t seed, void* stream);
+int mdhs_sq_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, float* out,
+                     float* probs, int B, int T, int D, float scale, void* stream);
+int mdhs_sq_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const float* dout,
+                     const float* probs, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int B, int T,
+                     int D, float scale, void* stream);
+
 /* Fused optimizer step on the flat parameter buffer (scripts/train.py:257-309) */
 int mdhs_adam_flat(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, int64_t n,
                    float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,

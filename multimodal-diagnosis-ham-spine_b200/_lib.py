@@ -85,6 +85,12 @@ SIGNATURES = {
     "mdhs_randn_f32": "plup",
     "mdhs_moe_combine_fwd": "pppiiii" "p",
     "mdhs_moe_combine_bwd": "pppppiiii" "p",
+    "mdhs_dwconv7_fwd": "ppppiiiiip",
+    "mdhs_dwconv7_wgrad": "ppppiiiip",
+    "mdhs_layer_scale_fwd": "pppplii" "fup",
+    "mdhs_layer_scale_bwd": "ppppplii" "fup",
+    "mdhs_sq_attn_fwd": "plplplpp" "iiifp",
+    "mdhs_sq_attn_bwd": "plplplpp" "plplpl" "iiifp",
     "mdhs_adam_flat": "ppppplfffffifiippp",
     "mdhs_sgd_flat": "pppplffffiippp",
     "mdhs_step_begin": "pp",

@@ -1,0 +1,189 @@
+"""ConvNeXt feature extractor (torchvision `ConvNeXt.features`: tiny / small / base / large) on the B200 kernels.
+
+Reference call sites: ConNexT/models/ourmodel.py:57-62,76 (`models.convnext_base(...).features`),
+ConNexT/models/pl_model_MOE2.py:36-53 (`ConvNeXtEncoder`: features -> flatten(2)).  The torchvision Sequential is only
+the parameter container (state_dict keys `0.0.weight` ... `7.N.block.5.bias`, `N.M.layer_scale`); the arithmetic is
+
+  stem / down-sampling : non-overlapping k x k stride-k convolution = patch gather + tcgen05 GEMM (+ bias), LayerNorm
+  CNBlock              : depthwise 7x7 (csrc/convnext.cu) -> LayerNorm(1e-6) -> GEMM + bias + GELU -> GEMM + bias
+                         -> x + layer_scale * stochastic_depth(row) * z  (one fused kernel)
+
+on NHWC bf16 token matrices [B*H*W, C].  Backward runs through torch.autograd Functions whose bodies are our kernels;
+parameter gradients are written straight into the ParamStore's flat fp32 gradient buffer.
+"""
+import torch
+
+from .. import functional as Fm
+from .. import ops
+
+
+class _PatchConv:
+    """Conv2d(k x k, stride k, pad 0, bias) lowered to patch-gather + GEMM.  Keeps the packed bf16 weight [O, (r,s,c)]."""
+
+    def __init__(self, store, conv, stem):
+        self.store, self.conv, self.stem = store, conv, stem
+        self.O, self.I, self.R, self.S = conv.weight.shape
+        assert conv.stride[0] == self.R and conv.padding[0] == 0 and conv.groups == 1
+        self.K = self.R * self.S * self.I
+        self.ldk = (self.K + 7) // 8 * 8
+        dev = store.device
+        self.wp = torch.zeros((self.O, self.ldk), device=dev, dtype=torch.bfloat16)
+        self.gp = torch.zeros((self.O, self.ldk), device=dev, dtype=torch.float32)
+        store.add_packer(self.repack)
+
+    def repack(self):
+        ops.conv_weight_pack(self.conv.weight.data, ldk=self.ldk, out=self.wp)
+
+
+class _PatchConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, anchor, rec, B, H, W):
+        if rec.stem:   # x: NCHW fp32 image
+            col, Ho, Wo = ops.im2col_nchw_f32(x.contiguous(), rec.R, rec.S, rec.R, 0, rec.ldk)
+        else:          # x: NHWC bf16 [B*H*W, I]
+            col, Ho, Wo = ops.im2col_nhwc(x.contiguous(), B, H, W, rec.I, rec.R, rec.S, rec.R, 0)
+        bias = rec.conv.bias.data if rec.conv.bias is not None else None
+        y = ops.gemm(col, rec.wp, bias=bias, N=rec.O)
+        ctx.rec, ctx.geom = rec, (B, H, W)
+        ctx.save_for_backward(col)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (col,) = ctx.saved_tensors
+        rec = ctx.rec
+        B, H, W = ctx.geom
+        st = rec.store
+        dy = dy.contiguous()
+        rows = dy.shape[0]
+        if rec.conv.weight.requires_grad:
+            rec.gp.zero_()
+            ops.gemm(dy, col, a_mn=True, b_mn=True, out=rec.gp, accumulate=True, split_k=-1, M=rec.O, N=rec.ldk, K=rows)
+            ops.conv_wgrad_unpack(rec.gp, st.g32(rec.conv.weight))
+            if rec.conv.bias is not None:
+                ops.col_stats(dy, sum32=st.g32(rec.conv.bias))
+        dx = None
+        if not rec.stem and ctx.needs_input_grad[0]:
+            dcol = ops.gemm(dy, rec.wp[:, :rec.K], b_mn=True, M=rows, N=rec.K, K=rec.O)
+            dx = ops.col2im_nhwc(dcol, B, H, W, rec.I, rec.R, rec.S, rec.R, 0)
+        return dx, None, None, None, None, None
+
+
+class _DwConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, bias, gw, gb, B, H, W):
+        x = x.contiguous()
+        y = ops.dwconv7(x, w, bias, B, H, W)
+        ctx.w, ctx.gw, ctx.gb, ctx.geom = w, gw, gb, (B, H, W)
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        B, H, W = ctx.geom
+        dy = dy.contiguous()
+        if ctx.gw is not None:
+            ops.dwconv7_wgrad(x, dy, ctx.gw, ctx.gb, B, H, W)
+        dx = ops.dwconv7(dy, ctx.w, None, B, H, W, flip=True) if ctx.needs_input_grad[0] else None
+        return dx, None, None, None, None, None, None, None
+
+
+class _LayerScaleFn(torch.autograd.Function):
+    """out = x + ls * keep(sample) * z  (CNBlock tail: layer_scale, StochasticDepth("row"), residual)."""
+
+    @staticmethod
+    def forward(ctx, x, z, ls, gls, rows_per_sample, p, seed):
+        x, z = x.contiguous(), z.contiguous()
+        out = ops.layer_scale_fwd(x, z, ls, rows_per_sample, p, seed)
+        ctx.ls, ctx.gls, ctx.cfg = ls, gls, (rows_per_sample, p, seed)
+        ctx.save_for_backward(z)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        (z,) = ctx.saved_tensors
+        rps, p, seed = ctx.cfg
+        dy = dy.contiguous()
+        dz = ops.layer_scale_bwd(dy, z, ctx.ls, ctx.gls, rps, p, seed)
+        return dy, dz, None, None, None, None, None
+
+
+class SqAttnFn(torch.autograd.Function):
+    """Single-query attention: q [B, D] bf16, k / v [B*T, D] bf16 -> out [B, D] fp32 (softmax over the T positions)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, B, T, scale):
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        out, probs = ops.sq_attn_fwd(q, k, v, B, T, scale)
+        ctx.cfg = (B, T, scale)
+        ctx.save_for_backward(q, k, v, probs)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, probs = ctx.saved_tensors
+        B, T, scale = ctx.cfg
+        dq, dk, dv = ops.sq_attn_bwd(q, k, v, dout.contiguous().float(), probs, B, T, scale)
+        return dq, dk, dv, None, None, None
+
+
+class ConvNeXtEngine:
+    """Runs `features` (a torchvision ConvNeXt feature Sequential) whose parameters live in `store`."""
+
+    def __init__(self, store, features):
+        self.store, self.features = store, features
+        self.step_seed = 0x5D000000
+        self.stages = []   # ("stem" | "down" | "blocks", payload)
+        for i, stage in enumerate(features):
+            first = stage[0]
+            if i == 0:
+                self.stages.append(("stem", (_PatchConv(store, stage[0], stem=True), stage[1])))
+            elif isinstance(first, torch.nn.Conv2d) or type(first).__name__ == "LayerNorm2d":
+                self.stages.append(("down", (stage[0], _PatchConv(store, stage[1], stem=False))))
+            else:
+                self.stages.append(("blocks", list(stage)))
+
+    @property
+    def out_channels(self):
+        kind, payload = self.stages[-1]
+        return payload[-1].block[0].weight.shape[0] if kind == "blocks" else payload[1].O
+
+    def _block(self, blk, x, B, H, W, training, seed):
+        st = self.store
+        dw, ln, fc1, fc2 = blk.block[0], blk.block[2], blk.block[3], blk.block[5]
+        tr = dw.weight.requires_grad
+        y = _DwConvFn.apply(x, dw.weight.data, dw.bias.data if dw.bias is not None else None,
+                            st.g32(dw.weight) if tr else None, st.g32(dw.bias) if (tr and dw.bias is not None) else None,
+                            B, H, W)
+        y = Fm.layernorm(y, st, ln)
+        y = Fm.linear(y, st, fc1.weight, fc1.bias, act=ops.ACT_GELU)
+        z = Fm.linear(y, st, fc2.weight, fc2.bias)
+        ls = blk.layer_scale
+        p = float(blk.stochastic_depth.p) if training else 0.0
+        return _LayerScaleFn.apply(x, z, ls.data.view(-1), st.g32(ls).view(-1) if ls.requires_grad else None, H * W, p, seed)
+
+    def forward(self, images, training):
+        """images: [B,3,H,W] fp32 CUDA -> (tokens [B*h*w, C] bf16, h, w)."""
+        st = self.store
+        B, _, H, W = images.shape
+        if training:
+            self.step_seed += 1000
+        x = None
+        n = 0
+        for kind, payload in self.stages:
+            if kind == "stem":
+                conv, ln = payload
+                x = _PatchConvFn.apply(images, st.anchor, conv, B, H, W)
+                H, W = H // conv.R, W // conv.S
+                x = Fm.layernorm(x, st, ln)
+            elif kind == "down":
+                ln, conv = payload
+                x = Fm.layernorm(x, st, ln)
+                x = _PatchConvFn.apply(x, st.anchor, conv, B, H, W)
+                H, W = H // conv.R, W // conv.S
+            else:
+                for blk in payload:
+                    n += 1
+                    x = self._block(blk, x, B, H, W, training, self.step_seed + n)
+        return x, H, W

@@ -11,6 +11,7 @@ void mdhs_seed_tick_norm(uint64_t, cudaStream_t);
 void mdhs_seed_tick_attention(uint64_t, cudaStream_t);
 void mdhs_seed_tick_elementwise(uint64_t, cudaStream_t);
 void mdhs_seed_tick_kan_moe(uint64_t, cudaStream_t);
+void mdhs_seed_tick_convnext(uint64_t, cudaStream_t);
 
 namespace {
 
@@ -142,5 +143,6 @@ extern "C" int mdhs_step_begin(int* step_dev, void* stream) {
   mdhs_seed_tick_attention(1, st);
   mdhs_seed_tick_elementwise(1, st);
   mdhs_seed_tick_kan_moe(1, st);
+  mdhs_seed_tick_convnext(1, st);
   MDHS_RETURN_LAST();
 }

@@ -193,6 +193,25 @@ def mul_f32(a, b):
     return MulF32Fn.apply(a, b)
 
 
+class AddF32Fn(torch.autograd.Function):
+    """Sum of two fp32 tensors of the same shape (pooled feature sums); the gradient passes to both."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        out = torch.empty_like(a)
+        ops.axpby(a.contiguous(), out, a=1.0, b=0.0)
+        ops.axpby(b.contiguous(), out, a=1.0, b=1.0)
+        return out
+
+    @staticmethod
+    def backward(ctx, dc):
+        return dc, dc
+
+
+def add_f32(a, b):
+    return AddF32Fn.apply(a, b)
+
+
 class MeanTokensFn(torch.autograd.Function):
     """[B*T, C] bf16 -> [B, C] fp32 mean over the T tokens of each sample (times `mult`)."""
 

@@ -490,3 +490,54 @@ def moe_combine_bwd(gates, Y, dy):
     dY = torch.empty_like(Y)
     _lib.call("mdhs_moe_combine_bwd", _p(gates), _p(Y), _p(dy), _p(dgates), _p(dY), B, E, C, ldy, _s())
     return dgates, dY
+
+
+# --------------------------------------------------------------------------------------------
+# ConvNeXt pieces (csrc/convnext.cu)
+# --------------------------------------------------------------------------------------------
+def dwconv7(x, w, bias, B, H, W, flip=False):
+    """Depthwise 7x7 (pad 3) on NHWC bf16 [B*H*W, C]; w is the Conv2d weight [C,1,7,7] fp32.  flip=True: input gradient."""
+    C = x.shape[1]
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.shape[0] == B * H * W and w.is_contiguous()
+    y = torch.empty_like(x)
+    _lib.call("mdhs_dwconv7_fwd", _p(x), _p(w), _p(bias), _p(y), B, H, W, C, int(flip), _s())
+    return y
+
+
+def dwconv7_wgrad(x, dy, dw, db, B, H, W):
+    C = x.shape[1]
+    assert x.is_contiguous() and dy.is_contiguous() and dw.is_contiguous()
+    _lib.call("mdhs_dwconv7_wgrad", _p(x), _p(dy), _p(dw), _p(db), B, H, W, C, _s())
+
+
+def layer_scale_fwd(x, z, ls, rows_per_sample, p=0.0, seed=0):
+    rows, C = x.shape
+    out = torch.empty_like(x)
+    _lib.call("mdhs_layer_scale_fwd", _p(x), _p(z), _p(ls), _p(out), rows, C, int(rows_per_sample), float(p), int(seed), _s())
+    return out
+
+
+def layer_scale_bwd(dy, z, ls, dls, rows_per_sample, p=0.0, seed=0):
+    rows, C = dy.shape
+    dz = torch.empty_like(dy)
+    _lib.call("mdhs_layer_scale_bwd", _p(dy), _p(z), _p(ls), _p(dz), _p(dls), rows, C, int(rows_per_sample), float(p), int(seed), _s())
+    return dz
+
+
+def sq_attn_fwd(q, k, v, B, T, scale=1.0):
+    D = q.shape[1]
+    out = torch.empty((B, D), device=q.device, dtype=torch.float32)
+    probs = torch.empty((B, T), device=q.device, dtype=torch.float32)
+    _lib.call("mdhs_sq_attn_fwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), _p(probs), B, T, D,
+              float(scale), _s())
+    return out, probs
+
+
+def sq_attn_bwd(q, k, v, dout, probs, B, T, scale=1.0):
+    D = q.shape[1]
+    dq = torch.empty((B, D), device=q.device, dtype=torch.bfloat16)
+    dk = torch.empty((B * T, D), device=q.device, dtype=torch.bfloat16)
+    dv = torch.empty((B * T, D), device=q.device, dtype=torch.bfloat16)
+    _lib.call("mdhs_sq_attn_bwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(dout), _p(probs), _p(dq),
+              dq.stride(0), _p(dk), dk.stride(0), _p(dv), dv.stride(0), B, T, D, float(scale), _s())
+    return dq, dk, dv

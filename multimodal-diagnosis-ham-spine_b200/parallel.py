@@ -21,6 +21,9 @@ def split_offset(store, tail_module):
 
 
 class GradSync:
+    """Buckets are arbitrary [lo, hi) slices of the flat gradient buffer, reduced asynchronously as soon as the caller
+    declares them final (`reduce_range`); `finish()` reduces whatever is left and waits for everything."""
+
     def __init__(self, flat_grad, split, group=None):
         self.grad = flat_grad
         self.total = flat_grad.numel()
@@ -28,24 +31,43 @@ class GradSync:
         self.group = group
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         self._works = []
+        self._done = []      # [lo, hi) ranges already handed to the collective this step
 
     def _reduce(self, lo, hi):
         if self.world > 1 and hi > lo:
             self._works.append(dist.all_reduce(self.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
+    def reduce_range(self, lo, hi):
+        """Call when every gradient in [lo, hi) is final.  Ranges must not overlap within one step."""
+        lo, hi = max(0, int(lo)), min(self.total, int(hi))
+        if hi <= lo:
+            return
+        for a, b in self._done:
+            assert hi <= a or lo >= b, "overlapping gradient buckets"
+        self._done.append((lo, hi))
+        self._reduce(lo, hi)
+
     def reduce_tail(self):
         """Call when every gradient in [split, total) is final (after the text-encoder backward)."""
-        self._tail_done = True
-        self._reduce(self.split, self.total)
+        self.reduce_range(self.split, self.total)
 
     def finish(self):
         """Call after backward: reduces what is left and waits for all outstanding collectives."""
-        if getattr(self, "_tail_done", False):
-            self._reduce(0, self.split)
-        else:
-            self._reduce(0, self.total)
+        pos = 0
+        for a, b in sorted(self._done):
+            self._reduce(pos, a)
+            pos = b
+        self._reduce(pos, self.total)
         for w in self._works:
             w.wait()
         self._works = []
-        self._tail_done = False
+        self._done = []
         return 1.0 / self.world   # scale that turns the summed gradient into the data-parallel mean
+
+
+def param_range(store, module):
+    """[lo, hi) of the flat buffer covered by `module`'s parameters (contiguous by construction of ParamStore)."""
+    spans = [(store.offsets[id(p)], store.offsets[id(p)] + p.numel()) for p in module.parameters() if id(p) in store.offsets]
+    if not spans:
+        return 0, 0
+    return min(a for a, _ in spans), max(b for _, b in spans)

@@ -80,6 +80,9 @@ class ResNetEngine:
                 blocks.append((convs, down))
             self.layers.append(blocks)
         self._stats = None
+        # called with the stage index (3 = layer4 ... 0 = layer1) right after that stage's backward kernels have been
+        # enqueued: the data-parallel trainer uses it to start the stage's gradient all-reduce early
+        self.on_stage_backward_done = None
 
     # ------------------------------------------------------------------ forward pieces
     def _conv_bn(self, c, x, B, H, W, relu, residual, training, saved):
@@ -223,6 +226,8 @@ class ResNetEngine:
                 else:
                     d_idn = dz
                 dx, _ = self._conv_bn_bwd(main[0], d, d_idn)
+            if self.on_stage_backward_done is not None and dx is not None:
+                self.on_stage_backward_done(li)
         if dx is None:
             return
         idx, H1, W1, C = ctx["pool"]

@@ -15,7 +15,7 @@ import torch.distributed as dist
 
 from . import functional as Fm
 from . import ops
-from .parallel import GradSync, split_offset
+from .parallel import GradSync, param_range, split_offset
 
 
 class Trainer:
@@ -73,6 +73,7 @@ class Trainer:
         st = self.store
         ops.step_begin(self.step_dev)
         hook = None
+        img_eng = None
         if self.overlap and self.split > 0:
             eng = self.model.text_encoder._engine
             orig = eng.backward
@@ -83,6 +84,19 @@ class Trainer:
 
             eng.backward = bert_backward_then_reduce
             hook = (eng, orig)
+        if self.overlap:
+            # ResNet stages finish in the order layer4 .. layer1: layer4 + layer3 hold 94 % of the trunk's parameters, so
+            # their buckets leave while the (activation-heavy) early stages are still back-propagating
+            img_eng = getattr(getattr(self.model, "image_encoder", None), "_engine", None)
+            if img_eng is not None and hasattr(img_eng, "on_stage_backward_done"):
+                net = img_eng.net
+                stages = [net.layer1, net.layer2, net.layer3, net.layer4]
+
+                def stage_done(li):
+                    if li >= 2:
+                        self.sync.reduce_range(*param_range(st, stages[li]))
+
+                img_eng.on_stage_backward_done = stage_done
         try:
             feats = self.model.forward_features(images, ids, mask)
             logits = self.model.classifier(feats)
@@ -91,6 +105,8 @@ class Trainer:
         finally:
             if hook is not None:
                 hook[0].backward = hook[1]
+            if img_eng is not None:
+                img_eng.on_stage_backward_done = None
         scale = self.sync.finish()
         if self.opt == "sgd":
             ops.sgd_flat(st.flat, st.grad, self.m if self.momentum > 0 else None, st.shadow, self.lr, self.momentum, self.wd,

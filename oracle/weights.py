@@ -30,6 +30,8 @@ def synth_tensor(key, shape, dtype=torch.float32, seed=0):
         return None
     if key.endswith("position_ids") or key.endswith("token_type_ids"):
         return None
+    if key.endswith("layer_scale"):   # ConvNeXt CNBlock: the default 1e-6 would make every block the identity
+        return torch.rand(shape, generator=g) * 0.3 + 0.1
     if len(shape) <= 1:
         if key.endswith("bn3.weight"):
             return torch.rand(shape, generator=g) * 0.2 + 0.1          # last BN of a bottleneck: damp the residual sum
@@ -48,6 +50,8 @@ def synth_tensor(key, shape, dtype=torch.float32, seed=0):
     for s in shape[1:]:
         fan_in *= s
     gain = 2.0 if ("conv" in key or "downsample.0" in key) else 1.0    # ReLU convs keep activations O(1)
+    if "cross_attention.query_conv" in key or "cross_attention.key_conv" in key:
+        gain = 0.1   # ConNexT attention has no 1/sqrt(d): keep the 768-term logits O(1) so the softmax is not one-hot
     return torch.randn(shape, generator=g) * (gain / fan_in) ** 0.5
 
 

@@ -64,3 +64,37 @@ def build_ours(fusion="basic", head="mlp", num_classes=7, backbone="resnet50", g
             num_classes=num_classes, hidden_dim=256, dropout=0.2, pretrained_image=False, image_weights_path=None,
             text_model_name=bert_dir(), num_heads=8, image_backbone=backbone, classifier_type=head, fusion_type=fusion,
             gate_enabled=gate, **kw)
+
+
+def build_reference_connext(variant="tiny", num_labels=7):
+    """The reference's OurClassfierConvnextV2 (torchvision branch) with the recipe of SURVEY.md section 8c step 5:
+    BertModel.from_pretrained is pointed at the local random-init bert-base; convnext_base is swapped for `variant`."""
+    import torchvision
+    import transformers
+    cn = os.path.join(REF_ROOT, "ConNexT")
+    if cn not in sys.path:
+        sys.path.insert(0, cn)
+    orig_fp = transformers.BertModel.from_pretrained
+    orig_base = torchvision.models.convnext_base
+    try:
+        transformers.BertModel.from_pretrained = classmethod(lambda cls, *a, **k: orig_fp.__func__(cls, bert_dir()))
+        torchvision.models.convnext_base = lambda weights=None: getattr(torchvision.models, f"convnext_{variant}")(weights=None)
+        with quiet():
+            import importlib
+            om = importlib.import_module("models.ourmodel")
+            m = om.OurClassfierConvnextV2(num_labels=num_labels, pretrained=False, pretrained_path=None)
+            c_last = m.image_encoder[-1][-1].block[0].weight.shape[0]
+            if c_last != 1024:   # the reference hard-codes the Base width for its 1x1 reduction (ourmodel.py:62)
+                m.conv = torch.nn.Conv2d(c_last, 768, kernel_size=1)
+    finally:
+        transformers.BertModel.from_pretrained = orig_fp
+        torchvision.models.convnext_base = orig_base
+    return m
+
+
+def build_ours_connext(variant="tiny", num_labels=7):
+    import mdhs_b200  # noqa: F401
+    from mdhs_b200.connext.ourmodel import OurClassfierConvnextV2
+    with quiet():
+        return OurClassfierConvnextV2(num_labels=num_labels, pretrained=False, pretrained_path=None, bert_path=bert_dir(),
+                                      variant=variant)

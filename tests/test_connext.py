@@ -1,0 +1,202 @@
+"""ConvNeXt / ConNexT classifier: oracle pinned to the golden outputs of the real reference
+(CPU), per-kernel parity of the ConvNeXt kernels against plain PyTorch fp32, and the CUDA model against the golden
+vectors (GPU).  Tolerances: bf16 activations / fp32 accumulation -> 1e-2 per kernel, 2e-2 on end-to-end logits."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from oracle import port, weights  # noqa: E402
+from refutil import build_ours_connext  # noqa: E402
+
+GOLD = torch.load(os.path.join(ROOT, "tests", "golden", "reference_connext.pt"), weights_only=False)
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return (a - b).abs().max().item() / (b.abs().max().item() + 1e-12)
+
+
+def sample(t, n=4096):
+    f = t.detach().flatten()
+    return f.clone() if f.numel() <= n else f[::f.numel() // n].clone()
+
+
+def _template_sd(seed=5):
+    return weights.synth_state_dict(build_ours_connext("tiny").state_dict(), seed=seed)
+
+
+# ----------------------------------------------------------------------------------------------- CPU: oracle vs golden
+def test_state_dict_keys_match_reference_layout():
+    keys = set(build_ours_connext("tiny").state_dict().keys())
+    for k in ("image_encoder.0.0.weight", "image_encoder.1.0.layer_scale", "image_encoder.7.2.block.5.bias", "conv.weight",
+              "textbased_cross_attention.query_conv.weight", "imagbased_cross_attention.value_conv.bias", "fc.weight",
+              "text_encoder.bert.embeddings.word_embeddings.weight"):
+        assert k in keys, k
+
+
+def test_oracle_reproduces_reference_connext_eval():
+    sd = _template_sd()
+    g = GOLD["eval"]
+    im, ii, mm, _ = weights.synthetic_batch(g["batch"], g["seq"], 7, image_hw=g["hw"], unit_range=True)
+    with torch.no_grad():
+        assert rel(port.convnext_features(sd, "image_encoder.", im), g["features"]) < 1e-5
+        assert rel(port.connext_forward(sd, im, ii, mm), g["logits"]) < 1e-5
+
+
+def test_oracle_reproduces_reference_connext_train_step():
+    g = GOLD["train"]
+    sd = _template_sd()
+    sd_g = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    im, ii, mm, ll = weights.synthetic_batch(g["batch"], g["seq"], 7, image_hw=g["hw"], unit_range=True)
+    logits = port.connext_forward(sd_g, im, ii, mm)
+    loss = F.cross_entropy(logits, ll)
+    loss.backward()
+    assert rel(logits, g["logits"]) < 1e-5 and abs(loss.item() - g["loss"].item()) < 1e-5
+    for k, want in g["grads"].items():
+        got = sd_g[k].grad
+        if want.abs().max() < 1e-6:     # dead branches: query_conv of image -> text (softmax over one key), and the key
+            assert got is None or got.abs().max() < 1e-6, k   # bias of text -> image (a constant shift of every logit)
+        else:
+            assert rel(sample(got), want) < 2e-4, k
+
+
+# ----------------------------------------------------------------------------------------------- GPU: kernels
+@pytest.fixture(scope="module")
+def ops():
+    import mdhs_b200  # noqa: F401
+    from mdhs_b200 import ops as o
+    return o
+
+
+def _nhwc(t):   # (B,C,H,W) fp32 -> [B*H*W, C] bf16 cuda
+    B, C, H, W = t.shape
+    return t.permute(0, 2, 3, 1).reshape(B * H * W, C).contiguous().bfloat16().cuda()
+
+
+def _nchw(t2d, B, H, W):
+    return t2d.float().cpu().view(B, H, W, -1).permute(0, 3, 1, 2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,C,H,W", [(2, 96, 14, 14), (3, 192, 7, 7), (2, 72, 9, 13), (1, 128, 5, 3)])
+def test_dwconv7_fwd_bwd(ops, B, C, H, W):
+    torch.manual_seed(0)
+    x = torch.randn(B, C, H, W).bfloat16().float()
+    w = (torch.randn(C, 1, 7, 7) / 7).float()
+    b = torch.randn(C) * 0.1
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = F.conv2d(xr, wr, br, padding=3, groups=C)
+    y = ops.dwconv7(_nhwc(x), w.cuda(), b.cuda(), B, H, W)
+    assert rel(_nchw(y, B, H, W), ref) < 1e-2
+    dy = torch.randn_like(ref).bfloat16().float()
+    ref.backward(dy)
+    dx = ops.dwconv7(_nhwc(dy), w.cuda(), None, B, H, W, flip=True)
+    assert rel(_nchw(dx, B, H, W), xr.grad) < 1e-2
+    gw, gb = torch.zeros(C, 1, 7, 7, device="cuda"), torch.zeros(C, device="cuda")
+    ops.dwconv7_wgrad(_nhwc(x), _nhwc(dy), gw, gb, B, H, W)
+    assert rel(gw, wr.grad) < 2e-3 and rel(gb, br.grad) < 2e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("p", [0.0, 0.4])
+def test_layer_scale_residual(ops, p):
+    torch.manual_seed(1)
+    B, T, C = 6, 49, 96
+    x = torch.randn(B * T, C).bfloat16()
+    z = torch.randn(B * T, C).bfloat16()
+    ls = torch.rand(C) * 0.5 + 0.1
+    out = ops.layer_scale_fwd(x.cuda(), z.cuda(), ls.cuda(), T, p, 77).float().cpu()
+    # recover the per-sample keep factor from the output itself, then check it is 0 or 1/(1-p) and constant per sample
+    ratio = ((out - x.float()) / (z.float() * ls)).view(B, T * C)
+    keep = ratio.median(dim=1).values
+    for kf in keep.tolist():
+        assert min(abs(kf), abs(kf - 1.0 / (1.0 - p))) < 2e-2
+    ref = x.float() + z.float() * ls * keep.view(B, 1).repeat_interleave(T, 0)
+    assert rel(out, ref) < 1e-2
+    dy = torch.randn(B * T, C).bfloat16()
+    dls = torch.zeros(C, device="cuda")
+    dz = ops.layer_scale_bwd(dy.cuda(), z.cuda(), ls.cuda(), dls, T, p, 77)
+    kk = keep.round(decimals=3).view(B, 1).repeat_interleave(T, 0)
+    kk = torch.where(kk > 0.5, torch.full_like(kk, 1.0 / (1.0 - p)), torch.zeros_like(kk))
+    assert rel(dz, dy.float() * ls * kk) < 1e-2
+    assert rel(dls, (dy.float() * z.float() * kk).sum(0)) < 2e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T,D", [(5, 49, 768), (3, 4, 64), (2, 130, 256)])
+def test_single_query_attention(ops, B, T, D):
+    torch.manual_seed(2)
+    q = (torch.randn(B, D) * 0.2).bfloat16()
+    k = (torch.randn(B * T, D) * 0.2).bfloat16()
+    v = torch.randn(B * T, D).bfloat16()
+    qr, kr, vr = (t.float().clone().requires_grad_(True) for t in (q, k, v))
+    att = torch.softmax(torch.einsum("bd,btd->bt", qr, kr.view(B, T, D)), dim=-1)
+    ref = torch.einsum("bt,btd->bd", att, vr.view(B, T, D))
+    out, probs = ops.sq_attn_fwd(q.cuda(), k.cuda(), v.cuda(), B, T, 1.0)
+    assert rel(out, ref) < 2e-3 and rel(probs, att) < 2e-3
+    do = torch.randn(B, D)
+    ref.backward(do)
+    dq, dk, dv = ops.sq_attn_bwd(q.cuda(), k.cuda(), v.cuda(), do.cuda(), probs, B, T, 1.0)
+    assert rel(dq, qr.grad) < 1e-2 and rel(dk, kr.grad) < 1e-2 and rel(dv, vr.grad) < 1e-2
+
+
+# ----------------------------------------------------------------------------------------------- GPU: model
+@pytest.mark.gpu
+def test_cuda_connext_matches_reference_eval():
+    g = GOLD["eval"]
+    model = build_ours_connext("tiny")
+    sd = _template_sd()
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    im, ii, mm, _ = weights.synthetic_batch(g["batch"], g["seq"], 7, image_hw=g["hw"], unit_range=True)
+    with torch.no_grad():
+        logits = model({"transformed_image": im.cuda(), "input_ids": ii.cuda(), "attention_mask": mm.cuda()})
+        tokens, h, w = model._trunk.forward(im.cuda(), False)
+    feat = tokens.float().cpu().view(g["batch"], h, w, -1).permute(0, 3, 1, 2)
+    assert rel(feat, g["features"]) < 2e-2
+    err = rel(logits, g["logits"])
+    assert err < 2e-2, err
+    margin = g["logits"].topk(2, dim=1).values
+    sure = (margin[:, 0] - margin[:, 1]) > 2 * err * g["logits"].abs().max()
+    assert torch.equal(logits.float().cpu().argmax(1)[sure], g["logits"].argmax(1)[sure])
+
+
+@pytest.mark.gpu
+def test_cuda_connext_train_step_matches_reference():
+    g = GOLD["train"]
+    model = build_ours_connext("tiny")
+    model.load_state_dict(_template_sd())
+    model = model.cuda().train()
+    model.text_encoder.bert.eval()
+    model.text_encoder.eval()
+    for m in model.modules():
+        if type(m).__name__ == "StochasticDepth":
+            m.p = 0.0
+    im, ii, mm, ll = weights.synthetic_batch(g["batch"], g["seq"], 7, image_hw=g["hw"], unit_range=True)
+    from mdhs_b200 import functional as Fm
+    logits = model({"transformed_image": im.cuda(), "input_ids": ii.cuda(), "attention_mask": mm.cuda()})
+    loss = Fm.cross_entropy(logits, ll.cuda())
+    st = model.store("cuda")
+    st.zero_grad()
+    loss.backward()
+    torch.cuda.synchronize()
+    assert rel(logits, g["logits"]) < 3e-2
+    assert abs(loss.item() - g["loss"].item()) < 2e-2
+    named = dict(model.named_parameters())
+    cos_min = 1.0
+    for k, want in g["grads"].items():
+        got = sample(st.g32(named[k]).float().cpu())
+        if want.abs().max() < 1e-6:
+            assert got.abs().max() < 1e-3, k
+            continue
+        cos = F.cosine_similarity(got.flatten(), want.flatten(), dim=0).item()
+        cos_min = min(cos_min, cos)
+        assert cos > 0.97, (k, cos)
+        assert rel(got, want) < 0.15, (k, rel(got, want))
+    print("min gradient cosine", cos_min)

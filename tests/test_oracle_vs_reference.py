@@ -7,7 +7,7 @@ import sys
 import pytest
 import torch
 
-from refutil import REF_ROOT, build_reference_model, have_reference, quiet
+from refutil import REF_ROOT, build_reference_connext, build_reference_model, have_reference, quiet
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import port, weights  # noqa: E402
@@ -151,3 +151,17 @@ def test_moe_training_mode_matches_reference(monkeypatch):
     for key in ("w_gate", "w_noise", "experts.1.layers.0.spline_weight", "experts.2.layers.1.base_weight",
                 "experts.0.layers.0.spline_scaler"):
         assert rel(sd_g[key].grad, named[key].grad) < 1e-4, key
+
+
+def test_connext_classifier_matches_reference():
+    ref = build_reference_connext("tiny").eval()
+    sd = weights.synth_state_dict(ref.state_dict(), seed=5)
+    ref.load_state_dict(sd)
+    images, ids, mask, _ = weights.synthetic_batch(2, 16, 7, image_hw=64, unit_range=True)
+    with torch.no_grad():
+        want = ref({"transformed_image": images, "input_ids": ids, "attention_mask": mask})
+        got = port.connext_forward(sd, images, ids, mask)
+        feat_ref = ref.image_encoder(images)
+        feat = port.convnext_features(sd, "image_encoder.", images)
+    assert rel(feat, feat_ref) < 1e-5
+    assert rel(got, want) < 1e-5

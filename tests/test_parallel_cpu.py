@@ -35,6 +35,14 @@ def _worker(rank, world, port, ret):
     sync2 = GradSync(g2, split)
     sync2.finish()
     ok = ok and torch.allclose(g2, want, atol=1e-6)
+    # per-stage buckets inside the head slice (ResNet layer4 / layer3 leave early), in any order, plus the tail
+    g3 = mine.clone()
+    sync3 = GradSync(g3, split)
+    sync3.reduce_range(200, 290)
+    sync3.reduce_tail()
+    sync3.reduce_range(120, 200)
+    sync3.finish()
+    ok = ok and torch.allclose(g3, want, atol=1e-6)
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 
@@ -71,3 +79,6 @@ def test_split_offset_orders_text_encoder_after_image_encoder():
     st = FakeStore(m)
     assert split_offset(st, m.text_encoder) == 4 * 4 + 4
     assert split_offset(st, None) == 0
+    from mdhs_b200.parallel import param_range
+    assert param_range(st, m.text_encoder) == (20, 20 + 4 * 2 + 2)
+    assert param_range(st, nn.ReLU()) == (0, 0)
