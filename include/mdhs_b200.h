@@ -168,6 +168,10 @@ int mdhs_linear_f32_bwd(const float* dY, int64_t lddy, const float* X, int64_t l
 int mdhs_ce_loss(const float* logits, int64_t ld, const int64_t* labels, const float* class_weights, float* loss,
                  float* dlogits, int B, int C, float label_smoothing, int focal, float gamma, void* stream);
 int mdhs_axpby_f32(const float* x, float* y, int64_t n, const float* a_dev, float a, float b, void* stream);
+/* supervised contrastive loss on (B, D) fp32 features (scripts/train.py:23-44 SupConLoss, temperature 0.07): loss[0] and,
+ * when dx != NULL, d loss / d x.  Workspaces: f_ws [B*D], inv_norm_ws [B], g_ws [B*B] (fp32). */
+int mdhs_supcon_loss(const float* x, int64_t ldx, const int64_t* labels, float* loss, float* dx, int64_t lddx, float* f_ws,
+                     float* inv_norm_ws, float* g_ws, int B, int D, float temperature, void* stream);
 
 /* elementwise helpers between fused ops: g = dy * dropout_mask * act'(aux) (bf16), ReLU backward, product (fp32) */
 int mdhs_act_dropout_bwd(const void* dy, const void* aux, void* g, int64_t n, int act, float drop_p, uint64_t seed,

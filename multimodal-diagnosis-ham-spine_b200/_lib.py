@@ -68,6 +68,7 @@ SIGNATURES = {
     "mdhs_linear_f32_bwd": "plplppli" "pp" "iiip",
     "mdhs_ce_loss": "plppppiififp",
     "mdhs_axpby_f32": "pplpffp",
+    "mdhs_supcon_loss": "plppplppp" "iifp",
     "mdhs_act_dropout_bwd": "ppplifup",
     "mdhs_relu_bwd_f32": "ppplp",
     "mdhs_mul_f32": "ppplp",

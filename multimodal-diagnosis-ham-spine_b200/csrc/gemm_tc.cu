@@ -10,6 +10,7 @@
 // Tiles are 128 x BN x 64 (BN in {64,128,256}); operands are staged with the 128-byte TMA/UMMA
 // swizzle; both operands may be K-major or MN-major so forward, dgrad and wgrad need no transposes.
 #include <cuda.h>
+#include <cstdlib>
 #include "common.cuh"
 #include "../../include/mdhs_b200.h"
 
@@ -27,11 +28,13 @@ constexpr int SMEM_LIMIT = 232448;                           // 227 KiB opt-in m
 // LD = the epilogue reads bf16 operand boxes (act'(aux_in) and / or a bf16 residual): they are prefetched by TMA into a
 // dedicated shared-memory box per epilogue warp group, one tile ahead of the accumulator, so their HBM latency is
 // hidden under the main loop (one pipeline stage is traded for the boxes).  Only BN <= 128 (one 64-column box per group).
-template <int BN, bool LD> struct Cfg {
+template <int BN, bool LD, int CL = 1> struct Cfg {
   static_assert(!(LD && BN == 256), "operand prefetch needs BN <= 128");
-  static constexpr int B_TILE_BYTES = BN * BK * 2;
+  static_assert(CL == 1 || BN >= 128, "CTA pairs need BN >= 128");
+  static constexpr int B_TILE_BYTES = (BN / CL) * BK * 2;     // CL 2: each CTA of the pair stages half of the B tile
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? (LD ? 5 : 6) : (LD ? 7 : 8));
+  static constexpr int STAGES = CL == 2 ? (BN == 256 ? 6 : (LD ? 6 : 8))
+                                        : ((BN == 256) ? 4 : (BN == 128 ? (LD ? 5 : 6) : (LD ? 7 : 8)));
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int BAR_BYTES = 256;
   // two 16 KiB output staging boxes (128 rows x 128 bytes, 128B-swizzled) feeding the TMA store / reduce-add
@@ -92,6 +95,33 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// cta_group::2 variants (CTA pair): the destination is this CTA's shared memory, the mbarrier lives in the LEADER CTA
+// (shared::cluster address obtained with mapa).
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c, int w, int h,
+                                                    int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2], {%7, %8};" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// Remote arrive with the default (release, CTA scope) semantics: `.release.cluster` compiles to MEMBAR.ALL.GPU + ERRBAR
+// per arrive (ncu source view), which throttled the pair kernel to half speed.  The accumulator hand-over it guards is
+// ordered by tcgen05.fence::before_thread_sync on this side and tcgen05.fence::after_thread_sync after the leader's wait.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
 // im2col-mode TMA: the box is `pixelsPerColumn` consecutive output pixels (traversed W -> H -> N inside the padded
 // bounding box of the tensor map, with the convolution stride) x 64 channels starting at c; (off_w, off_h) select the
 // filter tap.  Out-of-image taps are zero-filled by the TMA unit, so no halo handling is needed in the kernel.
@@ -103,10 +133,37 @@ __device__ __forceinline__ void tma_load_im2col(uint32_t dst, const CUtensorMap*
       "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
       : "memory");
 }
+// one lane of a fully converged warp (the compiler keeps the guarded tcgen05 / TMA operands in uniform registers instead of
+// serialising "divergent" lanes through ELECT + R2UR + BRA.U.ANY loops around every instruction)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// CTA-pair MMA (issued by the leader CTA only): D rows 0-127 live in the leader's TMEM, rows 128-255 in the peer's; A comes
+// from both CTAs' shared memory (same offset), each CTA holds half of the B tile.
+__device__ __forceinline__ void tc_mma_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// commit of the pair's MMAs: arrives on the same-offset mbarrier of every CTA in `mask`
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
@@ -168,12 +225,21 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 
 // ------------------------------------------------------------------ kernel
-template <int BN, bool A_MN, bool B_MN, bool LD>
+// CL = 2: CTA pairs (clusters of two CTAs on one TPC) own vertically adjacent tiles (same column block, m_blk = 2j + rank)
+// and run them as ONE 256 x BN tcgen05.mma.cta_group::2: each CTA stages its own 128 A rows and HALF of the B tile, the
+// leader's elected thread issues the MMAs, each CTA's TMEM receives its 128 accumulator rows and each CTA runs its own
+// epilogue.  Why: ncu on the single-CTA kernel shows the main loop bound by shared-memory bandwidth -- per MMA the tensor
+// core reads (128 + BN) x 32 B of operands while TMA writes the next stage into the same memory, ~240 B/clk for BN = 128
+// and ~180 B/clk for BN = 256 against 128 B/clk/SM: tensor pipe 40 % / 58 % active.  The pair halves the B bytes per CTA.
+// Protocol: `full` barriers live in the leader (one arrival: the leader's expect_tx of both CTAs' bytes; both CTAs'
+// TMA loads complete on it); `empty` / `tmem_full` are signalled in both CTAs by multicast tcgen05.commit; both CTAs'
+// epilogue warps release an accumulator stage on the leader's `tmem_empty`.
+template <int BN, bool A_MN, bool B_MN, bool LD, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmAux,
                const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmAuxIn, const Params p) {
-  using C = Cfg<BN, LD>;
+  using C = Cfg<BN, LD, CL>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -208,38 +274,95 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int a = 0; a < 2; a++) {
       mbar_init(lbar(a), 1);
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4 * C::EPI_GROUPS);
+      mbar_init(tempty_bar(a), CL * 4 * C::EPI_GROUPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(C::TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CL > 1) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(C::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(C::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // the peer's barriers exist before anything is multicast into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
-  const int total_tiles = p.num_m * p.num_n * p.splits;
+  // work items: tiles (CL == 1) or vertical tile pairs (CL == 2); item w -> (split, n_blk, m_blk of THIS CTA)
+  const int cta_rank = CL > 1 ? (int)(blockIdx.x & 1) : 0;
+  const int w0 = CL > 1 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int wstep = CL > 1 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int total_tiles = (CL > 1 ? (p.num_m + 1) / 2 : p.num_m) * p.num_n * p.splits;   // number of work items
+  auto decode = [&](int w, int& split, int& n_blk, int& m_blk) {
+    split = w % p.splits;
+    const int mn = w / p.splits;
+    n_blk = mn % p.num_n;
+    m_blk = CL > 1 ? 2 * (mn / p.num_n) + cta_rank : mn / p.num_n;   // may be == num_m (phantom tile: TMA zero-fills / clips)
+  };
 
-  if (warp == 0 && lane == 0) {
-    // ------------------------------------------------------------ TMA producer
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (whole warp walks the loop, one lane issues)
     int stage = 0;
     uint32_t phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int split = t % p.splits;
-      const int mn = t / p.splits;
-      const int n_blk = mn % p.num_n, m_blk = mn / p.num_n;
+    for (int t = w0; t < total_tiles; t += wstep) {
+      int split, n_blk, m_blk;
+      decode(t, split, n_blk, m_blk);
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
       for (int kb = kb0; kb < kb1; kb++) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t fb = full_bar(stage);
-        mbar_expect_tx(fb, C::STAGE_BYTES);
         const uint32_t sA = tiles_base + stage * C::STAGE_BYTES;
         const uint32_t sB = sA + A_TILE_BYTES;
+        if (elect_one()) {
+        if (CL > 1) {
+          // ---- CTA pair: own A rows + own half of B, every load completes on the LEADER's full barrier
+          const uint32_t fbl = mapa_rank(fb, 0);
+          // only the leader arrives (with the byte count of BOTH CTAs); the peer's loads just complete bytes on it -- a
+          // complete_tx that overtakes the expect_tx of its phase is legal (the phase cannot flip before the arrive)
+          if (cta_rank == 0) mbar_expect_tx(fb, 2 * C::STAGE_BYTES);
+          if (!A_MN && p.conv_mode == 1) {
+            const int tap = kb / p.c_cblk, cb = kb - tap * p.c_cblk;
+            const int r = tap / p.cS, sx = tap - r * p.cS;
+            const int pix = m_blk * BM;
+            const int img = pix / (p.cHo * p.cWo), rem = pix - img * (p.cHo * p.cWo);
+            const int ph = rem / p.cWo, pw = rem - ph * p.cWo;
+            tma_load_im2col_2sm(sA, &tmA, fbl, cb * 64, pw * p.c_stride - p.c_pad, ph * p.c_stride - p.c_pad, img, (uint16_t)sx,
+                                (uint16_t)r);
+          } else if (!A_MN) {
+            tma_load_2d_2sm(sA, &tmA, fbl, kb * BK, m_blk * BM);
+          } else {
+            tma_load_2d_2sm(sA, &tmA, fbl, m_blk * BM, kb * BK);
+            tma_load_2d_2sm(sA + 8192, &tmA, fbl, m_blk * BM + 64, kb * BK);
+          }
+          const int n_base = n_blk * BN + cta_rank * (BN / 2);   // this CTA's half of the B tile
+          if (!B_MN) {
+            tma_load_2d_2sm(sB, &tmB, fbl, kb * BK, n_base);
+          } else if (p.conv_mode == 2) {
+            const int pix = kb * BK;
+            const int img = pix / (p.cHo * p.cWo), rem = pix - img * (p.cHo * p.cWo);
+            const int ph = rem / p.cWo, pw = rem - ph * p.cWo;
+#pragma unroll
+            for (int j = 0; j < BN / 128; j++) {
+              const int nb = n_base / 64 + j;
+              const int tap = nb / p.c_cblk, cb = nb - tap * p.c_cblk;
+              const int r = tap / p.cS, sx = tap - r * p.cS;
+              tma_load_im2col_2sm(sB + j * 8192, &tmB, fbl, cb * 64, pw * p.c_stride - p.c_pad, ph * p.c_stride - p.c_pad, img,
+                                  (uint16_t)sx, (uint16_t)r);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 128; j++) tma_load_2d_2sm(sB + j * 8192, &tmB, fbl, n_base + j * 64, kb * BK);
+          }
+        } else {
+        mbar_expect_tx(fb, C::STAGE_BYTES);
         if (!A_MN && p.conv_mode == 1) {
           // k-block = (filter tap, 64-channel block); the tile's first output pixel fixes the base coordinates
           const int tap = kb / p.c_cblk, cb = kb - tap * p.c_cblk;
@@ -274,21 +397,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < BN / 64; j++) tma_load_2d(sB + j * 8192, &tmB, fb, n_blk * BN + j * 64, kb * BK);
         }
+        }
+        }
+        __syncwarp();
         if (++stage == C::STAGES) {
           stage = 0;
           phase ^= 1u;
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------ MMA issuer
+  } else if (warp == 1 && cta_rank == 0) {
+    // ------------------------------------------------------------ MMA issuer (CTA pair: the leader issues for both)
+    // The whole warp walks the loop (uniform control flow, barrier waits by all lanes); one elected lane issues.  The
+    // single-thread form spent ~110 SASS instructions per k-block (ELECT / R2UR / BRA.U.ANY serialisation loops around each
+    // UTCHMMA): ~600 clk per k-block of issue time against 272 clk of tensor work at BN = 128 (ncu source view).
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CL) >> 4) << 24);
+    // descriptor = constant high word | 14-bit (address >> 4): stepping k or the stage is a plain add on the low word
+    constexpr uint32_t DESC_HI = (1u << 14) | (2u << 29);                  // version 1 (bit 46), SWIZZLE_128B (bits 61-63)
+    constexpr uint32_t A_LBO_SBO = A_MN ? ((8192u >> 4) << 16) : 0u;       // LBO field (bits 16-29) of the low word
+    constexpr uint32_t B_LBO_SBO = B_MN ? ((8192u >> 4) << 16) : 0u;
+    constexpr uint32_t SBO_HI = (1024u >> 4);                              // SBO field (bits 32-45) -> low bits of the high word
+    constexpr uint32_t A_KSTEP = (A_MN ? 2048u : 32u) >> 4, B_KSTEP = (B_MN ? 2048u : 32u) >> 4;
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = w0; t < total_tiles; t += wstep) {
       const int split = t % p.splits;
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
@@ -299,17 +434,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         const uint32_t sA = tiles_base + stage * C::STAGE_BYTES;
-        const uint32_t sB = sA + A_TILE_BYTES;
+        const uint32_t a_lo = ((sA >> 4) & 0x3FFFu) | A_LBO_SBO;
+        const uint32_t b_lo = (((sA + A_TILE_BYTES) >> 4) & 0x3FFFu) | B_LBO_SBO;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < BK / 16; k++) {
-          // K-major: 16 elements = 32 bytes inside the swizzle row; 8-row groups 1024 B apart.
-          // MN-major: 16 k-rows = 2048 bytes; 64-element MN groups 8192 B apart (LBO).
-          const uint64_t ad = A_MN ? umma_desc(sA + k * 2048, 8192, 1024) : umma_desc(sA + k * 32, 0, 1024);
-          const uint64_t bd = B_MN ? umma_desc(sB + k * 2048, 8192, 1024) : umma_desc(sB + k * 32, 0, 1024);
-          tc_mma(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / 16; k++) {
+            // K-major: 16 elements = 32 bytes inside the swizzle row; 8-row groups 1024 B apart (SBO).
+            // MN-major: 16 k-rows = 2048 bytes; 64-element MN groups 8192 B apart (LBO).
+            const uint64_t ad = ((uint64_t)(DESC_HI | SBO_HI) << 32) | (uint64_t)(a_lo + k * A_KSTEP);
+            const uint64_t bd = ((uint64_t)(DESC_HI | SBO_HI) << 32) | (uint64_t)(b_lo + k * B_KSTEP);
+            const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
+            if (CL > 1) tc_mma_2sm(tmem_d, ad, bd, idesc, accum);
+            else tc_mma(tmem_d, ad, bd, idesc, accum);
+          }
+          if (CL > 1) {
+            tc_commit_2sm(empty_bar(stage), (uint16_t)3);              // frees the stage in BOTH CTAs' producers
+            if (kb == kb1 - 1) tc_commit_2sm(tfull_bar(acc), (uint16_t)3);   // accumulators ready in both CTAs
+          } else {
+            tc_commit(empty_bar(stage));
+            if (kb == kb1 - 1) tc_commit(tfull_bar(acc));
+          }
         }
-        tc_commit(empty_bar(stage));
-        if (kb == kb1 - 1) tc_commit(tfull_bar(acc));
+        __syncwarp();
         if (++stage == C::STAGES) {
           stage = 0;
           phase ^= 1u;
@@ -392,7 +538,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool has_aux_in = p.dact != MDHS_ACT_NONE;
     const int n_items = (has_aux_in ? 1 : 0) + ((p.residual != nullptr && !p.r_f32) ? 1 : 0);
     auto issue_item = [&](int t, int q) {       // issuer thread only; splits == 1 in LD mode
-      const int n_blk = t % p.num_n, m_blk = t / p.num_n;
+      int split_, n_blk, m_blk;
+      decode(t, split_, n_blk, m_blk);
       const CUtensorMap* map = (has_aux_in && q == 0) ? &tmAuxIn : &tmRes;
       mbar_expect_tx(lbar(half), 16384);
       tma_load_2d(in_box, map, lbar(half), n_blk * BN + half * HALF_COLS, m_blk * BM);
@@ -417,15 +564,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       named_bar(bar_id, 128);                   // every thread of the group has copied its row out of the box
       if (issuer) {
         if (q + 1 < n_items) issue_item(t, q + 1);
-        else if (t + (int)gridDim.x < total_tiles) issue_item(t + (int)gridDim.x, 0);
+        else if (t + wstep < total_tiles) issue_item(t + wstep, 0);
       }
     };
-    if (LD && issuer && n_items > 0 && (int)blockIdx.x < total_tiles) issue_item(blockIdx.x, 0);
+    if (LD && issuer && n_items > 0 && w0 < total_tiles) issue_item(w0, 0);
 
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int split = t % p.splits;
-      const int mn = t / p.splits;
-      const int n_blk = mn % p.num_n, m_blk = mn / p.num_n;
+    for (int t = w0; t < total_tiles; t += wstep) {
+      int split, n_blk, m_blk;
+      decode(t, split, n_blk, m_blk);
       const int n_half0 = n_blk * BN + half * HALF_COLS;
       const int64_t m = (int64_t)m_blk * BM + wq * 32 + lane;
       const bool row_ok = m < p.M;
@@ -445,7 +591,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // this warp has read its whole slice: hand the TMEM stage back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc));
+          if (lane == 0) {
+            if (CL > 1) mbar_arrive_cluster(mapa_rank(tempty_bar(acc), 0));
+            else mbar_arrive(tempty_bar(acc));
+          }
         }
         const int n0 = n_half0 + pr * 64;
         // NOTE: no early exit for columns beyond N: the whole warp group must reach the named barriers; TMA clips
@@ -573,8 +722,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         acc_phase ^= 1u;
       }
     }
-    if (p.colsum != nullptr && (int)blockIdx.x < total_tiles) {
-      const int n_blk = blockIdx.x % p.num_n;
+    if (p.colsum != nullptr && w0 < total_tiles) {
+      const int n_blk = w0 % p.num_n;
 #pragma unroll
       for (int pr = 0; pr < PAIRS; pr++) {
         const int n = n_blk * BN + half * HALF_COLS + pr * 64 + 2 * lane;
@@ -591,9 +740,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it / arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+    if (CL > 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
   }
 }
 
@@ -678,9 +829,9 @@ int num_sms() {
   return n;
 }
 
-template <int BN, bool A_MN, bool B_MN, bool LD>
+template <int BN, bool A_MN, bool B_MN, bool LD, int CL>
 int launch(const mdhs_gemm_args* a, const Params& p0, cudaStream_t stream) {
-  using C = Cfg<BN, LD>;
+  using C = Cfg<BN, LD, CL>;
   Params p = p0;
   p.num_m = ceil_div(a->M, BM);
   p.num_n = ceil_div(a->N, BN);
@@ -703,35 +854,75 @@ int launch(const mdhs_gemm_args* a, const Params& p0, cudaStream_t stream) {
   else       rc = make_map(&tmA, a->A, a->M, a->K, a->lda, 64, BK);
   if (rc) return rc;
   if (a->conv_mode == 2) rc = make_im2col_map(&tmB, a->B, a->cN, a->cH, a->cW, a->cC, a->cR, a->cS, a->c_stride, a->c_pad, BK);
-  else if (!B_MN) rc = make_map(&tmB, a->B, a->K, a->N, a->ldb, BK, BN);
+  else if (!B_MN) rc = make_map(&tmB, a->B, a->K, a->N, a->ldb, BK, CL > 1 ? BN / 2 : BN);   // CL 2: half tile per CTA
   else       rc = make_map(&tmB, a->B, a->N, a->K, a->ldb, 64, BK);
   if (rc) return rc;
   static bool attr_set = false;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, LD>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, LD, CL>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  const int total = p.num_m * p.num_n * p.splits;
-  int grid = total < num_sms() ? total : num_sms();
+  // work items = tiles, or vertical tile pairs handled by a 2-CTA cluster; `units` = CTAs (CL 1) / clusters (CL 2)
+  const int total = (CL > 1 ? (p.num_m + 1) / 2 : p.num_m) * p.num_n * p.splits;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  int cap = num_sms() / CL;
+  if (CL > 1) {
+    // a persistent grid must be fully co-resident: GPCs with an odd number of usable SMs cannot host every pair
+    static int max_clusters = -1;
+    if (max_clusters < 0) {
+      cfg.gridDim = dim3(cap * CL);
+      int n = 0;
+      max_clusters = (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0) ? n : cap;
+      (void)cudaGetLastError();
+    }
+    if (cap > max_clusters) cap = max_clusters;
+  }
+  int units = total < cap ? total : cap;
   if (a->colsum) {
     // column statistics are accumulated in registers across a CTA's tiles: every CTA must keep one column block
-    if (p.num_n > grid) return MDHS_ERR_ARG;
-    grid = (grid / p.num_n) * p.num_n;
+    if (p.num_n > units) return MDHS_ERR_ARG;
+    units = (units / p.num_n) * p.num_n;
   }
-  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmD, tmAux, tmRes, tmAuxIn, p);
+  if (CL == 1) {
+    kern<<<units, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmD, tmAux, tmRes, tmAuxIn, p);
+  } else {
+    cfg.gridDim = dim3(units * CL);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmD, tmAux, tmRes, tmAuxIn, p);
+    if (e != cudaSuccess) return (int)e;
+  }
   MDHS_RETURN_LAST();
 }
 
-template <int BN, bool LD>
+template <int BN, bool LD, int CL>
 int dispatch_major(const mdhs_gemm_args* a, const Params& p, cudaStream_t s) {
   if (a->a_mn_major) {
     // MN-major A only occurs in weight-gradient GEMMs, which never read epilogue operand boxes
     if (LD) return MDHS_ERR_ARG;
-    return a->b_mn_major ? launch<BN, true, true, false>(a, p, s) : launch<BN, true, false, false>(a, p, s);
+    return a->b_mn_major ? launch<BN, true, true, false, CL>(a, p, s) : launch<BN, true, false, false, CL>(a, p, s);
   }
-  return a->b_mn_major ? launch<BN, false, true, LD>(a, p, s) : launch<BN, false, false, LD>(a, p, s);
+  return a->b_mn_major ? launch<BN, false, true, LD, CL>(a, p, s) : launch<BN, false, false, LD, CL>(a, p, s);
+}
+
+// MDHS_GEMM_CLUSTER: 0 disables the CTA-pair (cta_group::2) path, 2 forces it wherever it is legal (tests), default auto
+int cluster_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MDHS_GEMM_CLUSTER");
+    v = (e && e[0] == '0') ? 0 : ((e && e[0] == '2') ? 2 : 1);
+  }
+  return v;
 }
 
 }  // namespace
@@ -850,9 +1041,16 @@ extern "C" int mdhs_gemm_bf16(const mdhs_gemm_args* a, void* stream_) {
   }
   g_mdhs_launches++;
   const bool ld = wants_ld && bn != 256;
+  // CTA pairs (256 x bn cta_group::2 tiles) whenever there are at least two row blocks and enough pair tiles to occupy
+  // a good part of the 74 pairs
+  const int n_tiles_m = ceil_div(a->M, BM);
+  const bool cl2 = cluster_mode() != 0 && bn >= 128 && n_tiles_m >= 2 &&
+                   (cluster_mode() == 2 || (int64_t)((n_tiles_m + 1) / 2) * ceil_div(a->N, bn) * p.splits >= num_sms() / 4);
   switch (bn) {
-    case 256: return dispatch_major<256, false>(a, p, stream);
-    case 128: return ld ? dispatch_major<128, true>(a, p, stream) : dispatch_major<128, false>(a, p, stream);
-    default:  return ld ? dispatch_major<64, true>(a, p, stream) : dispatch_major<64, false>(a, p, stream);
+    case 256: return cl2 ? dispatch_major<256, false, 2>(a, p, stream) : dispatch_major<256, false, 1>(a, p, stream);
+    case 128:
+      if (cl2) return ld ? dispatch_major<128, true, 2>(a, p, stream) : dispatch_major<128, false, 2>(a, p, stream);
+      return ld ? dispatch_major<128, true, 1>(a, p, stream) : dispatch_major<128, false, 1>(a, p, stream);
+    default:  return ld ? dispatch_major<64, true, 1>(a, p, stream) : dispatch_major<64, false, 1>(a, p, stream);
   }
 }

@@ -145,9 +145,117 @@ __global__ void axpby_kernel(const float* __restrict__ x, float* __restrict__ y,
     y[i] = aa * x[i] + (b != 0.f ? b * y[i] : 0.f);
 }
 
+// ------------------------------------------------------------------ supervised contrastive loss (scripts/train.py:23-44)
+// f_i = x_i / max(|x_i|, 1e-12); s_ij = f_i.f_j / T; logp_ij = (s_ij - m_i) - log(sum_{k != i} exp(s_ik - m_i) + 1e-8);
+// loss = -mean_i [ sum_{j in pos(i)} logp_ij / (|pos(i)| + 1e-8) ].  Three small kernels (one CTA per sample):
+// normalise; loss row + G = d loss / d s (B x B, fp32); dx = normalise'( (G + G^T) f / T ).
+constexpr int SUPCON_MAXB = 2048;
+
+__global__ void __launch_bounds__(256) supcon_normalize_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ f,
+                                                               float* __restrict__ inv_norm, int D) {
+  __shared__ float red[32];
+  const int i = blockIdx.x;
+  float q = 0.f;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const float v = x[(int64_t)i * ldx + d];
+    q = fmaf(v, v, q);
+  }
+  q = block_sum(q, red);
+  const float inv = 1.f / fmaxf(sqrtf(q), 1e-12f);
+  if (threadIdx.x == 0) inv_norm[i] = inv;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) f[(int64_t)i * D + d] = x[(int64_t)i * ldx + d] * inv;
+}
+
+__global__ void __launch_bounds__(256) supcon_row_kernel(const float* __restrict__ f, const int64_t* __restrict__ labels,
+                                                         float* __restrict__ loss, float* __restrict__ G, int B, int D, float inv_t) {
+  __shared__ float s[SUPCON_MAXB];
+  __shared__ float red[32];
+  const int i = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float* fi = f + (int64_t)i * D;
+  for (int j = warp; j < B; j += nw) {
+    const float* fj = f + (int64_t)j * D;
+    float a = 0.f;
+    for (int d = lane; d < D; d += 32) a = fmaf(fi[d], fj[d], a);
+    a = warp_sum(a);
+    if (lane == 0) s[j] = a * inv_t;
+  }
+  __syncthreads();
+  float m = -INFINITY;
+  for (int j = threadIdx.x; j < B; j += blockDim.x) m = fmaxf(m, s[j]);
+  m = block_max(m, red);
+  const int64_t yi = labels[i];
+  float z = 0.f, npos = 0.f, lpos = 0.f;
+  for (int j = threadIdx.x; j < B; j += blockDim.x) {
+    if (j == i) continue;
+    const float l = s[j] - m;
+    z += __expf(l);
+    if (labels[j] == yi) {
+      npos += 1.f;
+      lpos += l;
+    }
+  }
+  z = block_sum(z, red);
+  npos = block_sum(npos, red);
+  lpos = block_sum(lpos, red);
+  const float Z = z + 1e-8f;
+  const float wpos = 1.f / (npos + 1e-8f);
+  if (threadIdx.x == 0) atomicAdd(loss, -(lpos - npos * logf(Z)) * wpos / (float)B);
+  if (G != nullptr) {
+    const float frac = npos * wpos;   // = sum_{j in pos} 1 / (|pos| + eps)
+    for (int j = threadIdx.x; j < B; j += blockDim.x) {
+      float g = 0.f;
+      if (j != i) {
+        const float e = __expf(s[j] - m) / Z;
+        g = -(((labels[j] == yi) ? wpos : 0.f) - frac * e) / (float)B;
+      }
+      G[(int64_t)i * B + j] = g;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) supcon_bwd_kernel(const float* __restrict__ f, const float* __restrict__ inv_norm,
+                                                         const float* __restrict__ G, float* __restrict__ dx, int64_t lddx, int B,
+                                                         int D, float inv_t) {
+  __shared__ float w[SUPCON_MAXB];
+  __shared__ float red[32];
+  const int i = blockIdx.x;
+  for (int j = threadIdx.x; j < B; j += blockDim.x) w[j] = (G[(int64_t)i * B + j] + G[(int64_t)j * B + i]) * inv_t;
+  __syncthreads();
+  // df = sum_j w_j f_j (threads over d), then the tangent projection of the normalisation
+  float dot = 0.f;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float a = 0.f;
+    for (int j = 0; j < B; j++) a = fmaf(w[j], f[(int64_t)j * D + d], a);
+    dx[(int64_t)i * lddx + d] = a;          // staged, rewritten below
+    dot = fmaf(a, f[(int64_t)i * D + d], dot);
+  }
+  dot = block_sum(dot, red);
+  const float inv = inv_norm[i];
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const float a = dx[(int64_t)i * lddx + d];
+    dx[(int64_t)i * lddx + d] = (a - f[(int64_t)i * D + d] * dot) * inv;
+  }
+}
+
 }  // namespace
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int mdhs_supcon_loss(const float* x, int64_t ldx, const int64_t* labels, float* loss, float* dx, int64_t lddx, float* f_ws,
+                                float* inv_norm_ws, float* g_ws, int B, int D, float temperature, void* stream) {
+  if (!x || !labels || !loss || !f_ws || !inv_norm_ws || B <= 0 || B > SUPCON_MAXB || D <= 0 || temperature <= 0.f) return MDHS_ERR_ARG;
+  if (dx && !g_ws) return MDHS_ERR_ARG;
+  cudaStream_t st = ST(stream);
+  cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float), st);
+  if (e != cudaSuccess) return (int)e;
+  g_mdhs_launches += dx ? 3 : 2;
+  supcon_normalize_kernel<<<B, 256, 0, st>>>(x, ldx, f_ws, inv_norm_ws, D);
+  supcon_row_kernel<<<B, 256, 0, st>>>(f_ws, labels, loss, dx ? g_ws : nullptr, B, D, 1.f / temperature);
+  if (dx) supcon_bwd_kernel<<<B, 256, 0, st>>>(f_ws, inv_norm_ws, g_ws, dx, lddx, B, D, 1.f / temperature);
+  MDHS_RETURN_LAST();
+}
+
 
 extern "C" int mdhs_linear_f32_fwd(const float* X, int64_t ldx, const float* W, const float* bias, float* Y, int64_t ldy, int M,
                                    int N, int K, int act, void* stream) {

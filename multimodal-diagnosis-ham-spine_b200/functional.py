@@ -304,3 +304,25 @@ class CrossEntropyFn(torch.autograd.Function):
 
 def cross_entropy(logits, labels, class_weights=None, label_smoothing=0.0, focal=False, gamma=2.0):
     return CrossEntropyFn.apply(logits, labels, class_weights, float(label_smoothing), bool(focal), float(gamma))
+
+
+class SupConFn(torch.autograd.Function):
+    """Supervised contrastive loss (scripts/train.py:23-44) on fp32 (B, D) features; the gradient is produced in the
+    same pass and scaled by the incoming gradient in backward."""
+
+    @staticmethod
+    def forward(ctx, features, labels, temperature):
+        loss, dx = ops.supcon_loss(features.contiguous(), labels, temperature, want_grad=True)
+        ctx.save_for_backward(dx)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (dx,) = ctx.saved_tensors
+        out = torch.empty_like(dx)
+        ops.axpby(dx, out, a=1.0, b=0.0, a_dev=dloss.contiguous().view(1))
+        return out, None, None
+
+
+def supcon_loss(features, labels, temperature=0.07):
+    return SupConFn.apply(features, labels, float(temperature))

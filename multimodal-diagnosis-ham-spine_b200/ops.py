@@ -336,6 +336,19 @@ def ce_loss(logits, labels, class_weights=None, label_smoothing=0.0, focal=False
     return loss, dl
 
 
+def supcon_loss(x, labels, temperature=0.07, want_grad=True):
+    B, D = x.shape
+    dev = x.device
+    loss = torch.empty(1, device=dev, dtype=torch.float32)
+    f = torch.empty((B, D), device=dev, dtype=torch.float32)
+    inv = torch.empty(B, device=dev, dtype=torch.float32)
+    g = torch.empty((B, B), device=dev, dtype=torch.float32) if want_grad else None
+    dx = torch.empty((B, D), device=dev, dtype=torch.float32) if want_grad else None
+    _lib.call("mdhs_supcon_loss", _p(x), x.stride(0), _p(labels), _p(loss), _p(dx), D, _p(f), _p(inv), _p(g), B, D,
+              float(temperature), _s())
+    return loss, dx
+
+
 def axpby(x, y, a=1.0, b=0.0, a_dev=None):
     _lib.call("mdhs_axpby_f32", _p(x), _p(y), x.numel(), _p(a_dev), float(a), float(b), _s())
     return y

@@ -152,3 +152,44 @@ def test_gemm_wgrad_accumulate_all_tiles(mdhs, bn, M, N, K, split):
     assert (acc - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
     out = ops.gemm(dy, x, a_mn=True, b_mn=True, out_dtype=torch.float32, bn_hint=bn)
     assert (out - (ref - 0.5) / 2).abs().max().item() <= 2e-3 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn,bn", [(8192, 768, 768, False, False, 0), (8192 - 128, 768, 320, False, True, 128),
+                                                 (4096 + 40, 1024, 512, False, False, 256), (768, 3072, 4096, True, True, 0),
+                                                 (1024, 512, 2048 + 64, True, False, 128), (640, 256, 192, False, False, 256)])
+def test_gemm_cta_pair_tiles(mdhs, M, N, K, a_mn, b_mn, bn):
+    """Shapes large enough for the CTA-pair (tcgen05.mma.cta_group::2, 256-row) path, incl. an odd number of row blocks
+    (the second CTA of the last pair runs a phantom tile) and every operand-major combination; fp32 and bf16 outputs,
+    plus the fused epilogues (bias + GELU + saved pre-activation, bf16 residual prefetch + dropout-free, column statistics)."""
+    from mdhs_b200 import ops
+    torch.manual_seed(5)
+    a = (torch.randn((K, M) if a_mn else (M, K), device="cuda") * 0.5).bfloat16()
+    b = (torch.randn((K, N) if b_mn else (N, K), device="cuda") * 0.1).bfloat16()
+    A = a.float().t() if a_mn else a.float()
+    Bm = b.float().t() if b_mn else b.float()
+    ref = A @ Bm.t()
+    scale = ref.abs().max().item()
+    out = ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn, bn_hint=bn, out_dtype=torch.float32)
+    assert (out - ref).abs().max().item() <= 2e-3 * scale + 1e-3
+    acc = torch.ones(M, N, device="cuda")
+    ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn, out=acc, accumulate=True, split_k=-1)
+    assert (acc - 1 - ref).abs().max().item() <= 2e-3 * scale + 1e-3
+    if not a_mn:
+        bias = torch.randn(N, device="cuda")
+        res = torch.randn(M, N, device="cuda").bfloat16()
+        aux = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        y = ops.gemm(a, b, b_mn=b_mn, bias=bias, act=ops.ACT_GELU, aux_out=aux, bn_hint=bn)
+        want = torch.nn.functional.gelu(ref + bias)
+        assert (y.float() - want).abs().max().item() <= 1e-2 * want.abs().max().item()
+        assert (aux.float() - (ref + bias)).abs().max().item() <= 1e-2 * (ref + bias).abs().max().item()
+        y = ops.gemm(a, b, b_mn=b_mn, bias=bias, residual=res, bn_hint=min(bn, 128))
+        want = ref + bias + res.float()
+        assert (y.float() - want).abs().max().item() <= 1e-2 * want.abs().max().item()
+        g = ops.gemm(a, b, b_mn=b_mn, aux_in=aux, dact=ops.ACT_RELU, bn_hint=min(bn, 128))
+        want = ref * (aux.float() > 0)
+        assert (g.float() - want).abs().max().item() <= 1e-2 * want.abs().max().item()
+        cs = torch.zeros(N, device="cuda", dtype=torch.float64)
+        cq = torch.zeros(N, device="cuda", dtype=torch.float64)
+        y = ops.gemm(a, b, b_mn=b_mn, colsum=cs, colsumsq=cq, bn_hint=bn)
+        assert torch.allclose(cs, y.double().sum(0), rtol=1e-5, atol=2e-2)
+        assert torch.allclose(cq, (y.double() ** 2).sum(0), rtol=1e-5, atol=2e-2)

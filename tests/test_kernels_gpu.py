@@ -419,3 +419,21 @@ def test_mp_loss_kernel(ops):
     assert abs(loss.item() - ref.item()) < 1e-4 * max(1.0, abs(ref.item()))
     for a, b in zip(g, cpu):
         assert relerr(a.cpu(), b.grad) < 1e-3
+
+
+@pytest.mark.parametrize("B,D", [(32, 256), (128, 256), (7, 40)])
+def test_supcon_loss_fwd_bwd(ops, B, D):
+    """SupConLoss (scripts/train.py:23-44) vs the oracle restatement (pinned to the reference): loss 1e-4, gradient 1e-3."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import port
+    torch.manual_seed(3)
+    x = torch.randn(B, D)
+    labels = torch.randint(0, 4, (B,))
+    xr = x.clone().requires_grad_(True)
+    want = port.supcon_loss(xr, labels, 0.07)
+    want.backward()
+    loss, dx = ops.supcon_loss(x.cuda(), labels.cuda(), 0.07)
+    assert abs(loss.item() - want.item()) <= 1e-4 * max(1.0, abs(want.item()))
+    assert relerr(dx, xr.grad.cuda()) < 1e-3
