@@ -40,7 +40,11 @@ int64_t mdhs_launch_count(void);
  * Epilogue order: +bias -> aux_out -> act -> *act'(aux_in) -> dropout -> +residual -> store (-> colsum).
  * Requirements: N % 8 == 0, all leading dimensions % 8 == 0, 16-byte aligned pointers (K is free).
  */
-enum { MDHS_ACT_NONE = 0, MDHS_ACT_RELU = 1, MDHS_ACT_GELU = 2 };
+enum {
+  MDHS_ACT_NONE = 0, MDHS_ACT_RELU = 1, MDHS_ACT_GELU = 2,
+  MDHS_ACT_GELU_DERIV = 3,   /* act: erf-GELU whose aux_out receives GELU'(pre-activation) instead of the pre-activation */
+  MDHS_ACT_MUL = 4           /* dact: multiply by aux_in itself (the derivative saved by MDHS_ACT_GELU_DERIV) */
+};
 enum { MDHS_DT_BF16 = 0, MDHS_DT_F32 = 1 };
 typedef struct {
   const void* A; int64_t lda; int32_t a_mn_major;

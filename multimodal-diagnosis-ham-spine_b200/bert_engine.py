@@ -81,7 +81,9 @@ class BertEngine:
             pre1 = ops.gemm(att, st.w16(L["wo"].weight), bias=L["wo"].bias.data, residual=x, dropout_p=ph, dropout_seed=s0 + 2)
             h1, _, m1, r1 = ops.layernorm_fwd(pre1, L["ln1"].weight.data, L["ln1"].bias.data, self.eps, save_stats=need_grad)
             ipre = torch.empty((T, L["wi"].weight.shape[0]), device=x.device, dtype=torch.bfloat16) if need_grad else None
-            inter = ops.gemm(h1, st.w16(L["wi"].weight), bias=L["wi"].bias.data, act=ops.ACT_GELU, aux_out=ipre)
+            # training: the epilogue also stores GELU'(pre-activation) (`ipre`), so the backward epilogue is one multiply
+            inter = ops.gemm(h1, st.w16(L["wi"].weight), bias=L["wi"].bias.data,
+                             act=ops.ACT_GELU_DERIV if need_grad else ops.ACT_GELU, aux_out=ipre)
             pre2 = ops.gemm(inter, st.w16(L["wo2"].weight), bias=L["wo2"].bias.data, residual=h1, dropout_p=ph,
                             dropout_seed=s0 + 3)
             h2, _, m2, r2 = ops.layernorm_fwd(pre2, L["ln2"].weight.data, L["ln2"].bias.data, self.eps, save_stats=need_grad)
@@ -129,7 +131,7 @@ class BertEngine:
                                                   st.g32(ln2.weight) if tr2 else None, st.g32(ln2.bias) if tr2 else None,
                                                   drop2_p=ph, seed2=s0 + 3, want_dx_drop=ph > 0)
             g2 = dpre2_d if ph > 0 else dpre2
-            dipre = self._linear_bwd(g2, R["inter"], L["wo2"], aux_in=R["ipre"], dact=ops.ACT_GELU)
+            dipre = self._linear_bwd(g2, R["inter"], L["wo2"], aux_in=R["ipre"], dact=ops.ACT_MUL)
             dh1 = self._linear_bwd(dipre, R["h1"], L["wi"], residual=dpre2)
             tr1 = ln1.weight.requires_grad
             dpre1, dpre1_d, _ = ops.layernorm_bwd(dh1, R["pre1"], R["m1"], R["r1"], ln1.weight.data,

@@ -79,6 +79,14 @@ __device__ __forceinline__ float gelu_erf(float x) {
   const float hq = 0.5f * gelu_q_(fabsf(x), e);
   return x * (x >= 0.f ? 1.f - hq : hq);
 }
+// GELU and its derivative from one exponential (forward epilogue that also saves the derivative for the backward pass)
+__device__ __forceinline__ void gelu_erf_both(float x, float& y, float& dy) {
+  float e;
+  const float hq = 0.5f * gelu_q_(fabsf(x), e);
+  const float cdf = x >= 0.f ? 1.f - hq : hq;
+  y = x * cdf;
+  dy = fmaf(x * 0.39894228040143267794f, e, cdf);
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   float e;
   const float hq = 0.5f * gelu_q_(fabsf(x), e);

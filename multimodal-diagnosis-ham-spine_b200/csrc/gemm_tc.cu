@@ -40,7 +40,10 @@ template <int BN, bool LD, int CL = 1> struct Cfg {
   // two 16 KiB output staging boxes (128 rows x 128 bytes, 128B-swizzled) feeding the TMA store / reduce-add
   static constexpr int STAGING_BYTES = 2 * 16384;
   static constexpr int EPI_GROUPS = (BN == 64) ? 1 : 2;   // warp groups (4 warps each) that drain the accumulator
-  static constexpr int IN_BYTES = LD ? EPI_GROUPS * 16384 : 0;
+  // operand boxes in flight per epilogue warp group.  Two slots (and one pipeline stage less) were measured: no gain on
+  // the epilogue-bound GEMMs and -6 % on the main-loop-bound ones, so one slot it is.
+  static constexpr int IN_SLOTS = 1;
+  static constexpr int IN_BYTES = LD ? EPI_GROUPS * IN_SLOTS * 16384 : 0;
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + IN_BYTES + BAR_BYTES;
   static_assert(SMEM_BYTES <= SMEM_LIMIT, "shared memory budget exceeded");
 };
@@ -253,7 +256,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * C::STAGES + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * C::STAGES + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * C::STAGES + 4);
-  auto lbar = [&](int h) { return bars + 8u * (2 * C::STAGES + 6 + h); };  // epilogue box-load barriers
+  auto lbar = [&](int h) { return bars + 8u * (2 * C::STAGES + 6 + h); };  // epilogue box-load barriers: [group][slot]
   volatile uint32_t* tmem_slot_gen =
       reinterpret_cast<volatile uint32_t*>(smem_gen + C::STAGES * C::STAGE_BYTES + C::STAGING_BYTES + C::IN_BYTES +
                                            8 * (2 * C::STAGES + 4));
@@ -271,8 +274,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
+    for (int a = 0; a < 4; a++) mbar_init(lbar(a), 1);
     for (int a = 0; a < 2; a++) {
-      mbar_init(lbar(a), 1);
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), CL * 4 * C::EPI_GROUPS);
     }
@@ -511,10 +514,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       named_bar(bar_id, 128);                   // every thread is done with the previous contents of the box
       if (issuer) {
         bulk_wait_read0();                      // ... and so is the TMA engine (previous store)
-        mbar_expect_tx(lbar(half), 16384);
-        tma_load_2d(stage_box, map, lbar(half), col0, row0);
+        mbar_expect_tx(lbar(2 * half), 16384);
+        tma_load_2d(stage_box, map, lbar(2 * half), col0, row0);
       }
-      mbar_wait(lbar(half), lphase);
+      mbar_wait(lbar(2 * half), lphase);
       lphase ^= 1u;
 #pragma unroll
       for (int c = 0; c < 8; c++) {
@@ -532,28 +535,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     };
 
-    // ---- LD: operand boxes run one item ahead.  Items of a tile, in consumption order: [aux_in] [bf16 residual].
-    const uint32_t in_box = in_base + half * 16384;
-    const uint32_t in_row = in_box + row_in_box * 128;
+    // ---- LD: operand boxes run IN_SLOTS items ahead of their consumption (16 KiB slots per warp group).  Items of a
+    // tile, in consumption order: [aux_in] [bf16 residual]; item g lives in slot g % IN_SLOTS.
+    const uint32_t in_box0 = in_base + half * (C::IN_SLOTS * 16384);
     const bool has_aux_in = p.dact != MDHS_ACT_NONE;
     const int n_items = (has_aux_in ? 1 : 0) + ((p.residual != nullptr && !p.r_f32) ? 1 : 0);
-    auto issue_item = [&](int t, int q) {       // issuer thread only; splits == 1 in LD mode
+    int consumed = 0;         // items this group has consumed so far
+    uint32_t lph = 0;         // phase bit of each slot's barrier
+    auto issue_item = [&](int g) {              // issuer thread only; splits == 1 in LD mode
+      const int t = w0 + (n_items == 2 ? (g >> 1) : g) * wstep;
+      if (t >= total_tiles) return;
+      const int q = n_items == 2 ? (g & 1) : 0;
+      const int slot = g % C::IN_SLOTS;
       int split_, n_blk, m_blk;
       decode(t, split_, n_blk, m_blk);
       const CUtensorMap* map = (has_aux_in && q == 0) ? &tmAuxIn : &tmRes;
-      mbar_expect_tx(lbar(half), 16384);
-      tma_load_2d(in_box, map, lbar(half), n_blk * BN + half * HALF_COLS, m_blk * BM);
+      mbar_expect_tx(lbar(2 * half + slot), 16384);
+      tma_load_2d(in_box0 + slot * 16384, map, lbar(2 * half + slot), n_blk * BN + half * HALF_COLS, m_blk * BM);
     };
-    auto consume_item = [&](int t, int q, float* out) {
-      mbar_wait(lbar(half), lphase);
-      lphase ^= 1u;
+    auto consume_item = [&](float* out) {
+      const int slot = consumed % C::IN_SLOTS;
+      mbar_wait(lbar(2 * half + slot), (lph >> slot) & 1u);
+      lph ^= (1u << slot);
+      const uint32_t in_row = in_box0 + slot * 16384 + row_in_box * 128;
 #pragma unroll
       for (int c = 0; c < 8; c++) {
-        uint32_t w0, w1, w2, w3;
+        uint32_t w0_, w1, w2, w3;
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                     : "=r"(w0_), "=r"(w1), "=r"(w2), "=r"(w3)
                      : "r"(in_row + ((c ^ swz) << 4)));
-        const uint32_t w[4] = {w0, w1, w2, w3};
+        const uint32_t w[4] = {w0_, w1, w2, w3};
 #pragma unroll
         for (int k = 0; k < 4; k++) {
           const float2 f = __bfloat1622float2(*reinterpret_cast<const bf162*>(&w[k]));
@@ -561,13 +572,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           out[c * 8 + 2 * k + 1] = f.y;
         }
       }
-      named_bar(bar_id, 128);                   // every thread of the group has copied its row out of the box
-      if (issuer) {
-        if (q + 1 < n_items) issue_item(t, q + 1);
-        else if (t + wstep < total_tiles) issue_item(t + wstep, 0);
-      }
+      named_bar(bar_id, 128);                   // every thread of the group has copied its row out of the slot
+      if (issuer) issue_item(consumed + C::IN_SLOTS);
+      consumed++;
     };
-    if (LD && issuer && n_items > 0 && w0 < total_tiles) issue_item(w0, 0);
+    if (LD && issuer && n_items > 0) {
+      for (int g = 0; g < C::IN_SLOTS; g++) issue_item(g);
+    }
 
     for (int t = w0; t < total_tiles; t += wstep) {
       int split, n_blk, m_blk;
@@ -612,29 +623,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
-        // ---- pre-activation copy (second TMA store through the same staging box)
-        if (p.aux_out != nullptr) {
+        // ---- pre-activation copy (second TMA store through the same staging box) and activation.  MDHS_ACT_GELU_DERIV
+        // stores GELU'(pre) instead of the pre-activation: the backward epilogue then is one multiply per element (erf-GELU'
+        // costs ~16 issue slots per element there and made that GEMM epilogue-bound), and the forward pays two extra FMAs
+        // because GELU and GELU' share their exponential.
+        if (p.act == MDHS_ACT_GELU_DERIV) {
           uint32_t pk[32];
 #pragma unroll
-          for (int j = 0; j < 32; j++) pk[j] = pack_bf16(x[2 * j], x[2 * j + 1]);
-          emit_bf16_box(&tmAux, pk, n0, m_blk * BM);
-        }
-        // ---- activation
-        if (p.act == MDHS_ACT_RELU) {
+          for (int j = 0; j < 32; j++) {
+            float y0, y1, d0, d1;
+            gelu_erf_both(x[2 * j], y0, d0);
+            gelu_erf_both(x[2 * j + 1], y1, d1);
+            x[2 * j] = y0;
+            x[2 * j + 1] = y1;
+            pk[j] = pack_bf16(d0, d1);
+          }
+          if (p.aux_out != nullptr) emit_bf16_box(&tmAux, pk, n0, m_blk * BM);
+        } else {
+          if (p.aux_out != nullptr) {
+            uint32_t pk[32];
 #pragma unroll
-          for (int j = 0; j < 64; j++) x[j] = fmaxf(x[j], 0.f);
-        } else if (p.act == MDHS_ACT_GELU) {
+            for (int j = 0; j < 32; j++) pk[j] = pack_bf16(x[2 * j], x[2 * j + 1]);
+            emit_bf16_box(&tmAux, pk, n0, m_blk * BM);
+          }
+          if (p.act == MDHS_ACT_RELU) {
 #pragma unroll
-          for (int j = 0; j < 64; j++) x[j] = gelu_erf(x[j]);
+            for (int j = 0; j < 64; j++) x[j] = fmaxf(x[j], 0.f);
+          } else if (p.act == MDHS_ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 64; j++) x[j] = gelu_erf(x[j]);
+          }
         }
         // ---- multiply by act'(aux_in) (backward through the activation); aux_in arrives by TMA
         if (p.dact != MDHS_ACT_NONE) {
           float a[64];
-          if (LD) consume_item(t, 0, a);
+          if (LD) consume_item(a);
           else load_box_row(&tmAuxIn, n0, m_blk * BM, a);
 #pragma unroll
           for (int j = 0; j < 64; j++) {
             if (p.dact == MDHS_ACT_RELU) x[j] = a[j] > 0.f ? x[j] : 0.f;
+            else if (p.dact == MDHS_ACT_MUL) x[j] *= a[j];
             else x[j] *= gelu_erf_grad(a[j]);
           }
         }
@@ -659,7 +687,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           } else {
             float a[64];
-            if (LD) consume_item(t, n_items - 1, a);
+            if (LD) consume_item(a);
             else load_box_row(&tmRes, n0, m_blk * BM, a);
 #pragma unroll
             for (int j = 0; j < 64; j++) x[j] += a[j];
@@ -915,6 +943,13 @@ int dispatch_major(const mdhs_gemm_args* a, const Params& p, cudaStream_t s) {
   return a->b_mn_major ? launch<BN, false, true, LD, CL>(a, p, s) : launch<BN, false, false, LD, CL>(a, p, s);
 }
 
+// Relative main-loop efficiency of a tile width (measured on the BERT shapes, B200): 256-wide pair tiles reach ~1.2 PF/s,
+// 128-wide pair tiles ~1.05, single-CTA 128-wide ~0.88, 64-wide (never paired) ~0.6.
+double tile_width_factor(int c, bool pairs) {
+  if (pairs) return c == 256 ? 1.0 : 0.80;
+  return c == 256 ? 0.85 : (c == 128 ? 0.75 : 0.50);
+}
+
 // MDHS_GEMM_CLUSTER: 0 disables the CTA-pair (cta_group::2) path, 2 forces it wherever it is legal (tests), default auto
 int cluster_mode() {
   static int v = -1;
@@ -980,12 +1015,15 @@ extern "C" int mdhs_gemm_bf16(const mdhs_gemm_args* a, void* stream_) {
     for (int i = 0; i < 3; i++) {
       const int c = cand[i];
       if (c > 64 && a->N <= c / 2) continue;
-      const int64_t mn = (int64_t)ceil_div(a->M, BM) * ceil_div(a->N, c);
+      // work items are CTA-pair tiles (256 x c) when the pair path applies, scheduled on sms / 2 pairs
+      const bool pairs = cluster_mode() != 0 && c >= 128 && ceil_div(a->M, BM) >= 2;
+      const int64_t mn = (int64_t)(pairs ? (ceil_div(a->M, BM) + 1) / 2 : ceil_div(a->M, BM)) * ceil_div(a->N, c);
+      const int units = pairs ? sms / 2 : sms;
       for (int sp = 1; sp <= max_s; sp++) {
         const int64_t tiles = mn * sp;
-        const int64_t waves = (tiles + sms - 1) / sms;
-        double eff = (double)tiles / (double)(waves * sms);
-        eff *= (c == 256 ? 1.0 : (c == 128 ? 0.93 : 0.80));
+        const int64_t waves = (tiles + units - 1) / units;
+        double eff = (double)tiles / (double)(waves * units);
+        eff *= tile_width_factor(c, pairs);
         eff *= (double)a->N / (double)((int64_t)ceil_div(a->N, c) * c);
         eff *= 1.0 - 0.004 * sp;   // every extra split re-reduces the whole output
         if (eff > best) {
@@ -1026,11 +1064,17 @@ extern "C" int mdhs_gemm_bf16(const mdhs_gemm_args* a, void* stream_) {
       const int c = cand[i];
       if (c > 64 && a->N <= c / 2) continue;
       if (c == 256 && wants_ld) continue;
-      const int64_t tiles = (int64_t)ceil_div(a->M, BM) * ceil_div(a->N, c) * p.splits;
-      const int64_t waves = (tiles + sms - 1) / sms;
-      double eff = (double)tiles / (double)(waves * sms);
-      // wider tiles re-read A less often and keep the tensor pipe busier per smem byte
-      eff *= (c == 256 ? 1.0 : (c == 128 ? 0.93 : 0.80));
+      const bool pairs = cluster_mode() != 0 && c >= 128 && ceil_div(a->M, BM) >= 2;
+      const int64_t tiles =
+          (int64_t)(pairs ? (ceil_div(a->M, BM) + 1) / 2 : ceil_div(a->M, BM)) * ceil_div(a->N, c) * p.splits;
+      const int units = pairs ? sms / 2 : sms;
+      const int64_t waves = (tiles + units - 1) / units;
+      double eff = (double)tiles / (double)(waves * units);
+      // wider tiles re-read A less often, need fewer MMA issues per flop and keep the tensor pipe busier per smem byte
+      eff *= tile_width_factor(c, pairs);
+      // ... but a 256-wide tile gives each epilogue thread 128 columns: with erf-GELU math per element the epilogue, not the
+      // tensor pipe, paces the kernel (measured: FFN1 forward 49 us at 128 vs 55 us at 256)
+      if (c == 256 && (a->act == MDHS_ACT_GELU || a->act == MDHS_ACT_GELU_DERIV)) eff *= 0.85;
       // padding waste inside the last column block
       eff *= (double)a->N / (double)((int64_t)ceil_div(a->N, c) * c);
       if (eff > best) {

@@ -370,29 +370,22 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_reduce_kernel(const bf16* __res
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
   const int64_t r1 = min(rows, r0 + rows_per_block);
   if (ok) {
-    for (int64_t r = r0 + rl; r < r1; r += 16) {
-      const bool two = r + 8 < r1;
-      float d[2][8], xv[2][8], yv[2][8];
-      load8(dy + r * Cw + c0, d[0]);
-      load8(x + r * Cw + c0, xv[0]);
-      if (relu && !remask) load8(y + r * Cw + c0, yv[0]);
-      if (two) {
-        load8(dy + (r + 8) * Cw + c0, d[1]);
-        load8(x + (r + 8) * Cw + c0, xv[1]);
-        if (relu && !remask) load8(y + (r + 8) * Cw + c0, yv[1]);
-      }
+    // a[k] = sum dy', b[k] = sum dy' * x; the per-channel affine map to xhat is applied once after the loop
+    for (int64_t r = r0 + rl; r < r1; r += 8) {
+      float d[8], xv[8], yv[8];
+      load8(dy + r * Cw + c0, d);
+      load8(x + r * Cw + c0, xv);
+      if (relu && !remask) load8(y + r * Cw + c0, yv);
 #pragma unroll
-      for (int u = 0; u < 2; u++) {
-        if (u == 1 && !two) break;
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-          const float act = remask ? fmaf(xv[u][k], sc[k], sf[k]) : yv[u][k];
-          const float dd = (relu && !(act > 0.f)) ? 0.f : d[u][k];
-          a[k] += dd;
-          b[k] += dd * (xv[u][k] - mu[k]) * is[k];
-        }
+      for (int k = 0; k < 8; k++) {
+        const float act = remask ? fmaf(xv[k], sc[k], sf[k]) : yv[k];
+        const float dd = (relu && !(act > 0.f)) ? 0.f : d[k];
+        a[k] += dd;
+        b[k] = fmaf(dd, xv[k] - mu[k], b[k]);
       }
     }
+#pragma unroll
+    for (int k = 0; k < 8; k++) b[k] *= is[k];
   }
 #pragma unroll
   for (int k = 0; k < 8; k++) {
@@ -718,7 +711,7 @@ extern "C" int mdhs_bn_bwd(const void* dy, const void* x, const void* y, const f
   int row_blocks = (148 * 8) / cslabs;
   if (row_blocks < 1) row_blocks = 1;
   int rpb = ceil_div(rows_w, row_blocks);
-  rpb = ((rpb + 15) / 16) * 16;
+  rpb = ((rpb + 7) / 8) * 8;
   row_blocks = ceil_div(rows_w, rpb);
   g_mdhs_launches += 3;
   const bool remask = relu && !y;

@@ -10,6 +10,7 @@ from . import _lib
 from ._lib import GemmArgs, check
 
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+ACT_GELU_DERIV, ACT_MUL = 3, 4   # forward GELU saving GELU'(pre) in aux_out / backward multiply by that aux_in
 DT_BF16, DT_F32 = 0, 1
 
 

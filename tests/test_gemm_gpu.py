@@ -63,6 +63,16 @@ def test_gemm_epilogues(mdhs):
     gp = 0.5 * (1 + torch.erf(x / 2 ** 0.5)) + x * torch.exp(-0.5 * x * x) / (2 * torch.pi) ** 0.5
     ref = (a.float() @ w.float().t()) * gp
     assert (g - ref).abs().max().item() <= 3e-3 * ref.abs().max().item()
+    # forward GELU that saves GELU'(pre) + backward multiply by the saved derivative
+    daux = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    out = ops.gemm(a, w, bias=bias, act=ops.ACT_GELU_DERIV, aux_out=daux, out_dtype=torch.float32)
+    assert (out - torch.nn.functional.gelu(pre)).abs().max().item() <= 2e-3 * pre.abs().max().item()
+    xp = pre
+    gpp = 0.5 * (1 + torch.erf(xp / 2 ** 0.5)) + xp * torch.exp(-0.5 * xp * xp) / (2 * torch.pi) ** 0.5
+    assert (daux.float() - gpp).abs().max().item() <= 1e-2
+    g = ops.gemm(a, w, aux_in=daux, dact=ops.ACT_MUL, out_dtype=torch.float32)
+    ref = (a.float() @ w.float().t()) * daux.float()
+    assert (g - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
     # relu' mask
     g = ops.gemm(a, w, aux_in=aux, dact=ops.ACT_RELU, out_dtype=torch.float32)
     ref = (a.float() @ w.float().t()) * (aux.float() > 0)

@@ -28,7 +28,12 @@ CASES = [
     ("ffn1_fwd", T, F, C, 0, 0, dict(bias=1, act=ops.ACT_GELU, aux_out=1)),
     ("ffn1_fwd_noaux", T, F, C, 0, 0, dict(bias=1, act=ops.ACT_GELU)),
     ("ffn2_fwd", T, C, F, 0, 0, dict(bias=1, residual=1, drop=0.1)),
+    ("ffn1_fwd_deriv", T, F, C, 0, 0, dict(bias=1, act=ops.ACT_GELU_DERIV, aux_out=1)),
     ("ffn2_dgrad", T, F, C, 0, 1, dict(dact=ops.ACT_GELU, aux_in=1)),
+    ("ffn2_dgrad_mul", T, F, C, 0, 1, dict(dact=ops.ACT_MUL, aux_in=1)),
+    ("plain_8192_3072_768_bn256", T, F, C, 0, 0, dict(bn=256)),
+    ("plain_8192_768_3072_bn256", T, C, F, 0, 0, dict(bn=256)),
+    ("qkv_fwd_bn128", T, 3 * C, C, 0, 0, dict(bias=1, bn=128)),
     ("ffn2_dgrad_plain", T, F, C, 0, 1, {}),
     ("ffn1_dgrad", T, C, F, 0, 1, dict(residual=1)),
     ("out_dgrad", T, C, C, 0, 1, {}),
@@ -61,7 +66,7 @@ def main():
         for _ in range(ROT):
             a = torch.randn((K, M) if a_mn else (M, K), device=dev).mul_(0.5).bfloat16()
             b = torch.randn((K, N) if b_mn else (N, K), device=dev).mul_(0.05).bfloat16()
-            kw = dict(a_mn=bool(a_mn), b_mn=bool(b_mn), bn_hint=bn_hint)
+            kw = dict(a_mn=bool(a_mn), b_mn=bool(b_mn), bn_hint=o.get("bn", bn_hint))
             if o.get("acc"):
                 kw.update(out=torch.zeros(M, N, device=dev), accumulate=True, split_k=-1)
             else:
