@@ -28,17 +28,20 @@ constexpr int SMEM_LIMIT = 232448;                           // 227 KiB opt-in m
 // LD = the epilogue reads bf16 operand boxes (act'(aux_in) and / or a bf16 residual): they are prefetched by TMA into a
 // dedicated shared-memory box per epilogue warp group, one tile ahead of the accumulator, so their HBM latency is
 // hidden under the main loop (one pipeline stage is traded for the boxes).  Only BN <= 128 (one 64-column box per group).
-template <int BN, bool LD, int CL = 1> struct Cfg {
+template <int BN, bool LD, int CL = 1, bool AUX = false> struct Cfg {
   static_assert(!(LD && BN == 256), "operand prefetch needs BN <= 128");
   static_assert(CL == 1 || BN >= 128, "CTA pairs need BN >= 128");
   static constexpr int B_TILE_BYTES = (BN / CL) * BK * 2;     // CL 2: each CTA of the pair stages half of the B tile
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int STAGES = CL == 2 ? (BN == 256 ? 6 : (LD ? 6 : 8))
-                                        : ((BN == 256) ? 4 : (BN == 128 ? (LD ? 5 : 6) : (LD ? 7 : 8)));
+  static_assert(!(LD && AUX), "aux_out and prefetched operand boxes are not combined");
+  // AUX (a second output tensor: pre-activation / GELU' copy) owns its own staging boxes and pays one pipeline stage
+  static constexpr int STAGES_BASE = CL == 2 ? (BN == 256 ? 6 : (LD ? 6 : 8))
+                                             : ((BN == 256) ? 4 : (BN == 128 ? (LD ? 5 : 6) : (LD ? 7 : 8)));
+  static constexpr int STAGES = STAGES_BASE - (AUX ? (STAGE_BYTES <= 24576 ? 2 : 1) : 0);
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int BAR_BYTES = 256;
   // two 16 KiB output staging boxes (128 rows x 128 bytes, 128B-swizzled) feeding the TMA store / reduce-add
-  static constexpr int STAGING_BYTES = 2 * 16384;
+  static constexpr int STAGING_BYTES = (AUX ? 4 : 2) * 16384;
   static constexpr int EPI_GROUPS = (BN == 64) ? 1 : 2;   // warp groups (4 warps each) that drain the accumulator
   // operand boxes in flight per epilogue warp group.  Two slots (and one pipeline stage less) were measured: no gain on
   // the epilogue-bound GEMMs and -6 % on the main-loop-bound ones, so one slot it is.
@@ -187,6 +190,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
@@ -211,6 +222,17 @@ __device__ __forceinline__ void named_bar(int id, int threads) {
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ void ld_shared_bf16x8(uint32_t addr, float* out) {
+  uint32_t w0, w1, w2, w3;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(addr));
+  const uint32_t w[4] = {w0, w1, w2, w3};
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const bf162*>(&w[k]));
+    out[2 * k] = f.x;
+    out[2 * k + 1] = f.y;
+  }
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   bf162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -227,6 +249,177 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
+// ------------------------------------------------------------------ epilogue chunk loop
+// Per-thread state of one epilogue warp-group thread (thread = accumulator row) for the current box.
+struct EpiCtx {
+  uint32_t stage_row, aux_row, in_row, taddr;
+  int swz, n0;
+  int64_t m;
+  float inv_keep;
+  bool row_ok, first_split, zero_row, has_bias, has_aux_in, box_is_aux, box_is_res;
+};
+enum : int { F_BIAS = 1, F_GELU_DERIV = 2, F_BOX_MUL = 4, F_BOX_RES = 8, F_DROP = 16, F_F32 = 32, F_GENERIC = 64 };
+
+// Walks chunks [it0, it1) of 16 accumulator columns: tcgen05.ld (the next chunk is already in flight while this one is
+// processed) -> fused element-wise work -> st.shared into the swizzled staging box.  FEAT selects the features at compile
+// time; F_GENERIC tests them at run time (everything the ABI allows).
+template <int FEAT, bool AUX>
+__device__ __forceinline__ void epi_chunks(const EpiCtx& ec, const Params& p, int it0, int it1) {
+  constexpr bool G = (FEAT & F_GENERIC) != 0;
+  const bool f_bias = G ? (ec.has_bias && ec.first_split) : ((FEAT & F_BIAS) != 0 && ec.first_split);
+  const bool f_gderiv = G ? (p.act == MDHS_ACT_GELU_DERIV) : (FEAT & F_GELU_DERIV) != 0;
+  const bool f_f32 = G ? (p.d_f32 != 0) : (FEAT & F_F32) != 0;
+  const bool f_drop = G ? (p.drop_p > 0.f) : (FEAT & F_DROP) != 0;
+  const bool f_boxmul = !G && (FEAT & F_BOX_MUL) != 0;
+  const bool f_boxres = !G && (FEAT & F_BOX_RES) != 0;
+  const int swz = ec.swz;
+  // light feature sets: the four chunks of a box are unrolled (independent loads in flight, as little code as one heavy
+  // chunk); heavy ones (erf math, dropout hashes, run-time tests) stay a rolled loop that lives in the L0 instruction cache
+  constexpr int UNROLL = (FEAT & (F_GELU_DERIV | F_DROP | F_GENERIC)) ? 1 : 4;
+  uint32_t r[16];
+  tmem_ld16(ec.taddr + it0 * 16, r);
+#pragma unroll UNROLL
+  for (int it = it0; it < it1; it++) {
+    const int nc = ec.n0 + it * 16;          // first column of this 16-column chunk
+    const bool cols_ok = nc < p.N, cols_ok2 = nc + 8 < p.N;
+    // operands that do not depend on the accumulator are requested before waiting for it
+    float4 bv[4];
+    if (f_bias) {
+#pragma unroll
+      for (int v = 0; v < 4; v++)
+        bv[v] = (v < 2 ? cols_ok : cols_ok2) ? __ldg(reinterpret_cast<const float4*>(p.bias + nc + v * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float bx[16];
+    if (f_boxmul || f_boxres) {
+      ld_shared_bf16x8(ec.in_row + (((2 * it) ^ swz) << 4), bx);
+      ld_shared_bf16x8(ec.in_row + (((2 * it + 1) ^ swz) << 4), bx + 8);
+    }
+    float x[16];
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; j++) x[j] = __uint_as_float(r[j]);
+    if (it + 1 < it1) tmem_ld16(ec.taddr + (it + 1) * 16, r);
+    // ---- bias (same address in every lane: one broadcast transaction per vector)
+    if (f_bias) {
+#pragma unroll
+      for (int v = 0; v < 4; v++) {
+        x[v * 4 + 0] += bv[v].x; x[v * 4 + 1] += bv[v].y; x[v * 4 + 2] += bv[v].z; x[v * 4 + 3] += bv[v].w;
+      }
+    }
+    // ---- activation (+ second output: the pre-activation, or GELU'(pre) for MDHS_ACT_GELU_DERIV so that the backward
+    // epilogue is one multiply per element; GELU and GELU' share their exponential)
+    if (f_gderiv) {
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        float y0, y1, d0, d1;
+        gelu_erf_both(x[2 * j], y0, d0);
+        gelu_erf_both(x[2 * j + 1], y1, d1);
+        x[2 * j] = y0;
+        x[2 * j + 1] = y1;
+        pk[j] = pack_bf16(d0, d1);
+      }
+      if (AUX) {
+        st_shared_v4(ec.aux_row + (((2 * it) ^ swz) << 4), pk[0], pk[1], pk[2], pk[3]);
+        st_shared_v4(ec.aux_row + (((2 * it + 1) ^ swz) << 4), pk[4], pk[5], pk[6], pk[7]);
+      }
+    } else if (G) {
+      if (AUX) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) pk[j] = pack_bf16(x[2 * j], x[2 * j + 1]);
+        st_shared_v4(ec.aux_row + (((2 * it) ^ swz) << 4), pk[0], pk[1], pk[2], pk[3]);
+        st_shared_v4(ec.aux_row + (((2 * it + 1) ^ swz) << 4), pk[4], pk[5], pk[6], pk[7]);
+      }
+      if (p.act == MDHS_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) x[j] = fmaxf(x[j], 0.f);
+      } else if (p.act == MDHS_ACT_GELU) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) x[j] = gelu_erf(x[j]);
+      }
+    }
+    // ---- multiply by act'(aux_in) (backward through the activation)
+    if (f_boxmul) {
+#pragma unroll
+      for (int j = 0; j < 16; j++) x[j] *= bx[j];
+    } else if (G && ec.has_aux_in) {
+      float a[16];
+      if (ec.box_is_aux) {
+        ld_shared_bf16x8(ec.in_row + (((2 * it) ^ swz) << 4), a);
+        ld_shared_bf16x8(ec.in_row + (((2 * it + 1) ^ swz) << 4), a + 8);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; j++) a[j] = 0.f;
+        if (ec.row_ok && cols_ok) load8(p.aux_in + ec.m * p.ld_aux_in + nc, a);
+        if (ec.row_ok && cols_ok2) load8(p.aux_in + ec.m * p.ld_aux_in + nc + 8, a + 8);
+      }
+      if (p.dact == MDHS_ACT_MUL) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) x[j] *= a[j];
+      } else if (p.dact == MDHS_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) x[j] = a[j] > 0.f ? x[j] : 0.f;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; j++) x[j] *= gelu_erf_grad(a[j]);
+      }
+    }
+    // ---- dropout (stateless: recomputed from (seed, element index) in the backward pass)
+    if (f_drop) {   // N % 8 == 0 and nc % 16 == 0: groups of 4 columns share one hash
+      const uint64_t e0 = (uint64_t)ec.m * (uint64_t)p.N + (uint64_t)nc;
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) dropout_apply4(p.drop_seed, e0 + j, p.drop_p, ec.inv_keep, x + j);
+    }
+    // ---- residual
+    if (f_boxres) {
+#pragma unroll
+      for (int j = 0; j < 16; j++) x[j] += bx[j];
+    } else if (G && p.residual != nullptr && ec.first_split) {
+      if (p.r_f32) {
+        if (ec.row_ok) {
+          const float* rp = reinterpret_cast<const float*>(p.residual) + ec.m * p.ldr + nc;
+#pragma unroll
+          for (int v = 0; v < 4; v++) {
+            if (v < 2 ? cols_ok : cols_ok2) {
+              const float4 rr = *reinterpret_cast<const float4*>(rp + v * 4);
+              x[v * 4 + 0] += rr.x; x[v * 4 + 1] += rr.y; x[v * 4 + 2] += rr.z; x[v * 4 + 3] += rr.w;
+            }
+          }
+        }
+      } else {
+        float a[16];
+        if (ec.box_is_res) {
+          ld_shared_bf16x8(ec.in_row + (((2 * it) ^ swz) << 4), a);
+          ld_shared_bf16x8(ec.in_row + (((2 * it + 1) ^ swz) << 4), a + 8);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; j++) a[j] = 0.f;
+          const bf16* rp = reinterpret_cast<const bf16*>(p.residual) + ec.m * p.ldr + nc;
+          if (ec.row_ok && cols_ok) load8(rp, a);
+          if (ec.row_ok && cols_ok2) load8(rp + 8, a + 8);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j++) x[j] += a[j];
+      }
+    }
+    // ---- into the staging box
+    if (f_f32) {
+      const int cb = (it & 1) * 4;        // 16 fp32 columns = 4 of the box row's 8 chunks
+#pragma unroll
+      for (int c = 0; c < 4; c++)
+        st_shared_v4(ec.stage_row + (((cb + c) ^ swz) << 4), __float_as_uint(x[4 * c]), __float_as_uint(x[4 * c + 1]),
+                     __float_as_uint(x[4 * c + 2]), __float_as_uint(x[4 * c + 3]));
+    } else {
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) pk[j] = ec.zero_row ? 0u : pack_bf16(x[2 * j], x[2 * j + 1]);
+      st_shared_v4(ec.stage_row + (((2 * it) ^ swz) << 4), pk[0], pk[1], pk[2], pk[3]);
+      st_shared_v4(ec.stage_row + (((2 * it + 1) ^ swz) << 4), pk[4], pk[5], pk[6], pk[7]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ kernel
 // CL = 2: CTA pairs (clusters of two CTAs on one TPC) own vertically adjacent tiles (same column block, m_blk = 2j + rank)
 // and run them as ONE 256 x BN tcgen05.mma.cta_group::2: each CTA stages its own 128 A rows and HALF of the B tile, the
@@ -237,12 +430,12 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 // Protocol: `full` barriers live in the leader (one arrival: the leader's expect_tx of both CTAs' bytes; both CTAs'
 // TMA loads complete on it); `empty` / `tmem_full` are signalled in both CTAs by multicast tcgen05.commit; both CTAs'
 // epilogue warps release an accumulator stage on the leader's `tmem_empty`.
-template <int BN, bool A_MN, bool B_MN, bool LD, int CL>
+template <int BN, bool A_MN, bool B_MN, bool LD, int CL, bool AUX>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmAux,
                const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmAuxIn, const Params p) {
-  using C = Cfg<BN, LD, CL>;
+  using C = Cfg<BN, LD, CL, AUX>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -471,112 +664,73 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= EPI_WARP0 && (warp - EPI_WARP0) < 4 * C::EPI_GROUPS) {
     // ------------------------------------------------------------ epilogue
-    // Warp (4+q) [and (8+q) when BN >= 128] owns TMEM lane quarter q; two groups split the tile's columns in
-    // halves and walk them 64 columns at a time.  Thread = accumulator row.  Results are written into a
-    // 128B-swizzled shared-memory box (128 rows x 128 bytes) and leave through one TMA store (bf16 / fp32) or
-    // TMA reduce-add (fp32 gradient accumulation, split-K) per box: full-line writes, no per-thread stores.
+    // Warp (4+q) [and (8+q) when BN >= 128] owns TMEM lane quarter q; two groups split the tile's columns in halves and
+    // walk them 64 columns (one output box) at a time.  Thread = accumulator row.  A box is produced by a COMPACT loop
+    // over 16-column chunks -- tcgen05.ld 16 columns -> bias / activation / act' / dropout / residual -> pack ->
+    // st.shared into the 128B-swizzled staging box -- and leaves through one TMA store (bf16 / fp32) or TMA reduce-add
+    // (fp32 gradient accumulation, split-K): full-line writes, no per-thread global stores.  The previous form unrolled
+    // every feature over 64 columns; its executed path wandered over ~100 KB of code and ncu showed the epilogue warps
+    // stalled on instruction fetch (stall_no_inst) for half of their samples.
     const int wq = (warp - EPI_WARP0) & 3;     // TMEM lane quarter
     const int half = (warp - EPI_WARP0) >> 2;  // column half of the tile
     constexpr int HALF_COLS = BN / C::EPI_GROUPS;
-    constexpr int PAIRS = HALF_COLS / 64;      // 64-column steps per warp (1 or 2)
+    constexpr int PAIRS = HALF_COLS / 64;      // 64-column boxes per warp group and tile (1 or 2)
     const uint32_t stage_box = staging_base + half * 16384;
+    const uint32_t aux_box = staging_base + (2 + half) * 16384;   // AUX kernels only
     const int row_in_box = wq * 32 + lane;
     const uint32_t stage_row = stage_box + row_in_box * 128;
+    const uint32_t aux_row = aux_box + row_in_box * 128;
     const int swz = row_in_box & 7;
     const bool issuer = (wq == 0 && lane == 0);
     const int bar_id = 1 + half;               // named barrier of this warp group (128 threads)
     const float inv_keep = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+    const bool has_bias = p.bias != nullptr;
+    const bool has_aux_in = p.dact != MDHS_ACT_NONE;
+    const bool res_bf16 = p.residual != nullptr && !p.r_f32;
+    // the prefetched operand box carries aux_in when there is one, else the bf16 residual; whatever is left is read with
+    // 16-byte row loads straight from global memory (slow path: both operands at once, or kernels without LD)
+    const bool box_is_aux = LD && has_aux_in;
+    const bool box_is_res = LD && !has_aux_in && res_bf16;
     int acc = 0;
     uint32_t acc_phase = 0;
     float cacc[PAIRS][4];
 #pragma unroll
     for (int i = 0; i < PAIRS; i++) cacc[i][0] = cacc[i][1] = cacc[i][2] = cacc[i][3] = 0.f;
 
-    // stage 64 bf16 columns (one box) from packed registers and hand the box to the TMA engine
-    auto emit_bf16_box = [&](const CUtensorMap* map, const uint32_t* pk, int col0, int row0) {
-      if (issuer) bulk_wait_read0();            // previous box has been read out of shared memory
-      named_bar(bar_id, 128);
-#pragma unroll
-      for (int c = 0; c < 8; c++)
-        st_shared_v4(stage_row + ((c ^ swz) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-      fence_async_smem();
-      named_bar(bar_id, 128);
-      if (issuer) {
-        tma_store_2d(map, stage_box, col0, row0);
-        bulk_commit();
-      }
-    };
+    // feature set of this launch -> which specialised chunk loop runs (see epi_chunks)
+    int feat;
+    {
+      const bool simple_act = p.act == MDHS_ACT_NONE && !AUX;
+      const bool no_res = p.residual == nullptr, no_aux_in = !has_aux_in, no_drop = !(p.drop_p > 0.f);
+      if (p.d_f32) feat = (simple_act && no_res && no_aux_in && no_drop && !has_bias) ? F_F32 : F_GENERIC;
+      else if (AUX) feat = (p.act == MDHS_ACT_GELU_DERIV && has_bias && no_res && no_aux_in && no_drop) ? (F_BIAS | F_GELU_DERIV) : F_GENERIC;
+      else if (!simple_act) feat = F_GENERIC;
+      else if (box_is_aux) feat = (p.dact == MDHS_ACT_MUL && no_res && no_drop && !has_bias) ? F_BOX_MUL : F_GENERIC;
+      else if (!no_aux_in) feat = F_GENERIC;
+      else if (box_is_res) feat = (has_bias ? F_BIAS : 0) | F_BOX_RES | (no_drop ? 0 : F_DROP);
+      else if (!no_res) feat = F_GENERIC;
+      else feat = no_drop ? (has_bias ? F_BIAS : 0) : F_GENERIC;
+      if (feat == (F_BOX_RES | F_DROP)) feat = F_GENERIC;   // not instantiated
+    }
+    EpiCtx ec;
+    ec.stage_row = stage_row; ec.aux_row = aux_row; ec.swz = swz; ec.inv_keep = inv_keep;
+    ec.has_bias = has_bias; ec.has_aux_in = has_aux_in; ec.box_is_aux = box_is_aux; ec.box_is_res = box_is_res;
 
-    // TMA-load one bf16 box (128 rows x 64 columns) of a residual / activation tensor into the staging buffer and
-    // return this thread's row as 64 floats.  Replaces 8 row-strided 16-byte global loads per thread.
-    uint32_t lphase = 0;
-    auto load_box_row = [&](const CUtensorMap* map, int col0, int row0, float* out) {
-      named_bar(bar_id, 128);                   // every thread is done with the previous contents of the box
-      if (issuer) {
-        bulk_wait_read0();                      // ... and so is the TMA engine (previous store)
-        mbar_expect_tx(lbar(2 * half), 16384);
-        tma_load_2d(stage_box, map, lbar(2 * half), col0, row0);
-      }
-      mbar_wait(lbar(2 * half), lphase);
-      lphase ^= 1u;
-#pragma unroll
-      for (int c = 0; c < 8; c++) {
-        uint32_t w0, w1, w2, w3;
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
-                     : "r"(stage_row + ((c ^ swz) << 4)));
-        const uint32_t w[4] = {w0, w1, w2, w3};
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const float2 f = __bfloat1622float2(*reinterpret_cast<const bf162*>(&w[k]));
-          out[c * 8 + 2 * k] = f.x;
-          out[c * 8 + 2 * k + 1] = f.y;
-        }
-      }
-    };
-
-    // ---- LD: operand boxes run IN_SLOTS items ahead of their consumption (16 KiB slots per warp group).  Items of a
-    // tile, in consumption order: [aux_in] [bf16 residual]; item g lives in slot g % IN_SLOTS.
+    // ---- LD: one operand box per tile and group, prefetched IN_SLOTS tiles ahead of its consumption
     const uint32_t in_box0 = in_base + half * (C::IN_SLOTS * 16384);
-    const bool has_aux_in = p.dact != MDHS_ACT_NONE;
-    const int n_items = (has_aux_in ? 1 : 0) + ((p.residual != nullptr && !p.r_f32) ? 1 : 0);
-    int consumed = 0;         // items this group has consumed so far
+    int consumed = 0;         // boxes this group has consumed so far
     uint32_t lph = 0;         // phase bit of each slot's barrier
     auto issue_item = [&](int g) {              // issuer thread only; splits == 1 in LD mode
-      const int t = w0 + (n_items == 2 ? (g >> 1) : g) * wstep;
+      const int t = w0 + g * wstep;
       if (t >= total_tiles) return;
-      const int q = n_items == 2 ? (g & 1) : 0;
       const int slot = g % C::IN_SLOTS;
       int split_, n_blk, m_blk;
       decode(t, split_, n_blk, m_blk);
-      const CUtensorMap* map = (has_aux_in && q == 0) ? &tmAuxIn : &tmRes;
       mbar_expect_tx(lbar(2 * half + slot), 16384);
-      tma_load_2d(in_box0 + slot * 16384, map, lbar(2 * half + slot), n_blk * BN + half * HALF_COLS, m_blk * BM);
+      tma_load_2d(in_box0 + slot * 16384, box_is_aux ? &tmAuxIn : &tmRes, lbar(2 * half + slot), n_blk * BN + half * HALF_COLS,
+                  m_blk * BM);
     };
-    auto consume_item = [&](float* out) {
-      const int slot = consumed % C::IN_SLOTS;
-      mbar_wait(lbar(2 * half + slot), (lph >> slot) & 1u);
-      lph ^= (1u << slot);
-      const uint32_t in_row = in_box0 + slot * 16384 + row_in_box * 128;
-#pragma unroll
-      for (int c = 0; c < 8; c++) {
-        uint32_t w0_, w1, w2, w3;
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(w0_), "=r"(w1), "=r"(w2), "=r"(w3)
-                     : "r"(in_row + ((c ^ swz) << 4)));
-        const uint32_t w[4] = {w0_, w1, w2, w3};
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const float2 f = __bfloat1622float2(*reinterpret_cast<const bf162*>(&w[k]));
-          out[c * 8 + 2 * k] = f.x;
-          out[c * 8 + 2 * k + 1] = f.y;
-        }
-      }
-      named_bar(bar_id, 128);                   // every thread of the group has copied its row out of the slot
-      if (issuer) issue_item(consumed + C::IN_SLOTS);
-      consumed++;
-    };
-    if (LD && issuer && n_items > 0) {
+    if (LD && issuer && (box_is_aux || box_is_res)) {
       for (int g = 0; g < C::IN_SLOTS; g++) issue_item(g);
     }
 
@@ -587,138 +741,69 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int64_t m = (int64_t)m_blk * BM + wq * 32 + lane;
       const bool row_ok = m < p.M;
       const bool first_split = (split == 0);
+      const bool zero_row = (p.colsum != nullptr) && !row_ok;   // rows beyond M must not reach the statistics
 
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN + half * HALF_COLS);
+      ec.m = m; ec.row_ok = row_ok; ec.first_split = first_split; ec.zero_row = zero_row;
+      uint32_t in_row = 0;
+      if (LD && (box_is_aux || box_is_res)) {     // PAIRS == 1 in LD kernels: one box per tile
+        const int slot = consumed % C::IN_SLOTS;
+        mbar_wait(lbar(2 * half + slot), (lph >> slot) & 1u);
+        lph ^= (1u << slot);
+        in_row = in_box0 + slot * 16384 + row_in_box * 128;
+      }
+      ec.in_row = in_row;
 
 #pragma unroll
       for (int pr = 0; pr < PAIRS; pr++) {
-        uint32_t r[64];
-        tmem_ld32(taddr + pr * 64, r);
-        tmem_ld32(taddr + pr * 64 + 32, r + 32);
-        tmem_ld_wait();
-        if (pr == PAIRS - 1) {
-          // this warp has read its whole slice: hand the TMEM stage back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (CL > 1) mbar_arrive_cluster(mapa_rank(tempty_bar(acc), 0));
-            else mbar_arrive(tempty_bar(acc));
-          }
-        }
         const int n0 = n_half0 + pr * 64;
         // NOTE: no early exit for columns beyond N: the whole warp group must reach the named barriers; TMA clips
-        // out-of-range columns / rows and every direct global access below is bounds-checked.
-        float x[64];
-#pragma unroll
-        for (int j = 0; j < 64; j++) x[j] = __uint_as_float(r[j]);
-        // ---- bias (same address in every lane: one broadcast transaction per vector)
-        if (p.bias != nullptr && first_split) {
-#pragma unroll
-          for (int v = 0; v < 16; v++) {
-            if (n0 + v * 4 < p.N) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + v * 4));
-              x[v * 4 + 0] += b.x; x[v * 4 + 1] += b.y; x[v * 4 + 2] += b.z; x[v * 4 + 3] += b.w;
+        // out-of-range columns / rows and every direct global access below is bounds-checked (N % 8 == 0).
+        constexpr int NBOX_MAX = 2;
+        const int nbox = p.d_f32 ? 2 : 1;        // an fp32 box holds 32 columns, a bf16 box 64
+        for (int hb = 0; hb < NBOX_MAX; hb++) {
+          if (hb >= nbox) break;
+          if (issuer) bulk_wait_read0();          // the TMA engine has read the previous contents of the staging boxes
+          named_bar(bar_id, 128);
+          const int it0 = p.d_f32 ? hb * 2 : 0, it1 = p.d_f32 ? hb * 2 + 2 : 4;
+          ec.n0 = n0;
+          ec.taddr = taddr + pr * 64;
+          // one compact, branch-free loop per hot feature combination (L0 instruction cache resident after its first
+          // iteration); anything else takes the generic loop with run-time feature tests
+          switch (feat) {
+            case 0: epi_chunks<0, AUX>(ec, p, 0, 4); break;
+            case F_BIAS: epi_chunks<F_BIAS, AUX>(ec, p, 0, 4); break;
+            case F_BOX_RES: epi_chunks<F_BOX_RES, AUX>(ec, p, 0, 4); break;
+            case F_BIAS | F_BOX_RES: epi_chunks<F_BIAS | F_BOX_RES, AUX>(ec, p, 0, 4); break;
+            case F_BIAS | F_BOX_RES | F_DROP: epi_chunks<F_BIAS | F_BOX_RES | F_DROP, AUX>(ec, p, 0, 4); break;
+            case F_BOX_MUL: epi_chunks<F_BOX_MUL, AUX>(ec, p, 0, 4); break;
+            case F_BIAS | F_GELU_DERIV: epi_chunks<F_BIAS | F_GELU_DERIV, AUX>(ec, p, 0, 4); break;
+            case F_F32: epi_chunks<F_F32, AUX>(ec, p, hb * 2, hb * 2 + 2); break;
+            default: epi_chunks<F_GENERIC, AUX>(ec, p, it0, it1); break;
+          }
+          if (pr == PAIRS - 1 && hb == nbox - 1) {
+            // this warp has read its whole accumulator slice: hand the TMEM stage back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (CL > 1) mbar_arrive_cluster(mapa_rank(tempty_bar(acc), 0));
+              else mbar_arrive(tempty_bar(acc));
             }
           }
-        }
-        // ---- pre-activation copy (second TMA store through the same staging box) and activation.  MDHS_ACT_GELU_DERIV
-        // stores GELU'(pre) instead of the pre-activation: the backward epilogue then is one multiply per element (erf-GELU'
-        // costs ~16 issue slots per element there and made that GEMM epilogue-bound), and the forward pays two extra FMAs
-        // because GELU and GELU' share their exponential.
-        if (p.act == MDHS_ACT_GELU_DERIV) {
-          uint32_t pk[32];
-#pragma unroll
-          for (int j = 0; j < 32; j++) {
-            float y0, y1, d0, d1;
-            gelu_erf_both(x[2 * j], y0, d0);
-            gelu_erf_both(x[2 * j + 1], y1, d1);
-            x[2 * j] = y0;
-            x[2 * j + 1] = y1;
-            pk[j] = pack_bf16(d0, d1);
-          }
-          if (p.aux_out != nullptr) emit_bf16_box(&tmAux, pk, n0, m_blk * BM);
-        } else {
-          if (p.aux_out != nullptr) {
-            uint32_t pk[32];
-#pragma unroll
-            for (int j = 0; j < 32; j++) pk[j] = pack_bf16(x[2 * j], x[2 * j + 1]);
-            emit_bf16_box(&tmAux, pk, n0, m_blk * BM);
-          }
-          if (p.act == MDHS_ACT_RELU) {
-#pragma unroll
-            for (int j = 0; j < 64; j++) x[j] = fmaxf(x[j], 0.f);
-          } else if (p.act == MDHS_ACT_GELU) {
-#pragma unroll
-            for (int j = 0; j < 64; j++) x[j] = gelu_erf(x[j]);
-          }
-        }
-        // ---- multiply by act'(aux_in) (backward through the activation); aux_in arrives by TMA
-        if (p.dact != MDHS_ACT_NONE) {
-          float a[64];
-          if (LD) consume_item(a);
-          else load_box_row(&tmAuxIn, n0, m_blk * BM, a);
-#pragma unroll
-          for (int j = 0; j < 64; j++) {
-            if (p.dact == MDHS_ACT_RELU) x[j] = a[j] > 0.f ? x[j] : 0.f;
-            else if (p.dact == MDHS_ACT_MUL) x[j] *= a[j];
-            else x[j] *= gelu_erf_grad(a[j]);
-          }
-        }
-        // ---- dropout (stateless: recomputed from (seed, element index) in the backward pass)
-        if (p.drop_p > 0.f) {   // N % 8 == 0 and n0 % 64 == 0: groups of 4 columns share one hash
-#pragma unroll
-          for (int j = 0; j < 64; j += 4)
-            dropout_apply4(p.drop_seed, (uint64_t)m * (uint64_t)p.N + (uint64_t)(n0 + j), p.drop_p, inv_keep, x + j);
-        }
-        // ---- residual (bf16: TMA box load; fp32: direct row loads)
-        if (p.residual != nullptr && first_split) {
-          if (p.r_f32) {
-            if (row_ok) {
-              const float* rp = reinterpret_cast<const float*>(p.residual) + m * p.ldr + n0;
-#pragma unroll
-              for (int v = 0; v < 16; v++) {
-                if (n0 + v * 4 < p.N) {
-                  const float4 rr = *reinterpret_cast<const float4*>(rp + v * 4);
-                  x[v * 4 + 0] += rr.x; x[v * 4 + 1] += rr.y; x[v * 4 + 2] += rr.z; x[v * 4 + 3] += rr.w;
-                }
-              }
-            }
-          } else {
-            float a[64];
-            if (LD) consume_item(a);
-            else load_box_row(&tmRes, n0, m_blk * BM, a);
-#pragma unroll
-            for (int j = 0; j < 64; j++) x[j] += a[j];
-          }
-        }
-        // ---- store through the staging box + TMA
-        if (p.d_f32) {
-          // 32 fp32 columns == one full box (128 bytes per row): two boxes per 64-column step
-#pragma unroll
-          for (int hb = 0; hb < 2; hb++) {
-            if (issuer) bulk_wait_read0();
-            named_bar(bar_id, 128);
-#pragma unroll
-            for (int c = 0; c < 8; c++)
-              st_shared_v4(stage_row + ((c ^ swz) << 4), __float_as_uint(x[hb * 32 + 4 * c]), __float_as_uint(x[hb * 32 + 4 * c + 1]),
-                           __float_as_uint(x[hb * 32 + 4 * c + 2]), __float_as_uint(x[hb * 32 + 4 * c + 3]));
-            fence_async_smem();
-            named_bar(bar_id, 128);
-            if (issuer) {
+          fence_async_smem();
+          named_bar(bar_id, 128);                 // the box is complete (and every thread is done with the operand box)
+          if (issuer) {
+            if (p.d_f32) {
               if (p.accumulate) tma_reduce_add_2d(&tmD, stage_box, n0 + hb * 32, m_blk * BM);
               else tma_store_2d(&tmD, stage_box, n0 + hb * 32, m_blk * BM);
-              bulk_commit();
+            } else {
+              tma_store_2d(&tmD, stage_box, n0, m_blk * BM);
             }
+            if (AUX && hb == nbox - 1) tma_store_2d(&tmAux, aux_box, n0, m_blk * BM);
+            bulk_commit();
           }
-        } else {
-          // round to bf16 first so that the statistics below describe exactly what was stored
-          uint32_t pk[32];
-          const bool zero_row = (p.colsum != nullptr) && !row_ok;   // rows beyond M must not reach the statistics
-#pragma unroll
-          for (int j = 0; j < 32; j++) pk[j] = zero_row ? 0u : pack_bf16(x[2 * j], x[2 * j + 1]);
-          emit_bf16_box(&tmD, pk, n0, m_blk * BM);
         }
         // ---- per-column sum / sum of squares (train-mode BN statistics) of exactly what was stored: the staged bf16 box
         // is re-read column-wise (lane = column pair, warp = 32-row quarter; one conflict-free 4-byte word per lane and
@@ -744,6 +829,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           cacc[pr][2] += q0;
           cacc[pr][3] += q1;
         }
+      }
+      if (LD && (box_is_aux || box_is_res)) {
+        // every thread of the group passed the box-complete barrier above, i.e. has copied its operand row
+        if (issuer) issue_item(consumed + C::IN_SLOTS);
+        consumed++;
       }
       if (++acc == 2) {
         acc = 0;
@@ -857,9 +947,9 @@ int num_sms() {
   return n;
 }
 
-template <int BN, bool A_MN, bool B_MN, bool LD, int CL>
+template <int BN, bool A_MN, bool B_MN, bool LD, int CL, bool AUX>
 int launch(const mdhs_gemm_args* a, const Params& p0, cudaStream_t stream) {
-  using C = Cfg<BN, LD, CL>;
+  using C = Cfg<BN, LD, CL, AUX>;
   Params p = p0;
   p.num_m = ceil_div(a->M, BM);
   p.num_n = ceil_div(a->N, BN);
@@ -886,7 +976,7 @@ int launch(const mdhs_gemm_args* a, const Params& p0, cudaStream_t stream) {
   else       rc = make_map(&tmB, a->B, a->N, a->K, a->ldb, 64, BK);
   if (rc) return rc;
   static bool attr_set = false;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, LD, CL>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, LD, CL, AUX>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
@@ -935,12 +1025,17 @@ int launch(const mdhs_gemm_args* a, const Params& p0, cudaStream_t stream) {
 
 template <int BN, bool LD, int CL>
 int dispatch_major(const mdhs_gemm_args* a, const Params& p, cudaStream_t s) {
+  if (a->aux_out) {
+    // a second output tensor only occurs in forward Linear layers (K-major A, no operand boxes)
+    if (a->a_mn_major || LD) return MDHS_ERR_ARG;
+    return a->b_mn_major ? launch<BN, false, true, false, CL, true>(a, p, s) : launch<BN, false, false, false, CL, true>(a, p, s);
+  }
   if (a->a_mn_major) {
     // MN-major A only occurs in weight-gradient GEMMs, which never read epilogue operand boxes
     if (LD) return MDHS_ERR_ARG;
-    return a->b_mn_major ? launch<BN, true, true, false, CL>(a, p, s) : launch<BN, true, false, false, CL>(a, p, s);
+    return a->b_mn_major ? launch<BN, true, true, false, CL, false>(a, p, s) : launch<BN, true, false, false, CL, false>(a, p, s);
   }
-  return a->b_mn_major ? launch<BN, false, true, LD, CL>(a, p, s) : launch<BN, false, false, LD, CL>(a, p, s);
+  return a->b_mn_major ? launch<BN, false, true, LD, CL, false>(a, p, s) : launch<BN, false, false, LD, CL, false>(a, p, s);
 }
 
 // Relative main-loop efficiency of a tile width (measured on the BERT shapes, B200): 256-wide pair tiles reach ~1.2 PF/s,
@@ -1051,7 +1146,7 @@ extern "C" int mdhs_gemm_bf16(const mdhs_gemm_args* a, void* stream_) {
 
   // epilogue operand boxes (act'(aux_in), bf16 residual) are prefetched one tile ahead when the tile is <= 128 wide
   const bool wants_ld = (a->aux_in != nullptr || (a->residual != nullptr && a->r_dtype == MDHS_DT_BF16)) && p.splits == 1 &&
-                        !a->a_mn_major;
+                        !a->a_mn_major && a->aux_out == nullptr;
   int bn = a->bn_hint;
   if (bn != 64 && bn != 128 && bn != 256 && auto_bn) bn = auto_bn;
   if (bn != 64 && bn != 128 && bn != 256) {
