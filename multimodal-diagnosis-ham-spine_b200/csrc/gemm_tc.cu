@@ -30,12 +30,12 @@ constexpr int SMEM_LIMIT = 232448;                           // 227 KiB opt-in m
 // hidden under the main loop (one pipeline stage is traded for the boxes).  Only BN <= 128 (one 64-column box per group).
 template <int BN, bool LD, int CL = 1, bool AUX = false> struct Cfg {
   static_assert(!(LD && BN == 256), "operand prefetch needs BN <= 128");
-  static_assert(CL == 1 || BN >= 128, "CTA pairs need BN >= 128");
+  // (CTA pairs with BN == 64 exist for K-major B only: an MN-major B tile is loaded in 64-column chunks that cannot be halved)
   static constexpr int B_TILE_BYTES = (BN / CL) * BK * 2;     // CL 2: each CTA of the pair stages half of the B tile
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   static_assert(!(LD && AUX), "aux_out and prefetched operand boxes are not combined");
   // AUX (a second output tensor: pre-activation / GELU' copy) owns its own staging boxes and pays one pipeline stage
-  static constexpr int STAGES_BASE = CL == 2 ? (BN == 256 ? 6 : (LD ? 6 : 8))
+  static constexpr int STAGES_BASE = CL == 2 ? (BN == 256 ? 6 : (BN == 64 ? 8 : (LD ? 6 : 8)))
                                              : ((BN == 256) ? 4 : (BN == 128 ? (LD ? 5 : 6) : (LD ? 7 : 8)));
   static constexpr int STAGES = STAGES_BASE - (AUX ? (STAGE_BYTES <= 24576 ? 2 : 1) : 0);
   static constexpr int TMEM_COLS = 2 * BN;
@@ -436,6 +436,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmAux,
                const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmAuxIn, const Params p) {
   using C = Cfg<BN, LD, CL, AUX>;
+  static_assert(CL == 1 || BN >= 128 || !B_MN, "64-wide CTA-pair tiles need a K-major B operand");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -1038,10 +1039,24 @@ int dispatch_major(const mdhs_gemm_args* a, const Params& p, cudaStream_t s) {
   return a->b_mn_major ? launch<BN, false, true, LD, CL, false>(a, p, s) : launch<BN, false, false, LD, CL, false>(a, p, s);
 }
 
+// 64-wide CTA-pair tiles: K-major B only
+template <bool LD>
+int dispatch_pair64(const mdhs_gemm_args* a, const Params& p, cudaStream_t s) {
+  if (a->aux_out) {
+    if (a->a_mn_major || LD) return MDHS_ERR_ARG;
+    return launch<64, false, false, false, 2, true>(a, p, s);
+  }
+  if (a->a_mn_major) {
+    if (LD) return MDHS_ERR_ARG;
+    return launch<64, true, false, false, 2, false>(a, p, s);
+  }
+  return launch<64, false, false, LD, 2, false>(a, p, s);
+}
+
 // Relative main-loop efficiency of a tile width (measured on the BERT shapes, B200): 256-wide pair tiles reach ~1.2 PF/s,
 // 128-wide pair tiles ~1.05, single-CTA 128-wide ~0.88, 64-wide (never paired) ~0.6.
 double tile_width_factor(int c, bool pairs) {
-  if (pairs) return c == 256 ? 1.0 : 0.80;
+  if (pairs) return c == 256 ? 1.0 : (c == 128 ? 0.80 : 0.60);
   return c == 256 ? 0.85 : (c == 128 ? 0.75 : 0.50);
 }
 
@@ -1111,7 +1126,7 @@ extern "C" int mdhs_gemm_bf16(const mdhs_gemm_args* a, void* stream_) {
       const int c = cand[i];
       if (c > 64 && a->N <= c / 2) continue;
       // work items are CTA-pair tiles (256 x c) when the pair path applies, scheduled on sms / 2 pairs
-      const bool pairs = cluster_mode() != 0 && c >= 128 && ceil_div(a->M, BM) >= 2;
+      const bool pairs = cluster_mode() != 0 && (c >= 128 || !a->b_mn_major) && ceil_div(a->M, BM) >= 2;
       const int64_t mn = (int64_t)(pairs ? (ceil_div(a->M, BM) + 1) / 2 : ceil_div(a->M, BM)) * ceil_div(a->N, c);
       const int units = pairs ? sms / 2 : sms;
       for (int sp = 1; sp <= max_s; sp++) {
@@ -1159,7 +1174,7 @@ extern "C" int mdhs_gemm_bf16(const mdhs_gemm_args* a, void* stream_) {
       const int c = cand[i];
       if (c > 64 && a->N <= c / 2) continue;
       if (c == 256 && wants_ld) continue;
-      const bool pairs = cluster_mode() != 0 && c >= 128 && ceil_div(a->M, BM) >= 2;
+      const bool pairs = cluster_mode() != 0 && (c >= 128 || !a->b_mn_major) && ceil_div(a->M, BM) >= 2;
       const int64_t tiles =
           (int64_t)(pairs ? (ceil_div(a->M, BM) + 1) / 2 : ceil_div(a->M, BM)) * ceil_div(a->N, c) * p.splits;
       const int units = pairs ? sms / 2 : sms;
@@ -1183,13 +1198,15 @@ extern "C" int mdhs_gemm_bf16(const mdhs_gemm_args* a, void* stream_) {
   // CTA pairs (256 x bn cta_group::2 tiles) whenever there are at least two row blocks and enough pair tiles to occupy
   // a good part of the 74 pairs
   const int n_tiles_m = ceil_div(a->M, BM);
-  const bool cl2 = cluster_mode() != 0 && bn >= 128 && n_tiles_m >= 2 &&
+  const bool cl2 = cluster_mode() != 0 && (bn >= 128 || !a->b_mn_major) && n_tiles_m >= 2 &&
                    (cluster_mode() == 2 || (int64_t)((n_tiles_m + 1) / 2) * ceil_div(a->N, bn) * p.splits >= num_sms() / 4);
   switch (bn) {
     case 256: return cl2 ? dispatch_major<256, false, 2>(a, p, stream) : dispatch_major<256, false, 1>(a, p, stream);
     case 128:
       if (cl2) return ld ? dispatch_major<128, true, 2>(a, p, stream) : dispatch_major<128, false, 2>(a, p, stream);
       return ld ? dispatch_major<128, true, 1>(a, p, stream) : dispatch_major<128, false, 1>(a, p, stream);
-    default:  return ld ? dispatch_major<64, true, 1>(a, p, stream) : dispatch_major<64, false, 1>(a, p, stream);
+    default:
+      if (cl2) return ld ? dispatch_pair64<true>(a, p, stream) : dispatch_pair64<false>(a, p, stream);
+      return ld ? dispatch_major<64, true, 1>(a, p, stream) : dispatch_major<64, false, 1>(a, p, stream);
   }
 }
