@@ -310,6 +310,48 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
 
+    # ---- inference throughput (BASELINE.json's second metric): eval-mode forward of the same batch, one CUDA graph
+    infer = None
+    if not args.no_inference:
+        try:
+            model.eval()
+            s_in = [t.clone() for t in d_in[:3]]
+            with torch.no_grad():
+                for _ in range(3):
+                    model(*s_in)
+                torch.cuda.synchronize()
+                use_g = not args.no_graph
+                g_inf = None
+                if use_g:
+                    try:
+                        g_inf = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g_inf):
+                            logits_inf = model(*s_in)
+                    except Exception:
+                        g_inf = None
+                        torch.cuda.synchronize()
+                n_inf = max(args.steps, 10)
+                for _ in range(3):
+                    g_inf.replay() if g_inf is not None else model(*s_in)
+                torch.cuda.synchronize()
+                i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                i0.record()
+                for _ in range(n_inf):
+                    g_inf.replay() if g_inf is not None else model(*s_in)
+                i1.record()
+                torch.cuda.synchronize()
+            ti = torch.tensor([i0.elapsed_time(i1) / n_inf], device=dev)
+            if world > 1:
+                dist.all_reduce(ti, op=dist.ReduceOp.MAX)
+            infer = {"value": round(world * B / (ti.item() / 1e3), 1), "unit": UNIT, "ms_per_batch": round(ti.item(), 3),
+                     "per_gpu_batch": B, "cuda_graph": g_inf is not None, "mode": "eval forward, logits on device"}
+            g_inf = None
+            model.train()
+        except Exception as e:  # the training numbers above stay valid
+            infer = {"error": f"{type(e).__name__}: {e}"}
+    if world > 1:
+        dist.barrier()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sps, sec = cpu_train_samples_per_sec(32, 2, 1)
@@ -326,7 +368,7 @@ def run_ours(args):
                        "l2": "per-step working set (>10 GB of activations) far exceeds the 126 MB L2; no explicit flush"},
             "clocks": clocks, "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches_per_step) * args.steps, "gpu_launches_per_step": int(launches_per_step),
-            "roofline": roof, "cpu_baseline": cpu, "final_loss": round(final_loss, 4),
+            "roofline": roof, "cpu_baseline": cpu, "inference": infer, "final_loss": round(final_loss, 4),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -351,6 +393,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=8, help="samples per CPU step of the reference arm")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-inference", action="store_true", help="skip the eval-forward throughput measurement")
     ap.add_argument("--graph-multi-gpu", action="store_true", help="(default now; kept for old command lines)")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--dump-gemms", action="store_true", help="write per-shape GEMM timings to gpurun_out/gemm_shapes.txt")

@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ 
 // Block = 256 threads = 32 channel-vectors(8) x 8 row lanes over a `Cw`-wide view of the matrix: Cw = C, or 256 when
 // C in {64, 128} (the contiguous [rows, C] matrix re-read as [rows*C/256, 256]; column j holds channel j % C), so
 // narrow layers keep all 32 vector lanes busy.  grid = (Cw/256 ceil, row blocks).
-__global__ void __launch_bounds__(256, 3) bn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+__global__ void __launch_bounds__(256, 4) bn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                             const bf16* __restrict__ y, const float* __restrict__ mean,
                                                             const float* __restrict__ invstd, const float* __restrict__ scale,
                                                             const float* __restrict__ shift, double* __restrict__ sum_dy,
@@ -358,12 +358,11 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_reduce_kernel(const bf16* __res
   const bool ok = c0 < Cw;
   const int ch0 = c0 % C;
   const bool remask = relu && (y == nullptr);
-  float a[8], b[8], mu[8], is[8], sc[8], sf[8];
+  float a[8], b[8], mu[8], sc[8], sf[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) {
     a[k] = b[k] = 0.f;
     mu[k] = ok ? mean[ch0 + k] : 0.f;
-    is[k] = ok ? invstd[ch0 + k] : 0.f;
     sc[k] = (ok && remask) ? scale[ch0 + k] : 0.f;
     sf[k] = (ok && remask) ? shift[ch0 + k] : 0.f;
   }
@@ -385,7 +384,7 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_reduce_kernel(const bf16* __res
       }
     }
 #pragma unroll
-    for (int k = 0; k < 8; k++) b[k] *= is[k];
+    for (int k = 0; k < 8; k++) b[k] *= invstd[ch0 + k];   // loaded here, not held across the streaming loop
   }
 #pragma unroll
   for (int k = 0; k < 8; k++) {
@@ -739,6 +738,9 @@ extern "C" int mdhs_col_stats(const void* x, int64_t ldx, double* sum64, double*
   if (fold_view(rows, C, ldx, &rows_w, &Cw)) ldx = Cw;
   const int cslabs = ceil_div(Cw, 256);
   int row_blocks = (148 * 8) / cslabs;
+  // short matrices (bias gradients of [8192, N] token matrices): at least 128 rows per block, otherwise the kernel is all
+  // prologue + atomics (394 blocks of 24 rows each for N = 768)
+  if (row_blocks > rows_w / 128) row_blocks = (int)(rows_w / 128);
   if (row_blocks < 1) row_blocks = 1;
   int rpb = ceil_div(rows_w, row_blocks);
   rpb = ((rpb + 31) / 32) * 32;
