@@ -161,6 +161,10 @@ int mdhs_embed_gather(const int64_t* ids, const int64_t* type_ids, const float* 
 int mdhs_embed_scatter(const float* de, const int64_t* ids, const int64_t* type_ids, float* gword, float* gpos,
                        float* gtype, int rows, int S, int C, int vocab, void* stream);
 
+/* test-time augmentation (scripts/predict.py:33-42): V variants of a square NCHW fp32 batch stacked on the batch axis;
+ * codes = 4 bits per variant: 0 identity, 1 hflip (flip(-1)), 2 vflip (flip(-2)), 3 rot90 (torch.rot90 k=1, dims (-2,-1)) */
+int mdhs_tta_expand(const float* x, float* y, int B, int C, int H, int W, int V, uint32_t codes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Small fp32 head kernels: nn.Linear with few outputs (model.py:195-200 classifier, gating.py:10-14),
  * cross entropy with label smoothing / class weights / focal form (scripts/train.py:46-61,252-254).

@@ -51,6 +51,7 @@ SIGNATURES = {
     "mdhs_col2im_nhwc": "pppiiiiiiiip",
     "mdhs_maxpool3x3s2_fwd": "pppiiiip",
     "mdhs_maxpool3x3s2_bwd": "pppiiiip",
+    "mdhs_tta_expand": "ppiiiiiip",
     "mdhs_mean_tokens_fwd": "pppiiifip",
     "mdhs_mean_tokens_bwd": "pppiiifp",
     "mdhs_conv_weight_pack": "ppiiiiip",

@@ -349,6 +349,27 @@ __global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, bf16* 
   }
 }
 
+// Test-time-augmentation variants stacked on the batch axis (scripts/predict.py:33-42: identity, hflip = flip(-1),
+// vflip = flip(-2), rot90 = torch.rot90(k=1, dims=(-2,-1)); square images): y[v, b, c, i, j] = x[b, c, src(i, j)].
+// `codes` packs one 4-bit transform id per variant (0 identity, 1 hflip, 2 vflip, 3 rot90).  One pass writes all variants.
+__global__ void __launch_bounds__(256) tta_expand_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t per_variant,
+                                                         int H, int W, int V, uint32_t codes) {
+  const int64_t total = per_variant * V;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i / per_variant);
+    const int64_t e = i - (int64_t)v * per_variant;
+    const int j = (int)(e % W);
+    const int r = (int)((e / W) % H);
+    const int64_t plane = e / ((int64_t)W * H);
+    const int code = (codes >> (4 * v)) & 15;
+    int sr = r, sj = j;
+    if (code == 1) sj = W - 1 - j;
+    else if (code == 2) sr = H - 1 - r;
+    else if (code == 3) { sr = j; sj = W - 1 - r; }   // rot90(k=1): out[i][j] = x[j][W-1-i]
+    y[i] = x[(plane * H + sr) * W + sj];
+  }
+}
+
 }  // namespace
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
@@ -468,5 +489,17 @@ extern "C" int mdhs_nchw_f32_to_nhwc_bf16(const float* x, void* y, int B, int H,
   if (!x || !y) return MDHS_ERR_ARG;
   g_mdhs_launches++;
   nchw_f32_to_nhwc_bf16_kernel<<<grid_for((int64_t)B * H * W * C, 256), 256, 0, ST(stream)>>>(x, (bf16*)y, B, H, W, C);
+  MDHS_RETURN_LAST();
+}
+
+extern "C" int mdhs_tta_expand(const float* x, float* y, int B, int C, int H, int W, int V, uint32_t codes, void* stream) {
+  if (!x || !y || B <= 0 || C <= 0 || H <= 0 || W <= 0 || V <= 0 || V > 8) return MDHS_ERR_ARG;
+  for (int v = 0; v < V; v++) {
+    const int code = (codes >> (4 * v)) & 15;
+    if (code > 3 || (code == 3 && H != W)) return MDHS_ERR_ARG;
+  }
+  const int64_t per_variant = (int64_t)B * C * H * W;
+  g_mdhs_launches++;
+  tta_expand_kernel<<<grid_for(per_variant * V, 256), 256, 0, ST(stream)>>>(x, y, per_variant, H, W, V, codes);
   MDHS_RETURN_LAST();
 }

@@ -1,0 +1,39 @@
+"""Batched test-time augmentation (scripts/predict.py:33-81, scripts/ablation_eval.py:35-74).
+
+The reference calls the whole model once per variant (identity, hflip, vflip, rot90) and averages the logits.  Here the V
+variants are produced by ONE kernel stacked on the batch axis, the image encoder runs once on V*B images, the text encoder
+once on the B texts (it does not depend on the image variant), and fusion + head run per variant on contiguous slices.
+Results equal the reference's `torch.stack(logits_list).mean(0)`.
+"""
+import torch
+
+from . import functional as Fm
+from . import ops
+
+
+def _slice_tokens(tokens, v, B):
+    if isinstance(tokens, dict):
+        return {k: t[v * B:(v + 1) * B] for k, t in tokens.items()}
+    return tokens[v * B:(v + 1) * B]
+
+
+@torch.no_grad()
+def predict_tta(model, images, input_ids, attention_mask, transforms=("hflip",)):
+    """Mean logits over [identity] + transforms for a MultimodalBaselineModel in eval mode.  Returns (B, C) fp32."""
+    model.eval()
+    B = images.shape[0]
+    V = 1 + len(transforms)
+    big = ops.tta_expand(images, transforms)
+    if getattr(model, "gate_enabled", False):
+        # the gated model evaluates two feature sets per variant (model.py:257-281): keep its own forward per variant
+        outs = [model(big[v * B:(v + 1) * B], input_ids, attention_mask).float() for v in range(V)]
+    else:
+        model.store(images.device)
+        tokens = model.image_encoder(big)
+        text = model.text_encoder(input_ids, attention_mask)
+        outs = [model.classifier(model.fusion(_slice_tokens(tokens, v, B), text, attention_mask)).float() for v in range(V)]
+    acc = torch.empty_like(outs[0])
+    ops.axpby(outs[0].contiguous(), acc, a=1.0 / V, b=0.0)
+    for o in outs[1:]:
+        ops.axpby(o.contiguous(), acc, a=1.0 / V, b=1.0)
+    return acc

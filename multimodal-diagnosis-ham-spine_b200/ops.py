@@ -555,3 +555,21 @@ def sq_attn_bwd(q, k, v, dout, probs, B, T, scale=1.0):
     _lib.call("mdhs_sq_attn_bwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(dout), _p(probs), _p(dq),
               dq.stride(0), _p(dk), dk.stride(0), _p(dv), dv.stride(0), B, T, D, float(scale), _s())
     return dq, dk, dv
+
+
+TTA_CODES = {"identity": 0, "hflip": 1, "vflip": 2, "rot90": 3}
+
+
+def tta_expand(images, transforms):
+    """[B,3,H,W] fp32 -> [V*B,3,H,W]: identity followed by the named transforms (scripts/predict.py:33-42)."""
+    B, C, H, W = images.shape
+    names = ["identity"] + list(transforms)
+    codes = 0
+    for v, n in enumerate(names):
+        if n not in TTA_CODES:
+            raise ValueError(f"unknown TTA transform {n!r}")
+        codes |= TTA_CODES[n] << (4 * v)
+    x = images.contiguous().float()
+    y = torch.empty((len(names) * B, C, H, W), device=x.device, dtype=torch.float32)
+    _lib.call("mdhs_tta_expand", _p(x), _p(y), B, C, H, W, len(names), codes, _s())
+    return y

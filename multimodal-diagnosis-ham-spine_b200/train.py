@@ -21,7 +21,7 @@ from .parallel import GradSync, param_range, split_offset
 class Trainer:
     def __init__(self, model, optimizer="adamw", lr=2e-4, weight_decay=None, betas=(0.9, 0.999), eps=1e-8, momentum=0.9,
                  loss="ce", label_smoothing=0.02, focal_gamma=2.0, class_weights=None, process_group=None,
-                 overlap_comm=True):
+                 overlap_comm=True, supcon_weight=0.0, supcon_stage="finetune", supcon_temperature=0.07):
         self.model = model
         self.opt = optimizer.lower()
         if self.opt not in ("adamw", "adam", "sgd"):
@@ -31,6 +31,11 @@ class Trainer:
         self.lr, self.wd, self.betas, self.eps, self.momentum = lr, weight_decay, betas, eps, momentum
         self.loss_type, self.label_smoothing, self.focal_gamma = loss, label_smoothing, focal_gamma
         self.class_weights = class_weights
+        # supervised contrastive term on the fused (B, hidden) features (scripts/train.py:341-346,363-383): stage "pretrain"
+        # trains on SupCon alone, "finetune" adds supcon_weight * SupCon to the classification loss
+        if supcon_stage not in ("pretrain", "finetune"):
+            raise ValueError(f"Unsupported supcon stage: {supcon_stage}")
+        self.supcon_weight, self.supcon_stage, self.supcon_temperature = float(supcon_weight), supcon_stage, supcon_temperature
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.overlap = overlap_comm and self.world > 1
@@ -100,7 +105,12 @@ class Trainer:
         try:
             feats = self.model.forward_features(images, ids, mask)
             logits = self.model.classifier(feats)
-            loss = self._loss(logits, labels)
+            if self.supcon_weight > 0.0 and self.supcon_stage == "pretrain":
+                loss = Fm.supcon_loss(feats.float(), labels, self.supcon_temperature)
+            else:
+                loss = self._loss(logits, labels)
+                if self.supcon_weight > 0.0:
+                    loss = loss + self.supcon_weight * Fm.supcon_loss(feats.float(), labels, self.supcon_temperature)
             loss.backward()
         finally:
             if hook is not None:

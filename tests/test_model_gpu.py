@@ -155,3 +155,42 @@ def test_trunk_error_vs_torch_autocast():
         ours = rel(ops.nhwc_bf16_to_nchw_f32(x2d, images.shape[0], H, W, C), want[name])
         theirs = rel(auto[name].float(), want[name])
         assert ours <= 1.5 * theirs + 5e-3, (name, ours, theirs)
+
+
+@pytest.mark.gpu
+def test_batched_tta_equals_per_variant_mean():
+    """inference.predict_tta (one expand kernel, image encoder on V*B, BERT once) == mean over per-variant model() calls
+    on torch-made variants (scripts/predict.py:33-81)."""
+    import mdhs_b200  # noqa: F401
+    from mdhs_b200 import ops
+    from mdhs_b200.inference import predict_tta
+    model = build_ours(fusion="basic", head="mlp")
+    sd = weights.synth_state_dict(model.state_dict(), seed=1)
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    images, ids, mask, _ = weights.synthetic_batch(3, 16, 7, image_hw=64)
+    images, ids, mask = images.cuda(), ids.cuda(), mask.cuda()
+    tr = ("hflip", "vflip", "rot90")
+    big = ops.tta_expand(images, tr)
+    want_big = torch.cat([images, images.flip(-1), images.flip(-2), torch.rot90(images, k=1, dims=(-2, -1))], dim=0)
+    assert torch.equal(big, want_big)
+    with torch.no_grad():
+        want = torch.stack([model(v, ids, mask).float() for v in want_big.split(3)], dim=0).mean(dim=0)
+    got = predict_tta(model, images, ids, mask, tr)
+    assert (got - want).abs().max().item() <= 1e-3 * want.abs().max().item() + 1e-5
+
+
+@pytest.mark.gpu
+def test_trainer_supcon_finetune_step_runs_and_changes_loss():
+    import mdhs_b200  # noqa: F401
+    from mdhs_b200.train import Trainer
+    torch.manual_seed(0)
+    model = build_ours(fusion="concat", head="mlp").cuda()
+    images, ids, mask, labels = weights.synthetic_batch(8, 16, 7, image_hw=64)
+    batch = [t.cuda() for t in (images, ids, mask, labels)]
+    l0, _ = Trainer(model, lr=0.0, supcon_weight=0.0).step(*batch)
+    l1, _ = Trainer(model, lr=0.0, supcon_weight=0.5, supcon_stage="finetune").step(*batch)
+    l2, _ = Trainer(model, lr=0.0, supcon_weight=1.0, supcon_stage="pretrain").step(*batch)
+    for l in (l0, l1, l2):
+        assert torch.isfinite(l).all()
+    assert l1.item() > l0.item() - 1.0 and abs(l1.item() - l0.item()) > 1e-4   # the contrastive term is present
