@@ -187,6 +187,10 @@ int mdhs_act_dropout_bwd(const void* dy, const void* aux, void* g, int64_t n, in
 int mdhs_relu_bwd_f32(const float* dy, const float* y, float* dx, int64_t n, void* stream);
 int mdhs_mul_f32(const float* a, const float* b, float* c, int64_t n, void* stream);
 int mdhs_dropout_f32(const float* x, float* y, int64_t n, float p, uint64_t seed, void* stream);
+/* global-local branch (model.py:292-315): out = a*x (+ b*y) on bf16 token tensors (0.5 * (global + local)); the
+ * [global | centre-crop resized bilinearly, align_corners = False] image pair stacked on the batch axis */
+int mdhs_axpby_bf16(const void* x, const void* y, void* out, int64_t n, float a, float b, void* stream);
+int mdhs_global_local(const float* x, float* y, int B, int C, int H, int W, float crop_ratio, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * MIBF-Net: IBFA cross-attention with one token per modality (mibf_net/attention.py:47-70; keys/values of x and

@@ -74,6 +74,8 @@ SIGNATURES = {
     "mdhs_relu_bwd_f32": "ppplp",
     "mdhs_mul_f32": "ppplp",
     "mdhs_dropout_f32": "pplfup",
+    "mdhs_axpby_bf16": "ppplffp",
+    "mdhs_global_local": "ppiiiifp",
     "mdhs_ibfa_fwd": "plplppiiip",
     "mdhs_ibfa_bwd": "plplppppiiip",
     "mdhs_mp_loss": "ppppppppiip",

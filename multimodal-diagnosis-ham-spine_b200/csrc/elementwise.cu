@@ -55,6 +55,72 @@ __global__ void dropout_f32_kernel(const float* __restrict__ x, float* __restric
 
 }  // namespace
 
+namespace {
+// out = a * x (+ b * y) on bf16 vectors of 8 (token-tensor averages of the global / local crops, model.py:303-315)
+__global__ void __launch_bounds__(256) axpby_bf16_kernel(const bf16* __restrict__ x, const bf16* __restrict__ y, bf16* __restrict__ out,
+                                                         int64_t nvec, float a, float b) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    float xv[8], yv[8];
+    load8(x + i * 8, xv);
+    if (y != nullptr) load8(y + i * 8, yv);
+#pragma unroll
+    for (int k = 0; k < 8; k++) xv[k] = y != nullptr ? fmaf(a, xv[k], b * yv[k]) : a * xv[k];
+    store8(out + i * 8, xv);
+  }
+}
+
+// Global + local views of an NCHW fp32 batch (model.py:292-301): y[0:B] = x, y[B:2B] = the centre crop [y0:y0+ch, x0:x0+cw]
+// resized back to (H, W) with F.interpolate(mode="bilinear", align_corners=False) semantics.
+__global__ void __launch_bounds__(256) global_local_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t planes, int H,
+                                                           int W, int y0, int x0, int ch, int cw) {
+  const int64_t per = planes * H * W;
+  const float sh = (float)ch / (float)H, sw = (float)cw / (float)W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * per; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i < per) {
+      y[i] = x[i];
+      continue;
+    }
+    const int64_t e = i - per;
+    const int j = (int)(e % W);
+    const int r = (int)((e / W) % H);
+    const int64_t plane = e / ((int64_t)W * H);
+    float fr = ((float)r + 0.5f) * sh - 0.5f, fc = ((float)j + 0.5f) * sw - 0.5f;
+    fr = fr < 0.f ? 0.f : fr;
+    fc = fc < 0.f ? 0.f : fc;
+    const int r0 = (int)fr, c0 = (int)fc;
+    const int r1 = r0 + 1 < ch ? r0 + 1 : ch - 1, c1 = c0 + 1 < cw ? c0 + 1 : cw - 1;
+    const float lr = fr - (float)r0, lc = fc - (float)c0;
+    const float* pl = x + plane * H * W;
+    const float v00 = pl[(int64_t)(y0 + r0) * W + x0 + c0], v01 = pl[(int64_t)(y0 + r0) * W + x0 + c1];
+    const float v10 = pl[(int64_t)(y0 + r1) * W + x0 + c0], v11 = pl[(int64_t)(y0 + r1) * W + x0 + c1];
+    y[i] = (1.f - lr) * ((1.f - lc) * v00 + lc * v01) + lr * ((1.f - lc) * v10 + lc * v11);
+  }
+}
+}  // namespace
+
+extern "C" int mdhs_axpby_bf16(const void* x, const void* y, void* out, int64_t n, float a, float b, void* stream) {
+  if (!x || !out || n <= 0 || (n % 8)) return MDHS_ERR_ARG;
+  int64_t g = (n / 8 + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  g_mdhs_launches++;
+  axpby_bf16_kernel<<<(int)g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const bf16*)x, (const bf16*)y, (bf16*)out, n / 8, a, b);
+  MDHS_RETURN_LAST();
+}
+
+extern "C" int mdhs_global_local(const float* x, float* y, int B, int C, int H, int W, float crop_ratio, void* stream) {
+  if (!x || !y || B <= 0 || C <= 0 || H <= 0 || W <= 0 || !(crop_ratio > 0.f) || crop_ratio > 1.f) return MDHS_ERR_ARG;
+  int ch = (int)((float)H * crop_ratio), cw = (int)((float)W * crop_ratio);   // int(h * ratio), model.py:294-295
+  ch = ch < 1 ? 1 : ch;
+  cw = cw < 1 ? 1 : cw;
+  const int y0 = (H - ch) / 2 > 0 ? (H - ch) / 2 : 0, x0 = (W - cw) / 2 > 0 ? (W - cw) / 2 : 0;
+  const int64_t planes = (int64_t)B * C;
+  int64_t g = (2 * planes * H * W + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  g_mdhs_launches++;
+  global_local_kernel<<<(int)g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, planes, H, W, y0, x0, ch, cw);
+  MDHS_RETURN_LAST();
+}
+
 extern "C" int mdhs_act_dropout_bwd(const void* dy, const void* aux, void* g, int64_t n, int act, float drop_p, uint64_t seed,
                                     void* stream) {
   if (!dy || !g || n <= 0 || (n % 8) || (act != MDHS_ACT_NONE && !aux)) return MDHS_ERR_ARG;

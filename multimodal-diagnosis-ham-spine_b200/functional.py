@@ -326,3 +326,20 @@ class SupConFn(torch.autograd.Function):
 
 def supcon_loss(features, labels, temperature=0.07):
     return SupConFn.apply(features, labels, float(temperature))
+
+
+class AvgBf16Fn(torch.autograd.Function):
+    """0.5 * (a + b) on bf16 token tensors (global / local token average, model.py:303-315)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        return ops.axpby_bf16(a.contiguous(), b.contiguous(), 0.5, 0.5)
+
+    @staticmethod
+    def backward(ctx, dy):
+        g = ops.axpby_bf16(dy.contiguous(), None, 0.5, 0.0)
+        return g, g
+
+
+def avg_bf16(a, b):
+    return AvgBf16Fn.apply(a, b)

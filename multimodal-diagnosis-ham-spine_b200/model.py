@@ -17,6 +17,7 @@ from .modules.fusion_blocks import (BilinearFusionModule, ConcatFusionModule, Fu
                                     WeightedConcatFusionModule, _pool_image)
 from .modules.gating import DualExpertGate
 from .modules.heads import AttentionPoolingClassifier, MLPHead, ResidualClassifier, build_kan_head
+from .modules.tabular import TabularEncoder, TabularFusion
 
 
 class MultimodalBaselineModel(MdhsModule):
@@ -66,14 +67,16 @@ class MultimodalBaselineModel(MdhsModule):
         self.global_local_enabled = global_local_enabled
         self.global_local_crop_ratio = global_local_crop_ratio
         self.global_local_combine = global_local_combine
-        if tabular_enabled or sequence_enabled or global_local_enabled:
-            raise NotImplementedError(
-                "tabular / sequence / global-local branches are outside the B200 hot-path scope (SURVEY.md 8f)")
+        if sequence_enabled:
+            raise NotImplementedError("the sequence (multi-slice LSTM / Transformer) branch is outside the B200 hot-path scope "
+                                      "(SURVEY.md 8f-4)")
 
         self.image_encoder = ImageEncoder(feature_dim=hidden_dim, pretrained=pretrained_image,
                                           weights_path=image_weights_path, backbone=image_backbone,
                                           multi_scale=(fusion_type == "multiscale"))
         self.global_local_proj = None
+        if global_local_enabled and global_local_combine == "concat":
+            self.global_local_proj = nn.Linear(hidden_dim * 2, hidden_dim)   # model.py:97-99 (unused by the multiscale dict path)
         self.text_encoder = TextEncoder(model_path=text_model_name, feature_dim=text_feature_dim)
 
         if fusion_type == "multiscale":
@@ -94,6 +97,12 @@ class MultimodalBaselineModel(MdhsModule):
         else:
             self.fusion = FusionModule(text_dim=text_feature_dim, hidden_dim=hidden_dim, num_heads=num_heads,
                                        dropout=fusion_dropout)
+
+        if self.tabular_enabled:   # model.py:155-167
+            if tabular_input_dim <= 0:
+                raise ValueError("tabular_input_dim must be > 0 when tabular is enabled.")
+            self.tabular_encoder = TabularEncoder(tabular_input_dim, hidden_dim=tabular_hidden_dim, dropout=tabular_dropout)
+            self.tabular_fusion = TabularFusion(hidden_dim + tabular_hidden_dim, hidden_dim, head_dropout)
 
         self.gate_enabled = gate_enabled
         self.gate_local_mode = gate_local_mode
@@ -122,7 +131,14 @@ class MultimodalBaselineModel(MdhsModule):
         text_tokens = self.text_encoder(text_input_ids, text_attention_mask)
         if ablation_mode == "text_off":
             text_tokens = torch.zeros_like(text_tokens)
-        return self.fusion(image_tokens, text_tokens, text_attention_mask)
+        fused = self.fusion(image_tokens, text_tokens, text_attention_mask)
+        if self.tabular_enabled:   # model.py:229-235
+            if tabular_input is None:
+                raise ValueError("tabular_input is required when tabular is enabled.")
+            tab = self.tabular_encoder(tabular_input)
+            fused32 = Fm.to_f32(fused) if fused.dtype == torch.bfloat16 else fused.float()
+            fused = self.tabular_fusion(torch.cat([fused32, tab], dim=1))
+        return fused
 
     def forward(self, image_input, text_input_ids, text_attention_mask, tabular_input=None, ablation_mode=None):
         if ablation_mode is not None or not self.gate_enabled:
@@ -149,9 +165,41 @@ class MultimodalBaselineModel(MdhsModule):
     def _encode_image_tokens(self, image_input, want_pooled=True):
         if image_input.dim() == 5:
             raise ValueError("Sequence input provided but sequence encoder is disabled.")
-        tokens = self.image_encoder(image_input)
+        if self.global_local_enabled:
+            tokens = self._global_local_tokens(image_input)
+        else:
+            tokens = self.image_encoder(image_input)
         pooled = self._pool_image_tokens(tokens) if want_pooled else None
         return tokens, pooled
+
+    def _global_local_tokens(self, image_input):
+        """model.py:292-315,337-341: encode the image and its centre crop (resized back, bilinear) and combine the tokens.
+        Eval mode runs ONE encoder pass over the 2B stacked views; train mode keeps the reference's two passes because
+        BatchNorm batch statistics are per pass."""
+        from . import ops
+        B = image_input.shape[0]
+        both = ops.global_local(image_input, self.global_local_crop_ratio)
+        if self.training:
+            g, l = self.image_encoder(both[:B]), self.image_encoder(both[B:])
+        else:
+            t = self.image_encoder(both)
+            if isinstance(t, dict):
+                g, l = {k: v[:B] for k, v in t.items()}, {k: v[B:] for k, v in t.items()}
+            else:
+                g, l = t[:B], t[B:]
+        if isinstance(g, dict):
+            return {k: self._avg_tokens(g[k], l[k]) for k in g}
+        if self.global_local_combine == "concat":
+            Bt, T, Hd = g.shape
+            cat = torch.cat([g, l], dim=-1).reshape(Bt * T, 2 * Hd)
+            st = self.store(image_input.device)
+            return Fm.linear(cat, st, self.global_local_proj.weight, self.global_local_proj.bias).view(Bt, T, Hd)
+        return self._avg_tokens(g, l)
+
+    @staticmethod
+    def _avg_tokens(a, b):
+        shp = a.shape
+        return Fm.avg_bf16(a.reshape(-1, shp[-1]), b.reshape(-1, shp[-1])).view(shp)
 
     def freeze_encoders(self):
         for param in self.image_encoder.parameters():

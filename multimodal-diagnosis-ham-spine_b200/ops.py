@@ -573,3 +573,19 @@ def tta_expand(images, transforms):
     y = torch.empty((len(names) * B, C, H, W), device=x.device, dtype=torch.float32)
     _lib.call("mdhs_tta_expand", _p(x), _p(y), B, C, H, W, len(names), codes, _s())
     return y
+
+
+def axpby_bf16(x, y, a, b):
+    """out = a * x + b * y on bf16 tensors (y may be None)."""
+    out = torch.empty_like(x)
+    _lib.call("mdhs_axpby_bf16", _p(x), _p(y), _p(out), x.numel(), float(a), float(b), _s())
+    return out
+
+
+def global_local(images, crop_ratio):
+    """[B,3,H,W] fp32 -> [2B,3,H,W]: the images followed by their centre crop resized back (model.py:292-301)."""
+    B, C, H, W = images.shape
+    x = images.contiguous().float()
+    y = torch.empty((2 * B, C, H, W), device=x.device, dtype=torch.float32)
+    _lib.call("mdhs_global_local", _p(x), _p(y), B, C, H, W, float(crop_ratio), _s())
+    return y

@@ -14,7 +14,10 @@ from . import ops
 
 # Train-mode BN statistics: fused into the conv GEMM epilogue (column sums of the staged bf16 output box, accumulated in
 # registers across the persistent CTA's tiles) or, when False, one extra column pass (col_stats) over the raw conv output.
-FUSE_BN_STATS_IN_GEMM = True
+import os as _os
+FUSE_BN_STATS_IN_GEMM = _os.environ.get("MDHS_FUSE_BN_STATS", "1") != "0"
+# convolutions with a shorter reduction than this take the separate col_stats pass (their GEMM is epilogue / HBM paced)
+FUSE_BN_STATS_MIN_K = int(_os.environ.get("MDHS_FUSE_BN_MIN_K", "100"))
 
 
 def _out_hw(h, k, s, p):
@@ -110,7 +113,7 @@ class ResNetEngine:
         gkw = dict(conv=c.conv_desc(1, B, H, W), M=rows, K=c.K) if c.implicit else {}
         if training:
             st = self._stats_ws[c.stats_off:c.stats_off + 2 * c.O].view(2, c.O)
-            if FUSE_BN_STATS_IN_GEMM:
+            if FUSE_BN_STATS_IN_GEMM and c.K >= FUSE_BN_STATS_MIN_K:
                 raw = ops.gemm(A, c.wp, colsum=st[0], colsumsq=st[1], N=c.O, **gkw)
             else:
                 raw = ops.gemm(A, c.wp, N=c.O, **gkw)

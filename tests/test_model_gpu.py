@@ -194,3 +194,40 @@ def test_trainer_supcon_finetune_step_runs_and_changes_loss():
     for l in (l0, l1, l2):
         assert torch.isfinite(l).all()
     assert l1.item() > l0.item() - 1.0 and abs(l1.item() - l0.item()) > 1e-4   # the contrastive term is present
+
+
+@pytest.mark.gpu
+def test_tabular_branch_matches_oracle():
+    """TabularEncoder + tabular_fusion (modules/tabular.py, model.py:155-167,229-235) on the fp32 head kernels."""
+    model = build_ours(fusion="concat", head="mlp", tabular_enabled=True, tabular_input_dim=12)
+    sd = weights.synth_state_dict(model.state_dict(), seed=7)
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    images, ids, mask, _ = weights.synthetic_batch(3, 16, 7, image_hw=64)
+    tab = torch.randn(3, 12, generator=torch.Generator().manual_seed(9))
+    with torch.no_grad():
+        got = model(images.cuda(), ids.cuda(), mask.cuda(), tabular_input=tab.cuda()).float().cpu()
+        want = port.model_forward(sd, images, ids, mask, fusion="concat", head="mlp", tabular=tab)
+    assert (got - want).abs().max().item() <= 2e-2 * want.abs().max().item()
+    with pytest.raises(ValueError):
+        model(images.cuda(), ids.cuda(), mask.cuda())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fusion,combine", [("basic", "avg"), ("concat", "concat"), ("multiscale", "avg")])
+def test_global_local_branch_matches_oracle(fusion, combine):
+    """Global + centre-crop views (model.py:292-315): crop/resize kernel vs F.interpolate, then eval logits vs the oracle."""
+    from mdhs_b200 import ops
+    images, ids, mask, _ = weights.synthetic_batch(2, 16, 7, image_hw=64)
+    both = ops.global_local(images.cuda(), 0.6).cpu()
+    assert torch.equal(both[:2], images)
+    assert (both[2:] - port.center_crop_resize(images, 0.6)).abs().max().item() < 1e-5
+    model = build_ours(fusion=fusion, head="mlp", global_local_enabled=True, global_local_crop_ratio=0.6,
+                       global_local_combine=combine)
+    sd = weights.synth_state_dict(model.state_dict(), seed=8)
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    with torch.no_grad():
+        got = model(images.cuda(), ids.cuda(), mask.cuda()).float().cpu()
+        want = port.model_forward(sd, images, ids, mask, fusion=fusion, head="mlp", global_local=0.6, global_local_combine=combine)
+    assert (got - want).abs().max().item() <= 2e-2 * want.abs().max().item()

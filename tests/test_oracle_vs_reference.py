@@ -165,3 +165,28 @@ def test_connext_classifier_matches_reference():
         feat = port.convnext_features(sd, "image_encoder.", images)
     assert rel(feat, feat_ref) < 1e-5
     assert rel(got, want) < 1e-5
+
+
+def test_tabular_branch_matches_reference():
+    ref = build_reference_model(fusion="concat", head="mlp", tabular_enabled=True, tabular_input_dim=12).eval()
+    sd = weights.synth_state_dict(ref.state_dict(), seed=7)
+    ref.load_state_dict(sd)
+    images, ids, mask, _ = weights.synthetic_batch(3, 16, 7, image_hw=64)
+    tab = torch.randn(3, 12, generator=torch.Generator().manual_seed(9))
+    with torch.no_grad():
+        want = ref(images, ids, mask, tabular_input=tab)
+        got = port.model_forward(sd, images, ids, mask, fusion="concat", head="mlp", tabular=tab)
+    assert rel(got, want) < 1e-5
+
+
+@pytest.mark.parametrize("fusion,combine", [("basic", "avg"), ("concat", "concat"), ("multiscale", "avg")])
+def test_global_local_branch_matches_reference(fusion, combine):
+    ref = build_reference_model(fusion=fusion, head="mlp", global_local_enabled=True, global_local_crop_ratio=0.6,
+                                global_local_combine=combine).eval()
+    sd = weights.synth_state_dict(ref.state_dict(), seed=8)
+    ref.load_state_dict(sd)
+    images, ids, mask, _ = weights.synthetic_batch(2, 16, 7, image_hw=64)
+    with torch.no_grad():
+        want = ref(images, ids, mask)
+        got = port.model_forward(sd, images, ids, mask, fusion=fusion, head="mlp", global_local=0.6, global_local_combine=combine)
+    assert rel(got, want) < 1e-5
