@@ -191,6 +191,11 @@ int mdhs_dropout_f32(const float* x, float* y, int64_t n, float p, uint64_t seed
  * [global | centre-crop resized bilinearly, align_corners = False] image pair stacked on the batch axis */
 int mdhs_axpby_bf16(const void* x, const void* y, void* out, int64_t n, float a, float b, void* stream);
 int mdhs_global_local(const float* x, float* y, int B, int C, int H, int W, float crop_ratio, void* stream);
+/* sequence branch (modules/sequence_blocks.py:21-33,60-64, nn.LSTM): pointwise LSTM cell on the summed gate projections
+ * [B, 4H] (gate order i, f, g, o); act keeps the gate activations for the backward; NULL c_prev / dh / dc mean zeros */
+int mdhs_lstm_cell_fwd(const float* gates, const float* c_prev, float* h, float* c, float* act, int B, int H, void* stream);
+int mdhs_lstm_cell_bwd(const float* dh, const float* dc, const float* act, const float* c_prev, const float* c, float* dgates,
+                       float* dc_prev, int B, int H, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * MIBF-Net: IBFA cross-attention with one token per modality (mibf_net/attention.py:47-70; keys/values of x and

@@ -76,6 +76,8 @@ SIGNATURES = {
     "mdhs_dropout_f32": "pplfup",
     "mdhs_axpby_bf16": "ppplffp",
     "mdhs_global_local": "ppiiiifp",
+    "mdhs_lstm_cell_fwd": "pppppiip",
+    "mdhs_lstm_cell_bwd": "pppppppiip",
     "mdhs_ibfa_fwd": "plplppiiip",
     "mdhs_ibfa_bwd": "plplppppiiip",
     "mdhs_mp_loss": "ppppppppiip",

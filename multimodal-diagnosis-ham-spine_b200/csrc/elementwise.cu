@@ -98,6 +98,69 @@ __global__ void __launch_bounds__(256) global_local_kernel(const float* __restri
 }
 }  // namespace
 
+namespace {
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// LSTM cell, pointwise part (torch nn.LSTM gate order i, f, g, o; modules/sequence_blocks.py:21-33): gates [B, 4H] fp32 are
+// the summed input / hidden projections incl. both biases.  Saves the gate activations for the backward pass.
+__global__ void lstm_cell_fwd_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev, float* __restrict__ h,
+                                     float* __restrict__ c, float* __restrict__ act, int B, int H) {
+  const int64_t n = (int64_t)B * H;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = e / H;
+    const int j = (int)(e - b * H);
+    const float* g4 = gates + b * 4 * H;
+    const float i = sigmoidf_(g4[j]), f = sigmoidf_(g4[H + j]), g = tanhf(g4[2 * H + j]), o = sigmoidf_(g4[3 * H + j]);
+    const float cp = c_prev ? c_prev[e] : 0.f;
+    const float cn = fmaf(f, cp, i * g);
+    c[e] = cn;
+    h[e] = o * tanhf(cn);
+    float* a4 = act + b * 4 * H;
+    a4[j] = i; a4[H + j] = f; a4[2 * H + j] = g; a4[3 * H + j] = o;
+  }
+}
+// dh, dc (either may be NULL = zero) -> dgates [B, 4H], dc_prev [B, H]
+__global__ void lstm_cell_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ dc, const float* __restrict__ act,
+                                     const float* __restrict__ c_prev, const float* __restrict__ c, float* __restrict__ dgates,
+                                     float* __restrict__ dc_prev, int B, int H) {
+  const int64_t n = (int64_t)B * H;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = e / H;
+    const int j = (int)(e - b * H);
+    const float* a4 = act + b * 4 * H;
+    const float i = a4[j], f = a4[H + j], g = a4[2 * H + j], o = a4[3 * H + j];
+    const float tc = tanhf(c[e]);
+    const float dhe = dh ? dh[e] : 0.f;
+    const float dct = (dc ? dc[e] : 0.f) + dhe * o * (1.f - tc * tc);
+    const float cp = c_prev ? c_prev[e] : 0.f;
+    float* d4 = dgates + b * 4 * H;
+    d4[j] = dct * g * i * (1.f - i);
+    d4[H + j] = dct * cp * f * (1.f - f);
+    d4[2 * H + j] = dct * i * (1.f - g * g);
+    d4[3 * H + j] = dhe * tc * o * (1.f - o);
+    dc_prev[e] = dct * f;
+  }
+}
+}  // namespace
+
+extern "C" int mdhs_lstm_cell_fwd(const float* gates, const float* c_prev, float* h, float* c, float* act, int B, int H, void* stream) {
+  if (!gates || !h || !c || !act || B <= 0 || H <= 0) return MDHS_ERR_ARG;
+  int64_t g = ((int64_t)B * H + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  g_mdhs_launches++;
+  lstm_cell_fwd_kernel<<<(int)g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(gates, c_prev, h, c, act, B, H);
+  MDHS_RETURN_LAST();
+}
+extern "C" int mdhs_lstm_cell_bwd(const float* dh, const float* dc, const float* act, const float* c_prev, const float* c,
+                                  float* dgates, float* dc_prev, int B, int H, void* stream) {
+  if (!act || !c || !dgates || !dc_prev || B <= 0 || H <= 0) return MDHS_ERR_ARG;
+  int64_t g = ((int64_t)B * H + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  g_mdhs_launches++;
+  lstm_cell_bwd_kernel<<<(int)g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dh, dc, act, c_prev, c, dgates, dc_prev, B, H);
+  MDHS_RETURN_LAST();
+}
+
 extern "C" int mdhs_axpby_bf16(const void* x, const void* y, void* out, int64_t n, float a, float b, void* stream) {
   if (!x || !out || n <= 0 || (n % 8)) return MDHS_ERR_ARG;
   int64_t g = (n / 8 + 255) / 256;

@@ -343,3 +343,28 @@ class AvgBf16Fn(torch.autograd.Function):
 
 def avg_bf16(a, b):
     return AvgBf16Fn.apply(a, b)
+
+
+class LstmCellFn(torch.autograd.Function):
+    """(gates [B,4H], c_prev [B,H] | None) -> (h, c): pointwise LSTM cell; BPTT runs through autograd over these nodes."""
+
+    @staticmethod
+    def forward(ctx, gates, c_prev):
+        gates = gates.contiguous()
+        c_prev = c_prev.contiguous() if c_prev is not None else None
+        h, c, act = ops.lstm_cell_fwd(gates, c_prev)
+        ctx.has_prev = c_prev is not None
+        ctx.save_for_backward(act, c_prev if c_prev is not None else c, c)
+        return h, c
+
+    @staticmethod
+    def backward(ctx, dh, dc):
+        act, c_prev, c = ctx.saved_tensors
+        dh = dh.contiguous() if dh is not None else None
+        dc = dc.contiguous() if dc is not None else None
+        dgates, dc_prev = ops.lstm_cell_bwd(dh, dc, act, c_prev if ctx.has_prev else None, c)
+        return dgates, (dc_prev if ctx.has_prev else None)
+
+
+def lstm_cell(gates, c_prev):
+    return LstmCellFn.apply(gates, c_prev)

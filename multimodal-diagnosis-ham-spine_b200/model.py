@@ -17,6 +17,7 @@ from .modules.fusion_blocks import (BilinearFusionModule, ConcatFusionModule, Fu
                                     WeightedConcatFusionModule, _pool_image)
 from .modules.gating import DualExpertGate
 from .modules.heads import AttentionPoolingClassifier, MLPHead, ResidualClassifier, build_kan_head
+from .modules.sequence_blocks import SequenceEncoder
 from .modules.tabular import TabularEncoder, TabularFusion
 
 
@@ -67,13 +68,15 @@ class MultimodalBaselineModel(MdhsModule):
         self.global_local_enabled = global_local_enabled
         self.global_local_crop_ratio = global_local_crop_ratio
         self.global_local_combine = global_local_combine
-        if sequence_enabled:
-            raise NotImplementedError("the sequence (multi-slice LSTM / Transformer) branch is outside the B200 hot-path scope "
-                                      "(SURVEY.md 8f-4)")
 
         self.image_encoder = ImageEncoder(feature_dim=hidden_dim, pretrained=pretrained_image,
                                           weights_path=image_weights_path, backbone=image_backbone,
                                           multi_scale=(fusion_type == "multiscale"))
+        if self.sequence_enabled:   # model.py:81-95
+            self.sequence_encoder = SequenceEncoder(input_dim=hidden_dim, hidden_dim=sequence_hidden_dim, encoder_type=sequence_type,
+                                                    num_layers=sequence_num_layers, bidirectional=sequence_bidirectional,
+                                                    dropout=sequence_dropout, num_heads=sequence_num_heads)
+            self.sequence_proj = nn.Linear(sequence_hidden_dim, hidden_dim) if sequence_hidden_dim != hidden_dim else nn.Identity()
         self.global_local_proj = None
         if global_local_enabled and global_local_combine == "concat":
             self.global_local_proj = nn.Linear(hidden_dim * 2, hidden_dim)   # model.py:97-99 (unused by the multiscale dict path)
@@ -131,6 +134,8 @@ class MultimodalBaselineModel(MdhsModule):
         text_tokens = self.text_encoder(text_input_ids, text_attention_mask)
         if ablation_mode == "text_off":
             text_tokens = torch.zeros_like(text_tokens)
+        if self.sequence_enabled and self.fusion_type == "multiscale" and not isinstance(image_tokens, dict):
+            image_tokens = {"layer2": image_tokens, "layer3": image_tokens, "layer4": image_tokens}   # model.py:220-225
         fused = self.fusion(image_tokens, text_tokens, text_attention_mask)
         if self.tabular_enabled:   # model.py:229-235
             if tabular_input is None:
@@ -163,8 +168,19 @@ class MultimodalBaselineModel(MdhsModule):
         return _pool_image(image_tokens)
 
     def _encode_image_tokens(self, image_input, want_pooled=True):
-        if image_input.dim() == 5:
-            raise ValueError("Sequence input provided but sequence encoder is disabled.")
+        if image_input.dim() == 5:   # model.py:317-331: (B, T, 3, H, W) slices -> pooled per slice -> sequence encoder
+            if not self.sequence_enabled:
+                raise ValueError("Sequence input provided but sequence encoder is disabled.")
+            Bs, Ts = image_input.shape[0], image_input.shape[1]
+            flat = image_input.reshape(Bs * Ts, *image_input.shape[2:])
+            tokens = self._global_local_tokens(flat) if self.global_local_enabled else self.image_encoder(flat)
+            pooled = self._pool_image_tokens(tokens)
+            pooled = Fm.to_f32(pooled) if pooled.dtype == torch.bfloat16 else pooled.float()
+            seq = self.sequence_encoder(pooled.view(Bs, Ts, -1))
+            if not isinstance(self.sequence_proj, nn.Identity):
+                seq = Fm.linear_f32(seq, self.store(image_input.device), self.sequence_proj)
+            seq_tokens = Fm.to_bf16(seq).view(Bs, 1, -1)
+            return seq_tokens, seq
         if self.global_local_enabled:
             tokens = self._global_local_tokens(image_input)
         else:

@@ -589,3 +589,21 @@ def global_local(images, crop_ratio):
     y = torch.empty((2 * B, C, H, W), device=x.device, dtype=torch.float32)
     _lib.call("mdhs_global_local", _p(x), _p(y), B, C, H, W, float(crop_ratio), _s())
     return y
+
+
+def lstm_cell_fwd(gates, c_prev):
+    B, H4 = gates.shape
+    H = H4 // 4
+    h = torch.empty((B, H), device=gates.device, dtype=torch.float32)
+    c = torch.empty_like(h)
+    act = torch.empty_like(gates)
+    _lib.call("mdhs_lstm_cell_fwd", _p(gates), _p(c_prev), _p(h), _p(c), _p(act), B, H, _s())
+    return h, c, act
+
+
+def lstm_cell_bwd(dh, dc, act, c_prev, c):
+    B, H = c.shape
+    dgates = torch.empty_like(act)
+    dc_prev = torch.empty_like(c)
+    _lib.call("mdhs_lstm_cell_bwd", _p(dh), _p(dc), _p(act), _p(c_prev), _p(c), _p(dgates), _p(dc_prev), B, H, _s())
+    return dgates, dc_prev

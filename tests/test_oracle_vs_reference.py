@@ -190,3 +190,17 @@ def test_global_local_branch_matches_reference(fusion, combine):
         want = ref(images, ids, mask)
         got = port.model_forward(sd, images, ids, mask, fusion=fusion, head="mlp", global_local=0.6, global_local_combine=combine)
     assert rel(got, want) < 1e-5
+
+
+@pytest.mark.parametrize("fusion,layers,bidir,hid", [("concat", 1, True, 256), ("basic", 2, False, 128), ("multiscale", 1, True, 256)])
+def test_sequence_lstm_branch_matches_reference(fusion, layers, bidir, hid):
+    ref = build_reference_model(fusion=fusion, head="mlp", sequence_enabled=True, sequence_type="lstm", sequence_hidden_dim=hid,
+                                sequence_num_layers=layers, sequence_bidirectional=bidir, sequence_dropout=0.0).eval()
+    sd = weights.synth_state_dict(ref.state_dict(), seed=11)
+    ref.load_state_dict(sd)
+    images, ids, mask, _ = weights.synthetic_batch(2 * 3, 16, 7, image_hw=64)
+    images = images.view(2, 3, 3, 64, 64)
+    with torch.no_grad():
+        want = ref(images, ids[:2], mask[:2])
+        got = port.model_forward(sd, images, ids[:2], mask[:2], fusion=fusion, head="mlp")
+    assert rel(got, want) < 1e-5
