@@ -196,6 +196,10 @@ int mdhs_global_local(const float* x, float* y, int B, int C, int H, int W, floa
 int mdhs_lstm_cell_fwd(const float* gates, const float* c_prev, float* h, float* c, float* act, int B, int H, void* stream);
 int mdhs_lstm_cell_bwd(const float* dh, const float* dc, const float* act, const float* c_prev, const float* c, float* dgates,
                        float* dc_prev, int B, int H, void* stream);
+/* nn.GRU cell (gate order r, z, n): gi = W_i x + b_i and gh = W_h h + b_h, both [B, 3H]; act keeps r, z, n */
+int mdhs_gru_cell_fwd(const float* gi, const float* gh, const float* h_prev, float* h, float* act, int B, int H, void* stream);
+int mdhs_gru_cell_bwd(const float* dh, const float* act, const float* gh, const float* h_prev, float* dgi, float* dgh,
+                      float* dh_prev, int B, int H, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * MIBF-Net: IBFA cross-attention with one token per modality (mibf_net/attention.py:47-70; keys/values of x and

@@ -78,6 +78,8 @@ SIGNATURES = {
     "mdhs_global_local": "ppiiiifp",
     "mdhs_lstm_cell_fwd": "pppppiip",
     "mdhs_lstm_cell_bwd": "pppppppiip",
+    "mdhs_gru_cell_fwd": "pppppiip",
+    "mdhs_gru_cell_bwd": "pppppppiip",
     "mdhs_ibfa_fwd": "plplppiiip",
     "mdhs_ibfa_bwd": "plplppppiiip",
     "mdhs_mp_loss": "ppppppppiip",

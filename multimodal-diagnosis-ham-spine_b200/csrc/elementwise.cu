@@ -143,6 +143,65 @@ __global__ void lstm_cell_bwd_kernel(const float* __restrict__ dh, const float* 
 }
 }  // namespace
 
+namespace {
+// GRU cell, pointwise part (torch nn.GRU gate order r, z, n): gi = W_i x + b_i, gh = W_h h + b_h, both [B, 3H];
+// n = tanh(gi_n + r * gh_n), h' = (1 - z) n + z h.  act keeps r, z, n for the backward.
+__global__ void gru_cell_fwd_kernel(const float* __restrict__ gi, const float* __restrict__ gh, const float* __restrict__ h_prev,
+                                    float* __restrict__ h, float* __restrict__ act, int B, int H) {
+  const int64_t n_el = (int64_t)B * H;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_el; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = e / H;
+    const int j = (int)(e - b * H);
+    const float* a = gi + b * 3 * H;
+    const float* c = gh + b * 3 * H;
+    const float r = sigmoidf_(a[j] + c[j]), z = sigmoidf_(a[H + j] + c[H + j]);
+    const float n = tanhf(a[2 * H + j] + r * c[2 * H + j]);
+    h[e] = (1.f - z) * n + z * h_prev[e];
+    float* s3 = act + b * 3 * H;
+    s3[j] = r; s3[H + j] = z; s3[2 * H + j] = n;
+  }
+}
+__global__ void gru_cell_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ act, const float* __restrict__ gh,
+                                    const float* __restrict__ h_prev, float* __restrict__ dgi, float* __restrict__ dgh,
+                                    float* __restrict__ dh_prev, int B, int H) {
+  const int64_t n_el = (int64_t)B * H;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_el; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = e / H;
+    const int j = (int)(e - b * H);
+    const float* s3 = act + b * 3 * H;
+    const float r = s3[j], z = s3[H + j], n = s3[2 * H + j];
+    const float d = dh[e];
+    const float dn_pre = d * (1.f - z) * (1.f - n * n);
+    const float dz_pre = d * (h_prev[e] - n) * z * (1.f - z);
+    const float dr_pre = dn_pre * gh[b * 3 * H + 2 * H + j] * r * (1.f - r);
+    float* a = dgi + b * 3 * H;
+    float* c = dgh + b * 3 * H;
+    a[j] = dr_pre; a[H + j] = dz_pre; a[2 * H + j] = dn_pre;
+    c[j] = dr_pre; c[H + j] = dz_pre; c[2 * H + j] = dn_pre * r;
+    dh_prev[e] = d * z;
+  }
+}
+}  // namespace
+
+extern "C" int mdhs_gru_cell_fwd(const float* gi, const float* gh, const float* h_prev, float* h, float* act, int B, int H,
+                                 void* stream) {
+  if (!gi || !gh || !h_prev || !h || !act || B <= 0 || H <= 0) return MDHS_ERR_ARG;
+  int64_t g = ((int64_t)B * H + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  g_mdhs_launches++;
+  gru_cell_fwd_kernel<<<(int)g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(gi, gh, h_prev, h, act, B, H);
+  MDHS_RETURN_LAST();
+}
+extern "C" int mdhs_gru_cell_bwd(const float* dh, const float* act, const float* gh, const float* h_prev, float* dgi, float* dgh,
+                                 float* dh_prev, int B, int H, void* stream) {
+  if (!dh || !act || !gh || !h_prev || !dgi || !dgh || !dh_prev || B <= 0 || H <= 0) return MDHS_ERR_ARG;
+  int64_t g = ((int64_t)B * H + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  g_mdhs_launches++;
+  gru_cell_bwd_kernel<<<(int)g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dh, act, gh, h_prev, dgi, dgh, dh_prev, B, H);
+  MDHS_RETURN_LAST();
+}
+
 extern "C" int mdhs_lstm_cell_fwd(const float* gates, const float* c_prev, float* h, float* c, float* act, int B, int H, void* stream) {
   if (!gates || !h || !c || !act || B <= 0 || H <= 0) return MDHS_ERR_ARG;
   int64_t g = ((int64_t)B * H + 255) / 256;

@@ -368,3 +368,24 @@ class LstmCellFn(torch.autograd.Function):
 
 def lstm_cell(gates, c_prev):
     return LstmCellFn.apply(gates, c_prev)
+
+
+class GruCellFn(torch.autograd.Function):
+    """(gi [B,3H], gh [B,3H], h_prev [B,H]) -> h: pointwise GRU cell (gate order r, z, n)."""
+
+    @staticmethod
+    def forward(ctx, gi, gh, h_prev):
+        gi, gh, h_prev = gi.contiguous(), gh.contiguous(), h_prev.contiguous()
+        h, act = ops.gru_cell_fwd(gi, gh, h_prev)
+        ctx.save_for_backward(act, gh, h_prev)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        act, gh, h_prev = ctx.saved_tensors
+        dgi, dgh, dhp = ops.gru_cell_bwd(dh.contiguous(), act, gh, h_prev)
+        return dgi, dgh, dhp
+
+
+def gru_cell(gi, gh, h_prev):
+    return GruCellFn.apply(gi, gh, h_prev)

@@ -607,3 +607,18 @@ def lstm_cell_bwd(dh, dc, act, c_prev, c):
     dc_prev = torch.empty_like(c)
     _lib.call("mdhs_lstm_cell_bwd", _p(dh), _p(dc), _p(act), _p(c_prev), _p(c), _p(dgates), _p(dc_prev), B, H, _s())
     return dgates, dc_prev
+
+
+def gru_cell_fwd(gi, gh, h_prev):
+    B, H3 = gi.shape
+    h = torch.empty((B, H3 // 3), device=gi.device, dtype=torch.float32)
+    act = torch.empty_like(gi)
+    _lib.call("mdhs_gru_cell_fwd", _p(gi), _p(gh), _p(h_prev), _p(h), _p(act), B, H3 // 3, _s())
+    return h, act
+
+
+def gru_cell_bwd(dh, act, gh, h_prev):
+    B, H = h_prev.shape
+    dgi, dgh, dhp = torch.empty_like(act), torch.empty_like(act), torch.empty_like(h_prev)
+    _lib.call("mdhs_gru_cell_bwd", _p(dh), _p(act), _p(gh), _p(h_prev), _p(dgi), _p(dgh), _p(dhp), B, H, _s())
+    return dgi, dgh, dhp

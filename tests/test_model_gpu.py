@@ -278,12 +278,13 @@ def test_full_size_properties_config2():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("fusion,layers,bidir,hid", [("concat", 1, True, 256), ("basic", 2, False, 128)])
-def test_sequence_lstm_branch_matches_oracle(fusion, layers, bidir, hid):
+@pytest.mark.parametrize("fusion,layers,bidir,hid,kind", [("concat", 1, True, 256, "lstm"), ("basic", 2, False, 128, "lstm"),
+                                                          ("concat", 2, True, 128, "gru"), ("concat", 2, True, 128, "transformer")])
+def test_sequence_lstm_branch_matches_oracle(fusion, layers, bidir, hid, kind):
     """Multi-slice input (B, T, 3, H, W) -> SequenceEncoder (LSTM) (model.py:316-331, modules/sequence_blocks.py): eval logits
     and the LSTM parameter gradients of a train step against the oracle (pinned to the reference's nn.LSTM)."""
     from mdhs_b200 import functional as Fm
-    kw = dict(sequence_enabled=True, sequence_type="lstm", sequence_hidden_dim=hid, sequence_num_layers=layers,
+    kw = dict(sequence_enabled=True, sequence_type=kind, sequence_hidden_dim=hid, sequence_num_layers=layers,
               sequence_bidirectional=bidir, sequence_dropout=0.0)
     model = build_ours(fusion=fusion, head="mlp", **kw)
     sd = weights.synth_state_dict(model.state_dict(), seed=11)
@@ -309,11 +310,19 @@ def test_sequence_lstm_branch_matches_oracle(fusion, layers, bidir, hid):
     loss.backward()
     assert abs(loss.item() - loss_ref.item()) < 2e-2
     named = dict(model.named_parameters())
+    if kind == "transformer":
+        keys = ("sequence_encoder.encoder.layers.0.self_attn.in_proj_weight", "sequence_encoder.encoder.layers.1.linear2.weight",
+                "sequence_encoder.encoder.layers.0.norm1.weight")
+        for key in keys:
+            g, g_ref = st.g32(named[key]).float().cpu(), sd_g[key].grad
+            cos = torch.nn.functional.cosine_similarity(g.flatten(), g_ref.flatten(), dim=0).item()
+            assert cos > 0.95, (key, cos)
+        return
     for key in ("sequence_encoder.rnn.weight_ih_l0", "sequence_encoder.rnn.weight_hh_l0", "sequence_encoder.rnn.bias_hh_l0"):
         g, g_ref = st.g32(named[key]).float().cpu(), sd_g[key].grad
         cos = torch.nn.functional.cosine_similarity(g.flatten(), g_ref.flatten(), dim=0).item()
         # B = 2 samples through a bf16 trunk: the bias gradient (a sum of only 2 x T gate gradients) is the noisiest
         assert cos > (0.95 if "bias" in key else 0.98), (key, cos)
-    # both LSTM biases see the same gate gradients: must agree to fp32 rounding
-    gi, gh = st.g32(named["sequence_encoder.rnn.bias_ih_l0"]), st.g32(named["sequence_encoder.rnn.bias_hh_l0"])
-    assert (gi - gh).abs().max().item() <= 1e-5 * gi.abs().max().item() + 1e-9
+    if kind == "lstm":   # both LSTM biases see the same gate gradients: must agree to fp32 rounding
+        gi, gh = st.g32(named["sequence_encoder.rnn.bias_ih_l0"]), st.g32(named["sequence_encoder.rnn.bias_hh_l0"])
+        assert (gi - gh).abs().max().item() <= 1e-5 * gi.abs().max().item() + 1e-9

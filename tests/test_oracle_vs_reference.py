@@ -192,9 +192,11 @@ def test_global_local_branch_matches_reference(fusion, combine):
     assert rel(got, want) < 1e-5
 
 
-@pytest.mark.parametrize("fusion,layers,bidir,hid", [("concat", 1, True, 256), ("basic", 2, False, 128), ("multiscale", 1, True, 256)])
-def test_sequence_lstm_branch_matches_reference(fusion, layers, bidir, hid):
-    ref = build_reference_model(fusion=fusion, head="mlp", sequence_enabled=True, sequence_type="lstm", sequence_hidden_dim=hid,
+@pytest.mark.parametrize("fusion,layers,bidir,hid,kind", [("concat", 1, True, 256, "lstm"), ("basic", 2, False, 128, "lstm"),
+                                                          ("multiscale", 1, True, 256, "lstm"), ("concat", 2, True, 128, "gru"),
+                                                          ("concat", 2, True, 128, "transformer")])
+def test_sequence_lstm_branch_matches_reference(fusion, layers, bidir, hid, kind):
+    ref = build_reference_model(fusion=fusion, head="mlp", sequence_enabled=True, sequence_type=kind, sequence_hidden_dim=hid,
                                 sequence_num_layers=layers, sequence_bidirectional=bidir, sequence_dropout=0.0).eval()
     sd = weights.synth_state_dict(ref.state_dict(), seed=11)
     ref.load_state_dict(sd)
