@@ -119,6 +119,11 @@ def run_reference(args):
 # our arm
 # ----------------------------------------------------------------------------------------------
 def run_ours(args):
+    # rank 0's stdout must carry exactly ONE JSON line, but native libraries write there too (NCCL prints its version banner
+    # with printf): park the real stdout, point fd 1 at stderr for the whole run, and emit the line on the parked descriptor
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -127,6 +132,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # rank 0's stdout carries exactly ONE JSON line: NCCL's own banner / debug output (NCCL_DEBUG=VERSION prints
+        # "NCCL version ..." to stdout) goes to stderr instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         # collectives are captured into the step's CUDA graph: the NCCL watchdog's async error handling must not
         # poll events of a capturing stream (torch CUDA-graphs notes)
         os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
@@ -370,7 +378,8 @@ def run_ours(args):
             "gpu_launches": int(launches_per_step) * args.steps, "gpu_launches_per_step": int(launches_per_step),
             "roofline": roof, "cpu_baseline": cpu, "inference": infer, "final_loss": round(final_loss, 4),
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         # the captured step holds NCCL work inside a CUDA graph; tearing the communicator down under it can block, so
         # drop the graph first, drain the device, and leave without the (optional) communicator destruction
