@@ -95,6 +95,21 @@ def cpu_train_samples_per_sec(batch, steps, warmup, seq=64, hw=224):
     return batch * len(times) / total, total / len(times)
 
 
+def synthetic_batch(B, S, num_classes, seed=123, image_hw=224):
+    """Synthetic inputs of SURVEY.md section 8d (ImageNet-normalised-like randn images, ids with CLS = 101, tail-padded mask,
+    labels) -- bench.py's own copy: our arm does not touch anything under oracle/."""
+    import torch
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    images = torch.randn(B, 3, image_hw, image_hw, generator=g)
+    ids = torch.randint(0, 30522, (B, S), generator=g)
+    ids[:, 0] = 101
+    lens = torch.randint(min(8, S), S + 1, (B,), generator=g)
+    mask = (torch.arange(S)[None, :] < lens[:, None]).long()
+    labels = torch.randint(0, num_classes, (B,), generator=g)
+    return images, ids, mask, labels
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -142,8 +157,7 @@ def run_ours(args):
     import mdhs_b200
     from mdhs_b200 import _lib, ops
     from mdhs_b200.train import Trainer
-    from oracle import weights
-    from refutil import bert_dir, quiet
+    from refutil import bert_dir, quiet   # tests/refutil.py: builds the local random-init bert-base directory
 
     B, S, HW, C = args.batch, args.seq, 224, 7
     if rank == 0:
@@ -157,7 +171,7 @@ def run_ours(args):
                                                   image_backbone="resnet50", classifier_type="mlp", fusion_type="basic")
     model = model.to(dev)
     trainer = Trainer(model, optimizer="adamw", lr=2e-4, label_smoothing=0.02)
-    images, ids, mask, labels = weights.synthetic_batch(B, S, C, seed=123 + rank, image_hw=HW)
+    images, ids, mask, labels = synthetic_batch(B, S, C, seed=123 + rank, image_hw=HW)
     h_in = [t.pin_memory() for t in (images, ids, mask, labels)]
     d_in = [t.to(dev, non_blocking=True) for t in h_in]
     torch.cuda.synchronize()

@@ -10,11 +10,13 @@ FFN1 GEMM with bias + GELU(erf) epilogue (pre-activation kept for the backward),
 dropout + residual, LayerNorm.  Activations bf16 [B*S, features]; LN statistics / parameters fp32.
 The pooler is never evaluated (the reference discards it; its parameters get no gradient there either).
 """
+import contextlib
 import math
 
 import torch
 
 from . import ops
+from . import runtime
 
 
 def qkv_groups(bert):
@@ -103,16 +105,22 @@ class BertEngine:
         N, K = w16.shape
         T = dy.shape[0]
         train = (w.requires_grad if w is not None else True)
+        side = None
         if train:
             gw = st.g32(w) if gw is None else gw
             gb = (st.g32(lin.bias) if gb is None else gb)
-            tiles = ((N + 127) // 128) * ((K + 255) // 256)
-            splits = max(1, min((T + 63) // 64 // 4, (148 + tiles - 1) // tiles))
-            ops.gemm(dy, x_in, a_mn=True, b_mn=True, out=gw, accumulate=True, split_k=-1, M=N, N=K, K=T)
-            ops.col_stats(dy, sum32=gb)
+            # weight / bias gradients do not feed the dgrad chain: a side stream lets them fill the dgrad kernel's last wave
+            if runtime.OVERLAP_WGRAD and need_dx:
+                side = runtime.fork_side()
+            with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
+                ops.gemm(dy, x_in, a_mn=True, b_mn=True, out=gw, accumulate=True, split_k=-1, M=N, N=K, K=T)
+                ops.col_stats(dy, sum32=gb)
         if not need_dx:
             return None
-        return ops.gemm(dy, w16, b_mn=True, residual=residual, aux_in=aux_in, dact=dact, M=T, N=K, K=N)
+        dx = ops.gemm(dy, w16, b_mn=True, residual=residual, aux_in=aux_in, dact=dact, M=T, N=K, K=N)
+        if side is not None:
+            runtime.join_side(side)
+        return dx
 
     def backward(self, ctx, dh):
         """dh: grad of the last hidden state, [B*S, C] bf16."""

@@ -7,9 +7,12 @@ Reference path: encoder.py:61-72,88-99 (ImageEncoder stem/layer1-4) and mibf_net
 (torchvision resnet50 incl. avg-pool + fc).  The nn.Module objects only hold parameters / buffers with
 the reference's state_dict keys; all arithmetic happens here.
 """
+import contextlib
+
 import torch
 
 from . import ops
+from . import runtime
 
 
 # Train-mode BN statistics: fused into the conv GEMM epilogue (column sums of the staged bf16 output box, accumulated in
@@ -18,6 +21,9 @@ import os as _os
 FUSE_BN_STATS_IN_GEMM = _os.environ.get("MDHS_FUSE_BN_STATS", "1") != "0"
 # convolutions with a shorter reduction than this take the separate col_stats pass (their GEMM is epilogue / HBM paced)
 FUSE_BN_STATS_MIN_K = int(_os.environ.get("MDHS_FUSE_BN_MIN_K", "100"))
+
+
+_nullctx = contextlib.nullcontext
 
 
 def _out_hw(h, k, s, p):
@@ -169,6 +175,29 @@ class ResNetEngine:
         return feats, ctx
 
     # ------------------------------------------------------------------ backward pieces
+    def _wgrad(self, c, rec, draw, A, rows, st):
+        """Weight gradient of one convolution (accumulates into the flat fp32 gradient buffer)."""
+        if c.implicit:
+            # wgrad as an implicit GEMM: B operand = im2col(x) through TMA; plain 1x1 (strided) convs accumulate
+            # straight into the flat gradient buffer, k x k ones into the packed buffer
+            cd = c.conv_desc(2, rec["B"], rec["H"], rec["W"])
+            if c.plain:
+                gw = st.g32(c.conv.weight).view(c.O, c.I)
+                ops.gemm(draw, A, a_mn=True, b_mn=True, out=gw, accumulate=True, split_k=-1, M=c.O, N=c.K, K=rows, conv=cd)
+            else:
+                c.gp.zero_()
+                ops.gemm(draw, A, a_mn=True, b_mn=True, out=c.gp, accumulate=True, split_k=-1, M=c.O, N=c.K, K=rows, conv=cd)
+                ops.conv_wgrad_unpack(c.gp, st.g32(c.conv.weight))
+        elif c.plain:
+            gw = st.g32(c.conv.weight).view(c.O, c.I)
+            ops.gemm(draw, A, a_mn=True, b_mn=True, out=gw, accumulate=True, split_k=-1,
+                     M=c.O, N=c.I, K=rows)
+        else:
+            c.gp.zero_()
+            ops.gemm(draw, A, a_mn=True, b_mn=True, out=c.gp, accumulate=True, split_k=-1,
+                     M=c.O, N=c.ldk, K=rows)
+            ops.conv_wgrad_unpack(c.gp, st.g32(c.conv.weight))
+
     def _conv_bn_bwd(self, rec, dy, add_to_dx, need_dx=True):
         """dy: grad wrt the BN(+res)(+relu) output.  Returns (dx, dz) where dz is the masked dy (identity branch)."""
         c = rec["c"]
@@ -181,27 +210,12 @@ class ResNetEngine:
                               relu=rec["relu"], want_dz=rec["has_res"], scale=rec["scale"], shift=rec["shift"])
         A = rec["A"]
         rows = rec["B"] * rec["Ho"] * rec["Wo"]
+        side = None
         if train_w:
-            if c.implicit:
-                # wgrad as an implicit GEMM: B operand = im2col(x) through TMA; plain 1x1 (strided) convs accumulate
-                # straight into the flat gradient buffer, k x k ones into the packed buffer
-                cd = c.conv_desc(2, rec["B"], rec["H"], rec["W"])
-                if c.plain:
-                    gw = st.g32(c.conv.weight).view(c.O, c.I)
-                    ops.gemm(draw, A, a_mn=True, b_mn=True, out=gw, accumulate=True, split_k=-1, M=c.O, N=c.K, K=rows, conv=cd)
-                else:
-                    c.gp.zero_()
-                    ops.gemm(draw, A, a_mn=True, b_mn=True, out=c.gp, accumulate=True, split_k=-1, M=c.O, N=c.K, K=rows, conv=cd)
-                    ops.conv_wgrad_unpack(c.gp, st.g32(c.conv.weight))
-            elif c.plain:
-                gw = st.g32(c.conv.weight).view(c.O, c.I)
-                ops.gemm(draw, A, a_mn=True, b_mn=True, out=gw, accumulate=True, split_k=-1,
-                         M=c.O, N=c.I, K=rows)
-            else:
-                c.gp.zero_()
-                ops.gemm(draw, A, a_mn=True, b_mn=True, out=c.gp, accumulate=True, split_k=-1,
-                         M=c.O, N=c.ldk, K=rows)
-                ops.conv_wgrad_unpack(c.gp, st.g32(c.conv.weight))
+            if runtime.OVERLAP_WGRAD and need_dx:
+                side = runtime.fork_side()
+            with torch.cuda.stream(side) if side is not None else _nullctx():
+                self._wgrad(c, rec, draw, A, rows, st)
         dx = None
         if need_dx:
             if c.direct:
@@ -213,6 +227,8 @@ class ResNetEngine:
             else:
                 dcol = ops.gemm(draw, c.wp[:, :c.K], b_mn=True, M=rows, N=c.K, K=c.O)
                 dx = ops.col2im_nhwc(dcol, rec["B"], rec["H"], rec["W"], c.I, c.R, c.S, c.stride, c.pad, add=add_to_dx)
+        if side is not None:
+            runtime.join_side(side)
         return dx, dz
 
     def backward(self, ctx, dfeats):

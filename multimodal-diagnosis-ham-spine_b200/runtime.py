@@ -129,3 +129,28 @@ class ParamStore:
 
     def zero_grad(self):
         self.grad.zero_()
+
+
+# ------------------------------------------------------------------ side stream for independent backward work
+# Weight-gradient GEMMs do not feed the data-gradient chain: running them on a second stream could let their CTAs start on
+# the SMs that the persistent dgrad kernel leaves idle in its last, partially filled wave.  fork() / join() also work inside
+# CUDA-graph capture.  MEASURED (round 1, B200, config 2): no gain -- 22.89 ms/step with the overlap vs 22.76 without -- so it
+# is OFF by default (MDHS_OVERLAP_WGRAD=1 enables it for experiments).
+import os as _os
+
+_SIDE = {}
+OVERLAP_WGRAD = _os.environ.get("MDHS_OVERLAP_WGRAD", "0") == "1"
+
+
+def fork_side():
+    """Side stream that has waited for everything enqueued so far on the current stream."""
+    dev = torch.cuda.current_device()
+    s = _SIDE.get(dev)
+    if s is None:
+        s = _SIDE[dev] = torch.cuda.Stream(device=dev)
+    s.wait_stream(torch.cuda.current_stream())
+    return s
+
+
+def join_side(s):
+    torch.cuda.current_stream().wait_stream(s)

@@ -13,15 +13,15 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import mdhs_b200  # noqa
 from mdhs_b200.train import Trainer
-from oracle import weights
 from refutil import bert_dir, quiet
+from bench import synthetic_batch
 
 with quiet():
     model = mdhs_b200.MultimodalBaselineModel(num_classes=7, hidden_dim=256, dropout=0.2, pretrained_image=False,
                                               image_weights_path=None, text_model_name=bert_dir(), num_heads=8,
                                               image_backbone="resnet50", classifier_type="mlp", fusion_type="basic").cuda()
 tr = Trainer(model)
-batch = [t.cuda() for t in weights.synthetic_batch(128, 64, 7)]
+batch = [t.cuda() for t in synthetic_batch(128, 64, 7)]
 tr.capture(*batch, warmup=3)
 for _ in range(5):
     tr.replay()

@@ -9,8 +9,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import mdhs_b200  # noqa
 from mdhs_b200.train import Trainer
-from oracle import weights
 from refutil import bert_dir, quiet
+from bench import synthetic_batch
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 fusion = sys.argv[2] if len(sys.argv) > 2 else "basic"
@@ -19,7 +19,7 @@ with quiet():
                                               image_weights_path=None, text_model_name=bert_dir(), num_heads=8,
                                               image_backbone="resnet50", classifier_type="mlp", fusion_type=fusion).cuda()
 tr = Trainer(model)
-batch = [t.cuda() for t in weights.synthetic_batch(B, 64, 7)]
+batch = [t.cuda() for t in synthetic_batch(B, 64, 7)]
 for _ in range(2):
     tr.step(*batch)
 torch.cuda.synchronize()
