@@ -1037,7 +1037,12 @@ int dispatch_pair64(const mdhs_gemm_args* a, const Params& p, cudaStream_t s) {
 // Relative main-loop efficiency of a tile width (measured on the BERT shapes, B200): 256-wide pair tiles reach ~1.2 PF/s,
 // 128-wide pair tiles ~1.05, single-CTA 128-wide ~0.88, 64-wide (never paired) ~0.6.
 double tile_width_factor(int c, bool pairs) {
-  if (pairs) return c == 256 ? 1.0 : (c == 128 ? 0.80 : 0.60);
+  static double f128 = -1.0;
+  if (f128 < 0.0) {   // MDHS_TILE128_FACTOR: experiment knob for the 128-wide pair-tile weight
+    const char* e = getenv("MDHS_TILE128_FACTOR");
+    f128 = e ? atof(e) : 0.80;
+  }
+  if (pairs) return c == 256 ? 1.0 : (c == 128 ? f128 : 0.60);
   return c == 256 ? 0.85 : (c == 128 ? 0.75 : 0.50);
 }
 
