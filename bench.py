@@ -24,6 +24,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 METRIC = "train_samples_per_sec"
 UNIT = "samples/s"
 FWD_BWD_GFLOP_PER_SAMPLE = 57.50   # ResNet-50 + BERT `basic` fusion, S=64 (FlopCounterMode, 2xMAC)
+# SURVEY.md section 8d table (fwd+bwd GFLOP per sample) for the other --fusion / --seq combinations
+_GFLOP = {("basic", 64): 57.50, ("basic", 128): 90.27, ("multiscale", 64): 59.37, ("multiscale", 128): 92.57, ("concat", 64): 57.06}
 
 
 def _peaks():
@@ -168,7 +170,7 @@ def run_ours(args):
     with quiet():
         model = mdhs_b200.MultimodalBaselineModel(num_classes=C, hidden_dim=256, dropout=0.2, pretrained_image=False,
                                                   image_weights_path=None, text_model_name=bert_dir(), num_heads=8,
-                                                  image_backbone="resnet50", classifier_type="mlp", fusion_type="basic")
+                                                  image_backbone="resnet50", classifier_type="mlp", fusion_type=args.fusion)
     model = model.to(dev)
     trainer = Trainer(model, optimizer="adamw", lr=2e-4, label_smoothing=0.02)
     images, ids, mask, labels = synthetic_batch(B, S, C, seed=123 + rank, image_hw=HW)
@@ -328,7 +330,7 @@ def run_ours(args):
                     "peak_source": f"{src} bf16_tflops_sustained", "launches_per_step": len(recs),
                     "gemm_ms_per_step": round(gms, 3), "gemm_gflop_per_step": round(gflop, 1),
                     "gemm_share_of_eager_step": round(gms / s_all.elapsed_time(e_all), 3),
-                    "model_flops_frac": round(value / world * FWD_BWD_GFLOP_PER_SAMPLE / 1e3 / peak, 4)}
+                    "model_flops_frac": round(value / world * _GFLOP.get((args.fusion, S), FWD_BWD_GFLOP_PER_SAMPLE) / 1e3 / peak, 4)}
     if world > 1:
         dist.barrier()
 
@@ -384,7 +386,7 @@ def run_ours(args):
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "ResNet-50 + BERT-base, basic (cross-attention) fusion, MLP head, HAM 7-class, train step "
+            "config": {"workload": f"ResNet-50 + BERT-base, {args.fusion} (cross-attention) fusion, MLP head, HAM 7-class, train step "
                                    "(fwd+bwd+all-reduce+AdamW)", "per_gpu_batch": B, "global_batch": B * world, "seq_len": S,
                        "image": "3x224x224", "parallelism": f"dp{world}", "cuda_graph": use_graph,
                        "l2": "per-step working set (>10 GB of activations) far exceeds the 126 MB L2; no explicit flush"},
@@ -413,6 +415,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=128, help="per-GPU batch")
     ap.add_argument("--seq", type=int, default=64)
+    ap.add_argument("--fusion", default="basic", choices=["basic", "multiscale", "concat"],
+                    help="fusion_type of the benchmarked model (default: the headline cross-attention block; "
+                         "`multiscale` is what configs/ham_fusion_crossattn_v1.yml ships)")
     ap.add_argument("--ref-batch", type=int, default=8, help="samples per CPU step of the reference arm")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
