@@ -37,3 +37,23 @@ def predict_tta(model, images, input_ids, attention_mask, transforms=("hflip",))
     for o in outs[1:]:
         ops.axpby(o.contiguous(), acc, a=1.0 / V, b=1.0)
     return acc
+
+
+@torch.no_grad()
+def predict_tta_batchdict(model, images, input_ids, attention_mask, transforms=("hflip", "vflip", "rot90"), key=None):
+    """Batched TTA for the batch-dict models (MIBF-Net `Resnet50WithOurs`, ConNexT `OurClassfierConvnextV2`; BASELINE config 5:
+    "batched TTA inference").  The V variants go through the model as ONE batch of V*B images (text inputs tiled), logits are
+    averaged per sample.  `key` selects the logit set of a dict-valued output (MIBF: "image_text")."""
+    model.eval()
+    B = images.shape[0]
+    V = 1 + len(transforms)
+    big = ops.tta_expand(images, transforms)
+    out = model({"transformed_image": big, "input_ids": input_ids.repeat(V, 1), "attention_mask": attention_mask.repeat(V, 1)})
+    if isinstance(out, dict):
+        out = out[key or "image_text"]
+    out = out.float().contiguous()
+    acc = torch.empty((B, out.shape[1]), device=out.device, dtype=torch.float32)
+    ops.axpby(out[:B].contiguous(), acc, a=1.0 / V, b=0.0)
+    for v in range(1, V):
+        ops.axpby(out[v * B:(v + 1) * B].contiguous(), acc, a=1.0 / V, b=1.0)
+    return acc

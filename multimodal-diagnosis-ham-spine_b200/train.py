@@ -18,10 +18,25 @@ from . import ops
 from .parallel import GradSync, param_range, split_offset
 
 
+def mibf_forward_loss(model, images, ids, mask, labels):
+    """forward_loss for mibf_net.Resnet50WithOurs (mibf_net/train_resnet.py:21-41): batch dict -> three logit sets -> MP-Loss."""
+    out = model({"transformed_image": images, "input_ids": ids, "attention_mask": mask})
+    return model.cal_loss(out, labels), out["image_text"]
+
+
+def connext_forward_loss(model, images, ids, mask, labels):
+    """forward_loss for connext.OurClassfierConvnextV2 (ConNexT/models/pl_model_MOE2.py:144-154): logits -> cross entropy."""
+    logits = model({"transformed_image": images, "input_ids": ids, "attention_mask": mask})
+    return Fm.cross_entropy(logits, labels), logits
+
+
 class Trainer:
     def __init__(self, model, optimizer="adamw", lr=2e-4, weight_decay=None, betas=(0.9, 0.999), eps=1e-8, momentum=0.9,
                  loss="ce", label_smoothing=0.02, focal_gamma=2.0, class_weights=None, process_group=None,
-                 overlap_comm=True, supcon_weight=0.0, supcon_stage="finetune", supcon_temperature=0.07):
+                 overlap_comm=True, supcon_weight=0.0, supcon_stage="finetune", supcon_temperature=0.07, forward_loss=None):
+        """forward_loss: optional callable (model, images, ids, mask, labels) -> (loss, logits) for the model families whose
+        call surface differs from MultimodalBaselineModel (MIBF-Net: batch dict + cal_loss, mibf_net/train_resnet.py:21-41;
+        ConNexT: batch dict -> logits).  Everything else -- CUDA graph, gradient sync, fused optimizer -- is shared."""
         self.model = model
         self.opt = optimizer.lower()
         if self.opt not in ("adamw", "adam", "sgd"):
@@ -37,8 +52,11 @@ class Trainer:
             raise ValueError(f"Unsupported supcon stage: {supcon_stage}")
         self.supcon_weight, self.supcon_stage, self.supcon_temperature = float(supcon_weight), supcon_stage, supcon_temperature
         self.pg = process_group
+        self.forward_loss = forward_loss
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
-        self.overlap = overlap_comm and self.world > 1
+        # the early buckets assume MultimodalBaselineModel's parameter order [image encoder | text encoder | fusion | head];
+        # other model families reduce everything after backward
+        self.overlap = overlap_comm and self.world > 1 and forward_loss is None
         self.store = None
         self._graph = None
         self._static = None
@@ -103,14 +121,17 @@ class Trainer:
 
                 img_eng.on_stage_backward_done = stage_done
         try:
-            feats = self.model.forward_features(images, ids, mask)
-            logits = self.model.classifier(feats)
-            if self.supcon_weight > 0.0 and self.supcon_stage == "pretrain":
-                loss = Fm.supcon_loss(feats.float(), labels, self.supcon_temperature)
+            if self.forward_loss is not None:
+                loss, logits = self.forward_loss(self.model, images, ids, mask, labels)
             else:
-                loss = self._loss(logits, labels)
-                if self.supcon_weight > 0.0:
-                    loss = loss + self.supcon_weight * Fm.supcon_loss(feats.float(), labels, self.supcon_temperature)
+                feats = self.model.forward_features(images, ids, mask)
+                logits = self.model.classifier(feats)
+                if self.supcon_weight > 0.0 and self.supcon_stage == "pretrain":
+                    loss = Fm.supcon_loss(feats.float(), labels, self.supcon_temperature)
+                else:
+                    loss = self._loss(logits, labels)
+                    if self.supcon_weight > 0.0:
+                        loss = loss + self.supcon_weight * Fm.supcon_loss(feats.float(), labels, self.supcon_temperature)
             loss.backward()
         finally:
             if hook is not None:

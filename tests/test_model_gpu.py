@@ -326,3 +326,35 @@ def test_sequence_lstm_branch_matches_oracle(fusion, layers, bidir, hid, kind):
     if kind == "lstm":   # both LSTM biases see the same gate gradients: must agree to fp32 rounding
         gi, gh = st.g32(named["sequence_encoder.rnn.bias_ih_l0"]), st.g32(named["sequence_encoder.rnn.bias_hh_l0"])
         assert (gi - gh).abs().max().item() <= 1e-5 * gi.abs().max().item() + 1e-9
+
+
+@pytest.mark.gpu
+def test_trainer_custom_forward_loss_mibf_and_batched_tta():
+    """Trainer(forward_loss=...) drives MIBF-Net (batch dict + MP-Loss) through the shared CUDA-graph / fused-optimizer step:
+    the captured replay reproduces the eager loss trajectory's first value and the loss goes down; batched TTA over the
+    batch-dict model equals the per-variant mean."""
+    import mdhs_b200  # noqa: F401
+    from mdhs_b200 import ops
+    from mdhs_b200.inference import predict_tta_batchdict
+    from mdhs_b200.mibf_net.model_resnet import Resnet50WithOurs
+    from mdhs_b200.train import Trainer, mibf_forward_loss
+    from refutil import bert_dir, quiet
+    torch.manual_seed(0)
+    with quiet():
+        model = Resnet50WithOurs(num_labels=6, bert_path=bert_dir(), pretrained=False).cuda()
+    images, ids, mask, labels = weights.synthetic_batch(8, 16, 6, image_hw=64, unit_range=True)
+    batch = [t.cuda() for t in (images, ids, mask, labels)]
+    tr = Trainer(model, optimizer="sgd", lr=1e-3, forward_loss=mibf_forward_loss)
+    l0, _ = tr.step(*batch)
+    tr.capture(*batch, warmup=1)
+    ls = [tr.replay()[0].item() for _ in range(6)]
+    assert all(map(lambda v: v == v and abs(v) < 1e4, ls))
+    assert ls[-1] < l0.item()
+    model.eval()
+    tr_names = ("hflip", "rot90")
+    big = ops.tta_expand(batch[0], tr_names)
+    with torch.no_grad():
+        want = torch.stack([model({"transformed_image": v, "input_ids": batch[1], "attention_mask": batch[2]})["image_text"].float()
+                            for v in big.split(8)], dim=0).mean(dim=0)
+    got = predict_tta_batchdict(model, batch[0], batch[1], batch[2], tr_names)
+    assert (got - want).abs().max().item() <= 2e-3 * want.abs().max().item() + 1e-5
