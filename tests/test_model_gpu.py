@@ -358,3 +358,21 @@ def test_trainer_custom_forward_loss_mibf_and_batched_tta():
                             for v in big.split(8)], dim=0).mean(dim=0)
     got = predict_tta_batchdict(model, batch[0], batch[1], batch[2], tr_names)
     assert (got - want).abs().max().item() <= 2e-3 * want.abs().max().item() + 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,S,hw,fusion", [(1, 8, 32, "basic"), (5, 33, 96, "basic"), (3, 17, 64, "multiscale"), (1, 64, 224, "concat")])
+def test_edge_shapes_match_oracle(B, S, hw, fusion):
+    """Ragged / minimal inputs: one sample, a single 1x1 layer-4 token (32x32 image), sequence lengths that are not multiples
+    of 8, a fully padded tail, the full-resolution single image.  Eval logits against the oracle (<= 2e-2 max-norm)."""
+    model = build_ours(fusion=fusion, head="mlp")
+    sd = weights.synth_state_dict(model.state_dict(), seed=1)
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    images, ids, mask, _ = weights.synthetic_batch(B, S, 7, image_hw=hw, seed=5)
+    mask[0, 1:] = 0          # first sample: only the CLS token is valid
+    with torch.no_grad():
+        got = model(images.cuda(), ids.cuda(), mask.cuda()).float().cpu()
+        want = port.model_forward(sd, images, ids, mask, fusion=fusion, head="mlp")
+    assert got.shape == want.shape and torch.isfinite(got).all()
+    assert (got - want).abs().max().item() <= 2e-2 * want.abs().max().item()
