@@ -1,14 +1,18 @@
-// bf16 GEMM for sm_100a: tcgen05.mma with TMEM accumulators, TMA-fed shared-memory pipeline,
-// persistent warp-specialised CTAs (one per SM).  See include/mdhs_b200.h for the contract.
+// bf16 GEMM for sm_100a: tcgen05.mma with TMEM accumulators, TMA-fed shared-memory pipeline, persistent warp-specialised
+// CTAs (one per SM), optionally paired (cta_group::2).  See include/mdhs_b200.h for the contract, DESIGN.md section 3.1 and
+// profiles/r01_summary.md for the measurements behind each design point.
 //
-//   warp 0      : TMA producer (one elected lane) -> smem ring of STAGES {A tile, B tile}
-//   warp 1      : MMA issuer (one lane) -> tcgen05.mma into one of two TMEM accumulator stages
+//   warp 0      : TMA producer -- the whole warp walks the loop, one elected lane issues -> smem ring of STAGES {A tile, B tile}
+//                 (tiled maps, or im2col maps for implicit-GEMM convolutions; 2SM loads in pair mode)
+//   warp 1      : MMA issuer (elect.sync; the pair's leader CTA only) -> tcgen05.mma into one of two TMEM accumulator stages
 //   warp 2      : TMEM allocator / deallocator
-//   warps 4..11 : epilogue: tcgen05.ld -> registers (thread = row) -> fused bias / activation / act' /
-//                 dropout / residual / BN column statistics -> 16-byte row-contiguous global stores
+//   warps 4..11 : epilogue, two groups of four warps (one TMEM lane quarter each): per 64-column box a compact loop over
+//                 16-column chunks: tcgen05.ld -> registers (thread = accumulator row) -> fused bias / activation (+ second
+//                 output) / act' / dropout / residual -> 128B-swizzled staging box -> ONE TMA store or TMA reduce-add;
+//                 BN column statistics are taken from the staged box; act' / residual operands arrive by prefetched TMA boxes
 //
-// Tiles are 128 x BN x 64 (BN in {64,128,256}); operands are staged with the 128-byte TMA/UMMA
-// swizzle; both operands may be K-major or MN-major so forward, dgrad and wgrad need no transposes.
+// Tiles are 128 x BN x 64 per CTA (BN in {64,128,256}; 256 x BN per CTA pair); operands are staged with the 128-byte
+// TMA/UMMA swizzle; both operands may be K-major or MN-major so forward, dgrad and wgrad need no transposes.
 #include <cuda.h>
 #include <cstdlib>
 #include "common.cuh"
