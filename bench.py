@@ -1,13 +1,19 @@
 #!/usr/bin/env python
 """bench.py -- training throughput of the multimodal hot path on B200 (BASELINE.json: train samples/sec).
 
-  python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun for N>1)
-  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on the host cores
+  python bench.py --gpus N --steps K --warmup W              # our arm (one process per GPU under torchrun for N>1)
+  python bench.py --impl reference --gpus N --steps K ...    # the UNMODIFIED reference (oracle/_ref) on the host cores
+  python bench.py --impl torch_gpu --steps K ...             # the UNMODIFIED reference, torch eager on the same B200
+  python bench.py --config {1..5}                            # the other BASELINE.json configurations (default 2)
 
-Workload at N=1 = BASELINE.json configs[1]: ResNet-50 + BERT-base, cross-attention fusion (`fusion_type: basic`),
-MLP head, HAM 7 classes, per-GPU batch 128, 3x224x224 images, sequence length 64, bf16 tensor-core math,
-label-smoothed CE, AdamW lr 2e-4 -- forward + backward + gradient all-reduce + optimizer step, synthetic data,
+Workload at N=1 (default, --config 2) = BASELINE.json configs[1]: ResNet-50 + BERT-base, cross-attention fusion
+(`fusion_type: basic`), MLP head, HAM 7 classes, per-GPU batch 128, 3x224x224 images, sequence length 64, bf16 tensor-core
+math, label-smoothed CE, AdamW lr 2e-4 -- forward + backward + gradient all-reduce + optimizer step, synthetic data,
 random-init weights.  One JSON line is printed by rank 0 (see the task contract for the keys).
+
+The line also carries: `roofline` (dominant kernel = the tcgen05 GEMM: its own 2MNK FLOPs / its in-graph CUPTI time),
+`cpu_baseline` (the reference on the host cores, bounded sample), `gpu_baseline` (the reference with torch eager on the
+same B200: fp32 as shipped and bf16 autocast + channels_last -- the stock-GPU yardstick of SURVEY 2b / 8d), `e2e`.
 """
 import argparse
 import json
@@ -23,9 +29,21 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "train_samples_per_sec"
 UNIT = "samples/s"
-FWD_BWD_GFLOP_PER_SAMPLE = 57.50   # ResNet-50 + BERT `basic` fusion, S=64 (FlopCounterMode, 2xMAC)
-# SURVEY.md section 8d table (fwd+bwd GFLOP per sample) for the other --fusion / --seq combinations
-_GFLOP = {("basic", 64): 57.50, ("basic", 128): 90.27, ("multiscale", 64): 59.37, ("multiscale", 128): 92.57, ("concat", 64): 57.06}
+
+# BASELINE.json configs -> concrete shapes.  gflop = fwd+bwd GFLOP per sample (FlopCounterMode on the
+# reference, 2 x MAC); config 4 = ConvNeXt-Tiny features (8.91 fwd) + BERT S=64 (10.87 fwd), x3.
+CONFIGS = {
+    1: dict(family="baseline", fusion="concat", classes=7, batch=32, seq=64, gflop=57.06,
+            name="ResNet-50 + BERT-base, concat fusion, MLP head, HAM 7-class"),
+    2: dict(family="baseline", fusion="basic", classes=7, batch=128, seq=64, gflop=57.50,
+            name="ResNet-50 + BERT-base, basic (cross-attention) fusion, MLP head, HAM 7-class"),
+    3: dict(family="baseline", fusion="multiscale", classes=6, batch=128, seq=64, gflop=59.37,
+            name="ResNet-50 layer2/3/4 x BERT-base, multiscale cross-attention fusion, MLP head, Spine 6-class"),
+    4: dict(family="connext_moe", fusion=None, classes=7, batch=128, seq=64, gflop=59.3,
+            name="ConvNeXt-Tiny + BERT-base CLS -> MoE head (4 KAN experts, top-2), HAM 7-class"),
+    5: dict(family="mibf", fusion=None, classes=6, batch=128, seq=256, gflop=154.80,
+            name="MIBF-Net: ResNet-50 + BERT-base, IBFA attention, MP-Loss, Spine 6-class"),
+}
 
 
 def _peaks():
@@ -34,6 +52,28 @@ def _peaks():
         d = json.load(open(path))
         return d.get("bf16_tflops_sustained", 1401.0), d.get("hbm_gbs", 6530.0), "measured"
     return 1590.0, 6650.0, "fallback"
+
+
+def workload(args):
+    cfg = dict(CONFIGS[args.config])
+    if args.batch:
+        cfg["batch"] = args.batch
+    if args.seq:
+        cfg["seq"] = args.seq
+    if args.fusion and cfg["family"] == "baseline":
+        cfg["fusion"] = args.fusion
+        cfg["name"] = f"ResNet-50 + BERT-base, {args.fusion} fusion, MLP head, {cfg['classes']}-class"
+        cfg["gflop"] = {("basic", 64): 57.50, ("basic", 128): 90.27, ("multiscale", 64): 59.37, ("multiscale", 128): 92.57,
+                        ("concat", 64): 57.06}.get((args.fusion, cfg["seq"]), cfg["gflop"])
+    return cfg
+
+
+def config_dict(cfg, args, world, use_graph=True):
+    """The `config` object of the JSON line -- identical for our arm and the reference arms (same workload)."""
+    return {"workload": f"{cfg['name']}, train step (fwd+bwd+all-reduce+optimizer)", "baseline_config": args.config,
+            "per_gpu_batch": cfg["batch"], "global_batch": cfg["batch"] * world, "seq_len": cfg["seq"], "image": "3x224x224",
+            "parallelism": f"dp{world}", "cuda_graph": use_graph,
+            "l2": "per-step working set (>10 GB of activations) far exceeds the 126 MB L2; no explicit flush"}
 
 
 class ClockSampler(threading.Thread):
@@ -68,42 +108,14 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-# ----------------------------------------------------------------------------------------------
-# reference arm / CPU baseline: the oracle port (plain PyTorch, fp32) on the host cores
-# ----------------------------------------------------------------------------------------------
-def cpu_train_samples_per_sec(batch, steps, warmup, seq=64, hw=224):
-    import torch
-    from oracle import port, weights
-    from refutil import build_ours  # only used for the state_dict template (keys/shapes), never for compute
-    torch.set_num_threads(os.cpu_count())
-    tmpl = build_ours(fusion="basic", head="mlp").state_dict()
-    sd = weights.synth_state_dict(tmpl, seed=0)
-    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
-    state = dict(sd)
-    state.update(params)
-    opt = torch.optim.AdamW(list(params.values()), lr=2e-4)
-    images, ids, mask, labels = weights.synthetic_batch(batch, seq, 7, image_hw=hw)
-    times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        opt.zero_grad(set_to_none=True)
-        logits = port.model_forward(state, images, ids, mask, fusion="basic", head="mlp", training_bn=True)
-        loss = port.ce_label_smoothing(logits, labels, label_smoothing=0.02)
-        loss.backward()
-        opt.step()
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
-    total = sum(times)
-    return batch * len(times) / total, total / len(times)
-
-
-def synthetic_batch(B, S, num_classes, seed=123, image_hw=224):
-    """Synthetic inputs of SURVEY.md section 8d (ImageNet-normalised-like randn images, ids with CLS = 101, tail-padded mask,
-    labels) -- bench.py's own copy: our arm does not touch anything under oracle/."""
+def synthetic_batch(B, S, num_classes, seed=123, image_hw=224, unit_range=False):
+    """Synthetic inputs of SURVEY.md section 8d (ImageNet-normalised-like randn images -- [0,1] `rand` for the MIBF / ConNexT
+    families, which feed un-normalised pixels --, ids with CLS = 101, tail-padded mask, labels): bench.py's own copy, our arm
+    does not touch anything under oracle/."""
     import torch
     g = torch.Generator(device="cpu")
     g.manual_seed(seed)
-    images = torch.randn(B, 3, image_hw, image_hw, generator=g)
+    images = torch.rand(B, 3, image_hw, image_hw, generator=g) if unit_range else torch.randn(B, 3, image_hw, image_hw, generator=g)
     ids = torch.randint(0, 30522, (B, S), generator=g)
     ids[:, 0] = 101
     lens = torch.randint(min(8, S), S + 1, (B,), generator=g)
@@ -112,29 +124,221 @@ def synthetic_batch(B, S, num_classes, seed=123, image_hw=224):
     return images, ids, mask, labels
 
 
+# ----------------------------------------------------------------------------------------------
+# reference arms: the unmodified reference (oracle/_ref, vendored verbatim by oracle/make_ref.py) through its own public
+# API and its own training loop body (scripts/train.py:364-387: CrossEntropyLoss(label_smoothing) + AdamW; MIBF:
+# mibf_net/train_resnet.py:21-41).  Falls back to the oracle port (plain-PyTorch restatement) when oracle/_ref is absent.
+# ----------------------------------------------------------------------------------------------
+def reference_step_fn(cfg, device, batch, mode="fp32"):
+    """Returns (step callable -> loss tensor, kind).  mode: "fp32" (as shipped) | "bf16_cl" (autocast + channels_last)."""
+    import torch
+    import torch.nn as nn
+    from oracle import make_ref
+    from refutil import bert_dir, quiet
+    images, ids, mask, labels = [t.to(device) for t in batch]
+    autocast = mode == "bf16_cl"
+    if autocast:
+        images = images.contiguous(memory_format=torch.channels_last)
+    torch.manual_seed(0)
+    fam = cfg["family"]
+    if make_ref.available() or os.path.isdir("/root/reference"):
+        kind = "reference"
+        if fam == "baseline":
+            from refutil import build_reference_model
+            model = build_reference_model(fusion=cfg["fusion"], head="mlp", num_classes=cfg["classes"])
+            crit = nn.CrossEntropyLoss(label_smoothing=0.02)
+
+            def fwd():
+                return crit(model(images, ids, mask), labels)
+        elif fam == "mibf":
+            import torchvision
+            from refutil import REF_ROOT
+            if REF_ROOT not in sys.path:
+                sys.path.insert(0, REF_ROOT)
+            orig = torchvision.models.resnet50
+            torchvision.models.resnet50 = lambda *a, **k: orig(weights=None)   # offline: random init instead of the download
+            try:
+                with quiet():
+                    from mibf_net.model_resnet import Resnet50WithOurs
+                    model = Resnet50WithOurs(num_labels=cfg["classes"], bert_path=bert_dir())
+            finally:
+                torchvision.models.resnet50 = orig
+
+            def fwd():
+                out = model({"transformed_image": images, "input_ids": ids, "attention_mask": mask})
+                return model.cal_loss(out, labels)
+        else:
+            kind = None
+    else:
+        kind = None
+    if kind is None:
+        # oracle port (configs without an importable reference composite, or no vendored reference on this box)
+        kind = "port"
+        from oracle import port, weights
+        import mdhs_b200  # noqa: F401  (state_dict template only: keys / shapes; never used for compute here)
+        if fam == "baseline":
+            from refutil import build_ours
+            tmpl = build_ours(fusion=cfg["fusion"], head="mlp", num_classes=cfg["classes"]).state_dict()
+        elif fam == "mibf":
+            from mdhs_b200.mibf_net.model_resnet import Resnet50WithOurs as Ours
+            with quiet():
+                tmpl = Ours(num_labels=cfg["classes"], bert_path=bert_dir(), pretrained=False).state_dict()
+        else:
+            raise RuntimeError("no reference composite for this configuration (pl_model_MOE2 needs pytorch_lightning)")
+        sd = weights.synth_state_dict(tmpl, seed=0)
+        params = {k: v.clone().to(device).requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
+        state = {k: v.to(device) for k, v in sd.items()}
+        state.update(params)
+
+        class _Holder(nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.plist = nn.ParameterList([nn.Parameter(p) for p in params.values()])
+        model = _Holder()
+        for (k, _), p in zip(params.items(), model.plist):
+            state[k] = p
+
+        if fam == "baseline":
+            def fwd():
+                logits = port.model_forward(state, images, ids, mask, fusion=cfg["fusion"], head="mlp", training_bn=True)
+                return port.ce_label_smoothing(logits, labels, label_smoothing=0.02)
+        else:
+            def fwd():
+                out = port.mibf_forward(state, images, ids, mask, training_bn=True)
+                return port.mp_loss(out["image"], out["text"], out["image_text"], labels)
+    model = model.to(device).train()
+    if autocast:
+        model = model.to(memory_format=torch.channels_last)
+    if fam == "mibf":
+        opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9)   # mibf_net/train_resnet.py:136-139
+    else:
+        opt = torch.optim.AdamW(model.parameters(), lr=2e-4)               # scripts/train.py:283-299, config.yml:80-84
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast(device_type=device.type, dtype=torch.bfloat16, enabled=autocast):
+            loss = fwd()
+        loss.backward()
+        opt.step()
+        return loss.detach()
+    return step, kind
+
+
+def cpu_reference_samples_per_sec(cfg, batch_size, steps, warmup):
+    import torch
+    torch.set_num_threads(os.cpu_count())
+    unit = cfg["family"] != "baseline"
+    batch = synthetic_batch(batch_size, cfg["seq"], cfg["classes"], unit_range=unit)
+    step, kind = reference_step_fn(cfg, torch.device("cpu"), batch)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return batch_size * len(times) / total, total / len(times), kind
+
+
+def torch_gpu_samples_per_sec(cfg, dev, steps, warmup, mode):
+    """The reference modules with torch eager (cuDNN / cuBLAS / ATen) on the same B200; CUDA-event timed."""
+    import torch
+    unit = cfg["family"] != "baseline"
+    batch = synthetic_batch(cfg["batch"], cfg["seq"], cfg["classes"], unit_range=unit)
+    step, kind = reference_step_fn(cfg, dev, batch, mode)
+    for _ in range(max(warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": round(cfg["batch"] / (ms / 1e3), 1), "unit": UNIT, "ms_per_step": round(ms, 3), "steps": steps,
+            "kind": kind, "final_loss": round(float(loss.item()), 4)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = args.ref_batch
-    sps, sec = cpu_train_samples_per_sec(batch, args.steps, args.warmup)
+    cfg = workload(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    batch = min(args.ref_batch, cfg["batch"])
+    sps, sec, kind = cpu_reference_samples_per_sec(cfg, batch, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": round(sps, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "ResNet-50 + BERT-base, basic (cross-attention) fusion, MLP head, HAM 7-class, 3x224x224, seq 64, "
-                               "fwd+bwd+AdamW", "per_step_batch": batch,
-                   "note": "reference's own CPU PyTorch path (oracle port of the pure-Python reference), bounded sample per step"},
-        "cpu_baseline": {"value": round(sps, 3), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+        "config": config_dict(cfg, args, world),
+        "note": f"the reference's own CPU PyTorch path ({'unmodified reference modules from oracle/_ref' if kind == 'reference' else 'oracle port'}"
+                f", fp32, {os.cpu_count()} host threads); each step is a bounded sample of {batch} of the {cfg['batch']} samples",
+        "cpu_baseline": {"value": round(sps, 3), "unit": UNIT, "cores": os.cpu_count(), "kind": kind,
                          "sample": f"{args.steps} steps of batch {batch} after {args.warmup} warm-up"},
         "e2e": {"value": round(sps, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
+def run_torch_gpu(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    cfg = workload(args)
+    dev = torch.device("cuda", 0)
+    res = {}
+    for mode in ("fp32", "bf16_cl"):
+        try:
+            res[mode] = torch_gpu_samples_per_sec(cfg, dev, args.steps, args.warmup, mode)
+        except Exception as e:
+            res[mode] = {"error": f"{type(e).__name__}: {e}"}
+        torch.cuda.empty_cache()
+    best = max((r["value"] for r in res.values() if "value" in r), default=None)
+    line = {"impl": "torch_gpu", "metric": METRIC, "value": best, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 / bf16-autocast", "data": "synthetic", "config": config_dict(cfg, args, 1, use_graph=False),
+            "gpu_baseline": {"fp32_as_shipped": res["fp32"], "bf16_autocast_channels_last": res["bf16_cl"]},
+            "note": "the reference's modules with torch eager (cuDNN/cuBLAS/ATen) on one B200; `value` = the faster of the two"}
+    print(json.dumps(line), flush=True)
+
+
 # ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
+def build_ours_model(cfg, dev):
+    """Our B200 model + Trainer for one BASELINE configuration."""
+    import torch
+    import mdhs_b200
+    from mdhs_b200.train import Trainer, mibf_forward_loss
+    from mdhs_b200 import functional as Fm
+    from refutil import bert_dir, quiet
+    torch.manual_seed(0)
+    fam = cfg["family"]
+    with quiet():
+        if fam == "baseline":
+            model = mdhs_b200.MultimodalBaselineModel(num_classes=cfg["classes"], hidden_dim=256, dropout=0.2, pretrained_image=False,
+                                                      image_weights_path=None, text_model_name=bert_dir(), num_heads=8,
+                                                      image_backbone="resnet50", classifier_type="mlp", fusion_type=cfg["fusion"])
+            model = model.to(dev)
+            trainer = Trainer(model, optimizer="adamw", lr=2e-4, label_smoothing=0.02)
+        elif fam == "mibf":
+            from mdhs_b200.mibf_net.model_resnet import Resnet50WithOurs
+            model = Resnet50WithOurs(num_labels=cfg["classes"], bert_path=bert_dir(), pretrained=False).to(dev)
+            trainer = Trainer(model, optimizer="sgd", lr=1e-3, momentum=0.9, forward_loss=mibf_forward_loss)
+        else:
+            from mdhs_b200.connext.ourmodel import ConvNeXtMoEClassifier
+            model = ConvNeXtMoEClassifier(num_labels=cfg["classes"], variant="tiny", use_text=True, bert_path=bert_dir()).to(dev)
+
+            def moe_forward_loss(m, images, ids, mask, labels):
+                logits, aux = m({"transformed_image": images, "input_ids": ids, "attention_mask": mask})
+                return Fm.cross_entropy(logits, labels) + aux, logits
+            trainer = Trainer(model, optimizer="adamw", lr=2e-4, forward_loss=moe_forward_loss)
+    return model, trainer
+
+
 def run_ours(args):
     # rank 0's stdout must carry exactly ONE JSON line, but native libraries write there too (NCCL prints its version banner
     # with printf): park the real stdout, point fd 1 at stderr for the whole run, and emit the line on the parked descriptor
@@ -156,29 +360,24 @@ def run_ours(args):
         # poll events of a capturing stream (torch CUDA-graphs notes)
         os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
         dist.init_process_group("nccl", device_id=dev)
-    import mdhs_b200
+    import mdhs_b200  # noqa: F401
     from mdhs_b200 import _lib, ops
-    from mdhs_b200.train import Trainer
-    from refutil import bert_dir, quiet   # tests/refutil.py: builds the local random-init bert-base directory
+    from refutil import bert_dir
 
-    B, S, HW, C = args.batch, args.seq, 224, 7
+    cfg = workload(args)
+    B, S, HW, C = cfg["batch"], cfg["seq"], 224, cfg["classes"]
     if rank == 0:
         bert_dir()
     if world > 1:
         dist.barrier()
-    torch.manual_seed(0)
-    with quiet():
-        model = mdhs_b200.MultimodalBaselineModel(num_classes=C, hidden_dim=256, dropout=0.2, pretrained_image=False,
-                                                  image_weights_path=None, text_model_name=bert_dir(), num_heads=8,
-                                                  image_backbone="resnet50", classifier_type="mlp", fusion_type=args.fusion)
-    model = model.to(dev)
-    trainer = Trainer(model, optimizer="adamw", lr=2e-4, label_smoothing=0.02)
-    images, ids, mask, labels = synthetic_batch(B, S, C, seed=123 + rank, image_hw=HW)
+    model, trainer = build_ours_model(cfg, dev)
+    images, ids, mask, labels = synthetic_batch(B, S, C, seed=123 + rank, image_hw=HW, unit_range=cfg["family"] != "baseline")
     h_in = [t.pin_memory() for t in (images, ids, mask, labels)]
     d_in = [t.to(dev, non_blocking=True) for t in h_in]
     torch.cuda.synchronize()
 
     use_graph = not args.no_graph
+
     def _mark(msg):
         if args.verbose:
             print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
@@ -186,19 +385,13 @@ def run_ours(args):
     launches_per_step = None
     if use_graph:
         try:
-            c0 = _lib.launch_count()
             trainer.capture(*d_in, warmup=3)
-            # warm-up (3 eager) + 1 captured pass were recorded by the host-side counter
-            launches_per_step = (_lib.launch_count() - c0) // 4
+            c0 = _lib.launch_count()
         except Exception as e:  # e.g. a collective that cannot be captured: fall back to eager launches
             if rank == 0:
                 print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); running eager", file=sys.stderr)
             use_graph = False
             torch.cuda.synchronize()
-    if not use_graph:
-        c0 = _lib.launch_count()
-        trainer.step(*d_in)
-        launches_per_step = _lib.launch_count() - c0
 
     def one_step():
         if use_graph:
@@ -275,9 +468,11 @@ def run_ours(args):
     e2e_value = world * B * args.steps / e2e_s.item()
     h2d = sum(t.numel() * t.element_size() for t in h_in)
 
-    # ---- roofline of the dominant kernel (the tcgen05 GEMM): one instrumented eager step, CUDA events per launch
+    # ---- roofline of the dominant kernel (the tcgen05 GEMM).  FLOPs: the kernel's OWN work, sum of 2*M*N*K over the GEMM
+    # launches of one step (recorded by wrapping the C-ABI call in one eager step).  Time: CUPTI durations of exactly those
+    # kernels inside the graph-replayed step (warm, no launch gaps); falls back to CUDA-event pairs around eager launches.
     roof = None
-    if rank == 0:
+    if rank == 0 and world == 1:
         recs = []
         real_gemm = ops.gemm
 
@@ -290,53 +485,101 @@ def run_ours(args):
             M = kw.get("M") or (a.shape[1] if a_mn else a.shape[0])
             N = kw.get("N") or (b.shape[1] if b_mn else b.shape[0])
             K = kw.get("K") or (a.shape[0] if a_mn else a.shape[1])
-            recs.append((2.0 * M * N * K, s_, e_, (M, N, K, int(a_mn), int(b_mn), int(bool(kw.get("accumulate"))), kw.get("split_k", 1))))
+            recs.append((2.0 * M * N * K, s_, e_, (M, N, K, int(a_mn), int(b_mn), int(bool(kw.get("accumulate"))), kw.get("split_k", 1),
+                                                   int(kw.get("conv") is not None))))
             return out
         ops.gemm = timed_gemm
+        c0 = _lib.launch_count()
         try:
             s_all, e_all = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize()
-            if world == 1:
-                trainer.step(*d_in)          # allocator warm-up on this stream (the captured graph owns its own pool)
-                recs.clear()
-                torch.cuda.synchronize()
-                torch.cuda._sleep(int(60e6))  # ~30 ms of GPU spin: the host runs ahead, so event pairs bracket kernels only
-                s_all.record()
-                trainer.step(*d_in)
-                e_all.record()
-                torch.cuda.synchronize()
+            trainer.step(*d_in)          # allocator warm-up on this stream (the captured graph owns its own pool)
+            recs.clear()
+            torch.cuda.synchronize()
+            c0 = _lib.launch_count()
+            torch.cuda._sleep(int(60e6))  # ~30 ms of GPU spin: the host runs ahead, so event pairs bracket kernels only
+            s_all.record()
+            trainer.step(*d_in)
+            e_all.record()
+            torch.cuda.synchronize()
+            launches_per_step = _lib.launch_count() - c0
         finally:
             ops.gemm = real_gemm
+        gemm_us = other = None
+        top = None
+        if use_graph:
+            try:
+                import collections
+                from torch.profiler import ProfilerActivity, profile
+                reps = 2
+                with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                    for _ in range(reps):
+                        trainer.replay()
+                    torch.cuda.synchronize()
+                agg = collections.defaultdict(lambda: [0, 0.0])
+                for e in prof.events():
+                    if e.device_type == torch.autograd.DeviceType.CUDA and e.name and "Memcpy" not in e.name and "Memset" not in e.name:
+                        k = e.name.replace("void ", "").replace("(anonymous namespace)::", "").replace("<unnamed>::", "").split("(")[0]
+                        k = k.split("<")[0]
+                        agg[k][0] += 1
+                        agg[k][1] += e.time_range.end - e.time_range.start
+                gemm_us = agg["gemm_tc_kernel"][1] / reps if "gemm_tc_kernel" in agg else None
+                busy = sum(v[1] for v in agg.values()) / reps
+                top = [[k, round(v[0] / reps, 1), round(v[1] / reps, 1)] for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:12]]
+                other = busy
+            except Exception as e:
+                print(f"[bench] CUPTI timeline unavailable ({type(e).__name__}: {e}); using eager CUDA-event pairs", file=sys.stderr)
         if recs:
             gflop = sum(r[0] for r in recs) / 1e9
-            gms = sum(r[1].elapsed_time(r[2]) for r in recs)
+            gms_eager = sum(r[1].elapsed_time(r[2]) for r in recs)
+            gms = gemm_us / 1e3 if gemm_us else gms_eager
             peak, hbm, src = _peaks()
             ach = gflop / gms  # GFLOP/ms == TFLOP/s
             if args.dump_gemms:
                 import collections
-                agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
+                agg2 = collections.defaultdict(lambda: [0, 0.0, 0.0])
                 for r in recs:
-                    a_ = agg[r[3]]
+                    a_ = agg2[r[3]]
                     a_[0] += 1
                     a_[1] += r[1].elapsed_time(r[2])
                     a_[2] += r[0]
                 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-                with open(os.path.join(ROOT, "gpurun_out", "gemm_shapes.txt"), "w") as fh:
-                    fh.write("M N K a_mn b_mn acc split | count total_ms TFLOP/s\n")
-                    for k_, (c_, ms_, fl_) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                with open(os.path.join(ROOT, "gpurun_out", f"gemm_shapes_c{args.config}.txt"), "w") as fh:
+                    fh.write("M N K a_mn b_mn acc split conv | count total_ms TFLOP/s   (eager CUDA-event pairs)\n")
+                    for k_, (c_, ms_, fl_) in sorted(agg2.items(), key=lambda kv: -kv[1][1]):
                         fh.write(f"{k_} | {c_} {ms_:.3f} {fl_ / ms_ / 1e9:.1f}\n")
+            # DRAM traffic of the same kernels: from the committed ncu capture of this command (profiles/), per launch
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "r02_gemm_dram_traffic.json")
+            if os.path.exists(tpath) and args.config == 2:
+                try:
+                    tj = json.load(open(tpath))
+                    traffic = round(tj["dram_bytes_per_step"] / tj["launches_per_step"])
+                except Exception:
+                    traffic = None
             roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM: all Linear / conv contractions)",
-                    "achieved": round(ach, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": None,
+                    "achieved": round(ach, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": traffic,
+                    "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read+write, mean over the step's GEMM launches; "
+                                    "profiles/r02_gemm_dram_traffic.json)",
                     "peak_source": f"{src} bf16_tflops_sustained", "launches_per_step": len(recs),
-                    "gemm_ms_per_step": round(gms, 3), "gemm_gflop_per_step": round(gflop, 1),
-                    "gemm_share_of_eager_step": round(gms / s_all.elapsed_time(e_all), 3),
-                    "model_flops_frac": round(value / world * _GFLOP.get((args.fusion, S), FWD_BWD_GFLOP_PER_SAMPLE) / 1e3 / peak, 4)}
+                    "timing": "CUPTI kernel durations inside the graph-replayed step" if gemm_us else "CUDA-event pairs, eager step",
+                    "gemm_ms_per_step": round(gms, 3), "gemm_ms_per_step_eager_events": round(gms_eager, 3),
+                    "gemm_gflop_per_step": round(gflop, 1),
+                    "flops_per_launch": round(gflop * 1e9 / len(recs)), "us_per_launch": round(gms * 1e3 / len(recs), 2),
+                    "gemm_share_of_step": round(gms / (ms / args.steps), 3),
+                    "kernel_busy_ms_per_step": round(other / 1e3, 3) if other else None, "top_kernels_us": top,
+                    "model_flops_frac": round(value / world * cfg["gflop"] / 1e3 / peak, 4)}
+    if launches_per_step is None:
+        c0 = _lib.launch_count()
+        trainer.step(*d_in)
+        torch.cuda.synchronize()
+        launches_per_step = _lib.launch_count() - c0
     if world > 1:
         dist.barrier()
 
     # ---- inference throughput (BASELINE.json's second metric): eval-mode forward of the same batch, one CUDA graph
     infer = None
-    if not args.no_inference:
+    if not args.no_inference and cfg["family"] == "baseline":
         try:
             model.eval()
             s_in = [t.clone() for t in d_in[:3]]
@@ -350,7 +593,7 @@ def run_ours(args):
                     try:
                         g_inf = torch.cuda.CUDAGraph()
                         with torch.cuda.graph(g_inf):
-                            logits_inf = model(*s_in)
+                            logits_inf = model(*s_in)  # noqa: F841
                     except Exception:
                         g_inf = None
                         torch.cuda.synchronize()
@@ -376,23 +619,36 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sps, sec = cpu_train_samples_per_sec(32, 2, 1)
-        cpu = {"value": round(sps, 3), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-               "sample": "2 steps of batch 32 (BASELINE config 1 shape: S=64, 224x224, fwd+bwd+AdamW) after 1 warm-up, fp32 oracle port"}
+    # ---- baselines measured in the same run (rank 0, N = 1 only): the reference with torch eager on this B200, and on the
+    # host cores.  Both are REPORTED baselines; neither touches our package.
+    gpu_base = cpu = None
+    if rank == 0 and world == 1 and not args.no_gpu_baseline and cfg["family"] in ("baseline", "mibf"):
+        trainer.release_graph()
+        torch.cuda.empty_cache()
+        gpu_base = {}
+        for mode, key in (("fp32", "fp32_as_shipped"), ("bf16_cl", "bf16_autocast_channels_last")):
+            try:
+                gpu_base[key] = torch_gpu_samples_per_sec(cfg, dev, 5, 3, mode)
+            except Exception as e:
+                gpu_base[key] = {"error": f"{type(e).__name__}: {e}"}
+            torch.cuda.empty_cache()
+        gpu_base["note"] = ("the reference's own modules, torch eager (cuDNN/cuBLAS/ATen) on the same B200, same batch / "
+                            "optimizer / loss; 5 timed steps after 3 warm-up, CUDA events")
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and cfg["family"] in ("baseline", "mibf"):
+        cb = min(32, B)
+        sps, sec, kind = cpu_reference_samples_per_sec(cfg, cb, 2, 1)
+        cpu = {"value": round(sps, 3), "unit": UNIT, "cores": os.cpu_count(), "kind": kind,
+               "sample": f"2 steps of a {cb}-sample batch of this workload (S={S}, 224x224, fwd+bwd+optimizer) after 1 warm-up, fp32, "
+                         f"{'unmodified reference modules (oracle/_ref)' if kind == 'reference' else 'oracle port'}"}
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"ResNet-50 + BERT-base, {args.fusion} (cross-attention) fusion, MLP head, HAM 7-class, train step "
-                                   "(fwd+bwd+all-reduce+AdamW)", "per_gpu_batch": B, "global_batch": B * world, "seq_len": S,
-                       "image": "3x224x224", "parallelism": f"dp{world}", "cuda_graph": use_graph,
-                       "l2": "per-step working set (>10 GB of activations) far exceeds the 126 MB L2; no explicit flush"},
+            "config": config_dict(cfg, args, world, use_graph),
             "clocks": clocks, "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches_per_step) * args.steps, "gpu_launches_per_step": int(launches_per_step),
-            "roofline": roof, "cpu_baseline": cpu, "inference": infer, "final_loss": round(final_loss, 4),
+            "roofline": roof, "cpu_baseline": cpu, "gpu_baseline": gpu_base, "inference": infer, "final_loss": round(final_loss, 4),
         }
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
@@ -412,22 +668,25 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=128, help="per-GPU batch")
-    ap.add_argument("--seq", type=int, default=64)
-    ap.add_argument("--fusion", default="basic", choices=["basic", "multiscale", "concat"],
-                    help="fusion_type of the benchmarked model (default: the headline cross-attention block; "
-                         "`multiscale` is what configs/ham_fusion_crossattn_v1.yml ships)")
-    ap.add_argument("--ref-batch", type=int, default=8, help="samples per CPU step of the reference arm")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_gpu"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json configuration (1-based)")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the configuration's)")
+    ap.add_argument("--seq", type=int, default=0, help="sequence length (default: the configuration's)")
+    ap.add_argument("--fusion", default=None, choices=["basic", "multiscale", "concat"],
+                    help="override the fusion_type of a MultimodalBaselineModel configuration")
+    ap.add_argument("--ref-batch", type=int, default=32, help="samples per CPU step of the reference arm (bounded sample)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
     ap.add_argument("--no-inference", action="store_true", help="skip the eval-forward throughput measurement")
     ap.add_argument("--graph-multi-gpu", action="store_true", help="(default now; kept for old command lines)")
     ap.add_argument("--verbose", action="store_true")
-    ap.add_argument("--dump-gemms", action="store_true", help="write per-shape GEMM timings to gpurun_out/gemm_shapes.txt")
+    ap.add_argument("--dump-gemms", action="store_true", help="write per-shape GEMM timings to gpurun_out/gemm_shapes_c<N>.txt")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "torch_gpu":
+        run_torch_gpu(args)
     else:
         run_ours(args)
 

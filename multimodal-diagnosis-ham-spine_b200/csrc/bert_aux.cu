@@ -61,7 +61,7 @@ extern "C" int mdhs_embed_gather(const int64_t* ids, const int64_t* type_ids, co
   if (!ids || !word || !pos || !type || !e || rows <= 0 || (C % 4)) return MDHS_ERR_ARG;
   int64_t total = (int64_t)rows * (C / 4);
   int grid = (int)((total + 255) / 256);
-  if (grid > 148 * 16) grid = 148 * 16;
+  if (grid > (int64_t)mdhs_num_sms() * 16) grid = (int64_t)mdhs_num_sms() * 16;
   g_mdhs_launches++;
   embed_gather_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(ids, type_ids, word, pos, type, e, rows, S, C, vocab);
   MDHS_RETURN_LAST();

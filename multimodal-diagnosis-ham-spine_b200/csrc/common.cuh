@@ -152,3 +152,15 @@ __device__ __forceinline__ void dropout_apply4(uint64_t seed, uint64_t idx, floa
 }
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// Number of SMs of the current device (148 on B200), queried once per translation unit: grid-size heuristics are written
+// in units of it instead of a literal.
+static inline int mdhs_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}

@@ -10,7 +10,7 @@ namespace {
 
 int grid_for(int64_t items, int block) {
   int64_t g = (items + block - 1) / block;
-  const int64_t cap = 148 * 32;
+  const int64_t cap = (int64_t)mdhs_num_sms() * 32;
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 

@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(256) sq_attn_bwd_kernel(const bf16* __restrict
 
 int grid_cap(int64_t items, int block) {
   int64_t g = (items + block - 1) / block;
-  const int64_t cap = 148 * 16;
+  const int64_t cap = (int64_t)mdhs_num_sms() * 16;
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
@@ -363,7 +363,7 @@ extern "C" int mdhs_dwconv7_wgrad(const void* x, const void* dy, float* dw, floa
   if (!x || !dy || !dw || B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C % 8)) return MDHS_ERR_ARG;
   const int slabs = (C + 63) / 64;
   const int64_t total = (int64_t)B * H * W;
-  int chunks = (148 * 4 + slabs - 1) / slabs;
+  int chunks = (mdhs_num_sms() * 4 + slabs - 1) / slabs;
   if (chunks > total / 64) chunks = (int)(total / 64 > 0 ? total / 64 : 1);
   const int64_t ppb = (total + chunks - 1) / chunks;
   const dim3 grid((unsigned)((total + ppb - 1) / ppb), (unsigned)slabs);
@@ -385,7 +385,7 @@ extern "C" int mdhs_layer_scale_bwd(const void* dy, const void* z, const float* 
                                     int rows_per_sample, float p, uint64_t seed, void* stream) {
   if (!dy || !z || !ls || !dz || rows <= 0 || C <= 0 || (C % 8) || rows_per_sample <= 0 || p < 0.f || p >= 1.f) return MDHS_ERR_ARG;
   const int cslabs = (C + 255) / 256;
-  int row_blocks = (148 * 8) / cslabs;
+  int row_blocks = ((int64_t)mdhs_num_sms() * 8) / cslabs;
   if (row_blocks < 1) row_blocks = 1;
   int64_t rpb = (rows + row_blocks - 1) / row_blocks;
   rpb = ((rpb + 7) / 8) * 8;

@@ -10,7 +10,7 @@ namespace {
 
 int grid_for(int64_t items) {
   int64_t g = (items + 255) / 256;
-  const int64_t cap = 148 * 16;
+  const int64_t cap = (int64_t)mdhs_num_sms() * 16;
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
@@ -187,7 +187,7 @@ extern "C" int mdhs_gru_cell_fwd(const float* gi, const float* gh, const float* 
                                  void* stream) {
   if (!gi || !gh || !h_prev || !h || !act || B <= 0 || H <= 0) return MDHS_ERR_ARG;
   int64_t g = ((int64_t)B * H + 255) / 256;
-  if (g > 148 * 8) g = 148 * 8;
+  if (g > (int64_t)mdhs_num_sms() * 8) g = (int64_t)mdhs_num_sms() * 8;
   g_mdhs_launches++;
   gru_cell_fwd_kernel<<<(int)g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(gi, gh, h_prev, h, act, B, H);
   MDHS_RETURN_LAST();
@@ -196,7 +196,7 @@ extern "C" int mdhs_gru_cell_bwd(const float* dh, const float* act, const float*
                                  float* dh_prev, int B, int H, void* stream) {
   if (!dh || !act || !gh || !h_prev || !dgi || !dgh || !dh_prev || B <= 0 || H <= 0) return MDHS_ERR_ARG;
   int64_t g = ((int64_t)B * H + 255) / 256;
-  if (g > 148 * 8) g = 148 * 8;
+  if (g > (int64_t)mdhs_num_sms() * 8) g = (int64_t)mdhs_num_sms() * 8;
   g_mdhs_launches++;
   gru_cell_bwd_kernel<<<(int)g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dh, act, gh, h_prev, dgi, dgh, dh_prev, B, H);
   MDHS_RETURN_LAST();
@@ -205,7 +205,7 @@ extern "C" int mdhs_gru_cell_bwd(const float* dh, const float* act, const float*
 extern "C" int mdhs_lstm_cell_fwd(const float* gates, const float* c_prev, float* h, float* c, float* act, int B, int H, void* stream) {
   if (!gates || !h || !c || !act || B <= 0 || H <= 0) return MDHS_ERR_ARG;
   int64_t g = ((int64_t)B * H + 255) / 256;
-  if (g > 148 * 8) g = 148 * 8;
+  if (g > (int64_t)mdhs_num_sms() * 8) g = (int64_t)mdhs_num_sms() * 8;
   g_mdhs_launches++;
   lstm_cell_fwd_kernel<<<(int)g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(gates, c_prev, h, c, act, B, H);
   MDHS_RETURN_LAST();
@@ -214,7 +214,7 @@ extern "C" int mdhs_lstm_cell_bwd(const float* dh, const float* dc, const float*
                                   float* dgates, float* dc_prev, int B, int H, void* stream) {
   if (!act || !c || !dgates || !dc_prev || B <= 0 || H <= 0) return MDHS_ERR_ARG;
   int64_t g = ((int64_t)B * H + 255) / 256;
-  if (g > 148 * 8) g = 148 * 8;
+  if (g > (int64_t)mdhs_num_sms() * 8) g = (int64_t)mdhs_num_sms() * 8;
   g_mdhs_launches++;
   lstm_cell_bwd_kernel<<<(int)g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dh, dc, act, c_prev, c, dgates, dc_prev, B, H);
   MDHS_RETURN_LAST();
@@ -223,7 +223,7 @@ extern "C" int mdhs_lstm_cell_bwd(const float* dh, const float* dc, const float*
 extern "C" int mdhs_axpby_bf16(const void* x, const void* y, void* out, int64_t n, float a, float b, void* stream) {
   if (!x || !out || n <= 0 || (n % 8)) return MDHS_ERR_ARG;
   int64_t g = (n / 8 + 255) / 256;
-  if (g > 148 * 16) g = 148 * 16;
+  if (g > (int64_t)mdhs_num_sms() * 16) g = (int64_t)mdhs_num_sms() * 16;
   g_mdhs_launches++;
   axpby_bf16_kernel<<<(int)g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const bf16*)x, (const bf16*)y, (bf16*)out, n / 8, a, b);
   MDHS_RETURN_LAST();
@@ -237,7 +237,7 @@ extern "C" int mdhs_global_local(const float* x, float* y, int B, int C, int H, 
   const int y0 = (H - ch) / 2 > 0 ? (H - ch) / 2 : 0, x0 = (W - cw) / 2 > 0 ? (W - cw) / 2 : 0;
   const int64_t planes = (int64_t)B * C;
   int64_t g = (2 * planes * H * W + 255) / 256;
-  if (g > 148 * 16) g = 148 * 16;
+  if (g > (int64_t)mdhs_num_sms() * 16) g = (int64_t)mdhs_num_sms() * 16;
   g_mdhs_launches++;
   global_local_kernel<<<(int)g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, planes, H, W, y0, x0, ch, cw);
   MDHS_RETURN_LAST();

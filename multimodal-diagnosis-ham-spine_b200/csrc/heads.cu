@@ -291,7 +291,7 @@ extern "C" int mdhs_ce_loss(const float* logits, int64_t ld, const int64_t* labe
 extern "C" int mdhs_axpby_f32(const float* x, float* y, int64_t n, const float* a_dev, float a, float b, void* stream) {
   if (!x || !y || n <= 0) return MDHS_ERR_ARG;
   int grid = (int)((n + 255) / 256);
-  if (grid > 148 * 8) grid = 148 * 8;
+  if (grid > (int64_t)mdhs_num_sms() * 8) grid = (int64_t)mdhs_num_sms() * 8;
   g_mdhs_launches++;
   axpby_kernel<<<grid, 256, 0, ST(stream)>>>(x, y, n, a_dev, a, b);
   MDHS_RETURN_LAST();

@@ -368,7 +368,7 @@ __global__ void randn_f32_kernel(float* __restrict__ out, int64_t n, uint64_t se
 
 int grid_for(int64_t items) {
   int64_t g = (items + 255) / 256;
-  const int64_t cap = 148 * 16;
+  const int64_t cap = (int64_t)mdhs_num_sms() * 16;
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 

@@ -587,7 +587,7 @@ int grid_for_channels(int64_t total_vec, int C) {
   }
   const int unit = cvec / a;                     // grid must be a multiple of cvec / gcd(cvec, 256)
   int64_t g = (total_vec + 255) / 256;
-  const int64_t cap = 148 * 16;
+  const int64_t cap = (int64_t)mdhs_num_sms() * 16;
   if (g > cap) g = cap;
   g = (g / unit) * unit;
   if (g < unit) g = unit;
@@ -596,7 +596,7 @@ int grid_for_channels(int64_t total_vec, int C) {
 
 int grid_for(int64_t work_items, int block) {
   int64_t g = (work_items + block - 1) / block;
-  const int64_t cap = 148 * 16;
+  const int64_t cap = (int64_t)mdhs_num_sms() * 16;
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
@@ -653,7 +653,7 @@ extern "C" int mdhs_layernorm_bwd(const void* dy, int dy_f32, int64_t lddy, cons
 #undef LNB1
   if (params) {
     const int cslabs = ceil_div(C, 256);
-    int row_blocks = (148 * 4) / cslabs;
+    int row_blocks = ((int64_t)mdhs_num_sms() * 4) / cslabs;
     if (row_blocks < 1) row_blocks = 1;
     int rpb = ceil_div(rows, row_blocks);
     rpb = ((rpb + 7) / 8) * 8;
@@ -713,7 +713,7 @@ extern "C" int mdhs_bn_bwd(const void* dy, const void* x, const void* y, const f
   int Cw;
   fold_view(rows, C, C, &rows_w, &Cw);
   const int cslabs = ceil_div(Cw, 256);
-  int row_blocks = (148 * 8) / cslabs;
+  int row_blocks = ((int64_t)mdhs_num_sms() * 8) / cslabs;
   if (row_blocks < 1) row_blocks = 1;
   int rpb = ceil_div(rows_w, row_blocks);
   rpb = ((rpb + 7) / 8) * 8;
@@ -737,7 +737,7 @@ extern "C" int mdhs_col_stats(const void* x, int64_t ldx, double* sum64, double*
   int Cw;
   if (fold_view(rows, C, ldx, &rows_w, &Cw)) ldx = Cw;
   const int cslabs = ceil_div(Cw, 256);
-  int row_blocks = (148 * 8) / cslabs;
+  int row_blocks = ((int64_t)mdhs_num_sms() * 8) / cslabs;
   // short matrices (bias gradients of [8192, N] token matrices): at least 128 rows per block, otherwise the kernel is all
   // prologue + atomics (394 blocks of 24 rows each for N = 768)
   if (row_blocks > rows_w / 128) row_blocks = (int)(rows_w / 128);

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256) sgd_flat_kernel(float* __restrict__ p, fl
 
 int grid_for(int64_t items) {
   int64_t g = (items + 255) / 256;
-  const int64_t cap = 148 * 16;
+  const int64_t cap = (int64_t)mdhs_num_sms() * 16;
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
@@ -136,7 +136,7 @@ __global__ void step_begin_kernel(int* step_dev) {
 // captured CUDA graph of the whole step stays correct when replayed.
 extern "C" int mdhs_step_begin(int* step_dev, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  g_mdhs_launches += 5;
+  g_mdhs_launches += 7;
   step_begin_kernel<<<1, 1, 0, st>>>(step_dev);
   mdhs_seed_tick_gemm_tc(1, st);
   mdhs_seed_tick_norm(1, st);

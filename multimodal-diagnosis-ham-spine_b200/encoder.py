@@ -83,7 +83,8 @@ class _TrunkFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, anchor, images, engine, training, names, need):
         feats, c = engine.forward(images, training, need)
-        ctx.engine, ctx.c, ctx.names = engine, c, names
+        # frozen trunk (need == False): nothing was saved, the backward below must be a no-op
+        ctx.engine, ctx.c, ctx.names = engine, (c if need else None), names
         return tuple(feats[n][0] for n in names)
 
     @staticmethod

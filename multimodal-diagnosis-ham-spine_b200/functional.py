@@ -10,12 +10,6 @@ import torch
 from . import ops
 
 
-def _wgrad_splits(T, N, K):
-    tiles = ((N + 127) // 128) * ((K + 255) // 256)
-    kb = (T + 63) // 64
-    return max(1, min(max(kb // 4, 1), (148 + tiles - 1) // tiles))
-
-
 class LinearFn(torch.autograd.Function):
     """y = act(x W^T + b) (+ residual), bf16 [T,K] -> bf16 [T,N] on the tcgen05 GEMM."""
 

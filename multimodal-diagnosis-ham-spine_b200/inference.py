@@ -18,16 +18,27 @@ def _slice_tokens(tokens, v, B):
 
 
 @torch.no_grad()
-def predict_tta(model, images, input_ids, attention_mask, transforms=("hflip",)):
-    """Mean logits over [identity] + transforms for a MultimodalBaselineModel in eval mode.  Returns (B, C) fp32."""
+def predict_tta(model, images, input_ids, attention_mask, transforms=("hflip",), tabular_input=None):
+    """Mean logits over [identity] + transforms for a MultimodalBaselineModel in eval mode.  Returns (B, C) fp32.
+    `tabular_input` is forwarded like scripts/predict.py:62-69 does (`model(aug, ids, mask, tabular_input=tabular)`)."""
     model.eval()
     B = images.shape[0]
     V = 1 + len(transforms)
-    big = ops.tta_expand(images, transforms)
-    if getattr(model, "gate_enabled", False):
-        # the gated model evaluates two feature sets per variant (model.py:257-281): keep its own forward per variant
-        outs = [model(big[v * B:(v + 1) * B], input_ids, attention_mask).float() for v in range(V)]
+    side_branches = any(getattr(model, f, False) for f in ("gate_enabled", "tabular_enabled", "global_local_enabled",
+                                                           "sequence_enabled"))
+    if side_branches or images.dim() != 4:
+        # gate (two feature sets per variant, model.py:257-281), tabular fusion, global/local crops and 5-D slice inputs
+        # all live in the model's own forward: run it once per variant exactly like the reference loop does
+        if images.dim() == 5:
+            Bs, Ts = images.shape[:2]
+            big = ops.tta_expand(images.reshape(Bs * Ts, *images.shape[2:]), transforms).view(V, Bs, Ts, *images.shape[2:])
+            variants = [big[v] for v in range(V)]
+        else:
+            big = ops.tta_expand(images, transforms)
+            variants = [big[v * B:(v + 1) * B] for v in range(V)]
+        outs = [model(x, input_ids, attention_mask, tabular_input=tabular_input).float() for x in variants]
     else:
+        big = ops.tta_expand(images, transforms)
         model.store(images.device)
         tokens = model.image_encoder(big)
         text = model.text_encoder(input_ids, attention_mask)

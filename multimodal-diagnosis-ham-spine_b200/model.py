@@ -3,9 +3,11 @@ config.yml by scripts/train.py:179-211) and call surface (model.py:21-345): forw
 classifier, freeze_encoders(), ablation modes, optional dual-expert gate.
 
 Everything numeric runs on the sm_100a kernels; this file only wires modules together the way the
-reference does.  Side branches that are outside the hot-path scope (tabular MLP,
-LSTM/GRU sequence encoder, global/local crop) are accepted by the constructor for config compatibility
-and raise NotImplementedError when enabled.
+reference does.  The side branches of SURVEY.md section 8f-4 (tabular MLP + tabular fusion, LSTM / GRU /
+Transformer multi-slice sequence encoder, global / local centre-crop branch) are built as well; the only
+constructor values that raise are the ones whose arithmetic lives in un-vendored third-party packages
+(`classifier_type="kan"` -> ikan GroupKAN, `fusion_type in {"mamba", "vmamba"}`): ImportError, exactly like the
+reference without those packages.
 """
 import torch
 import torch.nn as nn

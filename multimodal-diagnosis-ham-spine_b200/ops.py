@@ -355,6 +355,18 @@ def axpby(x, y, a=1.0, b=0.0, a_dev=None):
     return y
 
 
+_NUM_SMS = {}
+
+
+def num_sms(device=None):
+    """SM count of the (current) CUDA device -- 148 on B200 -- for host-side split / grid heuristics."""
+    dev = torch.cuda.current_device() if device is None else torch.device(device).index
+    n = _NUM_SMS.get(dev)
+    if n is None:
+        n = _NUM_SMS[dev] = torch.cuda.get_device_properties(dev).multi_processor_count
+    return n
+
+
 def adam_flat(params, grads, exp_avg, exp_avg_sq, shadow, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0,
               adamw=True, zero_grad=True, lr_dev=None, step_dev=None):
     _lib.call("mdhs_adam_flat", _p(params), _p(grads), _p(exp_avg), _p(exp_avg_sq), _p(shadow), params.numel(), float(lr),

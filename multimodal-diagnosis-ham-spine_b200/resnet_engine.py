@@ -64,11 +64,6 @@ class _Conv:
     def conv_desc(self, mode, B, H, W):
         return (mode, B, H, W, self.I, self.R, self.S, self.stride, self.pad)
 
-    def wgrad_splits(self, rows):
-        tiles = ((self.O + 127) // 128) * ((self.ldk + 255) // 256)
-        kb = (rows + 63) // 64
-        return max(1, min(kb // 4 if kb >= 8 else 1, (148 * 2 + tiles - 1) // tiles))
-
 
 class ResNetEngine:
     def __init__(self, store, net):

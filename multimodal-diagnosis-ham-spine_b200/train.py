@@ -31,12 +31,14 @@ def connext_forward_loss(model, images, ids, mask, labels):
 
 
 class Trainer:
-    def __init__(self, model, optimizer="adamw", lr=2e-4, weight_decay=None, betas=(0.9, 0.999), eps=1e-8, momentum=0.9,
+    def __init__(self, model, optimizer="adamw", lr=2e-4, weight_decay=None, betas=(0.9, 0.999), eps=1e-8, momentum=0.0,
                  loss="ce", label_smoothing=0.02, focal_gamma=2.0, class_weights=None, process_group=None,
                  overlap_comm=True, supcon_weight=0.0, supcon_stage="finetune", supcon_temperature=0.07, forward_loss=None):
         """forward_loss: optional callable (model, images, ids, mask, labels) -> (loss, logits) for the model families whose
         call surface differs from MultimodalBaselineModel (MIBF-Net: batch dict + cal_loss, mibf_net/train_resnet.py:21-41;
-        ConNexT: batch dict -> logits).  Everything else -- CUDA graph, gradient sync, fused optimizer -- is shared."""
+        ConNexT: batch dict -> logits).  Everything else -- CUDA graph, gradient sync, fused optimizer -- is shared.
+        `momentum` only applies to optimizer="sgd": the default 0 is scripts/train.py:301-309's `optim.SGD(params, lr)`;
+        MIBF-Net's recipe (mibf_net/train_resnet.py:136-139) passes momentum=0.9 explicitly."""
         self.model = model
         self.opt = optimizer.lower()
         if self.opt not in ("adamw", "adam", "sgd"):
@@ -56,7 +58,10 @@ class Trainer:
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         # the early buckets assume MultimodalBaselineModel's parameter order [image encoder | text encoder | fusion | head];
         # other model families reduce everything after backward
-        self.overlap = overlap_comm and self.world > 1 and forward_loss is None
+        # ... and assume ONE image-encoder / text-encoder backward per step: the global-local and multi-slice branches run the
+        # trunk twice in train mode (model.py:292-315), so their stage hooks would fire before the gradients are final
+        twice = getattr(model, "global_local_enabled", False) or getattr(model, "sequence_enabled", False)
+        self.overlap = overlap_comm and self.world > 1 and forward_loss is None and not twice
         self.store = None
         self._graph = None
         self._static = None
@@ -76,10 +81,49 @@ class Trainer:
         # slice boundary for the overlapped all-reduce: everything from the text encoder on
         self.split = split_offset(st, getattr(self.model, "text_encoder", None))
         self.sync = GradSync(st.grad, self.split if self.overlap else 0, self.pg)
+        # the optimizer only touches what torch.optim would: parameters with requires_grad (scripts/train.py builds the
+        # optimizer from filter(requires_grad)) and, after the first backward, only those that actually received a gradient
+        # (torch skips `grad is None`: the BERT pooler, dead q/k projections of the 1-token attention-pooling head, ...)
+        self._opt_ranges = self._trainable_ranges(None)
+        self._probed_unused = False
         if self.world > 1:
             # same initial weights everywhere (rank 0 wins), like DistributedDataParallel's constructor
             dist.broadcast(st.flat, src=0, group=self.pg)
             st.refresh(force=True)
+
+    def _trainable_ranges(self, skip_ids):
+        """Merged [lo, hi) spans of the flat buffer that the optimizer updates.  Spans are merged across alignment padding
+        only (padding elements are zero and stay zero); a frozen or unused parameter in between splits the span."""
+        st = self.store
+        spans, cur = [], None
+        for p in st.params:                      # flat-buffer order
+            o = st.offsets[id(p)]
+            live = p.requires_grad and not (skip_ids and id(p) in skip_ids)
+            if live:
+                if cur is None:
+                    cur = [o, o + p.numel()]
+                else:
+                    cur[1] = o + p.numel()
+            elif cur is not None:
+                spans.append(cur)
+                cur = None
+        if cur is not None:
+            spans.append(cur)
+        out = []
+        for lo, hi in spans:                     # the kernels work on float4: round outwards inside the padded slot grid
+            lo4, hi4 = lo // 4 * 4, min(st.total, (hi + 3) // 4 * 4)
+            out.append((lo4, hi4))
+        return out
+
+    def _probe_unused(self):
+        """One-time (first eager step, after backward): parameters whose whole gradient is exactly zero never took part in
+        the graph -- torch would have left `.grad = None` and its optimizers would skip them."""
+        st = self.store
+        flags = torch.stack([st.g32(p).count_nonzero() for p in st.params if p.requires_grad])
+        live = [p for p in st.params if p.requires_grad]
+        dead = {id(p) for p, n in zip(live, flags.tolist()) if n == 0}
+        self._opt_ranges = self._trainable_ranges(dead)
+        self._probed_unused = True
 
     def set_lr(self, lr):
         self.lr = lr
@@ -139,12 +183,16 @@ class Trainer:
             if img_eng is not None:
                 img_eng.on_stage_backward_done = None
         scale = self.sync.finish()
-        if self.opt == "sgd":
-            ops.sgd_flat(st.flat, st.grad, self.m if self.momentum > 0 else None, st.shadow, self.lr, self.momentum, self.wd,
-                         grad_scale=scale, lr_dev=self.lr_dev, step_dev=self.step_dev)
-        else:
-            ops.adam_flat(st.flat, st.grad, self.m, self.v, st.shadow, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
-                          1, grad_scale=scale, adamw=(self.opt == "adamw"), lr_dev=self.lr_dev, step_dev=self.step_dev)
+        if not self._probed_unused and not torch.cuda.is_current_stream_capturing():
+            self._probe_unused()
+        for lo, hi in self._opt_ranges:
+            if self.opt == "sgd":
+                ops.sgd_flat(st.flat[lo:hi], st.grad[lo:hi], self.m[lo:hi] if self.momentum > 0 else None, st.shadow[lo:hi],
+                             self.lr, self.momentum, self.wd, grad_scale=scale, lr_dev=self.lr_dev, step_dev=self.step_dev)
+            else:
+                ops.adam_flat(st.flat[lo:hi], st.grad[lo:hi], self.m[lo:hi], self.v[lo:hi], st.shadow[lo:hi], self.lr,
+                              self.betas[0], self.betas[1], self.eps, self.wd, 1, grad_scale=scale,
+                              adamw=(self.opt == "adamw"), lr_dev=self.lr_dev, step_dev=self.step_dev)
         st.mark_fresh()
         return loss.detach(), logits.detach()
 
@@ -157,7 +205,8 @@ class Trainer:
     # ------------------------------------------------------------------ CUDA-graph step
     def capture(self, images, ids, mask, labels, warmup=3):
         """Capture the whole step for fixed shapes.  Afterwards `replay(images, ids, mask, labels)` copies the new
-        batch into the static input buffers and launches the graph."""
+        batch into the static input buffers and launches the graph.  NOTE: the `warmup` eager passes before the capture are
+        REAL optimizer steps on the given batch (they also size the caching allocator and probe unused parameters)."""
         self._ensure(images.device)
         self.model.train()
         self._static = [t.clone() for t in (images, ids, mask, labels)]
@@ -190,7 +239,10 @@ class Trainer:
 
 
 def warmup_cosine_lr(base_lr, epoch, warmup_epochs, total_epochs):
-    """LambdaLR factor of scripts/train.py:321-334 (linear warm-up then cosine decay)."""
+    """Learning rate of scripts/train.py:321-334's LambdaLR (linear warm-up then cosine decay).  The reference steps that
+    scheduler once per BATCH with `warmup_steps = warmup_epochs * len(loader)`: pass step counts for all three arguments
+    (`epoch` = global step, `warmup_epochs` = warm-up steps, `total_epochs` = total steps) to reproduce it exactly; with
+    epoch counts it is the per-epoch variant."""
     if warmup_epochs > 0 and epoch < warmup_epochs:
         return base_lr * float(epoch + 1) / float(warmup_epochs)
     progress = (epoch - warmup_epochs) / max(1, total_epochs - warmup_epochs)

@@ -6,7 +6,11 @@ import sys
 
 import torch
 
-REF_ROOT = "/root/reference"
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# the reference itself (dev container) or its verbatim vendored copy (oracle/make_ref.py -> oracle/_ref, travels to the GPU box)
+_CANDIDATES = ([os.environ["MDHS_REF_ROOT"]] if os.environ.get("MDHS_REF_ROOT") else []) + [
+    "/root/reference", os.path.join(_ROOT, "oracle", "_ref")]
+REF_ROOT = next((c for c in _CANDIDATES if os.path.exists(os.path.join(c, "model.py"))), _CANDIDATES[0])
 BERT_DIR = os.environ.get("MDHS_BERT_DIR", "/tmp/mdhs_bert_base")
 
 
