@@ -72,6 +72,13 @@ typedef struct {
    *                dW[o, (r,s,c)] = sum_pixels dY[pixel, o] * im2col(X)[pixel, (r,s,c)] with A = dY (a_mn_major = 1).
    * cC % 64 == 0, cR == cS, 1 <= c_stride <= 8. */
   int32_t conv_mode; int32_t cN, cH, cW, cC, cR, cS, c_stride, c_pad;
+  /* BatchNorm-backward reduction fused into the epilogue of the GEMM that PRODUCES dy (a dgrad GEMM whose output is the
+   * gradient wrt a BN(+ReLU) output; torchvision Bottleneck conv1/conv2 via encoder.py:61-72): with stat_x = the raw
+   * (pre-BN) activation [M, N] bf16, colsum receives sum_m dy'[m,n] and colsumsq sum_m dy'[m,n] * (stat_x[m,n] -
+   * stat_mean[n]), dy' = dy * [fmaf(stat_x, stat_scale, stat_shift) > 0] when stat_relu (else dy' = dy).  D itself stays
+   * the unmasked dy.  Needs colsum/colsumsq, bf16 D, no aux_in / aux_out / bf16 residual, no split-K, tile width <= 128. */
+  const void* stat_x; int64_t ld_stat_x; const float* stat_mean; const float* stat_scale; const float* stat_shift;
+  int32_t stat_relu;
 } mdhs_gemm_args;
 int mdhs_gemm_bf16(const mdhs_gemm_args* args, void* stream);
 
@@ -95,20 +102,30 @@ int mdhs_layernorm_bwd(const void* dy, int dy_f32, int64_t lddy, const void* x, 
  * mibf_net/model_resnet.py:15; eps 1e-5, momentum 0.1).  Train mode: the conv GEMM epilogue (or
  * mdhs_col_stats) produces fp64 per-channel sums; finalize turns them into mean/invstd, updates the
  * running statistics and emits scale/shift; apply fuses normalise + residual add + ReLU.
- * mdhs_bn_bwd = two passes (reduce, apply); relu != 0 masks dy with (y > 0); dz optionally receives the
- * masked dy (gradient of the identity branch); dgamma/dbeta accumulate (+=).  Workspaces: sum_dy, sum_dy_xhat
- * (fp64 [C]) and coef (fp32 [5*C]).  With relu != 0 and y == NULL the mask is recomputed from x as
- * fmaf(x, scale, shift) > 0 (bit-identical to what mdhs_bn_apply evaluated; only valid for layers without a
- * residual input), which saves one full read of y in both passes.
+ * mdhs_bn_fwd = finalize + apply in ONE launch (every thread derives the scale / shift of its 8 channels from the fp64
+ * sums -- or, training == 0, from the running statistics --; mean / invstd / scale / shift are published for the backward).
+ * mdhs_bn_bwd = two launches (reduce, apply); relu != 0 masks dy with (y > 0); dz optionally receives the
+ * masked dy (gradient of the identity branch); dgamma/dbeta accumulate (+=).  Workspaces: sum_dy = sum(dy'),
+ * sum_dy_xc = sum(dy' * (x - mean)) (fp64 [C] each); the per-channel coefficients are derived inside the apply kernel.
+ * With relu != 0 and y == NULL the mask is recomputed from x as fmaf(x, scale, shift) > 0 (bit-identical to what the
+ * forward evaluated; only valid for layers without a residual input), which saves one full read of y in both passes.
+ * training == 0: eval-mode backward, dx = gamma * invstd * dy' (running statistics are constants).
+ * sums_ready != 0: the two sums were already produced (by the epilogue of the GEMM that wrote dy, see
+ * mdhs_gemm_args.stat_x); the reduce launch is skipped.
  */
 int mdhs_bn_finalize(const double* colsum, const double* colsumsq, int64_t count, const float* gamma,
                      const float* beta, float* running_mean, float* running_var, float momentum, float eps,
                      float* mean, float* invstd, float* scale, float* shift, int C, int training, void* stream);
 int mdhs_bn_apply(const void* x, const float* scale, const float* shift, const void* residual, void* y,
                   int64_t rows, int C, int relu, void* stream);
+int mdhs_bn_fwd(const void* x, const double* colsum, const double* colsumsq, const float* gamma, const float* beta,
+                float* running_mean, float* running_var, float momentum, float eps, const void* residual, void* y,
+                float* mean, float* invstd, float* scale, float* shift, int64_t rows, int C, int relu, int training,
+                void* stream);
 int mdhs_bn_bwd(const void* dy, const void* x, const void* y, const float* mean, const float* invstd,
-                const float* gamma, const float* scale, const float* shift, double* sum_dy, double* sum_dy_xhat,
-                float* coef, void* dx, void* dz, float* dgamma, float* dbeta, int64_t rows, int C, int relu, void* stream);
+                const float* gamma, const float* scale, const float* shift, double* sum_dy, double* sum_dy_xc,
+                void* dx, void* dz, float* dgamma, float* dbeta, int64_t rows, int C, int relu, int training,
+                int sums_ready, void* stream);
 /* column sums of a bf16 [rows, C] matrix: fp64 sum / sum of squares (BN statistics) and/or fp32 += (bias grads) */
 int mdhs_col_stats(const void* x, int64_t ldx, double* sum64, double* sumsq64, float* sum32, int64_t rows, int C,
                    void* stream);

@@ -33,6 +33,8 @@ class GemmArgs(ctypes.Structure):
         ("conv_mode", ctypes.c_int32), ("cN", ctypes.c_int32), ("cH", ctypes.c_int32), ("cW", ctypes.c_int32),
         ("cC", ctypes.c_int32), ("cR", ctypes.c_int32), ("cS", ctypes.c_int32), ("c_stride", ctypes.c_int32),
         ("c_pad", ctypes.c_int32),
+        ("stat_x", ctypes.c_void_p), ("ld_stat_x", ctypes.c_int64), ("stat_mean", ctypes.c_void_p),
+        ("stat_scale", ctypes.c_void_p), ("stat_shift", ctypes.c_void_p), ("stat_relu", ctypes.c_int32),
     ]
 
 
@@ -44,7 +46,8 @@ SIGNATURES = {
     "mdhs_layernorm_bwd": "pilpilppp" "plpppp" "iifufup",
     "mdhs_bn_finalize": "pplppppffppppiip",
     "mdhs_bn_apply": "pppppliip",
-    "mdhs_bn_bwd": "ppppppppppppppp" "liip",
+    "mdhs_bn_fwd": "ppppppp" "ff" "pppppp" "liii" "p",
+    "mdhs_bn_bwd": "pppppppppppppp" "liiii" "p",
     "mdhs_col_stats": "plppplip",
     "mdhs_im2col_nchw_f32": "ppiiiiiiiiip",
     "mdhs_im2col_nhwc": "ppiiiiiiiip",

@@ -107,6 +107,17 @@ __device__ __forceinline__ void load8(const bf16* p, float* f) {
     f[2 * i + 1] = x.y;
   }
 }
+// split form: issue the 128-bit load now (4 registers), convert when the values are consumed -- keeps many independent loads
+// in flight without holding 8 fp32 registers per load
+__device__ __forceinline__ bf16x8 ldraw8(const bf16* p) { return *reinterpret_cast<const bf16x8*>(p); }
+__device__ __forceinline__ void cvt8(const bf16x8& t, float* f) {
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    float2 x = __bfloat1622float2(t.v[i]);
+    f[2 * i] = x.x;
+    f[2 * i + 1] = x.y;
+  }
+}
 __device__ __forceinline__ void store8(bf16* p, const float* f) {
   bf16x8 t;
 #pragma unroll

@@ -69,6 +69,9 @@ struct Params {
   // implicit-GEMM convolution: one operand is read straight from the NHWC activation through a TMA im2col map
   int conv_mode;                       // 0 none, 1 = A is im2col(X) (fprop / dgrad), 2 = B is im2col(X), MN-major (wgrad)
   int cHo, cWo, cS, c_stride, c_pad, c_cblk;   // output extent, filter width, stride, padding, C / 64
+  // BatchNorm-backward reduction of the layer whose output gradient D is (see mdhs_gemm_args.stat_x): the raw activation
+  // arrives through the prefetched operand box; colsum / colsumsq receive sum(dy') / sum(dy' * (x - mean))
+  const bf16* stat_x; const float* stat_mean; const float* stat_scale; const float* stat_shift; int stat_relu;
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -677,6 +680,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // 16-byte row loads straight from global memory (slow path: both operands at once, or kernels without LD)
     const bool box_is_aux = LD && has_aux_in;
     const bool box_is_res = LD && !has_aux_in && res_bf16;
+    // BN-backward statistics mode: the box carries the raw activation of the producer layer; the chunk loop ignores it
+    // (D = plain dy), the column pass below combines it with the staged dy
+    const bool box_is_stat = LD && !has_aux_in && !res_bf16 && p.stat_x != nullptr;
+    const bool box_any = box_is_aux || box_is_res || box_is_stat;
     int acc = 0;
     uint32_t acc_phase = 0;
     float cacc[PAIRS][4];
@@ -713,10 +720,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int split_, n_blk, m_blk;
       decode(t, split_, n_blk, m_blk);
       mbar_expect_tx(lbar(2 * half + slot), 16384);
-      tma_load_2d(in_box0 + slot * 16384, box_is_aux ? &tmAuxIn : &tmRes, lbar(2 * half + slot), n_blk * BN + half * HALF_COLS,
-                  m_blk * BM);
+      tma_load_2d(in_box0 + slot * 16384, (box_is_aux || box_is_stat) ? &tmAuxIn : &tmRes, lbar(2 * half + slot),
+                  n_blk * BN + half * HALF_COLS, m_blk * BM);
     };
-    if (LD && issuer && (box_is_aux || box_is_res)) {
+    if (LD && issuer && box_any) {
       for (int g = 0; g < C::IN_SLOTS; g++) issue_item(g);
     }
 
@@ -734,7 +741,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN + half * HALF_COLS);
       ec.m = m; ec.row_ok = row_ok; ec.first_split = first_split; ec.zero_row = zero_row;
       uint32_t in_row = 0;
-      if (LD && (box_is_aux || box_is_res)) {     // PAIRS == 1 in LD kernels: one box per tile
+      if (LD && box_any) {     // PAIRS == 1 in LD kernels: one box per tile
         const int slot = consumed % C::IN_SLOTS;
         mbar_wait(lbar(2 * half + slot), (lph >> slot) & 1u);
         lph ^= (1u << slot);
@@ -797,6 +804,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // CTA always sees the same column block); one fp64 atomic per column and warp when the CTA is done.
         if (p.colsum != nullptr) {
           float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+          if (LD && box_is_stat) {
+            // BN-backward reductions: dy (staged box) x raw activation (operand box), both [128 rows, 64 columns] with the
+            // same 128B swizzle; lane = column pair.  Per-column constants of this lane's two columns:
+            const int n = n0 + 2 * lane;
+            const bool cok = n < p.N;
+            const float mu0 = cok ? __ldg(p.stat_mean + n) : 0.f, mu1 = cok ? __ldg(p.stat_mean + n + 1) : 0.f;
+            const float sc0 = cok ? __ldg(p.stat_scale + n) : 0.f, sc1 = cok ? __ldg(p.stat_scale + n + 1) : 0.f;
+            const float sh0 = cok ? __ldg(p.stat_shift + n) : 0.f, sh1 = cok ? __ldg(p.stat_shift + n + 1) : 0.f;
+            const uint32_t xbox = in_row - row_in_box * 128;
+            const bool relu = p.stat_relu != 0;
+#pragma unroll 8
+            for (int r = 0; r < 32; r++) {
+              const int row = wq * 32 + r;
+              const uint32_t off = row * 128 + ((((lane >> 2) ^ (row & 7))) << 4) + ((lane & 3) << 2);
+              uint32_t w, xw;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(stage_box + off));
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(xw) : "r"(xbox + off));
+              const float2 f = __bfloat1622float2(*reinterpret_cast<const bf162*>(&w));
+              const float2 xr = __bfloat1622float2(*reinterpret_cast<const bf162*>(&xw));
+              const float d0 = (relu && !(fmaf(xr.x, sc0, sh0) > 0.f)) ? 0.f : f.x;
+              const float d1 = (relu && !(fmaf(xr.y, sc1, sh1) > 0.f)) ? 0.f : f.y;
+              s0 += d0;
+              s1 += d1;
+              q0 = fmaf(d0, xr.x - mu0, q0);
+              q1 = fmaf(d1, xr.y - mu1, q1);
+            }
+          } else {
 #pragma unroll 8
           for (int r = 0; r < 32; r++) {
             const int row = wq * 32 + r;
@@ -810,14 +844,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             q0 = fmaf(f.x, f.x, q0);
             q1 = fmaf(f.y, f.y, q1);
           }
+          }
           cacc[pr][0] += s0;
           cacc[pr][1] += s1;
           cacc[pr][2] += q0;
           cacc[pr][3] += q1;
         }
       }
-      if (LD && (box_is_aux || box_is_res)) {
-        // every thread of the group passed the box-complete barrier above, i.e. has copied its operand row
+      if (LD && box_any) {
+        // every thread of the group passed the box-complete barrier above, i.e. has copied its operand row; in statistics
+        // mode the operand box is also read by the column pass, so the group meets once more before it is overwritten
+        if (box_is_stat) named_bar(bar_id, 128);
         if (issuer) issue_item(consumed + C::IN_SLOTS);
         consumed++;
       }
@@ -951,6 +988,7 @@ int launch(const mdhs_gemm_args* a, const Params& p0, cudaStream_t stream) {
   else tmRes = tmD;
   if (rc) return rc;
   if (a->aux_in) rc = make_map(&tmAuxIn, a->aux_in, a->N, a->M, a->ld_aux_in, 64, BM, false);
+  else if (a->stat_x) rc = make_map(&tmAuxIn, a->stat_x, a->N, a->M, a->ld_stat_x, 64, BM, false);
   else tmAuxIn = tmD;
   if (rc) return rc;
   if (a->conv_mode == 1) rc = make_im2col_map(&tmA, a->A, a->cN, a->cH, a->cW, a->cC, a->cR, a->cS, a->c_stride, a->c_pad, BM);
@@ -1100,6 +1138,12 @@ extern "C" int mdhs_gemm_bf16(const mdhs_gemm_args* a, void* stream_) {
       ((uintptr_t)a->bias & 15))
     return MDHS_ERR_ARG;
   if (a->dropout_p < 0.f || a->dropout_p >= 1.f) return MDHS_ERR_ARG;
+  if (a->stat_x) {
+    if (!a->colsum || !a->stat_mean || !a->stat_scale || !a->stat_shift || a->aux_in || a->aux_out || a->a_mn_major ||
+        (a->residual && a->r_dtype == MDHS_DT_BF16) || a->split_k > 1 || (a->ld_stat_x % 8) || ((uintptr_t)a->stat_x & 15) ||
+        a->bn_hint == 256)
+      return MDHS_ERR_ARG;
+  }
 
   Params p;
   p.M = a->M; p.N = a->N; p.K = a->K;
@@ -1147,11 +1191,13 @@ extern "C" int mdhs_gemm_bf16(const mdhs_gemm_args* a, void* stream_) {
   p.drop_p = a->dropout_p; p.drop_seed = a->dropout_seed;
   p.conv_mode = a->conv_mode; p.cHo = cHo; p.cWo = cWo; p.cS = a->cS; p.c_stride = a->c_stride; p.c_pad = a->c_pad;
   p.c_cblk = a->conv_mode ? a->cC / 64 : 1;
+  p.stat_x = reinterpret_cast<const bf16*>(a->stat_x); p.stat_mean = a->stat_mean; p.stat_scale = a->stat_scale;
+  p.stat_shift = a->stat_shift; p.stat_relu = a->stat_relu;
   p.num_m = p.num_n = 0;
 
   // epilogue operand boxes (act'(aux_in), bf16 residual) are prefetched one tile ahead when the tile is <= 128 wide
-  const bool wants_ld = (a->aux_in != nullptr || (a->residual != nullptr && a->r_dtype == MDHS_DT_BF16)) && p.splits == 1 &&
-                        !a->a_mn_major && a->aux_out == nullptr;
+  const bool wants_ld = (a->aux_in != nullptr || (a->residual != nullptr && a->r_dtype == MDHS_DT_BF16) || a->stat_x != nullptr) &&
+                        p.splits == 1 && !a->a_mn_major && a->aux_out == nullptr;
   int bn = a->bn_hint;
   if (bn != 64 && bn != 128 && bn != 256 && auto_bn) bn = auto_bn;
   if (bn != 64 && bn != 128 && bn != 256) {
@@ -1185,6 +1231,7 @@ extern "C" int mdhs_gemm_bf16(const mdhs_gemm_args* a, void* stream_) {
   }
   g_mdhs_launches++;
   const bool ld = wants_ld && bn != 256;
+  if (a->stat_x && !ld) return MDHS_ERR_ARG;   // the statistics need the operand-box path
   // CTA pairs (256 x bn cta_group::2 tiles) whenever there are at least two row blocks and enough pair tiles to occupy
   // a good part of the 74 pairs
   const int n_tiles_m = ceil_div(a->M, BM);

@@ -1,6 +1,8 @@
 // LayerNorm and train-mode BatchNorm for the hot path: HBM-bound, 128-bit vectorised, warp-shuffle
 // reductions, fp32 statistics.  Activations are bf16 [rows, C] (tokens x features / NHWC pixels x
 // channels); parameters and their gradients are fp32.
+#include <cstdio>
+#include <cstdlib>
 #include "common.cuh"
 #include "../../include/mdhs_b200.h"
 
@@ -282,29 +284,25 @@ __global__ void bn_finalize_kernel(const double* __restrict__ colsum, const doub
   shift[c] = beta[c] - mu * sc;
 }
 
-// y = act(x * scale[c] + shift[c] (+ residual)); 8 channels per thread, grid-stride over rows*C/8.  The host sizes the
-// grid so that the stride is a multiple of C/8: a thread then stays on ONE channel vector and its scale / shift live in
-// registers (per-iteration parameter loads made this kernel L1-bound: ncu l1tex 89 % at 65 % of HBM peak).
-__global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ scale,
-                                                       const float* __restrict__ shift, const bf16* __restrict__ residual,
-                                                       bf16* __restrict__ y, int64_t total_vec, int C, int relu) {
-  const int cvec = C >> 3;
-  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int c0 = (int)(i0 % cvec) * 8;
-  float sc[8], sh[8];
-  *reinterpret_cast<float4*>(sc) = *reinterpret_cast<const float4*>(scale + c0);
-  *reinterpret_cast<float4*>(sc + 4) = *reinterpret_cast<const float4*>(scale + c0 + 4);
-  *reinterpret_cast<float4*>(sh) = *reinterpret_cast<const float4*>(shift + c0);
-  *reinterpret_cast<float4*>(sh + 4) = *reinterpret_cast<const float4*>(shift + c0 + 4);
+// Shared streaming body of the two forward kernels: y = act(x * sc + sh (+ residual)), 8 channels per thread held in
+// registers (the grid stride is a multiple of C/8), two independent 16-byte streams in flight per thread.
+__device__ __forceinline__ void bn_apply_stream(const bf16* __restrict__ x, const bf16* __restrict__ residual,
+                                                bf16* __restrict__ y, const float* sc, const float* sh, int64_t i0,
+                                                int64_t stride, int64_t total_vec, int relu) {
   int64_t i = i0;
-  for (; i + stride < total_vec; i += 2 * stride) {   // two independent 16-byte streams in flight per thread
+  for (; i + stride < total_vec; i += 2 * stride) {
     float v0[8], v1[8], r0[8], r1[8];
-    load8(x + i * 8, v0);
-    load8(x + (i + stride) * 8, v1);
+    const bf16x8 q0 = ldraw8(x + i * 8), q1 = ldraw8(x + (i + stride) * 8);
+    bf16x8 p0, p1;
     if (residual) {
-      load8(residual + i * 8, r0);
-      load8(residual + (i + stride) * 8, r1);
+      p0 = ldraw8(residual + i * 8);
+      p1 = ldraw8(residual + (i + stride) * 8);
+    }
+    cvt8(q0, v0);
+    cvt8(q1, v1);
+    if (residual) {
+      cvt8(p0, r0);
+      cvt8(p1, r1);
     }
 #pragma unroll
     for (int k = 0; k < 8; k++) {
@@ -339,21 +337,93 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ 
   }
 }
 
-// Per-channel reductions for BN backward: sum(dy') and sum(dy' * xhat), dy' = dy * [y > 0] when relu.  The ReLU mask
-// comes from y when the layer had a residual input, otherwise it is recomputed from x (fmaf(x, scale, shift) > 0 is
-// exactly what bn_apply evaluated), which saves one full read of y.
-// Block = 256 threads = 32 channel-vectors(8) x 8 row lanes over a `Cw`-wide view of the matrix: Cw = C, or 256 when
-// C in {64, 128} (the contiguous [rows, C] matrix re-read as [rows*C/256, 256]; column j holds channel j % C), so
-// narrow layers keep all 32 vector lanes busy.  grid = (Cw/256 ceil, row blocks).
-__global__ void __launch_bounds__(256, 4) bn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+// y = act(x * scale[c] + shift[c] (+ residual)); 8 channels per thread, grid-stride over rows*C/8.  The host sizes the
+// grid so that the stride is a multiple of C/8: a thread then stays on ONE channel vector and its scale / shift live in
+// registers (per-iteration parameter loads made this kernel L1-bound: ncu l1tex 89 % at 65 % of HBM peak).
+__global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ scale,
+                                                       const float* __restrict__ shift, const bf16* __restrict__ residual,
+                                                       bf16* __restrict__ y, int64_t total_vec, int C, int relu) {
+  const int cvec = C >> 3;
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int c0 = (int)(i0 % cvec) * 8;
+  float sc[8], sh[8];
+  *reinterpret_cast<float4*>(sc) = *reinterpret_cast<const float4*>(scale + c0);
+  *reinterpret_cast<float4*>(sc + 4) = *reinterpret_cast<const float4*>(scale + c0 + 4);
+  *reinterpret_cast<float4*>(sh) = *reinterpret_cast<const float4*>(shift + c0);
+  *reinterpret_cast<float4*>(sh + 4) = *reinterpret_cast<const float4*>(shift + c0 + 4);
+  bn_apply_stream(x, residual, y, sc, sh, i0, stride, total_vec, relu);
+}
+
+// Finalize + apply in ONE launch (round 2: the 53 bn_finalize launches of a ResNet-50 step cost ~5 us each for 64..2048
+// channels of work).  Every thread derives scale / shift of ITS 8 channels from the fp64 column sums (train) or the
+// running statistics (eval) with exactly bn_finalize_kernel's arithmetic; the first C/8 threads of the grid -- one per
+// channel vector -- also publish mean / invstd / scale / shift for the backward pass and update the running statistics.
+__global__ void __launch_bounds__(256) bn_fwd_kernel(const bf16* __restrict__ x, const double* __restrict__ colsum,
+                                                     const double* __restrict__ colsumsq, int64_t count,
+                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                     float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                     float momentum, float eps, const bf16* __restrict__ residual,
+                                                     bf16* __restrict__ y, float* __restrict__ mean, float* __restrict__ invstd,
+                                                     float* __restrict__ scale, float* __restrict__ shift, int64_t total_vec,
+                                                     int C, int relu, int training) {
+  const int cvec = C >> 3;
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int c0 = (int)(i0 % cvec) * 8;
+  const bool publish = i0 < cvec;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int c = c0 + k;
+    float mu, var;
+    if (training) {
+      const double m = colsum[c] / (double)count;
+      double v = colsumsq[c] / (double)count - m * m;
+      if (v < 0.0) v = 0.0;
+      mu = (float)m;
+      var = (float)v;
+      if (publish && running_mean) {
+        const double unbiased = count > 1 ? v * (double)count / (double)(count - 1) : v;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mu;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+      }
+    } else {
+      mu = running_mean[c];
+      var = running_var[c];
+    }
+    const float is = rsqrtf(var + eps);
+    sc[k] = gamma[c] * is;
+    sh[k] = beta[c] - mu * sc[k];
+    if (publish) {
+      if (mean) mean[c] = mu;
+      if (invstd) invstd[c] = is;
+      if (scale) scale[c] = sc[k];
+      if (shift) shift[c] = sh[k];
+    }
+  }
+  bn_apply_stream(x, residual, y, sc, sh, i0, stride, total_vec, relu);
+}
+
+// Per-channel reductions for BN backward: sum(dy') and sum(dy' * (x - mean)), dy' = dy * [y > 0] when relu.  The ReLU
+// mask comes from y when the layer had a residual input, otherwise it is recomputed from x (fmaf(x, scale, shift) > 0 is
+// exactly what the forward evaluated), which saves one full read of y.
+// Block = 32 channel-vectors(8) x RL row lanes over a `Cw`-wide view of the matrix: Cw = C, or 256 when C in {64, 128}
+// (the contiguous [rows, C] matrix re-read as [rows*C/256, 256]; column j holds channel j % C), so narrow layers keep all
+// 32 vector lanes busy.  grid = (Cw/256 ceil, row blocks).
+// Round 2: (i) four rows per thread are requested before any is consumed (8-12 independent 16-byte loads in flight),
+// (ii) the grid is ~2 fat blocks per SM instead of 8 thin ones -- every block ends with 512 fp64 atomics on the same
+// few cache lines, and with 1046 blocks those 535 k same-address atomics, not HBM, paced the small layers (27 us for a
+// 25 MB layer).  The (x - mean) centring happens here; the 1/sigma factor is applied by the consumer.
+template <int RL>
+__global__ void __launch_bounds__(32 * RL, 512 / (32 * RL)) bn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                             const bf16* __restrict__ y, const float* __restrict__ mean,
-                                                            const float* __restrict__ invstd, const float* __restrict__ scale,
-                                                            const float* __restrict__ shift, double* __restrict__ sum_dy,
-                                                            double* __restrict__ sum_dy_xhat, int64_t rows, int C, int Cw,
-                                                            int rows_per_block, int relu) {
+                                                            const float* __restrict__ scale, const float* __restrict__ shift,
+                                                            double* __restrict__ sum_dy, double* __restrict__ sum_dy_xc,
+                                                            int64_t rows, int C, int Cw, int rows_per_block, int relu) {
   __shared__ float sh[2][8][256 + 8];
   const int cv = threadIdx.x & 31;   // which 8-channel vector inside the 256-column slab
-  const int rl = threadIdx.x >> 5;   // row lane 0..7
+  const int rl = threadIdx.x >> 5;   // row lane 0..RL-1
   const int c0 = blockIdx.x * 256 + cv * 8;
   const bool ok = c0 < Cw;
   const int ch0 = c0 % C;
@@ -368,40 +438,69 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_reduce_kernel(const bf16* __res
   }
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
   const int64_t r1 = min(rows, r0 + rows_per_block);
+  auto accum = [&](const float* d, const float* xv, const float* yv) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const float act = remask ? fmaf(xv[k], sc[k], sf[k]) : yv[k];
+      const float dd = (relu && !(act > 0.f)) ? 0.f : d[k];
+      a[k] += dd;
+      b[k] = fmaf(dd, xv[k] - mu[k], b[k]);
+    }
+  };
   if (ok) {
-    // a[k] = sum dy', b[k] = sum dy' * x; the per-channel affine map to xhat is applied once after the loop
-    for (int64_t r = r0 + rl; r < r1; r += 8) {
+    constexpr int U = 4;
+    int64_t r = r0 + rl;
+    for (; r + (U - 1) * RL < r1; r += U * RL) {
+      bf16x8 rd[U], rx[U], ry[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        rd[u] = ldraw8(dy + (r + u * RL) * Cw + c0);
+        rx[u] = ldraw8(x + (r + u * RL) * Cw + c0);
+        if (relu && !remask) ry[u] = ldraw8(y + (r + u * RL) * Cw + c0);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        float d[8], xv[8], yv[8];
+        cvt8(rd[u], d);
+        cvt8(rx[u], xv);
+        if (relu && !remask) cvt8(ry[u], yv);
+        accum(d, xv, yv);
+      }
+    }
+    for (; r < r1; r += RL) {
       float d[8], xv[8], yv[8];
       load8(dy + r * Cw + c0, d);
       load8(x + r * Cw + c0, xv);
       if (relu && !remask) load8(y + r * Cw + c0, yv);
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const float act = remask ? fmaf(xv[k], sc[k], sf[k]) : yv[k];
-        const float dd = (relu && !(act > 0.f)) ? 0.f : d[k];
-        a[k] += dd;
-        b[k] = fmaf(dd, xv[k] - mu[k], b[k]);
-      }
+      accum(d, xv, yv);
     }
-#pragma unroll
-    for (int k = 0; k < 8; k++) b[k] *= invstd[ch0 + k];   // loaded here, not held across the streaming loop
   }
-#pragma unroll
-  for (int k = 0; k < 8; k++) {
-    sh[0][rl][cv * 8 + k] = a[k];
-    sh[1][rl][cv * 8 + k] = b[k];
-  }
-  __syncthreads();
+  // cross-lane reduction through shared memory, 8 row lanes per round
   float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-  for (int w = 0; w < 8; w++) {
-    s0 += sh[0][w][threadIdx.x];
-    s1 += sh[1][w][threadIdx.x];
+  for (int round = 0; round < RL / 8; round++) {
+    if ((rl >> 3) == round) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        sh[0][rl & 7][cv * 8 + k] = a[k];
+        sh[1][rl & 7][cv * 8 + k] = b[k];
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 256) {
+#pragma unroll
+      for (int w = 0; w < 8; w++) {
+        s0 += sh[0][w][threadIdx.x];
+        s1 += sh[1][w][threadIdx.x];
+      }
+    }
+    __syncthreads();
   }
   if (Cw != C) {   // folded view: columns t, t + C, t + 2C, ... belong to channel t
-    __syncthreads();
-    sh[0][0][threadIdx.x] = s0;
-    sh[1][0][threadIdx.x] = s1;
+    if (threadIdx.x < 256) {
+      sh[0][0][threadIdx.x] = s0;
+      sh[1][0][threadIdx.x] = s1;
+    }
     __syncthreads();
     if (threadIdx.x < C) {
       s0 = s1 = 0.f;
@@ -412,79 +511,91 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_reduce_kernel(const bf16* __res
     }
   }
   const int c = blockIdx.x * 256 + threadIdx.x;
-  if (c < C) {
+  if (threadIdx.x < 256 && c < C) {
     atomicAdd(sum_dy + c, (double)s0);
-    atomicAdd(sum_dy_xhat + c, (double)s1);
-  }
-}
-
-// Per-channel coefficients of the BN input gradient, from the fp64 reductions:
-//   dx = gamma*invstd * (dy' - sum_dy/M - xhat * sum_dy_xhat/M) = ca * dy' + cb * x + cc
-// Also accumulates dgamma / dbeta (one thread per channel).
-__global__ void bn_bwd_coeff_kernel(const float* __restrict__ mean, const float* __restrict__ invstd,
-                                    const float* __restrict__ gamma, const double* __restrict__ sum_dy,
-                                    const double* __restrict__ sum_dy_xhat, const float* __restrict__ scale,
-                                    const float* __restrict__ shift, float* __restrict__ coef, float* __restrict__ dgamma,
-                                    float* __restrict__ dbeta, int64_t rows, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const double inv_m = 1.0 / (double)rows;
-  const double is = invstd[c], mu = mean[c], g = gamma[c];
-  const double s1 = sum_dy[c], s2 = sum_dy_xhat[c];
-  const double ca = g * is;
-  const double cb = -g * is * is * s2 * inv_m;
-  coef[c] = (float)ca;
-  coef[C + c] = (float)cb;
-  coef[2 * C + c] = (float)(-ca * s1 * inv_m - cb * mu);
-  if (scale) {
-    coef[3 * C + c] = scale[c];
-    coef[4 * C + c] = shift[c];
-  }
-  if (dgamma) {
-    dgamma[c] += (float)s2;
-    dbeta[c] += (float)s1;
+    atomicAdd(sum_dy_xc + c, (double)s1);
   }
 }
 
 // dx = ca[c] * dy' + cb[c] * x + cc[c]; optionally also writes dy' (the ReLU-masked incoming gradient) for the
 // identity branch.  Pure streaming, 8 channels per thread; the grid stride is a multiple of C/8 (see bn_apply), so the
-// five coefficient vectors of a thread's channel group are loaded once.  coef rows 3 and 4 hold the forward scale /
-// shift when the ReLU mask is recomputed from x (y == nullptr).
+// per-channel coefficients of a thread's channel group live in registers.  Round 2: the coefficients are derived HERE from
+// the fp64 reductions (the separate 53 x ~4 us coefficient launches are gone):
+//   train: dx = gamma*invstd * (dy' - sum_dy/M - xhat * sum_dy_xhat/M) = ca * dy' + cb * x + cc
+//   eval : dx = gamma*invstd * dy'   (running statistics are constants: F.batch_norm(training=False) backward)
+// and the first C/8 threads of the grid accumulate dgamma += sum(dy' * xhat), dbeta += sum(dy').
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
-                                                           const bf16* __restrict__ y, const float* __restrict__ coef,
-                                                           bf16* __restrict__ dx, bf16* __restrict__ dz, int64_t rows, int C,
-                                                           int relu) {
+                                                           const bf16* __restrict__ y, const float* __restrict__ mean,
+                                                           const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                           const float* __restrict__ scale, const float* __restrict__ shift,
+                                                           const double* __restrict__ sum_dy,
+                                                           const double* __restrict__ sum_dy_xc, bf16* __restrict__ dx,
+                                                           bf16* __restrict__ dz, float* __restrict__ dgamma,
+                                                           float* __restrict__ dbeta, int64_t rows, int C, int relu,
+                                                           int training) {
   const int cvec = C >> 3;
   const int64_t total_vec = rows * cvec;
   const bool remask = relu && (y == nullptr);
   const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int c0 = (int)(i0 % cvec) * 8;
+  const bool publish = i0 < cvec;
   float ca[8], cb[8], cc[8], sc[8], sf[8];
-  *reinterpret_cast<float4*>(ca) = *reinterpret_cast<const float4*>(coef + c0);
-  *reinterpret_cast<float4*>(ca + 4) = *reinterpret_cast<const float4*>(coef + c0 + 4);
-  *reinterpret_cast<float4*>(cb) = *reinterpret_cast<const float4*>(coef + C + c0);
-  *reinterpret_cast<float4*>(cb + 4) = *reinterpret_cast<const float4*>(coef + C + c0 + 4);
-  *reinterpret_cast<float4*>(cc) = *reinterpret_cast<const float4*>(coef + 2 * C + c0);
-  *reinterpret_cast<float4*>(cc + 4) = *reinterpret_cast<const float4*>(coef + 2 * C + c0 + 4);
-  if (remask) {
-    *reinterpret_cast<float4*>(sc) = *reinterpret_cast<const float4*>(coef + 3 * C + c0);
-    *reinterpret_cast<float4*>(sc + 4) = *reinterpret_cast<const float4*>(coef + 3 * C + c0 + 4);
-    *reinterpret_cast<float4*>(sf) = *reinterpret_cast<const float4*>(coef + 4 * C + c0);
-    *reinterpret_cast<float4*>(sf + 4) = *reinterpret_cast<const float4*>(coef + 4 * C + c0 + 4);
+  const double inv_m = 1.0 / (double)rows;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int c = c0 + k;
+    const double is = invstd[c], mu = mean[c], g = gamma[c];
+    const double s1 = sum_dy[c], s2 = sum_dy_xc[c] * is;     // s2 = sum(dy' * xhat)
+    const double a = g * is;
+    const double b = training ? -g * is * is * s2 * inv_m : 0.0;
+    ca[k] = (float)a;
+    cb[k] = (float)b;
+    cc[k] = training ? (float)(-a * s1 * inv_m - b * mu) : 0.f;
+    if (remask) {
+      sc[k] = scale[c];
+      sf[k] = shift[c];
+    }
+    if (publish && dgamma) {
+      dgamma[c] += (float)s2;
+      dbeta[c] += (float)s1;
+    }
   }
-  for (int64_t i = i0; i < total_vec; i += stride) {
+  int64_t i = i0;
+  for (; i + stride < total_vec; i += 2 * stride) {   // two independent row groups in flight per thread
+    bf16x8 rd[2], rx[2], ry[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      rd[u] = ldraw8(dy + (i + u * stride) * 8);
+      rx[u] = ldraw8(x + (i + u * stride) * 8);
+      if (relu && !remask) ry[u] = ldraw8(y + (i + u * stride) * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      float d[8], xv[8], yv[8], o[8];
+      cvt8(rd[u], d);
+      cvt8(rx[u], xv);
+      if (relu && !remask) cvt8(ry[u], yv);
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const float act = remask ? fmaf(xv[k], sc[k], sf[k]) : yv[k];
+        const float dd = (relu && !(act > 0.f)) ? 0.f : d[k];
+        d[k] = dd;
+        o[k] = fmaf(ca[k], dd, fmaf(cb[k], xv[k], cc[k]));
+      }
+      store8(dx + (i + u * stride) * 8, o);
+      if (dz) store8(dz + (i + u * stride) * 8, d);
+    }
+  }
+  if (i < total_vec) {
     float d[8], xv[8], yv[8], o[8];
     load8(dy + i * 8, d);
     load8(x + i * 8, xv);
     if (relu && !remask) load8(y + i * 8, yv);
-    if (remask) {
-#pragma unroll
-      for (int k = 0; k < 8; k++) yv[k] = fmaf(xv[k], sc[k], sf[k]);
-    }
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      const float dd = (relu && !(yv[k] > 0.f)) ? 0.f : d[k];
+      const float act = remask ? fmaf(xv[k], sc[k], sf[k]) : yv[k];
+      const float dd = (relu && !(act > 0.f)) ? 0.f : d[k];
       d[k] = dd;
       o[k] = fmaf(ca[k], dd, fmaf(cb[k], xv[k], cc[k]));
     }
@@ -692,41 +803,84 @@ extern "C" int mdhs_bn_apply(const void* x, const float* scale, const float* shi
   MDHS_RETURN_LAST();
 }
 
-extern "C" int mdhs_bn_bwd(const void* dy, const void* x, const void* y, const float* mean, const float* invstd,
-                           const float* gamma, const float* scale, const float* shift, double* sum_dy, double* sum_dy_xhat,
-                           float* coef, void* dx, void* dz, float* dgamma, float* dbeta, int64_t rows, int C, int relu,
+extern "C" int mdhs_bn_fwd(const void* x, const double* colsum, const double* colsumsq, const float* gamma, const float* beta,
+                           float* running_mean, float* running_var, float momentum, float eps, const void* residual, void* y,
+                           float* mean, float* invstd, float* scale, float* shift, int64_t rows, int C, int relu, int training,
                            void* stream) {
-  if (!dy || !x || !mean || !invstd || !gamma || !sum_dy || !sum_dy_xhat || !coef || !dx || rows <= 0 || (C % 8)) return MDHS_ERR_ARG;
-  if (relu && !y && (!scale || !shift)) return MDHS_ERR_ARG;   // the mask comes from y or is recomputed from scale / shift
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  cudaError_t e;
-  if (sum_dy_xhat == sum_dy + C) {   // the usual [2, C] workspace: one memset node instead of two
-    e = cudaMemsetAsync(sum_dy, 0, sizeof(double) * 2 * C, st);
-    if (e != cudaSuccess) return (int)e;
-  } else {
-    e = cudaMemsetAsync(sum_dy, 0, sizeof(double) * C, st);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaMemsetAsync(sum_dy_xhat, 0, sizeof(double) * C, st);
-    if (e != cudaSuccess) return (int)e;
-  }
-  int64_t rows_w;
-  int Cw;
-  fold_view(rows, C, C, &rows_w, &Cw);
-  const int cslabs = ceil_div(Cw, 256);
-  int row_blocks = ((int64_t)mdhs_num_sms() * 8) / cslabs;
-  if (row_blocks < 1) row_blocks = 1;
-  int rpb = ceil_div(rows_w, row_blocks);
-  rpb = ((rpb + 7) / 8) * 8;
-  row_blocks = ceil_div(rows_w, rpb);
-  g_mdhs_launches += 3;
-  const bool remask = relu && !y;
-  bn_bwd_reduce_kernel<<<dim3(cslabs, row_blocks), 256, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, mean, invstd,
-                                                                 scale, shift, sum_dy, sum_dy_xhat, rows_w, C, Cw, rpb, relu);
-  bn_bwd_coeff_kernel<<<ceil_div(C, 128), 128, 0, st>>>(mean, invstd, gamma, sum_dy, sum_dy_xhat, remask ? scale : nullptr,
-                                                        remask ? shift : nullptr, coef, dgamma, dbeta, rows, C);
+  if (!x || !y || !gamma || !beta || rows <= 0 || C <= 0 || (C % 8)) return MDHS_ERR_ARG;
+  if (training && (!colsum || !colsumsq)) return MDHS_ERR_ARG;
+  if (!training && (!running_mean || !running_var)) return MDHS_ERR_ARG;
   const int64_t total_vec = rows * (C / 8);
-  bn_bwd_apply_kernel<<<grid_for_channels(total_vec, C), 256, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, coef, (bf16*)dx,
-                                                                (bf16*)dz, rows, C, relu);
+  g_mdhs_launches++;
+  bn_fwd_kernel<<<grid_for_channels(total_vec, C), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      (const bf16*)x, colsum, colsumsq, rows, gamma, beta, running_mean, running_var, momentum, eps, (const bf16*)residual,
+      (bf16*)y, mean, invstd, scale, shift, total_vec, C, relu, training);
+  MDHS_RETURN_LAST();
+}
+
+// MDHS_BN_REDUCE="RL,blocks_per_sm" (RL in {8, 16}): tuning knob for the backward reduction grid (default 8,2)
+static void bn_reduce_cfg(int* rl, int* bps) {
+  static int s_rl = 0, s_bps = 0;
+  if (s_rl == 0) {
+    s_rl = 8;
+    s_bps = 2;
+    const char* e = getenv("MDHS_BN_REDUCE");
+    if (e) {
+      int a = 0, b = 0;
+      if (sscanf(e, "%d,%d", &a, &b) == 2 && (a == 8 || a == 16) && b >= 1 && b <= 16) {
+        s_rl = a;
+        s_bps = b;
+      }
+    }
+  }
+  *rl = s_rl;
+  *bps = s_bps;
+}
+
+extern "C" int mdhs_bn_bwd(const void* dy, const void* x, const void* y, const float* mean, const float* invstd,
+                           const float* gamma, const float* scale, const float* shift, double* sum_dy, double* sum_dy_xc,
+                           void* dx, void* dz, float* dgamma, float* dbeta, int64_t rows, int C, int relu, int training,
+                           int sums_ready, void* stream) {
+  if (!dy || !x || !mean || !invstd || !gamma || !sum_dy || !sum_dy_xc || !dx || rows <= 0 || (C % 8)) return MDHS_ERR_ARG;
+  if (relu && !y && (!scale || !shift)) return MDHS_ERR_ARG;   // the mask comes from y or is recomputed from scale / shift
+  if ((dgamma == nullptr) != (dbeta == nullptr)) return MDHS_ERR_ARG;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!sums_ready) {
+    cudaError_t e;
+    if (sum_dy_xc == sum_dy + C) {   // the usual [2, C] workspace: one memset node instead of two
+      e = cudaMemsetAsync(sum_dy, 0, sizeof(double) * 2 * C, st);
+      if (e != cudaSuccess) return (int)e;
+    } else {
+      e = cudaMemsetAsync(sum_dy, 0, sizeof(double) * C, st);
+      if (e != cudaSuccess) return (int)e;
+      e = cudaMemsetAsync(sum_dy_xc, 0, sizeof(double) * C, st);
+      if (e != cudaSuccess) return (int)e;
+    }
+    int64_t rows_w;
+    int Cw;
+    fold_view(rows, C, C, &rows_w, &Cw);
+    const int cslabs = ceil_div(Cw, 256);
+    int rl, bps;
+    bn_reduce_cfg(&rl, &bps);
+    int row_blocks = (mdhs_num_sms() * bps) / cslabs;
+    if (row_blocks < 1) row_blocks = 1;
+    int rpb = ceil_div(rows_w, row_blocks);
+    rpb = ((rpb + 4 * rl - 1) / (4 * rl)) * (4 * rl);
+    row_blocks = ceil_div(rows_w, rpb);
+    g_mdhs_launches++;
+    const dim3 grid(cslabs, row_blocks);
+    if (rl == 16)
+      bn_bwd_reduce_kernel<16><<<grid, 512, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, mean, scale, shift, sum_dy,
+                                                     sum_dy_xc, rows_w, C, Cw, rpb, relu);
+    else
+      bn_bwd_reduce_kernel<8><<<grid, 256, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, mean, scale, shift, sum_dy,
+                                                    sum_dy_xc, rows_w, C, Cw, rpb, relu);
+  }
+  g_mdhs_launches++;
+  const int64_t total_vec = rows * (C / 8);
+  bn_bwd_apply_kernel<<<grid_for_channels(total_vec, C), 256, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, mean, invstd,
+                                                                       gamma, scale, shift, sum_dy, sum_dy_xc, (bf16*)dx,
+                                                                       (bf16*)dz, dgamma, dbeta, rows, C, relu, training);
   MDHS_RETURN_LAST();
 }
 

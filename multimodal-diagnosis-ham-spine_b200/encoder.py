@@ -76,6 +76,8 @@ class MdhsModule(nn.Module):
                     b.data = b.data.to(dev)
             st = bind(self, dev)
         st.refresh()
+        if torch.is_grad_enabled():
+            st.attach_grads()
         return st
 
 
@@ -93,6 +95,85 @@ class _TrunkFn(torch.autograd.Function):
             ctx.engine.backward(ctx.c, {n: (g.contiguous() if g is not None else None) for n, g in zip(ctx.names, grads)})
         ctx.c = None
         return None, None, None, None, None, None
+
+
+# ---- stage-wise trunk (only used while analysis hooks are registered on image_encoder.stem / layerN / layerN[-1]) ----------
+class _StemFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, anchor, images, engine, training, need):
+        engine.begin_forward(images, training)
+        y, H, W, c = engine.forward_stem(images, training, need)
+        ctx.engine, ctx.c = engine, c
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        if ctx.c is not None:
+            ctx.engine.backward_stem(ctx.c, dy.contiguous())
+        ctx.c = None
+        return None, None, None, None, None
+
+
+class _StageFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, engine, li, B, H, W, training, need, first_backward):
+        y, Ho, Wo, C, c = engine.forward_layer(li, x, B, H, W, training, need)
+        ctx.engine, ctx.c, ctx.li, ctx.first_backward = engine, c, li, first_backward
+        ctx.out_hw = (Ho, Wo, C)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        if ctx.c is None:
+            return (None,) * 9
+        if ctx.first_backward:
+            ctx.engine.begin_backward(dy.device)
+        dx = ctx.engine.backward_layer(ctx.li, ctx.c, dy.contiguous())
+        ctx.c = None
+        return (dx,) + (None,) * 8
+
+
+class _ToNchwFn(torch.autograd.Function):
+    """[B*H*W, C] bf16 (NHWC) -> [B, C, H, W] fp32 -- the layout / dtype the reference's hooks see."""
+
+    @staticmethod
+    def forward(ctx, x2d, B, H, W, C):
+        ctx.dims = (B, H, W, C)
+        return ops.nhwc_bf16_to_nchw_f32(x2d.contiguous(), B, H, W, C)
+
+    @staticmethod
+    def backward(ctx, g):
+        B, H, W, C = ctx.dims
+        return ops.nchw_f32_to_nhwc_bf16(g.contiguous().float()), None, None, None, None
+
+
+class _ToNhwcFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x4d):
+        B, C, H, W = x4d.shape
+        ctx.dims = (B, H, W, C)
+        return ops.nchw_f32_to_nhwc_bf16(x4d.contiguous().float())
+
+    @staticmethod
+    def backward(ctx, g2d):
+        B, H, W, C = ctx.dims
+        return ops.nhwc_bf16_to_nchw_f32(g2d.contiguous(), B, H, W, C)
+
+
+def _has_hooks(m):
+    return bool(m._forward_hooks or m._forward_pre_hooks or m._backward_hooks or getattr(m, "_backward_pre_hooks", None))
+
+
+def _fire_hooks(module, inp, out):
+    """Run `module`'s registered hooks around a precomputed output: module.__call__ is invoked with its `forward`
+    temporarily replaced by a function that returns `out`, so forward (pre-)hooks see (input, output) and full-backward
+    hooks receive grad_output exactly as they would around the reference's torchvision block.  `inp` carries no grad
+    (the real data path runs through our kernels), which makes torch deliver the backward hook when grad_output arrives."""
+    object.__setattr__(module, "forward", lambda *a, **k: out)
+    try:
+        return module(inp.detach())
+    finally:
+        object.__delattr__(module, "forward")
 
 
 class _BertFn(torch.autograd.Function):
@@ -157,12 +238,58 @@ class ImageEncoder(MdhsModule):
     def _trainable(self):
         return any(p.requires_grad for p in self.model.parameters())
 
+    def _hooked_stages(self):
+        """Analysis hooks (Grad-CAM: analysis_tools.py:29-31, scripts/run_analysis.py:126-132) on the stem or on a stage /
+        its last block: {stage index (-1 = stem): [modules whose hooks fire at that boundary]}."""
+        out = {}
+        if _has_hooks(self.stem):
+            out[-1] = [self.stem]
+        for li, layer in enumerate((self.layer1, self.layer2, self.layer3, self.layer4)):
+            mods = [m for m in (layer[-1], layer) if _has_hooks(m)]
+            if mods:
+                out[li] = mods
+        return out
+
+    def _forward_staged(self, st, x, hooked, names, need):
+        """Stage-by-stage trunk with NCHW fp32 taps at the hooked boundaries (slower than the fused path: extra layout
+        conversions; only taken while hooks are registered)."""
+        eng = self._engine
+        B = x.shape[0]
+        need = need or torch.is_grad_enabled()   # Grad-CAM back-propagates through a (possibly frozen / eval) trunk
+        cur = _StemFn.apply(st.anchor, x, eng, self.training, need)
+        H, W = _out_hw_stem(x.shape[2]), _out_hw_stem(x.shape[3])
+        C = eng.stem.O
+        prev4d = x
+        feats = {}
+        first_backward_at = max(i for i, n in enumerate(("layer1", "layer2", "layer3", "layer4")) if n in names)
+        for li in range(-1, 4):
+            if li >= 0:
+                cur = _StageFn.apply(cur, eng, li, B, H, W, self.training, need, li == first_backward_at)
+                blocks = eng.layers[li]
+                C = blocks[-1][0][-1].O
+                s = blocks[0][0][1].stride if len(blocks[0][0]) > 2 else blocks[0][0][0].stride
+                H, W = (H + s - 1) // s, (W + s - 1) // s
+            if li in hooked:
+                t4 = _ToNchwFn.apply(cur, B, H, W, C)
+                for m in hooked[li]:
+                    t4 = _fire_hooks(m, prev4d, t4)
+                prev4d = t4
+                cur = _ToNhwcFn.apply(t4)
+            if li >= 0 and f"layer{li + 1}" in names:
+                feats[f"layer{li + 1}"] = cur
+        eng.end_forward()
+        return tuple(feats[n] for n in names)
+
     def forward(self, x):
         st = self.store(x.device)
         B = x.shape[0]
         names = ("layer2", "layer3", "layer4") if self.multi_scale else ("layer4",)
         need = self._trainable() and torch.is_grad_enabled()
-        feats = _TrunkFn.apply(st.anchor, x.float(), self._engine, self.training, names, need)
+        hooked = self._hooked_stages()
+        if hooked:
+            feats = self._forward_staged(st, x.float(), hooked, names, need)
+        else:
+            feats = _TrunkFn.apply(st.anchor, x.float(), self._engine, self.training, names, need)
         if self.multi_scale:
             out = {}
             for name, f, proj in zip(names, feats, (self.proj2, self.proj3, self.proj4)):
@@ -171,6 +298,11 @@ class ImageEncoder(MdhsModule):
             return out
         t = Fm.linear(feats[0], st, self.proj4.weight, self.proj4.bias)
         return t.view(B, -1, t.shape[1])
+
+
+def _out_hw_stem(h):
+    h = (h + 2 * 3 - 7) // 2 + 1        # 7x7 / 2, pad 3
+    return (h + 2 * 1 - 3) // 2 + 1     # 3x3 / 2 max-pool, pad 1
 
 
 class TextEncoder(MdhsModule):

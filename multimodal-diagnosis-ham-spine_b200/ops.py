@@ -30,11 +30,14 @@ def _require_cuda(*ts):
 
 def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bias=None, act=ACT_NONE,
          aux_out=None, aux_in=None, dact=ACT_NONE, residual=None, accumulate=False, split_k=1,
-         bn_hint=0, colsum=None, colsumsq=None, M=None, N=None, K=None, dropout_p=0.0, dropout_seed=0, conv=None):
+         bn_hint=0, colsum=None, colsumsq=None, M=None, N=None, K=None, dropout_p=0.0, dropout_seed=0, conv=None,
+         stat_x=None, stat_mean=None, stat_scale=None, stat_shift=None, stat_relu=True):
     """D[M,N] (+)= epi(A . B^T).  `a` is [M,K] (K-major) or [K,M] when a_mn; `b` is [N,K] or [K,N] when b_mn.
     2-D bf16 tensors with unit inner stride (row stride may exceed the row length).
     conv = (mode, N, H, W, C, R, S, stride, pad): implicit-GEMM convolution, the NHWC activation [N*H*W, C] is passed as
-    `a` (mode 1: fprop / dgrad) or as `b` (mode 2: wgrad, with a_mn = b_mn = True) and M, N, K must be given."""
+    `a` (mode 1: fprop / dgrad) or as `b` (mode 2: wgrad, with a_mn = b_mn = True) and M, N, K must be given.
+    stat_x (+ stat_mean / stat_scale / stat_shift, colsum / colsumsq): the epilogue also accumulates the BatchNorm-backward
+    reductions sum(dy'), sum(dy' * (stat_x - mean)) of the layer whose output gradient this GEMM produces."""
     _require_cuda(a, b)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
@@ -87,6 +90,11 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bi
     if colsum is not None:
         assert colsum.dtype == torch.float64 and colsumsq.dtype == torch.float64
         args.colsum, args.colsumsq = colsum.data_ptr(), colsumsq.data_ptr()
+    if stat_x is not None:
+        assert stat_x.dtype == torch.bfloat16 and stat_x.shape == (M, N) and stat_x.stride(1) == 1 and colsum is not None
+        args.stat_x, args.ld_stat_x = stat_x.data_ptr(), stat_x.stride(0)
+        args.stat_mean, args.stat_scale, args.stat_shift = stat_mean.data_ptr(), stat_scale.data_ptr(), stat_shift.data_ptr()
+        args.stat_relu = int(bool(stat_relu))
     check(_lib.lib().mdhs_gemm_bf16(ctypes.byref(args), _stream()), "mdhs_gemm_bf16")
     return out
 
@@ -146,15 +154,28 @@ def bn_apply(x, scale, shift, residual=None, relu=True, out=None):
     return y
 
 
-def bn_bwd(dy, x, y, mean, invstd, gamma, dgamma, dbeta, relu=True, want_dz=False, scale=None, shift=None):
-    """y may be None when relu and the layer had no residual input: the mask is recomputed from (x, scale, shift)."""
+def bn_fwd(x, colsum, colsumsq, gamma, beta, running_mean, running_var, momentum, eps, residual=None, relu=True, training=True):
+    """Finalize + apply in one launch.  Returns (y, mean, invstd, scale, shift)."""
     rows, C = x.shape
-    ws = torch.empty((2, C), device=x.device, dtype=torch.float64)
-    coef = torch.empty((5, C), device=x.device, dtype=torch.float32)
+    stats = torch.empty((4, C), device=x.device, dtype=torch.float32)
+    y = torch.empty_like(x)
+    _lib.call("mdhs_bn_fwd", _p(x), _p(colsum), _p(colsumsq), _p(gamma), _p(beta), _p(running_mean), _p(running_var),
+              float(momentum), float(eps), _p(residual), _p(y), stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(),
+              stats[3].data_ptr(), rows, C, int(relu), int(training), _s())
+    return y, stats[0], stats[1], stats[2], stats[3]
+
+
+def bn_bwd(dy, x, y, mean, invstd, gamma, dgamma, dbeta, relu=True, want_dz=False, scale=None, shift=None, training=True,
+           sums=None):
+    """y may be None when relu and the layer had no residual input: the mask is recomputed from (x, scale, shift).
+    sums: optional fp64 [2, C] workspace already holding sum(dy'), sum(dy' * (x - mean)) (GEMM-epilogue fused reduction)."""
+    rows, C = x.shape
+    ws = torch.empty((2, C), device=x.device, dtype=torch.float64) if sums is None else sums
     dx = torch.empty_like(x)
     dz = torch.empty_like(x) if want_dz else None
     _lib.call("mdhs_bn_bwd", _p(dy), _p(x), _p(y), _p(mean), _p(invstd), _p(gamma), _p(scale), _p(shift), ws[0].data_ptr(),
-              ws[1].data_ptr(), _p(coef), _p(dx), _p(dz), _p(dgamma), _p(dbeta), rows, C, int(relu), _s())
+              ws[1].data_ptr(), _p(dx), _p(dz), _p(dgamma), _p(dbeta), rows, C, int(relu), int(training), int(sums is not None),
+              _s())
     return dx, dz
 
 
@@ -353,6 +374,9 @@ def supcon_loss(x, labels, temperature=0.07, want_grad=True):
 def axpby(x, y, a=1.0, b=0.0, a_dev=None):
     _lib.call("mdhs_axpby_f32", _p(x), _p(y), x.numel(), _p(a_dev), float(a), float(b), _s())
     return y
+
+
+HAS_GEMM_STAT = True   # mdhs_gemm_args.stat_x (BatchNorm-backward reduction in the dgrad epilogue) is available
 
 
 _NUM_SMS = {}

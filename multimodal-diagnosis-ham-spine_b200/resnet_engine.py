@@ -1,13 +1,20 @@
 """ResNet trunk (torchvision topology: BasicBlock for resnet18/34, Bottleneck for resnet50) on the B200
-kernels: NHWC bf16 activations, every convolution an (im2col +) tcgen05 GEMM whose epilogue also
-produces the train-mode BatchNorm statistics, BN-apply + residual + ReLU fused in one pass, and a
-hand-scheduled backward (BN reduce/apply, dgrad GEMM, split-K wgrad GEMM accumulating in fp32).
+kernels: NHWC bf16 activations, every convolution an (implicit) tcgen05 GEMM whose epilogue also produces the
+train-mode BatchNorm statistics, BN finalize + apply + residual + ReLU fused in one pass, and a hand-scheduled
+backward (BN reduce -- fused into the epilogue of the dgrad GEMM that produces dy where possible --, BN apply with
+in-kernel coefficients, dgrad GEMM, split-K wgrad GEMM accumulating in fp32).
 
 Reference path: encoder.py:61-72,88-99 (ImageEncoder stem/layer1-4) and mibf_net/model_resnet.py:15-16,40
 (torchvision resnet50 incl. avg-pool + fc).  The nn.Module objects only hold parameters / buffers with
 the reference's state_dict keys; all arithmetic happens here.
+
+The trunk can be driven as ONE unit (`forward` / `backward`, the fast path) or stage by stage (`forward_stem`,
+`forward_layer`, `backward_layer`, `backward_stem`) -- the latter is what encoder.py uses when analysis hooks are
+registered on `image_encoder.stem | layerN[-1]` (analysis_tools.py:29-31), so that activations / gradients can be
+exposed at the stage boundaries.
 """
 import contextlib
+import os as _os
 
 import torch
 
@@ -17,10 +24,12 @@ from . import runtime
 
 # Train-mode BN statistics: fused into the conv GEMM epilogue (column sums of the staged bf16 output box, accumulated in
 # registers across the persistent CTA's tiles) or, when False, one extra column pass (col_stats) over the raw conv output.
-import os as _os
 FUSE_BN_STATS_IN_GEMM = _os.environ.get("MDHS_FUSE_BN_STATS", "1") != "0"
 # convolutions with a shorter reduction than this take the separate col_stats pass (their GEMM is epilogue / HBM paced)
 FUSE_BN_STATS_MIN_K = int(_os.environ.get("MDHS_FUSE_BN_MIN_K", "100"))
+# backward: sum(dy'), sum(dy' (x - mean)) of the PRODUCER layer's BatchNorm taken in the epilogue of the dgrad GEMM that
+# writes dy (the raw activation arrives through the prefetched operand box), so the separate reduce pass disappears
+FUSE_BN_BWD_REDUCE = _os.environ.get("MDHS_FUSE_BN_BWD", "1") != "0"
 
 
 _nullctx = contextlib.nullcontext
@@ -64,6 +73,12 @@ class _Conv:
     def conv_desc(self, mode, B, H, W):
         return (mode, B, H, W, self.I, self.R, self.S, self.stride, self.pad)
 
+    @property
+    def dgrad_fusable(self):
+        """The dgrad of this convolution is ONE GEMM writing dx directly (no col2im), so its epilogue can carry the
+        producer BatchNorm's backward reduction."""
+        return self.direct or self.implicit_dgrad
+
 
 class ResNetEngine:
     def __init__(self, store, net):
@@ -83,9 +98,9 @@ class ResNetEngine:
                     down = _Conv(store, blk.downsample[0], blk.downsample[1])
                 blocks.append((convs, down))
             self.layers.append(blocks)
-        self._stats = None
         # one fp64 workspace for the batch statistics of every conv (zeroed with ONE fill per forward instead of one per
-        # layer) and one multi-tensor add for the BatchNorm step counters: ~100 fewer tiny launches per step
+        # layer) and one multi-tensor add for the BatchNorm step counters: ~100 fewer tiny launches per step.  The backward
+        # reductions sum(dy'), sum(dy' (x - mean)) get a same-shaped workspace (zeroed once per backward).
         self._all_convs = [self.stem] + [c for blocks in self.layers for convs, down in blocks
                                          for c in (convs + ([down] if down is not None else []))]
         off = 0
@@ -94,13 +109,15 @@ class ResNetEngine:
             off += 2 * c.O
         self._stats_total = off
         self._stats_ws = None
+        self._bwd_ws = None
+        self._nbt = []
         # called with the stage index (3 = layer4 ... 0 = layer1) right after that stage's backward kernels have been
         # enqueued: the data-parallel trainer uses it to start the stage's gradient all-reduce early
         self.on_stage_backward_done = None
 
     # ------------------------------------------------------------------ forward pieces
-    def _conv_bn(self, c, x, B, H, W, relu, residual, training, saved):
-        """x: [B*H*W, Cin] bf16 (or the NCHW fp32 image for the stem).  Returns y, Ho, Wo."""
+    def _conv_bn(self, c, x, B, H, W, relu, residual, training, need_grad):
+        """x: [B*H*W, Cin] bf16 (or the NCHW fp32 image for the stem).  Returns y, Ho, Wo, record-for-backward."""
         if c.stem:
             A, Ho, Wo = ops.im2col_nchw_f32(x, c.R, c.S, c.stride, c.pad, c.ldk)
         elif c.direct:
@@ -112,6 +129,7 @@ class ResNetEngine:
         rows = B * Ho * Wo
         bn = c.bn
         gkw = dict(conv=c.conv_desc(1, B, H, W), M=rows, K=c.K) if c.implicit else {}
+        track = bn.track_running_stats and bn.running_mean is not None
         if training:
             st = self._stats_ws[c.stats_off:c.stats_off + 2 * c.O].view(2, c.O)
             if FUSE_BN_STATS_IN_GEMM and c.K >= FUSE_BN_STATS_MIN_K:
@@ -120,56 +138,82 @@ class ResNetEngine:
                 raw = ops.gemm(A, c.wp, N=c.O, **gkw)
                 ops.col_stats(raw, st[0], st[1])
             mom = bn.momentum if bn.momentum is not None else 0.1
-            track = bn.track_running_stats and bn.running_mean is not None
-            mean, invstd, scale, shift = ops.bn_finalize(
-                st[0], st[1], rows, bn.weight.data, bn.bias.data, bn.running_mean if track else None,
-                bn.running_var if track else None, mom, bn.eps, training=True)
+            y, mean, invstd, scale, shift = ops.bn_fwd(raw, st[0], st[1], bn.weight.data, bn.bias.data,
+                                                       bn.running_mean if track else None, bn.running_var if track else None,
+                                                       mom, bn.eps, residual=residual, relu=relu, training=True)
             if track and bn.num_batches_tracked is not None:
                 self._nbt.append(bn.num_batches_tracked)
         else:
             raw = ops.gemm(A, c.wp, N=c.O, **gkw)
-            mean, invstd, scale, shift = ops.bn_finalize(None, None, rows, bn.weight.data, bn.bias.data, bn.running_mean,
-                                                         bn.running_var, 0.0, bn.eps, training=False)
-        y = ops.bn_apply(raw, scale, shift, residual=residual, relu=relu)
-        if saved is not None:
+            y, mean, invstd, scale, shift = ops.bn_fwd(raw, None, None, bn.weight.data, bn.bias.data, bn.running_mean,
+                                                       bn.running_var, 0.0, bn.eps, residual=residual, relu=relu, training=False)
+        rec = None
+        if need_grad:
             # y is only kept for the backward ReLU mask when a residual entered the activation; otherwise the mask is
             # recomputed from (raw, scale, shift)
-            saved.append(dict(c=c, A=A, raw=raw, y=y if (relu and residual is not None) else None, mean=mean, invstd=invstd,
-                              scale=scale, shift=shift, relu=relu, B=B, H=H, W=W, Ho=Ho, Wo=Wo, has_res=residual is not None))
-        return y, Ho, Wo
+            rec = dict(c=c, A=A, raw=raw, y=y if (relu and residual is not None) else None, mean=mean, invstd=invstd,
+                       scale=scale, shift=shift, relu=relu, B=B, H=H, W=W, Ho=Ho, Wo=Wo, has_res=residual is not None,
+                       training=training, sums=None)
+        return y, Ho, Wo, rec
 
-    def forward(self, images, training, need_grad):
-        """images: [B,3,H,W] fp32 CUDA.  Returns ({name: (feat2d bf16, h, w, C)}, ctx)."""
-        B, _, H, W = images.shape
-        saved = [] if need_grad else None
-        ctx = dict(saved=saved, B=B)
+    def begin_forward(self, images, training):
         self._nbt = []
         if training:
             self._stats_ws = torch.zeros(self._stats_total, device=images.device, dtype=torch.float64)
-        x, H1, W1 = self._conv_bn(self.stem, images.contiguous(), B, H, W, True, None, training, saved)
-        y, idx, H2, W2 = ops.maxpool_fwd(x, B, H1, W1, self.stem.O)
-        ctx["pool"] = (idx, H1, W1, self.stem.O)
-        x, H, W = y, H2, W2
-        feats = {}
-        for li, blocks in enumerate(self.layers):
-            for convs, down in blocks:
-                inp, Hi, Wi = x, H, W
-                t = inp
-                for ci, c in enumerate(convs[:-1]):
-                    t, H, W = self._conv_bn(c, t, B, H, W, True, None, training, saved)
-                if down is not None:
-                    idn, _, _ = self._conv_bn(down, inp, B, Hi, Wi, False, None, training, saved)
-                else:
-                    idn = inp
-                x, H, W = self._conv_bn(convs[-1], t, B, H, W, True, idn, training, saved)
-                if saved is not None:
-                    saved.append(dict(block_end=True, n_main=len(convs), has_down=down is not None))
-            feats[f"layer{li + 1}"] = (x, H, W, convs[-1].O)
+
+    def end_forward(self):
         if self._nbt:
             torch._foreach_add_(self._nbt, 1)
-        return feats, ctx
+            self._nbt = []
+
+    def forward_stem(self, images, training, need_grad):
+        """images [B,3,H,W] fp32 -> (x [B*H2*W2, 64] bf16 after the 3x3/2 max-pool, H2, W2, ctx)."""
+        B, _, H, W = images.shape
+        x, H1, W1, rec = self._conv_bn(self.stem, images.contiguous(), B, H, W, True, None, training, need_grad)
+        y, idx, H2, W2 = ops.maxpool_fwd(x, B, H1, W1, self.stem.O)
+        ctx = dict(rec=rec, pool=(idx, H1, W1, self.stem.O), B=B) if need_grad else None
+        return y, H2, W2, ctx
+
+    def forward_layer(self, li, x, B, H, W, training, need_grad):
+        """One ResNet stage (li = 0..3).  Returns (y, H, W, C, ctx)."""
+        blocks = [] if need_grad else None
+        for convs, down in self.layers[li]:
+            inp, Hi, Wi = x, H, W
+            t = inp
+            main = []
+            for c in convs[:-1]:
+                t, H, W, r = self._conv_bn(c, t, B, H, W, True, None, training, need_grad)
+                main.append(r)
+            rdown = None
+            if down is not None:
+                idn, _, _, rdown = self._conv_bn(down, inp, B, Hi, Wi, False, None, training, need_grad)
+            else:
+                idn = inp
+            x, H, W, r = self._conv_bn(convs[-1], t, B, H, W, True, idn, training, need_grad)
+            main.append(r)
+            if need_grad:
+                blocks.append(dict(main=main, down=rdown))
+        return x, H, W, self.layers[li][-1][0][-1].O, (dict(blocks=blocks, B=B) if need_grad else None)
+
+    def forward(self, images, training, need_grad):
+        """images: [B,3,H,W] fp32 CUDA.  Returns ({name: (feat2d bf16, h, w, C)}, ctx)."""
+        B = images.shape[0]
+        self.begin_forward(images, training)
+        x, H, W, sctx = self.forward_stem(images, training, need_grad)
+        feats, lctx = {}, []
+        for li in range(4):
+            x, H, W, C, c = self.forward_layer(li, x, B, H, W, training, need_grad)
+            feats[f"layer{li + 1}"] = (x, H, W, C)
+            lctx.append(c)
+        self.end_forward()
+        return feats, (dict(stem=sctx, layers=lctx, B=B) if need_grad else None)
 
     # ------------------------------------------------------------------ backward pieces
+    def begin_backward(self, device):
+        """One zero-fill for every fused backward reduction of this pass."""
+        self._bwd_ws = (torch.zeros(self._stats_total, device=device, dtype=torch.float64)
+                        if (FUSE_BN_BWD_REDUCE and ops.HAS_GEMM_STAT) else None)
+
     def _wgrad(self, c, rec, draw, A, rows, st):
         """Weight gradient of one convolution (accumulates into the flat fp32 gradient buffer)."""
         if c.implicit:
@@ -193,8 +237,10 @@ class ResNetEngine:
                      M=c.O, N=c.ldk, K=rows)
             ops.conv_wgrad_unpack(c.gp, st.g32(c.conv.weight))
 
-    def _conv_bn_bwd(self, rec, dy, add_to_dx, need_dx=True):
-        """dy: grad wrt the BN(+res)(+relu) output.  Returns (dx, dz) where dz is the masked dy (identity branch)."""
+    def _conv_bn_bwd(self, rec, dy, add_to_dx, need_dx=True, producer=None):
+        """dy: grad wrt the BN(+res)(+relu) output.  Returns (dx, dz) where dz is the masked dy (identity branch).
+        producer: record of the conv+BN whose OUTPUT is this convolution's input (same block, no residual in between):
+        when given (and fusable) the dgrad GEMM's epilogue also accumulates that BatchNorm's backward reductions."""
         c = rec["c"]
         st = self.store
         train_w = c.conv.weight.requires_grad
@@ -202,7 +248,8 @@ class ResNetEngine:
         dgamma = st.g32(bnw) if bnw.requires_grad else None
         dbeta = st.g32(c.bn.bias) if bnw.requires_grad else None
         draw, dz = ops.bn_bwd(dy, rec["raw"], rec["y"], rec["mean"], rec["invstd"], bnw.data, dgamma, dbeta,
-                              relu=rec["relu"], want_dz=rec["has_res"], scale=rec["scale"], shift=rec["shift"])
+                              relu=rec["relu"], want_dz=rec["has_res"], scale=rec["scale"], shift=rec["shift"],
+                              training=rec["training"], sums=rec["sums"])
         A = rec["A"]
         rows = rec["B"] * rec["Ho"] * rec["Wo"]
         side = None
@@ -213,12 +260,20 @@ class ResNetEngine:
                 self._wgrad(c, rec, draw, A, rows, st)
         dx = None
         if need_dx:
+            skw = {}
+            if (producer is not None and self._bwd_ws is not None and c.dgrad_fusable and add_to_dx is None
+                    and producer["y"] is None):
+                pc = producer["c"]
+                sums = self._bwd_ws[pc.stats_off:pc.stats_off + 2 * pc.O].view(2, pc.O)
+                skw = dict(stat_x=producer["raw"], stat_mean=producer["mean"], stat_scale=producer["scale"],
+                           stat_shift=producer["shift"], stat_relu=producer["relu"], colsum=sums[0], colsumsq=sums[1])
+                producer["sums"] = sums
             if c.direct:
-                dx = ops.gemm(draw, c.wp, b_mn=True, residual=add_to_dx, M=rows, N=c.I, K=c.O)
+                dx = ops.gemm(draw, c.wp, b_mn=True, residual=add_to_dx, M=rows, N=c.I, K=c.O, **skw)
             elif c.implicit_dgrad:
                 # stride-1 k x k dgrad = the same implicit GEMM over dY with the flipped / transposed filter
                 dx = ops.gemm(draw, c.wt, residual=add_to_dx, M=rec["B"] * rec["H"] * rec["W"], N=c.I, K=c.R * c.S * c.O,
-                              conv=(1, rec["B"], rec["Ho"], rec["Wo"], c.O, c.R, c.S, 1, c.R - 1 - c.pad))
+                              conv=(1, rec["B"], rec["Ho"], rec["Wo"], c.O, c.R, c.S, 1, c.R - 1 - c.pad), **skw)
             else:
                 dcol = ops.gemm(draw, c.wp[:, :c.K], b_mn=True, M=rows, N=c.K, K=c.O)
                 dx = ops.col2im_nhwc(dcol, rec["B"], rec["H"], rec["W"], c.I, c.R, c.S, c.stride, c.pad, add=add_to_dx)
@@ -226,39 +281,39 @@ class ResNetEngine:
             runtime.join_side(side)
         return dx, dz
 
+    def backward_layer(self, li, ctx, dx):
+        """dx: grad of the stage output [rows, C] bf16.  Returns the grad of the stage input."""
+        for blk in reversed(ctx["blocks"]):
+            main, down = blk["main"], blk["down"]
+            d, dz = self._conv_bn_bwd(main[-1], dx, None, producer=main[-2] if len(main) > 1 else None)
+            for j in range(len(main) - 2, 0, -1):
+                d, _ = self._conv_bn_bwd(main[j], d, None, producer=main[j - 1])
+            if down is not None:
+                d_idn, _ = self._conv_bn_bwd(down, dz, None)
+            else:
+                d_idn = dz
+            dx, _ = self._conv_bn_bwd(main[0], d, d_idn)
+        if self.on_stage_backward_done is not None:
+            self.on_stage_backward_done(li)
+        return dx
+
+    def backward_stem(self, ctx, dx):
+        idx, H1, W1, C = ctx["pool"]
+        d = ops.maxpool_bwd(dx, idx, ctx["B"], H1, W1, C)
+        self._conv_bn_bwd(ctx["rec"], d, None, need_dx=False)
+
     def backward(self, ctx, dfeats):
         """dfeats: {name: grad 2-D bf16 or None}.  Accumulates parameter gradients; images get no gradient."""
-        saved = ctx["saved"]
-        B = ctx["B"]
-        i = len(saved) - 1
         dx = None
         for li in range(3, -1, -1):
             g = dfeats.get(f"layer{li + 1}")
             if g is not None:
-                dx = g if dx is None else dx + g
-            for _ in self.layers[li]:
-                end = saved[i]
-                assert end.get("block_end")
-                n_main, has_down = end["n_main"], end["has_down"]
-                recs = saved[i - n_main - (1 if has_down else 0):i]
-                i -= n_main + (1 if has_down else 0) + 1
-                main = recs[:n_main - 1]
-                last = recs[-1]
-                down = recs[n_main - 1] if has_down else None
                 if dx is None:
-                    continue  # nothing downstream needs this block
-                d, dz = self._conv_bn_bwd(last, dx, None)
-                for rec in reversed(main[1:]):
-                    d, _ = self._conv_bn_bwd(rec, d, None)
-                if has_down:
-                    d_idn, _ = self._conv_bn_bwd(down, dz, None)
-                else:
-                    d_idn = dz
-                dx, _ = self._conv_bn_bwd(main[0], d, d_idn)
-            if self.on_stage_backward_done is not None and dx is not None:
-                self.on_stage_backward_done(li)
+                    self.begin_backward(g.device)
+                dx = g if dx is None else dx + g
+            if dx is None:
+                continue  # nothing downstream needs this stage
+            dx = self.backward_layer(li, ctx["layers"][li], dx)
         if dx is None:
             return
-        idx, H1, W1, C = ctx["pool"]
-        d = ops.maxpool_bwd(dx, idx, B, H1, W1, C)
-        self._conv_bn_bwd(saved[0], d, None, need_dx=False)
+        self.backward_stem(ctx["stem"], dx)

@@ -121,11 +121,24 @@ class ParamStore:
             self._versions = versions
 
     def attach_grads(self):
-        """Re-point .grad at the flat gradient buffer (torch.optim.zero_grad(set_to_none=True) drops it)."""
-        for p in self.params:
-            if p.requires_grad and p.grad is None:
+        """Stock-loop support (scripts/train.py:364-387: `optimizer.zero_grad()` ... `loss.backward()` ... `optimizer.step()`):
+        torch's `zero_grad(set_to_none=True)` drops `.grad`, while our backward kernels accumulate into the flat gradient
+        buffer.  Called at the start of every grad-enabled forward: parameters whose `.grad` was dropped get their slice of
+        the flat buffer ZEROED (the caller asked for fresh gradients) and re-attached, so torch optimizers see them again.
+        With the fused Trainer nothing is ever detached and this is a no-op scan."""
+        missing = [p for p in self.params if p.requires_grad and p.grad is None]
+        if not missing:
+            return
+        n_train = sum(1 for p in self.params if p.requires_grad)
+        if len(missing) == n_train:
+            self.grad.zero_()
+        with torch.no_grad():
+            for p in missing:
                 o = self.offsets[id(p)]
-                p.grad = self.grad[o:o + p.numel()].view(p.shape)
+                g = self.grad[o:o + p.numel()].view(p.shape)
+                if len(missing) != n_train:
+                    g.zero_()
+                p.grad = g
 
     def zero_grad(self):
         self.grad.zero_()

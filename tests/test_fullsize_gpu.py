@@ -1,0 +1,322 @@
+"""Parity at the sizes the benchmark times (GPU): our CUDA path against the fp32 oracle (oracle/port.py, pinned to the real
+reference by tests/test_oracle_vs_reference.py) evaluated ON THE SAME GPU in true fp32 (TF32 off), so that the large-M code
+paths -- 256-wide CTA-pair tiles, auto split-K with 99-296 splits, fused BN column statistics over 1.6 M rows, fp64 atomics --
+are checked end to end at BASELINE config sizes, not only at toy sizes.
+
+Tolerances (written here, justified in DESIGN.md section 4): bf16 activations / operands, fp32 accumulation.
+  * eval logits: max-norm relative error <= 2e-2, top-1 identical wherever the oracle's top-1/top-2 margin exceeds twice the
+    measured error;
+  * train step (train-mode BN over the whole batch, dropout off): logits <= 6e-2, loss <= 2e-2 relative, BN running statistics
+    <= 2e-2, gradient cosine >= 0.97 (head / fusion / BERT), >= 0.9 (late ResNet), >= 0.7 (stem: ill-conditioned, torch's own
+    bf16 autocast reaches 0.1-0.6 there).
+"""
+import os
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from refutil import bert_dir, build_ours, quiet  # noqa: E402
+from oracle import port, weights  # noqa: E402
+from test_model_gpu import _zero_dropout  # noqa: E402
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return (a - b).abs().max().item() / (b.abs().max().item() + 1e-12)
+
+
+def cos(a, b):
+    a, b = a.float().cpu().flatten().double(), b.float().cpu().flatten().double()
+    return (a @ b / (a.norm() * b.norm() + 1e-300)).item()
+
+
+@pytest.fixture(autouse=True)
+def _true_fp32():
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    torch.cuda.empty_cache()
+
+
+def _top1_check(got, want):
+    got, want = got.float().cpu(), want.float().cpu()
+    err = (got - want).abs().max()
+    top2 = want.topk(2, dim=1).values
+    safe = (top2[:, 0] - top2[:, 1]) > 2 * err
+    assert safe.float().mean().item() > 0.5, "tolerance check is vacuous: most margins are below the error"
+    assert torch.equal(got.argmax(1)[safe], want.argmax(1)[safe])
+
+
+def _oracle_train(sd, dev, fn):
+    """Runs fn(state) -> loss on `dev` in fp32 with autograd; returns (loss, {key: grad}, state)."""
+    state = {k: v.to(dev) for k, v in sd.items()}
+    for k, v in state.items():
+        if v.is_floating_point() and "running" not in k:
+            state[k] = v.clone().requires_grad_(True)
+    out = fn(state)
+    return out, state
+
+
+def _grad_checks(model, state, checks):
+    named = dict(model.named_parameters())
+    res = {}
+    for key, thr in checks:
+        g = named[key].grad
+        assert g is not None, key
+        c = cos(g, state[key].grad)
+        res[key] = round(c, 4)
+        assert c >= thr, (key, c, res)
+    return res
+
+
+# ---------------------------------------------------------------------------------------------- config 2, full size
+@pytest.mark.parametrize("fusion,classes", [("basic", 7), ("multiscale", 6)])
+def test_eval_logits_full_size(fusion, classes):
+    """BASELINE config 2 / 3: B = 128, 3x224x224, S = 64, eval-mode logits vs the fp32 oracle on the GPU."""
+    model = build_ours(fusion=fusion, head="mlp", num_classes=classes)
+    sd = weights.synth_state_dict(model.state_dict(), seed=1)
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    images, ids, mask, _ = weights.synthetic_batch(128, 64, classes, image_hw=224)
+    with torch.no_grad():
+        got = model(images.cuda(), ids.cuda(), mask.cuda()).float()
+        sdc = {k: v.cuda() for k, v in sd.items()}
+        want = torch.cat([port.model_forward(sdc, images[i:i + 32].cuda(), ids[i:i + 32].cuda(), mask[i:i + 32].cuda(), fusion=fusion,
+                                             head="mlp") for i in range(0, 128, 32)])
+    e = rel(got, want)
+    print(f"[fullsize eval {fusion}] rel logits err {e:.3e}")
+    assert e < 2e-2, e
+    _top1_check(got, want)
+
+
+@pytest.mark.parametrize("fusion,classes", [("basic", 7), ("multiscale", 6)])
+def test_train_step_full_size(fusion, classes):
+    """One training step at B = 128, 224x224, S = 64 (train-mode BN over all 128 samples, dropout off): loss, logits,
+    per-group gradient cosine and BN running statistics vs the fp32 oracle with autograd on the same GPU."""
+    import mdhs_b200.functional as Fm
+    model = build_ours(fusion=fusion, head="mlp", num_classes=classes)
+    sd = weights.synth_state_dict(model.state_dict(), seed=1)
+    model.load_state_dict(sd)
+    model = model.cuda().train()
+    _zero_dropout(model)
+    images, ids, mask, labels = weights.synthetic_batch(128, 64, classes, image_hw=224)
+    ci, cd, cm, cl = images.cuda(), ids.cuda(), mask.cuda(), labels.cuda()
+    feats = model.forward_features(ci, cd, cm)
+    _zero_dropout(model)   # engines are bound now: make sure their dropout probabilities are off as well
+    model.store("cuda").zero_grad()
+    feats = model.forward_features(ci, cd, cm)
+    logits = model.classifier(feats)
+    loss = Fm.cross_entropy(logits, cl, label_smoothing=0.02)
+    loss.backward()
+    torch.cuda.synchronize()
+    got_logits, got_loss = logits.detach().float().cpu(), loss.item()
+    rm = model.image_encoder.model.bn1.running_mean.detach().float().cpu().clone()
+    rv = model.image_encoder.model.bn1.running_var.detach().float().cpu().clone()
+
+    def fn(state):
+        lg = port.model_forward(state, ci, cd, cm, fusion=fusion, head="mlp", training_bn=True)
+        ls = port.ce_label_smoothing(lg, cl, label_smoothing=0.02)
+        ls.backward()
+        return lg.detach(), ls.item()
+    (want_logits, want_loss), state = _oracle_train(sd, "cuda", fn)
+    e = rel(got_logits, want_logits)
+    print(f"[fullsize train {fusion}] logits rel {e:.3e} loss {got_loss:.5f} vs {want_loss:.5f}")
+    assert e < 6e-2, e
+    assert abs(got_loss - want_loss) < 2e-2 * max(1.0, abs(want_loss))
+    checks = [("classifier.3.weight", 0.97), ("classifier.0.weight", 0.97),
+              ("text_encoder.model.encoder.layer.11.output.dense.weight", 0.97),
+              ("text_encoder.model.encoder.layer.5.intermediate.dense.weight", 0.97),
+              ("text_encoder.model.encoder.layer.0.attention.self.query.weight", 0.95),
+              ("text_encoder.model.embeddings.word_embeddings.weight", 0.95),
+              ("image_encoder.proj4.weight", 0.97),
+              ("image_encoder.model.layer4.2.conv3.weight", 0.9), ("image_encoder.model.layer4.0.conv2.weight", 0.9),
+              ("image_encoder.model.layer3.3.conv2.weight", 0.9), ("image_encoder.model.layer2.1.conv1.weight", 0.85),
+              ("image_encoder.model.layer1.0.conv1.weight", 0.7), ("image_encoder.model.conv1.weight", 0.7),
+              ("image_encoder.model.layer3.3.bn2.weight", 0.9)]
+    if fusion == "basic":
+        checks += [("fusion.transformer_block.attn2.v_proj_weight", 0.97), ("fusion.transformer_block.ff.0.weight", 0.97),
+                   ("fusion.transformer_block.attn1.in_proj_weight", 0.97)]
+    else:
+        checks += [("fusion.cross_l2.attn.in_proj_weight", 0.95), ("fusion.cross_l3.txt_proj.weight", 0.95),
+                   ("fusion.cross_l4.norm.weight", 0.95), ("image_encoder.proj2.weight", 0.95), ("image_encoder.proj3.weight", 0.95)]
+    res = _grad_checks(model, state, checks)
+    print(f"[fullsize train {fusion}] grad cosines {res}")
+    # BN running statistics follow F.batch_norm (momentum 0.1, unbiased variance).  Our model ran TWO train-mode forwards
+    # on this batch (running = 0.81 * initial + 0.19 * batch statistic); the batch statistics of the stem are recomputed in fp32.
+    with torch.no_grad():
+        z = torch.nn.functional.conv2d(ci, sd["image_encoder.model.conv1.weight"].cuda(), stride=2, padding=3)
+        mu_ref, var_ref = z.mean(dim=(0, 2, 3)).cpu(), z.var(dim=(0, 2, 3), unbiased=True).cpu()
+    rm0, rv0 = sd["image_encoder.model.bn1.running_mean"], sd["image_encoder.model.bn1.running_var"]
+    mu_got, var_got = (rm - 0.81 * rm0) / 0.19, (rv - 0.81 * rv0) / 0.19
+    assert (mu_got - mu_ref).abs().max().item() <= 2e-2 * mu_ref.abs().max().item() + 1e-3
+    assert (var_got - var_ref).abs().max().item() <= 2e-2 * var_ref.abs().max().item() + 1e-3
+
+
+# ---------------------------------------------------------------------------------------------- config 1 vs the CPU oracle
+def test_config1_concat_b32_vs_cpu_oracle():
+    """BASELINE config 1 exactly as the reference can run it: concat fusion, B = 32, 224x224, S = 64, one train step on the
+    host cores (fp32 oracle with autograd) vs our step."""
+    import mdhs_b200.functional as Fm
+    model = build_ours(fusion="concat", head="mlp")
+    sd = weights.synth_state_dict(model.state_dict(), seed=2)
+    model.load_state_dict(sd)
+    model = model.cuda().train()
+    images, ids, mask, labels = weights.synthetic_batch(32, 64, 7, image_hw=224)
+    model.eval()
+    with torch.no_grad():
+        got_eval = model(images.cuda(), ids.cuda(), mask.cuda()).float().cpu()
+        want_eval = port.model_forward(sd, images, ids, mask, fusion="concat", head="mlp")
+    e = rel(got_eval, want_eval)
+    print(f"[config1] eval rel {e:.3e}")
+    assert e < 2e-2
+    _top1_check(got_eval, want_eval)
+    model.train()
+    _zero_dropout(model)
+    model.store("cuda").zero_grad()
+    logits = model.classifier(model.forward_features(images.cuda(), ids.cuda(), mask.cuda()))
+    loss = Fm.cross_entropy(logits, labels.cuda(), label_smoothing=0.02)
+    loss.backward()
+    torch.cuda.synchronize()
+
+    def fn(state):
+        lg = port.model_forward(state, images, ids, mask, fusion="concat", head="mlp", training_bn=True)
+        ls = port.ce_label_smoothing(lg, labels, label_smoothing=0.02)
+        ls.backward()
+        return lg.detach(), ls.item()
+    (want_logits, want_loss), state = _oracle_train(sd, "cpu", fn)
+    assert rel(logits.detach(), want_logits) < 6e-2
+    assert abs(loss.item() - want_loss) < 2e-2 * max(1.0, abs(want_loss))
+    res = _grad_checks(model, state, [("classifier.3.weight", 0.97), ("fusion.proj.weight", 0.97),
+                                      ("text_encoder.model.encoder.layer.11.output.dense.weight", 0.97),
+                                      ("image_encoder.proj4.weight", 0.97), ("image_encoder.model.layer4.2.conv3.weight", 0.9),
+                                      ("image_encoder.model.layer1.0.conv1.weight", 0.7)])
+    print(f"[config1] grad cosines {res}")
+
+
+# ---------------------------------------------------------------------------------------------- gradient parity of every fusion / head
+@pytest.mark.parametrize("fusion,head,gate,keys", [
+    ("weighted_concat", "mlp", False, ["fusion.proj.weight", "fusion.w_img", "fusion.w_txt"]),
+    ("hadamard", "residual", False, ["fusion.img_proj.weight", "fusion.txt_proj.weight", "fusion.norm.weight",
+                                     "classifier.project.weight", "classifier.res_block.linear1.weight",
+                                     "classifier.res_block.linear2.weight", "classifier.res_block.norm.weight",
+                                     "classifier.classifier.weight"]),
+    ("bilinear", "attention_pooling", False, ["fusion.img_proj.weight", "fusion.txt_proj.weight", "fusion.out_proj.weight",
+                                              "classifier.attn.in_proj_weight", "classifier.attn.out_proj.weight",
+                                              "classifier.classifier.weight"]),
+    ("multiscale", "mlp", False, ["fusion.cross_l2.attn.in_proj_weight", "fusion.cross_l3.txt_proj.weight",
+                                  "fusion.cross_l4.norm.weight", "image_encoder.proj2.weight"]),
+    ("concat", "mlp", True, ["gate.fc.0.weight", "gate.fc.2.weight", "classifier.0.weight", "fusion.proj.weight"]),
+])
+def test_fusion_head_gate_gradients_match_oracle(fusion, head, gate, keys):
+    """Backward of F2 / F4 / F5 / F6, H2 / H3 and the dual-expert gate G1 against the fp32 oracle (B = 8, 128x128, S = 16;
+    eval-mode BN so that the comparison isolates the fusion / head arithmetic from train-mode BN conditioning)."""
+    import mdhs_b200.functional as Fm
+    model = build_ours(fusion=fusion, head=head, gate=gate)
+    sd = weights.synth_state_dict(model.state_dict(), seed=3)
+    model.load_state_dict(sd)
+    model = model.cuda().eval()          # eval: running-stat BN, no dropout -- gradients still flow
+    images, ids, mask, labels = weights.synthetic_batch(8, 16, 7, image_hw=128)
+    model.store("cuda").zero_grad()
+    logits = model(images.cuda(), ids.cuda(), mask.cuda())
+    loss = Fm.cross_entropy(logits.float(), labels.cuda(), label_smoothing=0.02)
+    loss.backward()
+    torch.cuda.synchronize()
+
+    def fn(state):
+        lg = port.model_forward(state, images, ids, mask, fusion=fusion, head=head, gate=gate)
+        ls = port.ce_label_smoothing(lg, labels, label_smoothing=0.02)
+        ls.backward()
+        return lg.detach(), ls.item()
+    (want_logits, want_loss), state = _oracle_train(sd, "cpu", fn)
+    assert rel(logits.detach(), want_logits) < 2e-2
+    assert abs(loss.item() - want_loss) < 2e-2 * max(1.0, abs(want_loss))
+    named = dict(model.named_parameters())
+    res = {}
+    for key in keys:
+        g_ref = state[key].grad
+        g = named[key].grad
+        assert g is not None, key
+        if g_ref is None or g_ref.abs().max().item() == 0.0:
+            # dead parameters of the reference (q/k projections of the 1-token attention-pooling head): zero there, zero here
+            assert g.abs().max().item() == 0.0, key
+            continue
+        res[key] = round(cos(g, g_ref), 4)
+    print(f"[grads {fusion}/{head}/gate={gate}] {res}")
+    for key, c in res.items():
+        assert c >= 0.97, (key, c, res)
+
+
+# ---------------------------------------------------------------------------------------------- MIBF-Net at S = 256 (config 5)
+def test_mibf_s256_full_size():
+    """MIBF-Net, B = 128, S = 256, 224x224, 6 classes: eval logits of the three heads and one MP-Loss train step vs the
+    fp32 oracle on the GPU."""
+    from mdhs_b200.mibf_net.model_resnet import Resnet50WithOurs
+    with quiet():
+        model = Resnet50WithOurs(num_labels=6, bert_path=bert_dir(), pretrained=False)
+    sd = weights.synth_state_dict(model.state_dict(), seed=4)
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    images, ids, mask, labels = weights.synthetic_batch(128, 256, 6, image_hw=224, unit_range=True)
+    ci, cd, cm, cl = images.cuda(), ids.cuda(), mask.cuda(), labels.cuda()
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        got = model({"transformed_image": ci, "input_ids": cd, "attention_mask": cm})
+        want = [port.mibf_forward(sdc, ci[i:i + 32], cd[i:i + 32], cm[i:i + 32]) for i in range(0, 128, 32)]
+    for key in ("image_text", "text", "image"):
+        w = torch.cat([o[key] for o in want])
+        e = rel(got[key], w)
+        print(f"[mibf S=256 eval] {key} rel {e:.3e}")
+        assert e < 2e-2, (key, e)
+    _top1_check(got["image_text"], torch.cat([o["image_text"] for o in want]))
+    # train step
+    model.train()
+    _zero_dropout(model)
+    out = model({"transformed_image": ci, "input_ids": cd, "attention_mask": cm})
+    _zero_dropout(model)
+    model.store("cuda").zero_grad()
+    out = model({"transformed_image": ci, "input_ids": cd, "attention_mask": cm})
+    loss = model.cal_loss(out, cl)
+    loss.backward()
+    torch.cuda.synchronize()
+
+    def fn(state):
+        o = port.mibf_forward(state, ci, cd, cm, training_bn=True)
+        ls = port.mp_loss(o["image"], o["text"], o["image_text"], cl)
+        ls.backward()
+        return o["image_text"].detach(), ls.item()
+    (want_logits, want_loss), state = _oracle_train(sd, "cuda", fn)
+    e = rel(out["image_text"].detach(), want_logits)
+    print(f"[mibf S=256 train] logits rel {e:.3e}, loss {loss.item():.5f} vs {want_loss:.5f}")
+    assert e < 6e-2
+    assert abs(loss.item() - want_loss) < 3e-2 * max(1.0, abs(want_loss))
+    res = _grad_checks(model, state, [("fc.weight", 0.97), ("fc_text.1.weight", 0.97), ("fc_image.3.weight", 0.97),
+                                      ("textbased_cross_attention.toV_y.weight", 0.95), ("imagbased_cross_attention.to_out.weight", 0.95),
+                                      ("text_encoder.bert.encoder.layer.11.output.dense.weight", 0.95),
+                                      ("text_encoder.bert.encoder.layer.0.attention.self.value.weight", 0.9),
+                                      ("image_encoder.fc.weight", 0.95), ("image_encoder.layer4.2.conv3.weight", 0.9)])
+    print(f"[mibf S=256 train] grad cosines {res}")
+
+
+# ---------------------------------------------------------------------------------------------- ConvNeXt-Base (the reference's width)
+def test_connext_base_eval_matches_oracle():
+    """OurClassfierConvnextV2 with the ConvNeXt-BASE trunk the reference uses (ourmodel.py:58), B = 16, 224x224, S = 64."""
+    from refutil import build_ours_connext
+    model = build_ours_connext("base", num_labels=7)
+    sd = weights.synth_state_dict(model.state_dict(), seed=5)
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    images, ids, mask, _ = weights.synthetic_batch(16, 64, 7, image_hw=224, unit_range=True)
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        got = model({"transformed_image": images.cuda(), "input_ids": ids.cuda(), "attention_mask": mask.cuda()}).float()
+        want = port.connext_forward(sdc, images.cuda(), ids.cuda(), mask.cuda())
+    e = rel(got, want)
+    print(f"[connext base eval] rel {e:.3e}")
+    assert e < 2e-2, e
+    _top1_check(got, want)

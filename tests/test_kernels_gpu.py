@@ -437,3 +437,93 @@ def test_supcon_loss_fwd_bwd(ops, B, D):
     loss, dx = ops.supcon_loss(x.cuda(), labels.cuda(), 0.07)
     assert abs(loss.item() - want.item()) <= 1e-4 * max(1.0, abs(want.item()))
     assert relerr(dx, xr.grad.cuda()) < 1e-3
+
+
+@pytest.mark.parametrize("rows,C,res", [(4 * 56 * 56, 64, False), (2 * 14 * 14, 1024, True), (1001, 256, True), (77, 2048, False)])
+def test_batchnorm_fwd_fused_equals_finalize_plus_apply(ops, rows, C, res):
+    """mdhs_bn_fwd (finalize + apply in one launch) is bit-identical to mdhs_bn_finalize + mdhs_bn_apply, in train mode
+    (incl. the running-statistics update) and in eval mode."""
+    torch.manual_seed(2)
+    x = (torch.randn(rows, C, device="cuda") * 1.5 + 0.3).bfloat16()
+    gamma = torch.rand(C, device="cuda") + 0.5
+    beta = torch.randn(C, device="cuda")
+    r = torch.randn(rows, C, device="cuda").bfloat16() if res else None
+    cs = torch.zeros(C, device="cuda", dtype=torch.float64)
+    cq = torch.zeros(C, device="cuda", dtype=torch.float64)
+    ops.col_stats(x, cs, cq)
+    for training in (True, False):
+        rm0, rv0 = torch.randn(C, device="cuda") * 0.1, torch.rand(C, device="cuda") + 0.5
+        rm1, rv1 = rm0.clone(), rv0.clone()
+        mean, invstd, scale, shift = ops.bn_finalize(cs if training else None, cq if training else None, rows, gamma, beta,
+                                                     rm0, rv0, 0.1, 1e-5, training=training)
+        y0 = ops.bn_apply(x, scale, shift, residual=r, relu=True)
+        y1, m1, i1, s1, h1 = ops.bn_fwd(x, cs if training else None, cq if training else None, gamma, beta, rm1, rv1, 0.1, 1e-5,
+                                        residual=r, relu=True, training=training)
+        assert torch.equal(y0, y1)
+        assert torch.equal(mean, m1) and torch.equal(invstd, i1) and torch.equal(scale, s1) and torch.equal(shift, h1)
+        assert torch.equal(rm0, rm1) and torch.equal(rv0, rv1)
+
+
+def test_batchnorm_bwd_eval_mode(ops):
+    """training=0: dx = gamma * rsqrt(running_var + eps) * dy' (what F.batch_norm(training=False) back-propagates);
+    dgamma / dbeta still are sum(dy' * xhat) / sum(dy')."""
+    torch.manual_seed(3)
+    rows, C = 1000, 256
+    x = (torch.randn(rows, C, device="cuda") * 1.5 + 0.3).bfloat16()
+    gamma = torch.rand(C, device="cuda") + 0.5
+    beta = torch.randn(C, device="cuda") * 0.3
+    rm, rv = torch.randn(C, device="cuda") * 0.2, torch.rand(C, device="cuda") + 0.5
+    y, mean, invstd, scale, shift = ops.bn_fwd(x, None, None, gamma, beta, rm, rv, 0.0, 1e-5, relu=True, training=False)
+    dy = torch.randn(rows, C, device="cuda").bfloat16()
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dx, _ = ops.bn_bwd(dy, x, None, mean, invstd, gamma, dg, db, relu=True, scale=scale, shift=shift, training=False)
+    xr = x.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    out = F.batch_norm(xr, rm, rv, gr, br, False, 0.0, 1e-5)
+    out.backward(dy.float() * (y.float() > 0))
+    assert relerr(dx, xr.grad) < 1e-2
+    assert relerr(dg, gr.grad) < 2e-3 and relerr(db, br.grad) < 2e-3
+
+
+@pytest.mark.parametrize("M,N,K,conv", [(4 * 28 * 28, 128, 512, None), (1000, 64, 256, None), (2 * 14 * 14, 256, 9 * 256, (2, 14, 14)),
+                                        (8 * 56 * 56, 64, 9 * 64, (8, 56, 56))])
+def test_gemm_epilogue_bn_backward_reduction(ops, M, N, K, conv):
+    """mdhs_gemm_args.stat_x: the dgrad GEMM that writes dy also accumulates sum(dy') and sum(dy' * (x - mean)) of the
+    producer BatchNorm (mask recomputed from the raw activation); feeding those sums to mdhs_bn_bwd(sums_ready) equals the
+    separate reduce pass."""
+    torch.manual_seed(4)
+    if conv is None:
+        a = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+        w = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
+        kw = {}
+    else:
+        Bc, H, W = conv
+        Co = K // 9
+        a = (torch.randn(M, Co, device="cuda") * 0.5).bfloat16()
+        w = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
+        kw = dict(conv=(1, Bc, H, W, Co, 3, 3, 1, 1), M=M, N=N, K=K)
+    x = (torch.randn(M, N, device="cuda") * 1.5 + 0.3).bfloat16()      # raw activation of the producer layer
+    gamma = torch.rand(N, device="cuda") + 0.5
+    beta = torch.randn(N, device="cuda") * 0.3
+    cs = torch.zeros(N, device="cuda", dtype=torch.float64)
+    cq = torch.zeros(N, device="cuda", dtype=torch.float64)
+    ops.col_stats(x, cs, cq)
+    y, mean, invstd, scale, shift = ops.bn_fwd(x, cs, cq, gamma, beta, None, None, 0.1, 1e-5, relu=True, training=True)
+    dy_plain = ops.gemm(a, w, **kw)
+    sums = torch.zeros(2, N, device="cuda", dtype=torch.float64)
+    dy = ops.gemm(a, w, stat_x=x, stat_mean=mean, stat_scale=scale, stat_shift=shift, stat_relu=True, colsum=sums[0],
+                  colsumsq=sums[1], **kw)
+    assert torch.equal(dy, dy_plain)
+    mask = (torch.addcmul(shift, x.float(), scale) > 0)      # fmaf(x, scale, shift): same rounding as the kernels up to ties
+    dm = dy.float() * (y.float() > 0)
+    want0 = dm.double().sum(0)
+    want1 = (dm.double() * (x.double() - mean.double())).sum(0)
+    assert relerr(sums[0].float(), want0.float()) < 2e-4, relerr(sums[0].float(), want0.float())
+    assert relerr(sums[1].float(), want1.float()) < 2e-4
+    del mask
+    dg0, db0 = torch.zeros(N, device="cuda"), torch.zeros(N, device="cuda")
+    dg1, db1 = torch.zeros(N, device="cuda"), torch.zeros(N, device="cuda")
+    dx0, _ = ops.bn_bwd(dy, x, None, mean, invstd, gamma, dg0, db0, relu=True, scale=scale, shift=shift)
+    dx1, _ = ops.bn_bwd(dy, x, None, mean, invstd, gamma, dg1, db1, relu=True, scale=scale, shift=shift, sums=sums)
+    assert relerr(dx1, dx0) < 4e-3
+    assert relerr(dg1, dg0) < 1e-4 and relerr(db1, db0) < 1e-4
