@@ -102,11 +102,11 @@ int mdhs_layernorm_bwd(const void* dy, int dy_f32, int64_t lddy, const void* x, 
  * mibf_net/model_resnet.py:15; eps 1e-5, momentum 0.1).  Train mode: the conv GEMM epilogue (or
  * mdhs_col_stats) produces fp64 per-channel sums; finalize turns them into mean/invstd, updates the
  * running statistics and emits scale/shift; apply fuses normalise + residual add + ReLU.
- * mdhs_bn_fwd = finalize + apply in ONE launch (every thread derives the scale / shift of its 8 channels from the fp64
- * sums -- or, training == 0, from the running statistics --; mean / invstd / scale / shift are published for the backward).
- * mdhs_bn_bwd = two launches (reduce, apply); relu != 0 masks dy with (y > 0); dz optionally receives the
+ * mdhs_bn_fwd = finalize + apply as one call (scale / shift from the fp64 sums or, training == 0, from the running
+ * statistics; mean / invstd / scale / shift are published for the backward).
+ * mdhs_bn_bwd = reduce, coefficients, apply; relu != 0 masks dy with (y > 0); dz optionally receives the
  * masked dy (gradient of the identity branch); dgamma/dbeta accumulate (+=).  Workspaces: sum_dy = sum(dy'),
- * sum_dy_xc = sum(dy' * (x - mean)) (fp64 [C] each); the per-channel coefficients are derived inside the apply kernel.
+ * sum_dy_xc = sum(dy' * (x - mean)) (fp64 [C] each) and coef (fp32 [5*C]).
  * With relu != 0 and y == NULL the mask is recomputed from x as fmaf(x, scale, shift) > 0 (bit-identical to what the
  * forward evaluated; only valid for layers without a residual input), which saves one full read of y in both passes.
  * training == 0: eval-mode backward, dx = gamma * invstd * dy' (running statistics are constants).
@@ -124,7 +124,7 @@ int mdhs_bn_fwd(const void* x, const double* colsum, const double* colsumsq, con
                 void* stream);
 int mdhs_bn_bwd(const void* dy, const void* x, const void* y, const float* mean, const float* invstd,
                 const float* gamma, const float* scale, const float* shift, double* sum_dy, double* sum_dy_xc,
-                void* dx, void* dz, float* dgamma, float* dbeta, int64_t rows, int C, int relu, int training,
+                float* coef, void* dx, void* dz, float* dgamma, float* dbeta, int64_t rows, int C, int relu, int training,
                 int sums_ready, void* stream);
 /* column sums of a bf16 [rows, C] matrix: fp64 sum / sum of squares (BN statistics) and/or fp32 += (bias grads) */
 int mdhs_col_stats(const void* x, int64_t ldx, double* sum64, double* sumsq64, float* sum32, int64_t rows, int C,
@@ -203,6 +203,12 @@ int mdhs_act_dropout_bwd(const void* dy, const void* aux, void* g, int64_t n, in
                          void* stream);
 int mdhs_relu_bwd_f32(const float* dy, const float* y, float* dx, int64_t n, void* stream);
 int mdhs_mul_f32(const float* a, const float* b, float* c, int64_t n, void* stream);
+/* adaptive level weighting of the hierarchical fusion (README.md:15; fusion_type "hierarchical"): out = sum_l softmax(logits)_l
+ * p[l] over L <= 4 fp32 vectors of n elements (p / dp are HOST arrays of device pointers); backward writes dp[l] = w_l * dout
+ * and accumulates dlogits (+=); g_ws = fp32 [4] workspace. */
+int mdhs_level_mix_fwd(const float* const* p, const float* logits, float* out, int64_t n, int L, void* stream);
+int mdhs_level_mix_bwd(const float* const* p, float* const* dp, const float* logits, const float* dout, float* g_ws,
+                       float* dlogits, int64_t n, int L, void* stream);
 int mdhs_dropout_f32(const float* x, float* y, int64_t n, float p, uint64_t seed, void* stream);
 /* global-local branch (model.py:292-315): out = a*x (+ b*y) on bf16 token tensors (0.5 * (global + local)); the
  * [global | centre-crop resized bilinearly, align_corners = False] image pair stacked on the batch axis */

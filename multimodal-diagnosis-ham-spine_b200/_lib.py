@@ -47,7 +47,7 @@ SIGNATURES = {
     "mdhs_bn_finalize": "pplppppffppppiip",
     "mdhs_bn_apply": "pppppliip",
     "mdhs_bn_fwd": "ppppppp" "ff" "pppppp" "liii" "p",
-    "mdhs_bn_bwd": "pppppppppppppp" "liiii" "p",
+    "mdhs_bn_bwd": "ppppppppppppppp" "liiii" "p",
     "mdhs_col_stats": "plppplip",
     "mdhs_im2col_nchw_f32": "ppiiiiiiiiip",
     "mdhs_im2col_nhwc": "ppiiiiiiiip",
@@ -77,6 +77,8 @@ SIGNATURES = {
     "mdhs_relu_bwd_f32": "ppplp",
     "mdhs_mul_f32": "ppplp",
     "mdhs_dropout_f32": "pplfup",
+    "mdhs_level_mix_fwd": "ppplip",
+    "mdhs_level_mix_bwd": "pppppplip",
     "mdhs_axpby_bf16": "ppplffp",
     "mdhs_global_local": "ppiiiifp",
     "mdhs_lstm_cell_fwd": "pppppiip",

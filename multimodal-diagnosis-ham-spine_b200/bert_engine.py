@@ -54,7 +54,9 @@ class BertEngine:
                 wi=layer.intermediate.dense, wo2=layer.output.dense, ln2=layer.output.LayerNorm))
 
     # ------------------------------------------------------------------ forward
-    def forward(self, input_ids, attention_mask, training, need_grad):
+    def forward(self, input_ids, attention_mask, training, need_grad, taps=()):
+        """taps: 1-based encoder-layer numbers whose OUTPUT hidden state is returned as well (HF `hidden_states[n]`,
+        `output_hidden_states=True`): forward returns (last_hidden, ctx, {n: hidden_n}) when taps is non-empty."""
         st = self.store
         B, S = input_ids.shape
         T, C, H, D = B * S, self.C, self.H, self.D
@@ -75,6 +77,7 @@ class BertEngine:
         ctx = dict(B=B, S=S, ids=ids, mask8=mask8, e=e, e_mean=e_mean, e_rstd=e_rstd, ph=ph, pa=pa, seed=seed,
                    layers=[]) if need_grad else None
         scale = 1.0 / math.sqrt(D)
+        tapped = {}
         for li, L in enumerate(self.layers):
             s0 = seed + 10 * (li + 1)
             qkv = ops.gemm(x, L["wqkv"][1], bias=L["bqkv"][0])
@@ -93,6 +96,10 @@ class BertEngine:
                 ctx["layers"].append(dict(x=x, qkv=qkv, att=att, lse=lse, pre1=pre1, m1=m1, r1=r1, h1=h1, ipre=ipre,
                                           inter=inter, pre2=pre2, m2=m2, r2=r2, s0=s0))
             x = h2
+            if (li + 1) in taps:
+                tapped[li + 1] = h2
+        if taps:
+            return x, ctx, tapped
         return x, ctx
 
     # ------------------------------------------------------------------ backward
@@ -122,15 +129,22 @@ class BertEngine:
             runtime.join_side(side)
         return dx
 
-    def backward(self, ctx, dh):
-        """dh: grad of the last hidden state, [B*S, C] bf16."""
+    def backward(self, ctx, dh, dtaps=None):
+        """dh: grad of the last hidden state, [B*S, C] bf16 (None = zero).  dtaps: {layer number: grad of that layer's output
+        hidden state} for the tapped hidden states of `forward(..., taps=...)`."""
         st = self.store
         B, S = ctx["B"], ctx["S"]
         C, H, D = self.C, self.H, self.D
         ph, pa = ctx["ph"], ctx["pa"]
         scale = 1.0 / math.sqrt(D)
         d = dh
+        dtaps = dtaps or {}
         for li in range(len(self.layers) - 1, -1, -1):
+            g_tap = dtaps.get(li + 1)
+            if g_tap is not None:
+                d = g_tap if d is None else ops.axpby_bf16(d, g_tap.contiguous(), 1.0, 1.0)
+            if d is None:
+                continue   # nothing downstream of this layer needs a gradient
             L, R = self.layers[li], ctx["layers"][li]
             s0 = R["s0"]
             ln2, ln1 = L["ln2"], L["ln1"]
@@ -158,7 +172,7 @@ class BertEngine:
             else:
                 d = ops.gemm(dqkv, L["wqkv"][1], b_mn=True, residual=dpre1)
         emb = self.bert.embeddings
-        if not emb.word_embeddings.weight.requires_grad:
+        if d is None or not emb.word_embeddings.weight.requires_grad:
             return
         _, _, de = ops.layernorm_bwd(d, ctx["e"], ctx["e_mean"], ctx["e_rstd"], emb.LayerNorm.weight.data,
                                      st.g32(emb.LayerNorm.weight), st.g32(emb.LayerNorm.bias), dx_bf16=False, dx_f32=True,

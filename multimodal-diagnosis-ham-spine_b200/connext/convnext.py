@@ -163,8 +163,9 @@ class ConvNeXtEngine:
         p = float(blk.stochastic_depth.p) if training else 0.0
         return _LayerScaleFn.apply(x, z, ls.data.view(-1), st.g32(ls).view(-1) if ls.requires_grad else None, H * W, p, seed)
 
-    def forward(self, images, training):
-        """images: [B,3,H,W] fp32 CUDA -> (tokens [B*h*w, C] bf16, h, w)."""
+    def forward(self, images, training, taps=None):
+        """images: [B,3,H,W] fp32 CUDA -> (tokens [B*h*w, C] bf16, h, w).  taps: optional list that receives
+        (tokens, h, w, C) after every residual stage (torchvision features[1], [3], [5], [7])."""
         st = self.store
         B, _, H, W = images.shape
         if training:
@@ -186,4 +187,6 @@ class ConvNeXtEngine:
                 for blk in payload:
                     n += 1
                     x = self._block(blk, x, B, H, W, training, self.step_seed + n)
+                if taps is not None:
+                    taps.append((x, H, W, x.shape[1]))
         return x, H, W

@@ -234,3 +234,13 @@ class KAN1(MdhsModule):
 
     def regularization_loss(self, regularize_activation=1.0, regularize_entropy=1.0):
         raise NotImplementedError("regularization_loss (kan1.py:216-236) is not used by any reference training loop")
+
+
+class KAN1Head(KAN1):
+    """KAN1 used as the classification head of MultimodalBaselineModel (`classifier_type="kan1"`): accepts the fused
+    (B, hidden) features in bf16 or fp32.  state_dict keys: classifier.layers.N.{base_weight,spline_weight,spline_scaler,grid}."""
+
+    def forward(self, x, update_grid=False):
+        from .. import functional as Fm
+        x32 = Fm.to_f32(x) if x.dtype == torch.bfloat16 else x.float()
+        return super().forward(x32, update_grid=update_grid)

@@ -296,3 +296,93 @@ extern "C" int mdhs_axpby_f32(const float* x, float* y, int64_t n, const float* 
   axpby_kernel<<<grid, 256, 0, ST(stream)>>>(x, y, n, a_dev, a, b);
   MDHS_RETURN_LAST();
 }
+
+// ---------------------------------------------------------------------------------------------
+// Adaptive level weighting of the hierarchical fusion (README.md:15 "layer-wise interaction with adaptive weighting"):
+// out = sum_l softmax(logits)_l * p_l over L <= 4 pooled feature sets [n] fp32.  Backward: dp_l = w_l * dout and
+// dlogits_l += w_l * (g_l - sum_k w_k g_k) with g_l = <dout, p_l> (block reduction + one atomic per block, then one thread).
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct LevelPtrs {
+  const float* p[4];
+  float* dp[4];
+};
+__device__ __forceinline__ void level_softmax(const float* logits, int L, float* w) {
+  float m = -INFINITY;
+  for (int l = 0; l < L; l++) m = fmaxf(m, logits[l]);
+  float s = 0.f;
+  for (int l = 0; l < L; l++) {
+    w[l] = __expf(logits[l] - m);
+    s += w[l];
+  }
+  for (int l = 0; l < L; l++) w[l] /= s;
+}
+__global__ void level_mix_fwd_kernel(LevelPtrs P, const float* __restrict__ logits, float* __restrict__ out, int64_t n, int L) {
+  float w[4];
+  level_softmax(logits, L, w);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int l = 0; l < L; l++) acc = fmaf(w[l], P.p[l][i], acc);
+    out[i] = acc;
+  }
+}
+__global__ void level_mix_bwd_kernel(LevelPtrs P, const float* __restrict__ logits, const float* __restrict__ dout, float* g_ws,
+                                     int64_t n, int L) {
+  __shared__ float red[32];
+  float w[4], g[4] = {0.f, 0.f, 0.f, 0.f};
+  level_softmax(logits, L, w);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float d = dout[i];
+    for (int l = 0; l < L; l++) {
+      g[l] = fmaf(d, P.p[l][i], g[l]);
+      P.dp[l][i] = w[l] * d;
+    }
+  }
+  for (int l = 0; l < L; l++) {
+    const float s = block_sum(g[l], red);
+    if (threadIdx.x == 0) atomicAdd(g_ws + l, s);
+  }
+}
+__global__ void level_mix_dlogits_kernel(const float* __restrict__ logits, const float* __restrict__ g_ws, float* dlogits, int L) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float w[4];
+  level_softmax(logits, L, w);
+  float mean = 0.f;
+  for (int l = 0; l < L; l++) mean = fmaf(w[l], g_ws[l], mean);
+  for (int l = 0; l < L; l++) dlogits[l] += w[l] * (g_ws[l] - mean);
+}
+}  // namespace
+
+extern "C" int mdhs_level_mix_fwd(const float* const* p, const float* logits, float* out, int64_t n, int L, void* stream) {
+  if (!p || !logits || !out || n <= 0 || L < 1 || L > 4) return MDHS_ERR_ARG;
+  LevelPtrs P = {};
+  for (int l = 0; l < L; l++) {
+    if (!p[l]) return MDHS_ERR_ARG;
+    P.p[l] = p[l];
+  }
+  int grid = (int)((n + 255) / 256);
+  if (grid > mdhs_num_sms() * 4) grid = mdhs_num_sms() * 4;
+  g_mdhs_launches++;
+  level_mix_fwd_kernel<<<grid, 256, 0, ST(stream)>>>(P, logits, out, n, L);
+  MDHS_RETURN_LAST();
+}
+
+// g_ws: fp32 [4] workspace.  dp[l] receive w_l * dout; dlogits (may be NULL) accumulates (+=).
+extern "C" int mdhs_level_mix_bwd(const float* const* p, float* const* dp, const float* logits, const float* dout, float* g_ws,
+                                  float* dlogits, int64_t n, int L, void* stream) {
+  if (!p || !dp || !logits || !dout || !g_ws || n <= 0 || L < 1 || L > 4) return MDHS_ERR_ARG;
+  LevelPtrs P = {};
+  for (int l = 0; l < L; l++) {
+    if (!p[l] || !dp[l]) return MDHS_ERR_ARG;
+    P.p[l] = p[l];
+    P.dp[l] = dp[l];
+  }
+  cudaError_t e = cudaMemsetAsync(g_ws, 0, 4 * sizeof(float), ST(stream));
+  if (e != cudaSuccess) return (int)e;
+  int grid = (int)((n + 255) / 256);
+  if (grid > mdhs_num_sms() * 4) grid = mdhs_num_sms() * 4;
+  g_mdhs_launches += 2;
+  level_mix_bwd_kernel<<<grid, 256, 0, ST(stream)>>>(P, logits, dout, g_ws, n, L);
+  if (dlogits) level_mix_dlogits_kernel<<<1, 32, 0, ST(stream)>>>(logits, g_ws, dlogits, L);
+  MDHS_RETURN_LAST();
+}

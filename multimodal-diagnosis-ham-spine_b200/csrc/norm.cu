@@ -262,15 +262,17 @@ __global__ void bn_finalize_kernel(const double* __restrict__ colsum, const doub
   if (c >= C) return;
   float mu, var;
   if (training) {
-    const double m = colsum[c] / (double)count;
-    double v = colsumsq[c] / (double)count - m * m;
+    const double inv_count = 1.0 / (double)count;
+    const double m = colsum[c] * inv_count;
+    double v = colsumsq[c] * inv_count - m * m;
     if (v < 0.0) v = 0.0;
     mu = (float)m;
     var = (float)v;
     if (running_mean) {
       const double unbiased = count > 1 ? v * (double)count / (double)(count - 1) : v;
-      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mu;
-      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+      // explicit fma form: identical rounding in bn_finalize_kernel and bn_fwd_kernel
+      running_mean[c] = fmaf(momentum, mu, (1.f - momentum) * running_mean[c]);
+      running_var[c] = fmaf(momentum, (float)unbiased, (1.f - momentum) * running_var[c]);
     }
   } else {
     mu = running_mean[c];
@@ -282,6 +284,22 @@ __global__ void bn_finalize_kernel(const double* __restrict__ colsum, const doub
   const float sc = gamma[c] * is;
   scale[c] = sc;
   shift[c] = beta[c] - mu * sc;
+}
+
+// 8 consecutive per-channel values with 128-bit loads (lanes of a warp read consecutive 32-byte / 64-byte pieces: fully
+// coalesced).  The scalar form -- 8 separate 4-byte loads at a 32-byte lane stride per array -- cost 8 L1 wavefronts per
+// load instruction and made the per-thread coefficient prologue, not HBM, the floor of the fused kernels (30 us on a 6 MB layer).
+__device__ __forceinline__ void ldvec8(const float* __restrict__ p, float* out) {
+  *reinterpret_cast<float4*>(out) = __ldg(reinterpret_cast<const float4*>(p));
+  *reinterpret_cast<float4*>(out + 4) = __ldg(reinterpret_cast<const float4*>(p + 4));
+}
+__device__ __forceinline__ void ldvec8(const double* __restrict__ p, double* out) {
+#pragma unroll
+  for (int i = 0; i < 4; i++) *reinterpret_cast<double2*>(out + 2 * i) = __ldg(reinterpret_cast<const double2*>(p + 2 * i));
+}
+__device__ __forceinline__ void stvec8(float* __restrict__ p, const float* v) {
+  *reinterpret_cast<float4*>(p) = *reinterpret_cast<const float4*>(v);
+  *reinterpret_cast<float4*>(p + 4) = *reinterpret_cast<const float4*>(v + 4);
 }
 
 // Shared streaming body of the two forward kernels: y = act(x * sc + sh (+ residual)), 8 channels per thread held in
@@ -352,56 +370,6 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ 
   *reinterpret_cast<float4*>(sc + 4) = *reinterpret_cast<const float4*>(scale + c0 + 4);
   *reinterpret_cast<float4*>(sh) = *reinterpret_cast<const float4*>(shift + c0);
   *reinterpret_cast<float4*>(sh + 4) = *reinterpret_cast<const float4*>(shift + c0 + 4);
-  bn_apply_stream(x, residual, y, sc, sh, i0, stride, total_vec, relu);
-}
-
-// Finalize + apply in ONE launch (round 2: the 53 bn_finalize launches of a ResNet-50 step cost ~5 us each for 64..2048
-// channels of work).  Every thread derives scale / shift of ITS 8 channels from the fp64 column sums (train) or the
-// running statistics (eval) with exactly bn_finalize_kernel's arithmetic; the first C/8 threads of the grid -- one per
-// channel vector -- also publish mean / invstd / scale / shift for the backward pass and update the running statistics.
-__global__ void __launch_bounds__(256) bn_fwd_kernel(const bf16* __restrict__ x, const double* __restrict__ colsum,
-                                                     const double* __restrict__ colsumsq, int64_t count,
-                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                     float* __restrict__ running_mean, float* __restrict__ running_var,
-                                                     float momentum, float eps, const bf16* __restrict__ residual,
-                                                     bf16* __restrict__ y, float* __restrict__ mean, float* __restrict__ invstd,
-                                                     float* __restrict__ scale, float* __restrict__ shift, int64_t total_vec,
-                                                     int C, int relu, int training) {
-  const int cvec = C >> 3;
-  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int c0 = (int)(i0 % cvec) * 8;
-  const bool publish = i0 < cvec;
-  float sc[8], sh[8];
-#pragma unroll
-  for (int k = 0; k < 8; k++) {
-    const int c = c0 + k;
-    float mu, var;
-    if (training) {
-      const double m = colsum[c] / (double)count;
-      double v = colsumsq[c] / (double)count - m * m;
-      if (v < 0.0) v = 0.0;
-      mu = (float)m;
-      var = (float)v;
-      if (publish && running_mean) {
-        const double unbiased = count > 1 ? v * (double)count / (double)(count - 1) : v;
-        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mu;
-        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
-      }
-    } else {
-      mu = running_mean[c];
-      var = running_var[c];
-    }
-    const float is = rsqrtf(var + eps);
-    sc[k] = gamma[c] * is;
-    sh[k] = beta[c] - mu * sc[k];
-    if (publish) {
-      if (mean) mean[c] = mu;
-      if (invstd) invstd[c] = is;
-      if (scale) scale[c] = sc[k];
-      if (shift) shift[c] = sh[k];
-    }
-  }
   bn_apply_stream(x, residual, y, sc, sh, i0, stride, total_vec, relu);
 }
 
@@ -517,49 +485,58 @@ __global__ void __launch_bounds__(32 * RL, 512 / (32 * RL)) bn_bwd_reduce_kernel
   }
 }
 
-// dx = ca[c] * dy' + cb[c] * x + cc[c]; optionally also writes dy' (the ReLU-masked incoming gradient) for the
-// identity branch.  Pure streaming, 8 channels per thread; the grid stride is a multiple of C/8 (see bn_apply), so the
-// per-channel coefficients of a thread's channel group live in registers.  Round 2: the coefficients are derived HERE from
-// the fp64 reductions (the separate 53 x ~4 us coefficient launches are gone):
+// Per-channel coefficients of the BN input gradient, from the fp64 reductions sum(dy') and sum(dy' * (x - mean)):
 //   train: dx = gamma*invstd * (dy' - sum_dy/M - xhat * sum_dy_xhat/M) = ca * dy' + cb * x + cc
 //   eval : dx = gamma*invstd * dy'   (running statistics are constants: F.batch_norm(training=False) backward)
-// and the first C/8 threads of the grid accumulate dgamma += sum(dy' * xhat), dbeta += sum(dy').
+// Also accumulates dgamma += sum(dy' * xhat), dbeta += sum(dy') (one thread per channel).
+// (Round 2 tried deriving these inside the apply kernel, per thread for its 8 channels: the fp64 prologue of ~600 k threads
+//  cost 20-30 us per launch -- profiles/r02_bn_microbench.md -- against ~4 us for this launch, so it stays separate.)
+__global__ void bn_bwd_coeff_kernel(const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ gamma, const double* __restrict__ sum_dy,
+                                    const double* __restrict__ sum_dy_xc, const float* __restrict__ scale,
+                                    const float* __restrict__ shift, float* __restrict__ coef, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta, int64_t rows, int C, int training) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double inv_m = 1.0 / (double)rows;
+  const double is = invstd[c], mu = mean[c], g = gamma[c];
+  const double s1 = sum_dy[c], s2 = sum_dy_xc[c] * is;    // s2 = sum(dy' * xhat)
+  const double ca = g * is;
+  const double cb = training ? -g * is * is * s2 * inv_m : 0.0;
+  coef[c] = (float)ca;
+  coef[C + c] = (float)cb;
+  coef[2 * C + c] = training ? (float)(-ca * s1 * inv_m - cb * mu) : 0.f;
+  if (scale) {
+    coef[3 * C + c] = scale[c];
+    coef[4 * C + c] = shift[c];
+  }
+  if (dgamma) {
+    dgamma[c] += (float)s2;
+    dbeta[c] += (float)s1;
+  }
+}
+
+// dx = ca[c] * dy' + cb[c] * x + cc[c]; optionally also writes dy' (the ReLU-masked incoming gradient) for the
+// identity branch.  Pure streaming, 8 channels per thread; the grid stride is a multiple of C/8 (see bn_apply), so the
+// five coefficient vectors of a thread's channel group are loaded once (128-bit loads).  coef rows 3 and 4 hold the forward
+// scale / shift when the ReLU mask is recomputed from x (y == nullptr).
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
-                                                           const bf16* __restrict__ y, const float* __restrict__ mean,
-                                                           const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                                           const float* __restrict__ scale, const float* __restrict__ shift,
-                                                           const double* __restrict__ sum_dy,
-                                                           const double* __restrict__ sum_dy_xc, bf16* __restrict__ dx,
-                                                           bf16* __restrict__ dz, float* __restrict__ dgamma,
-                                                           float* __restrict__ dbeta, int64_t rows, int C, int relu,
-                                                           int training) {
+                                                           const bf16* __restrict__ y, const float* __restrict__ coef,
+                                                           bf16* __restrict__ dx, bf16* __restrict__ dz, int64_t rows, int C,
+                                                           int relu) {
   const int cvec = C >> 3;
   const int64_t total_vec = rows * cvec;
   const bool remask = relu && (y == nullptr);
   const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int c0 = (int)(i0 % cvec) * 8;
-  const bool publish = i0 < cvec;
   float ca[8], cb[8], cc[8], sc[8], sf[8];
-  const double inv_m = 1.0 / (double)rows;
-#pragma unroll
-  for (int k = 0; k < 8; k++) {
-    const int c = c0 + k;
-    const double is = invstd[c], mu = mean[c], g = gamma[c];
-    const double s1 = sum_dy[c], s2 = sum_dy_xc[c] * is;     // s2 = sum(dy' * xhat)
-    const double a = g * is;
-    const double b = training ? -g * is * is * s2 * inv_m : 0.0;
-    ca[k] = (float)a;
-    cb[k] = (float)b;
-    cc[k] = training ? (float)(-a * s1 * inv_m - b * mu) : 0.f;
-    if (remask) {
-      sc[k] = scale[c];
-      sf[k] = shift[c];
-    }
-    if (publish && dgamma) {
-      dgamma[c] += (float)s2;
-      dbeta[c] += (float)s1;
-    }
+  ldvec8(coef + c0, ca);
+  ldvec8(coef + C + c0, cb);
+  ldvec8(coef + 2 * C + c0, cc);
+  if (remask) {
+    ldvec8(coef + 3 * C + c0, sc);
+    ldvec8(coef + 4 * C + c0, sf);
   }
   int64_t i = i0;
   for (; i + stride < total_vec; i += 2 * stride) {   // two independent row groups in flight per thread
@@ -688,7 +665,7 @@ static inline bool fold_view(int64_t rows, int C, int64_t ld, int64_t* rows_w, i
 }
 
 // Grid for the channel-vector streaming kernels: (grid * 256) % (C / 8) == 0, close to 16 blocks per SM.
-int grid_for_channels(int64_t total_vec, int C) {
+int grid_for_channels(int64_t total_vec, int C, int vec_per_thread = 1) {
   const int cvec = C >> 3;
   int a = cvec, b = 256;
   while (b) {
@@ -697,7 +674,8 @@ int grid_for_channels(int64_t total_vec, int C) {
     b = t;
   }
   const int unit = cvec / a;                     // grid must be a multiple of cvec / gcd(cvec, 256)
-  int64_t g = (total_vec + 255) / 256;
+  // vec_per_thread > 1: kernels with a per-thread coefficient prologue want it amortised over a few vectors
+  int64_t g = (total_vec + 256 * vec_per_thread - 1) / (256 * vec_per_thread);
   const int64_t cap = (int64_t)mdhs_num_sms() * 16;
   if (g > cap) g = cap;
   g = (g / unit) * unit;
@@ -803,18 +781,21 @@ extern "C" int mdhs_bn_apply(const void* x, const float* scale, const float* shi
   MDHS_RETURN_LAST();
 }
 
+// finalize + apply as one C-ABI call (two launches: the per-channel fp64 work runs once per channel, not once per thread)
 extern "C" int mdhs_bn_fwd(const void* x, const double* colsum, const double* colsumsq, const float* gamma, const float* beta,
                            float* running_mean, float* running_var, float momentum, float eps, const void* residual, void* y,
                            float* mean, float* invstd, float* scale, float* shift, int64_t rows, int C, int relu, int training,
                            void* stream) {
-  if (!x || !y || !gamma || !beta || rows <= 0 || C <= 0 || (C % 8)) return MDHS_ERR_ARG;
+  if (!x || !y || !gamma || !beta || !scale || !shift || rows <= 0 || C <= 0 || (C % 8)) return MDHS_ERR_ARG;
   if (training && (!colsum || !colsumsq)) return MDHS_ERR_ARG;
   if (!training && (!running_mean || !running_var)) return MDHS_ERR_ARG;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int64_t total_vec = rows * (C / 8);
-  g_mdhs_launches++;
-  bn_fwd_kernel<<<grid_for_channels(total_vec, C), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      (const bf16*)x, colsum, colsumsq, rows, gamma, beta, running_mean, running_var, momentum, eps, (const bf16*)residual,
-      (bf16*)y, mean, invstd, scale, shift, total_vec, C, relu, training);
+  g_mdhs_launches += 2;
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(colsum, colsumsq, rows, gamma, beta, running_mean, running_var, momentum,
+                                                       eps, mean, invstd, scale, shift, C, training);
+  bn_apply_kernel<<<grid_for_channels(total_vec, C), 256, 0, st>>>((const bf16*)x, scale, shift, (const bf16*)residual, (bf16*)y,
+                                                                  total_vec, C, relu);
   MDHS_RETURN_LAST();
 }
 
@@ -839,9 +820,9 @@ static void bn_reduce_cfg(int* rl, int* bps) {
 
 extern "C" int mdhs_bn_bwd(const void* dy, const void* x, const void* y, const float* mean, const float* invstd,
                            const float* gamma, const float* scale, const float* shift, double* sum_dy, double* sum_dy_xc,
-                           void* dx, void* dz, float* dgamma, float* dbeta, int64_t rows, int C, int relu, int training,
-                           int sums_ready, void* stream) {
-  if (!dy || !x || !mean || !invstd || !gamma || !sum_dy || !sum_dy_xc || !dx || rows <= 0 || (C % 8)) return MDHS_ERR_ARG;
+                           float* coef, void* dx, void* dz, float* dgamma, float* dbeta, int64_t rows, int C, int relu,
+                           int training, int sums_ready, void* stream) {
+  if (!dy || !x || !mean || !invstd || !gamma || !sum_dy || !sum_dy_xc || !coef || !dx || rows <= 0 || (C % 8)) return MDHS_ERR_ARG;
   if (relu && !y && (!scale || !shift)) return MDHS_ERR_ARG;   // the mask comes from y or is recomputed from scale / shift
   if ((dgamma == nullptr) != (dbeta == nullptr)) return MDHS_ERR_ARG;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -876,11 +857,13 @@ extern "C" int mdhs_bn_bwd(const void* dy, const void* x, const void* y, const f
       bn_bwd_reduce_kernel<8><<<grid, 256, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, mean, scale, shift, sum_dy,
                                                     sum_dy_xc, rows_w, C, Cw, rpb, relu);
   }
-  g_mdhs_launches++;
+  g_mdhs_launches += 2;
+  const bool remask = relu && !y;
+  bn_bwd_coeff_kernel<<<ceil_div(C, 128), 128, 0, st>>>(mean, invstd, gamma, sum_dy, sum_dy_xc, remask ? scale : nullptr,
+                                                        remask ? shift : nullptr, coef, dgamma, dbeta, rows, C, training);
   const int64_t total_vec = rows * (C / 8);
-  bn_bwd_apply_kernel<<<grid_for_channels(total_vec, C), 256, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, mean, invstd,
-                                                                       gamma, scale, shift, sum_dy, sum_dy_xc, (bf16*)dx,
-                                                                       (bf16*)dz, dgamma, dbeta, rows, C, relu, training);
+  bn_bwd_apply_kernel<<<grid_for_channels(total_vec, C), 256, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, coef,
+                                                                       (bf16*)dx, (bf16*)dz, rows, C, relu);
   MDHS_RETURN_LAST();
 }
 

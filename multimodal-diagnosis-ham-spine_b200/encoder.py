@@ -13,7 +13,7 @@ import os
 
 import torch
 import torch.nn as nn
-from torchvision.models import resnet18, resnet34, resnet50
+from torchvision.models import convnext_base, convnext_small, convnext_tiny, resnet18, resnet34, resnet50
 
 from . import functional as Fm
 from . import ops
@@ -178,17 +178,22 @@ def _fire_hooks(module, inp, out):
 
 class _BertFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, anchor, input_ids, attention_mask, engine, training, need):
+    def forward(ctx, anchor, input_ids, attention_mask, engine, training, need, taps):
+        if taps:
+            h, c, tapped = engine.forward(input_ids, attention_mask, training, need, taps=taps)
+            ctx.engine, ctx.c, ctx.taps = engine, c, tuple(taps)
+            return (h,) + tuple(tapped[n] for n in taps)
         h, c = engine.forward(input_ids, attention_mask, training, need)
-        ctx.engine, ctx.c = engine, c
+        ctx.engine, ctx.c, ctx.taps = engine, c, ()
         return h
 
     @staticmethod
-    def backward(ctx, dh):
+    def backward(ctx, dh, *dtaps):
         if ctx.c is not None:
-            ctx.engine.backward(ctx.c, dh.contiguous())
+            dt = {n: g for n, g in zip(ctx.taps, dtaps) if g is not None}
+            ctx.engine.backward(ctx.c, dh.contiguous() if dh is not None else None, dt or None)
         ctx.c = None
-        return None, None, None, None, None, None
+        return None, None, None, None, None, None, None
 
 
 _CHANNELS = {
@@ -197,6 +202,11 @@ _CHANNELS = {
     "resnet50": {"layer2": 512, "layer3": 1024, "layer4": 2048},
 }
 _BUILDERS = {"resnet18": resnet18, "resnet34": resnet34, "resnet50": resnet50}
+# ConvNeXt backbones (the reference only reaches ConvNeXt through ConNexT/models/ourmodel.py): the residual
+# stages 2 / 3 / 4 of torchvision `features` play the role of layer2 / layer3 / layer4
+_CONVNEXT = {"convnext_tiny": (convnext_tiny, {"layer2": 192, "layer3": 384, "layer4": 768}),
+             "convnext_small": (convnext_small, {"layer2": 192, "layer3": 384, "layer4": 768}),
+             "convnext_base": (convnext_base, {"layer2": 256, "layer3": 512, "layer4": 1024})}
 
 
 class ImageEncoder(MdhsModule):
@@ -206,10 +216,12 @@ class ImageEncoder(MdhsModule):
         super().__init__()
         self.multi_scale = multi_scale
         backbone = backbone.lower()
-        if backbone not in _BUILDERS:
-            raise ValueError(f"Unsupported backbone: {backbone}. Use resnet18, resnet34 or resnet50.")
-        build_model = _BUILDERS[backbone]
-        channels = _CHANNELS[backbone]
+        self.is_convnext = backbone in _CONVNEXT
+        if backbone not in _BUILDERS and not self.is_convnext:
+            raise ValueError(f"Unsupported backbone: {backbone}. Use resnet18, resnet34, resnet50, convnext_tiny, "
+                             "convnext_small or convnext_base.")
+        build_model = _CONVNEXT[backbone][0] if self.is_convnext else _BUILDERS[backbone]
+        channels = _CONVNEXT[backbone][1] if self.is_convnext else _CHANNELS[backbone]
         if weights_path:
             self.model = build_model(weights=None)
             if not os.path.exists(weights_path):
@@ -220,12 +232,17 @@ class ImageEncoder(MdhsModule):
             self.model = build_model(weights="DEFAULT")
         else:
             self.model = build_model(weights=None)
-        self.model.fc = nn.Identity()
-        self.stem = nn.Sequential(self.model.conv1, self.model.bn1, self.model.relu, self.model.maxpool)
-        self.layer1 = self.model.layer1
-        self.layer2 = self.model.layer2
-        self.layer3 = self.model.layer3
-        self.layer4 = self.model.layer4
+        if self.is_convnext:
+            # state_dict keys: image_encoder.model.features.* (torchvision ConvNeXt; avg-pool / classifier are bypassed)
+            self.model.classifier = nn.Identity()
+            self.model.avgpool = nn.Identity()
+        else:
+            self.model.fc = nn.Identity()
+            self.stem = nn.Sequential(self.model.conv1, self.model.bn1, self.model.relu, self.model.maxpool)
+            self.layer1 = self.model.layer1
+            self.layer2 = self.model.layer2
+            self.layer3 = self.model.layer3
+            self.layer4 = self.model.layer4
         if self.multi_scale:
             self.proj2 = nn.Linear(channels["layer2"], feature_dim)
             self.proj3 = nn.Linear(channels["layer3"], feature_dim)
@@ -233,10 +250,28 @@ class ImageEncoder(MdhsModule):
         object.__setattr__(self, "_engine", None)
 
     def _on_bind(self, store):
-        object.__setattr__(self, "_engine", ResNetEngine(store, self.model))
+        if self.is_convnext:
+            from .connext.convnext import ConvNeXtEngine
+            object.__setattr__(self, "_engine", ConvNeXtEngine(store, self.model.features))
+        else:
+            object.__setattr__(self, "_engine", ResNetEngine(store, self.model))
 
     def _trainable(self):
         return any(p.requires_grad for p in self.model.parameters())
+
+    def _forward_convnext(self, st, x):
+        """ConvNeXt trunk: autograd runs through the engine's own Functions; stage outputs are already NHWC token matrices."""
+        B = x.shape[0]
+        taps = []
+        self._engine.forward(x.float(), self.training, taps=taps)
+        stages = {"layer2": taps[1], "layer3": taps[2], "layer4": taps[3]}
+        names = ("layer2", "layer3", "layer4") if self.multi_scale else ("layer4",)
+        out = {}
+        for name in names:
+            proj = getattr(self, "proj" + name[-1])
+            t = Fm.linear(stages[name][0], st, proj.weight, proj.bias)
+            out[name] = t.view(B, -1, t.shape[1])
+        return out if self.multi_scale else out["layer4"]
 
     def _hooked_stages(self):
         """Analysis hooks (Grad-CAM: analysis_tools.py:29-31, scripts/run_analysis.py:126-132) on the stem or on a stage /
@@ -282,6 +317,8 @@ class ImageEncoder(MdhsModule):
 
     def forward(self, x):
         st = self.store(x.device)
+        if self.is_convnext:
+            return self._forward_convnext(st, x)
         B = x.shape[0]
         names = ("layer2", "layer3", "layer4") if self.multi_scale else ("layer4",)
         need = self._trainable() and torch.is_grad_enabled()
@@ -320,10 +357,25 @@ class TextEncoder(MdhsModule):
     def _on_bind(self, store):
         object.__setattr__(self, "_engine", BertEngine(store, self.model))
 
-    def forward(self, input_ids, attention_mask):
+    def forward(self, input_ids, attention_mask, hidden_states=None):
+        """hidden_states: optional tuple of encoder-layer numbers (1-based, HF `output_hidden_states` indexing): returns
+        {n: (B, S, 768)} of those layers' outputs instead of the last hidden state alone (README.md:15: text hidden states
+        4 / 8 / 12 paired with image layer2 / 3 / 4)."""
         st = self.store(input_ids.device)
         B, S = input_ids.shape
         trainable = any(p.requires_grad for p in self.model.encoder.parameters())
         need = trainable and torch.is_grad_enabled()
-        h = _BertFn.apply(st.anchor, input_ids, attention_mask, self._engine, self.training, need)
+        if hidden_states:
+            n_layers = len(self.model.encoder.layer)
+            taps = tuple(int(n) for n in hidden_states if int(n) != n_layers)
+            for n in taps:
+                if not 1 <= n <= n_layers:
+                    raise ValueError(f"hidden state {n} out of range 1..{n_layers}")
+            outs = _BertFn.apply(st.anchor, input_ids, attention_mask, self._engine, self.training, need, taps)
+            outs = outs if isinstance(outs, tuple) else (outs,)
+            res = {n: t.view(B, S, t.shape[1]) for n, t in zip(taps, outs[1:])}
+            if n_layers in [int(n) for n in hidden_states]:
+                res[n_layers] = outs[0].view(B, S, outs[0].shape[1])
+            return res
+        h = _BertFn.apply(st.anchor, input_ids, attention_mask, self._engine, self.training, need, ())
         return h.view(B, S, h.shape[1])

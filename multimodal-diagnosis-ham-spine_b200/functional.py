@@ -322,6 +322,28 @@ def supcon_loss(features, labels, temperature=0.07):
     return SupConFn.apply(features, labels, float(temperature))
 
 
+class LevelMixFn(torch.autograd.Function):
+    """sum_l softmax(logits)_l * p_l on fp32 (B, hidden) pooled features with LEARNABLE level logits (hierarchical fusion)."""
+
+    @staticmethod
+    def forward(ctx, logits, glogits, *levels):
+        levels = [t.contiguous() for t in levels]
+        ctx.logits, ctx.glogits = logits, glogits
+        ctx.save_for_backward(*levels)
+        return ops.level_mix_fwd(levels, logits)
+
+    @staticmethod
+    def backward(ctx, dout):
+        levels = list(ctx.saved_tensors)
+        dps = ops.level_mix_bwd(levels, ctx.logits, dout.contiguous(), ctx.glogits)
+        return (None, None) + tuple(dps)
+
+
+def level_mix(levels, store, logits_param):
+    g = store.g32(logits_param) if logits_param.requires_grad else None
+    return LevelMixFn.apply(logits_param.data, g, *levels)
+
+
 class AvgBf16Fn(torch.autograd.Function):
     """0.5 * (a + b) on bf16 token tensors (global / local token average, model.py:303-315)."""
 

@@ -23,5 +23,5 @@ class BertEncoder(MdhsModule):
         B, S = input_ids.shape
         trainable = any(p.requires_grad for p in self.bert.encoder.parameters())
         need = trainable and torch.is_grad_enabled()
-        h = _BertFn.apply(st.anchor, input_ids, attention_mask, self._engine, self.training, need)
+        h = _BertFn.apply(st.anchor, input_ids, attention_mask, self._engine, self.training, need, ())
         return h.view(B, S, h.shape[1])[:, 0, :]

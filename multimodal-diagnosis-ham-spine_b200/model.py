@@ -15,7 +15,7 @@ import torch.nn as nn
 from . import functional as Fm
 from .encoder import ImageEncoder, MdhsModule, TextEncoder
 from .modules.fusion_blocks import (BilinearFusionModule, ConcatFusionModule, FusionModule, HadamardFusionModule,
-                                    MultiScaleFusionModule, SSMFusionModule, VMambaFusionModule,
+                                    HierarchicalFusionModule, MultiScaleFusionModule, SSMFusionModule, VMambaFusionModule,
                                     WeightedConcatFusionModule, _pool_image)
 from .modules.gating import DualExpertGate
 from .modules.heads import AttentionPoolingClassifier, MLPHead, ResidualClassifier, build_kan_head
@@ -73,7 +73,7 @@ class MultimodalBaselineModel(MdhsModule):
 
         self.image_encoder = ImageEncoder(feature_dim=hidden_dim, pretrained=pretrained_image,
                                           weights_path=image_weights_path, backbone=image_backbone,
-                                          multi_scale=(fusion_type == "multiscale"))
+                                          multi_scale=(fusion_type in ("multiscale", "hierarchical")))
         if self.sequence_enabled:   # model.py:81-95
             self.sequence_encoder = SequenceEncoder(input_dim=hidden_dim, hidden_dim=sequence_hidden_dim, encoder_type=sequence_type,
                                                     num_layers=sequence_num_layers, bidirectional=sequence_bidirectional,
@@ -84,7 +84,11 @@ class MultimodalBaselineModel(MdhsModule):
             self.global_local_proj = nn.Linear(hidden_dim * 2, hidden_dim)   # model.py:97-99 (unused by the multiscale dict path)
         self.text_encoder = TextEncoder(model_path=text_model_name, feature_dim=text_feature_dim)
 
-        if fusion_type == "multiscale":
+        if fusion_type == "hierarchical":
+            # README.md:15 (image layer2/3/4 x BERT hidden 4/8/12 with adaptive weighting); opt-in, no reference code
+            self.fusion = HierarchicalFusionModule(text_dim=text_feature_dim, hidden_dim=hidden_dim, num_heads=num_heads,
+                                                   dropout=fusion_dropout)
+        elif fusion_type == "multiscale":
             self.fusion = MultiScaleFusionModule(text_dim=text_feature_dim, hidden_dim=hidden_dim, num_heads=num_heads,
                                                  dropout=fusion_dropout)
         elif fusion_type == "hadamard":
@@ -117,7 +121,12 @@ class MultimodalBaselineModel(MdhsModule):
                                        use_entropy=gate_use_entropy)
 
         self.classifier_type = classifier_type
-        if classifier_type == "kan":
+        if classifier_type == "kan1":
+            # KAN head variant of BASELINE config 5: the vendored efficient-KAN of ConNexT/models/block/kan1.py
+            # (KAN1([hidden, 256, C])) in place of the un-vendored GroupKAN of classifier_type="kan"
+            from .connext.kan1 import KAN1Head
+            self.classifier = KAN1Head([hidden_dim, 256, num_classes])
+        elif classifier_type == "kan":
             self.classifier = build_kan_head(hidden_dim=hidden_dim, num_classes=num_classes, dropout=head_dropout,
                                              num_groups=kan_num_groups, act_mode=kan_act_mode)
         elif classifier_type == "residual":
@@ -131,12 +140,20 @@ class MultimodalBaselineModel(MdhsModule):
     def forward_features(self, image_input, text_input_ids, text_attention_mask, tabular_input=None, ablation_mode=None):
         self.store(image_input.device)
         image_tokens, pooled_image = self._encode_image_tokens(image_input, want_pooled=(ablation_mode == "image_only"))
+        return self._features_from_tokens(image_tokens, pooled_image, text_input_ids, text_attention_mask, tabular_input,
+                                          ablation_mode)
+
+    def _features_from_tokens(self, image_tokens, pooled_image, text_input_ids, text_attention_mask, tabular_input,
+                              ablation_mode, text_tokens=None):
+        """model.py:212-237 after the image encoder: ablation switch, text encoder, fusion, tabular fusion."""
         if ablation_mode == "image_only":
             return pooled_image
-        text_tokens = self.text_encoder(text_input_ids, text_attention_mask)
+        if text_tokens is None:
+            text_tokens = self._encode_text(text_input_ids, text_attention_mask)
         if ablation_mode == "text_off":
-            text_tokens = torch.zeros_like(text_tokens)
-        if self.sequence_enabled and self.fusion_type == "multiscale" and not isinstance(image_tokens, dict):
+            text_tokens = ({k: torch.zeros_like(v) for k, v in text_tokens.items()} if isinstance(text_tokens, dict)
+                           else torch.zeros_like(text_tokens))
+        if self.sequence_enabled and self.fusion_type in ("multiscale", "hierarchical") and not isinstance(image_tokens, dict):
             image_tokens = {"layer2": image_tokens, "layer3": image_tokens, "layer4": image_tokens}   # model.py:220-225
         fused = self.fusion(image_tokens, text_tokens, text_attention_mask)
         if self.tabular_enabled:   # model.py:229-235
@@ -153,10 +170,26 @@ class MultimodalBaselineModel(MdhsModule):
                                           ablation_mode=ablation_mode)
             return self.classifier(fused)
         context_mode = None if self.gate_context_mode == "full" else self.gate_context_mode
-        context_feat = self.forward_features(image_input, text_input_ids, text_attention_mask, tabular_input=tabular_input,
-                                             ablation_mode=context_mode)
-        local_feat = self.forward_features(image_input, text_input_ids, text_attention_mask, tabular_input=tabular_input,
-                                           ablation_mode=self.gate_local_mode)
+        if self.training:
+            # the reference runs the whole feature path twice (model.py:257-271); in train mode that is observable
+            # (BatchNorm running statistics see two momentum updates), so it is kept
+            context_feat = self.forward_features(image_input, text_input_ids, text_attention_mask, tabular_input=tabular_input,
+                                                 ablation_mode=context_mode)
+            local_feat = self.forward_features(image_input, text_input_ids, text_attention_mask, tabular_input=tabular_input,
+                                               ablation_mode=self.gate_local_mode)
+        else:
+            # inference: ONE image-encoder pass and at most ONE text-encoder pass feed both experts (same numbers: eval-mode
+            # encoders are deterministic functions of the input)
+            self.store(image_input.device)
+            modes = (context_mode, self.gate_local_mode)
+            image_tokens, pooled = self._encode_image_tokens(image_input, want_pooled=("image_only" in modes))
+            text_tokens = None
+            if any(m != "image_only" for m in modes):
+                text_tokens = self._encode_text(text_input_ids, text_attention_mask)
+            context_feat = self._features_from_tokens(image_tokens, pooled, text_input_ids, text_attention_mask, tabular_input,
+                                                      context_mode, text_tokens)
+            local_feat = self._features_from_tokens(image_tokens, pooled, text_input_ids, text_attention_mask, tabular_input,
+                                                    self.gate_local_mode, text_tokens)
         logits_context = self.classifier(context_feat)
         logits_local = self.classifier(local_feat)
         entropy = None
@@ -165,6 +198,12 @@ class MultimodalBaselineModel(MdhsModule):
             entropy = -(probs * (probs + 1e-8).log()).sum(dim=1, keepdim=True)
         alpha = self.gate(local_feat, context_feat, entropy)
         return alpha * logits_local + (1 - alpha) * logits_context
+
+    def _encode_text(self, text_input_ids, text_attention_mask):
+        if self.fusion_type == "hierarchical":
+            return self.text_encoder(text_input_ids, text_attention_mask,
+                                     hidden_states=tuple(l for _, l in HierarchicalFusionModule.LEVELS))
+        return self.text_encoder(text_input_ids, text_attention_mask)
 
     def _pool_image_tokens(self, image_tokens):
         return _pool_image(image_tokens)

@@ -179,6 +179,35 @@ class MultiScaleFusionModule(MdhsModule):
         return pooled
 
 
+class HierarchicalFusionModule(MdhsModule):
+    """Hierarchical features (README.md:15, "provide-题4": image layer2 / 3 / 4 x text hidden states 4 / 8 / 12, layer-wise
+    interaction with adaptive weighting).  The reference describes this variant but ships no code for it, so the definition
+    is ours, assembled from the reference's own pieces: one CrossAttentionBlock (fusion_blocks.py:103-128) per level -- image
+    tokens of layer{2,3,4} attend to the BERT hidden state of encoder layer {4,8,12} --, token mean, and a learnable
+    softmax weighting `level_logits` (3,) of the three pooled vectors (zeros at init = the plain average of the multiscale
+    module).  `fusion_type="hierarchical"`; parity is pinned against oracle.port.fusion_hierarchical only."""
+
+    LEVELS = (("layer2", 4), ("layer3", 8), ("layer4", 12))
+
+    def __init__(self, text_dim, hidden_dim, num_heads=4, dropout=0.1):
+        super().__init__()
+        self.cross_l2 = CrossAttentionBlock(text_dim, hidden_dim, num_heads, dropout)
+        self.cross_l3 = CrossAttentionBlock(text_dim, hidden_dim, num_heads, dropout)
+        self.cross_l4 = CrossAttentionBlock(text_dim, hidden_dim, num_heads, dropout)
+        self.level_logits = nn.Parameter(torch.zeros(3))
+
+    def forward(self, img_tokens, txt_hidden, txt_mask=None):
+        """img_tokens: {"layer2|3|4": (B, N_l, hidden)}; txt_hidden: {4|8|12: (B, S, text_dim)}."""
+        any_t = next(iter(txt_hidden.values()))
+        st = self.store(any_t.device)
+        pooled = []
+        for (key, lvl), blk in zip(self.LEVELS, (self.cross_l2, self.cross_l3, self.cross_l4)):
+            t = blk(img_tokens[key], txt_hidden[lvl], txt_mask)
+            t2, B, N = _tok2d(t)
+            pooled.append(Fm.mean_tokens(t2, B, N))
+        return Fm.level_mix(pooled, st, self.level_logits)
+
+
 def _pool_image(image_tokens):
     """mean over tokens; a multi-scale dict averages the three pooled vectors (fusion_blocks.py:174-181)."""
     if isinstance(image_tokens, dict):

@@ -155,7 +155,7 @@ def bn_apply(x, scale, shift, residual=None, relu=True, out=None):
 
 
 def bn_fwd(x, colsum, colsumsq, gamma, beta, running_mean, running_var, momentum, eps, residual=None, relu=True, training=True):
-    """Finalize + apply in one launch.  Returns (y, mean, invstd, scale, shift)."""
+    """Finalize + apply in one C-ABI call.  Returns (y, mean, invstd, scale, shift)."""
     rows, C = x.shape
     stats = torch.empty((4, C), device=x.device, dtype=torch.float32)
     y = torch.empty_like(x)
@@ -171,11 +171,12 @@ def bn_bwd(dy, x, y, mean, invstd, gamma, dgamma, dbeta, relu=True, want_dz=Fals
     sums: optional fp64 [2, C] workspace already holding sum(dy'), sum(dy' * (x - mean)) (GEMM-epilogue fused reduction)."""
     rows, C = x.shape
     ws = torch.empty((2, C), device=x.device, dtype=torch.float64) if sums is None else sums
+    coef = torch.empty((5, C), device=x.device, dtype=torch.float32)
     dx = torch.empty_like(x)
     dz = torch.empty_like(x) if want_dz else None
     _lib.call("mdhs_bn_bwd", _p(dy), _p(x), _p(y), _p(mean), _p(invstd), _p(gamma), _p(scale), _p(shift), ws[0].data_ptr(),
-              ws[1].data_ptr(), _p(dx), _p(dz), _p(dgamma), _p(dbeta), rows, C, int(relu), int(training), int(sums is not None),
-              _s())
+              ws[1].data_ptr(), _p(coef), _p(dx), _p(dz), _p(dgamma), _p(dbeta), rows, C, int(relu), int(training),
+              int(sums is not None), _s())
     return dx, dz
 
 
@@ -609,6 +610,31 @@ def tta_expand(images, transforms):
     y = torch.empty((len(names) * B, C, H, W), device=x.device, dtype=torch.float32)
     _lib.call("mdhs_tta_expand", _p(x), _p(y), B, C, H, W, len(names), codes, _s())
     return y
+
+
+def _ptr_array(tensors):
+    import ctypes as _ct
+    arr = (_ct.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    return arr
+
+
+def level_mix_fwd(levels, logits):
+    """out = sum_l softmax(logits)_l * levels[l]; levels: list of same-shaped contiguous fp32 tensors (L <= 4)."""
+    import ctypes as _ct
+    out = torch.empty_like(levels[0])
+    arr = _ptr_array(levels)
+    _lib.call("mdhs_level_mix_fwd", _ct.cast(arr, _ct.c_void_p), _p(logits), _p(out), out.numel(), len(levels), _s())
+    return out
+
+
+def level_mix_bwd(levels, logits, dout, dlogits):
+    import ctypes as _ct
+    dps = [torch.empty_like(t) for t in levels]
+    ws = torch.empty(4, device=dout.device, dtype=torch.float32)
+    pa, da = _ptr_array(levels), _ptr_array(dps)
+    _lib.call("mdhs_level_mix_bwd", _ct.cast(pa, _ct.c_void_p), _ct.cast(da, _ct.c_void_p), _p(logits), _p(dout), _p(ws),
+              _p(dlogits), dout.numel(), len(levels), _s())
+    return dps
 
 
 def axpby_bf16(x, y, a, b):

@@ -30,6 +30,8 @@ FUSE_BN_STATS_MIN_K = int(_os.environ.get("MDHS_FUSE_BN_MIN_K", "100"))
 # backward: sum(dy'), sum(dy' (x - mean)) of the PRODUCER layer's BatchNorm taken in the epilogue of the dgrad GEMM that
 # writes dy (the raw activation arrives through the prefetched operand box), so the separate reduce pass disappears
 FUSE_BN_BWD_REDUCE = _os.environ.get("MDHS_FUSE_BN_BWD", "1") != "0"
+# 1x1 dgrad GEMMs carry the fused reduction only when their reduction (= the conv's output channels) is at least this long
+FUSE_BN_BWD_MIN_K = int(_os.environ.get("MDHS_FUSE_BN_BWD_MIN_K", "1024"))
 
 
 _nullctx = contextlib.nullcontext
@@ -261,8 +263,11 @@ class ResNetEngine:
         dx = None
         if need_dx:
             skw = {}
+            # (measured, tools/bench_gemm_step.py: the column pass is free under a main-loop-bound GEMM -- 3x3 dgrad, K >= 576 --
+            #  but an epilogue-bound 1x1 dgrad with a short reduction pays more for it than the separate reduce kernel costs:
+            #  401408x64x256: 43 -> 86 us against a 28 us reduce; 25088x256x1024: 19 -> 27 us against 13 us)
             if (producer is not None and self._bwd_ws is not None and c.dgrad_fusable and add_to_dx is None
-                    and producer["y"] is None):
+                    and producer["y"] is None and (c.implicit_dgrad or c.O >= FUSE_BN_BWD_MIN_K)):
                 pc = producer["c"]
                 sums = self._bwd_ws[pc.stats_off:pc.stats_off + 2 * pc.O].view(2, pc.O)
                 skw = dict(stat_x=producer["raw"], stat_mean=producer["mean"], stat_scale=producer["scale"],

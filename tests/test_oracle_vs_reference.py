@@ -206,3 +206,21 @@ def test_sequence_lstm_branch_matches_reference(fusion, layers, bidir, hid, kind
         want = ref(images, ids[:2], mask[:2])
         got = port.model_forward(sd, images, ids[:2], mask[:2], fusion=fusion, head="mlp")
     assert rel(got, want) < 1e-5
+
+
+def test_bert_hidden_states_4_8_12_match_hf():
+    """The hierarchical variant (README.md:15) consumes BERT hidden states 4 / 8 / 12: the oracle's truncated forward
+    (num_layers = n) equals transformers' `output_hidden_states=True` tuple at index n."""
+    from transformers import BertModel
+    from refutil import bert_dir
+    with quiet():
+        bert = BertModel.from_pretrained(bert_dir()).eval()
+    sd = {"text_encoder.model." + k: v for k, v in weights.synth_state_dict(bert.state_dict(), seed=3).items()}
+    bert.load_state_dict({k[len("text_encoder.model."):]: v for k, v in sd.items()})
+    _, ids, mask, _ = weights.synthetic_batch(3, 12, 7, image_hw=32)
+    with torch.no_grad():
+        hs = bert(input_ids=ids, attention_mask=mask, output_hidden_states=True).hidden_states
+        for n in (4, 8, 12):
+            got = port.bert_last_hidden(sd, "text_encoder.model.", ids, mask, num_layers=n)
+            valid = mask.bool()
+            assert rel(got[valid], hs[n][valid]) < 1e-5, n

@@ -52,6 +52,18 @@ CASES = [
     ("l4_1x1_2048_512", 6272, 512, 2048, 0, 0, {}),
     ("l3_wgrad_1024_256", 1024, 256, 25088, 1, 1, dict(acc=1)),
     ("l1_wgrad_256_64", 256, 64, 401408, 1, 1, dict(acc=1)),
+    # implicit-GEMM 3x3 convolutions (TMA im2col operand): conv = (B, H, W, C_in); fprop / stride-1 dgrad share the shape
+    ("l1_conv3x3_fprop", 401408, 64, 576, 0, 0, dict(conv=(128, 56, 56, 64), colsum=1)),
+    ("l2_conv3x3_fprop", 100352, 128, 1152, 0, 0, dict(conv=(128, 28, 28, 128), colsum=1)),
+    ("l3_conv3x3_fprop", 25088, 256, 2304, 0, 0, dict(conv=(128, 14, 14, 256), colsum=1)),
+    ("l4_conv3x3_fprop", 6272, 512, 4608, 0, 0, dict(conv=(128, 7, 7, 512), colsum=1)),
+    ("l1_conv3x3_dgrad_stat", 401408, 64, 576, 0, 0, dict(conv=(128, 56, 56, 64), stat=1)),
+    ("l3_conv3x3_dgrad_stat", 25088, 256, 2304, 0, 0, dict(conv=(128, 14, 14, 256), stat=1)),
+    ("l1_conv3x3_wgrad", 64, 576, 401408, 1, 1, dict(acc=1, wconv=(128, 56, 56, 64))),
+    ("l3_conv3x3_wgrad", 256, 2304, 25088, 1, 1, dict(acc=1, wconv=(128, 14, 14, 256))),
+    ("l1_1x1_64_256_colsum", 401408, 256, 64, 0, 0, dict(colsum=1)),
+    ("l1_dgrad_256_64_stat", 401408, 64, 256, 0, 1, dict(stat=1)),
+    ("l3_dgrad_1024_256_stat", 25088, 256, 1024, 0, 1, dict(stat=1)),
 ]
 
 
@@ -64,9 +76,29 @@ def main():
             continue
         sets = []
         for _ in range(ROT):
-            a = torch.randn((K, M) if a_mn else (M, K), device=dev).mul_(0.5).bfloat16()
-            b = torch.randn((K, N) if b_mn else (N, K), device=dev).mul_(0.05).bfloat16()
+            if o.get("conv"):
+                cb, ch, cw, cc = o["conv"]
+                a = torch.randn((cb * ch * cw, cc), device=dev).mul_(0.5).bfloat16()
+            else:
+                a = torch.randn((K, M) if a_mn else (M, K), device=dev).mul_(0.5).bfloat16()
+            if o.get("wconv"):
+                cb, ch, cw, cc = o["wconv"]
+                b = torch.randn((cb * ch * cw, cc), device=dev).mul_(0.5).bfloat16()
+            else:
+                b = torch.randn((K, N) if b_mn else (N, K), device=dev).mul_(0.05).bfloat16()
             kw = dict(a_mn=bool(a_mn), b_mn=bool(b_mn), bn_hint=o.get("bn", bn_hint))
+            if o.get("conv"):
+                kw.update(conv=(1, cb, ch, cw, cc, 3, 3, 1, 1), M=M, N=N, K=K)
+            if o.get("wconv"):
+                kw.update(conv=(2, cb, ch, cw, cc, 3, 3, 1, 1), M=M, N=N, K=K)
+            if o.get("colsum"):
+                st_ = torch.zeros(2, N, device=dev, dtype=torch.float64)
+                kw.update(colsum=st_[0], colsumsq=st_[1])
+            if o.get("stat"):
+                st_ = torch.zeros(2, N, device=dev, dtype=torch.float64)
+                kw.update(colsum=st_[0], colsumsq=st_[1], stat_x=torch.randn(M, N, device=dev).bfloat16(),
+                          stat_mean=torch.zeros(N, device=dev), stat_scale=torch.ones(N, device=dev),
+                          stat_shift=torch.zeros(N, device=dev), stat_relu=True)
             if o.get("acc"):
                 kw.update(out=torch.zeros(M, N, device=dev), accumulate=True, split_k=-1)
             else:
