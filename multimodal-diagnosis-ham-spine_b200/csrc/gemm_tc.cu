@@ -28,6 +28,9 @@ constexpr int NUM_THREADS = 384;  // 4 control warps + 8 epilogue warps
 constexpr int EPI_WARP0 = 4;
 constexpr int A_TILE_BYTES = BM * BK * 2;                    // 16 KiB
 constexpr int SMEM_LIMIT = 232448;                           // 227 KiB opt-in maximum
+#ifndef MDHS_GEMM_PINGPONG
+#define MDHS_GEMM_PINGPONG 1
+#endif
 
 // LD = the epilogue reads bf16 operand boxes (act'(aux_in) and / or a bf16 residual): they are prefetched by TMA into a
 // dedicated shared-memory box per epilogue warp group, one tile ahead of the accumulator, so their HBM latency is
@@ -41,16 +44,27 @@ template <int BN, bool LD, int CL = 1, bool AUX = false> struct Cfg {
   // AUX (a second output tensor: pre-activation / GELU' copy) owns its own staging boxes and pays one pipeline stage
   static constexpr int STAGES_BASE = CL == 2 ? (BN == 256 ? 6 : (BN == 64 ? 8 : (LD ? 6 : 8)))
                                              : ((BN == 256) ? 4 : (BN == 128 ? (LD ? 5 : 6) : (LD ? 7 : 8)));
-  static constexpr int STAGES = STAGES_BASE - (AUX ? (STAGE_BYTES <= 24576 ? 2 : 1) : 0);
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int BAR_BYTES = 256;
-  // two 16 KiB output staging boxes (128 rows x 128 bytes, 128B-swizzled) feeding the TMA store / reduce-add
-  static constexpr int STAGING_BYTES = (AUX ? 4 : 2) * 16384;
   static constexpr int EPI_GROUPS = (BN == 64) ? 1 : 2;   // warp groups (4 warps each) that drain the accumulator
+  // Output staging: 16 KiB boxes (128 rows x 128 bytes, 128B-swizzled) feeding the TMA store / reduce-add.  PP = each warp
+  // group owns TWO boxes and alternates: the next box is assembled while the TMA engine still reads the previous one
+  // (`wait_group.read 1`).  With a single box every output box paid the store's shared-memory read latency in series --
+  // ncu on the output-bound layer-1 GEMMs (K = 64 .. 256, one to four k-blocks per tile): DRAM 40 %, tensor 5-10 %, the
+  // epilogue warps parked on the named barrier behind `cp.async.bulk.wait_group.read 0`.  AUX kernels (second output
+  // tensor) keep one box per tensor.
+  static constexpr bool PP = !AUX && (MDHS_GEMM_PINGPONG != 0);
+  static constexpr int STAGING_BYTES = AUX ? 4 * 16384 : (PP ? 2 * EPI_GROUPS : 2) * 16384;
   // operand boxes in flight per epilogue warp group.  Two slots (and one pipeline stage less) were measured: no gain on
   // the epilogue-bound GEMMs and -6 % on the main-loop-bound ones, so one slot it is.
   static constexpr int IN_SLOTS = 1;
   static constexpr int IN_BYTES = LD ? EPI_GROUPS * IN_SLOTS * 16384 : 0;
+  // pipeline depth: the table above, minus what the staging / operand boxes take from the 227 KiB
+  static constexpr int fit_stages(int st) {
+    while (st > 2 && 1024 + st * STAGE_BYTES + STAGING_BYTES + IN_BYTES + BAR_BYTES > SMEM_LIMIT) --st;
+    return st;
+  }
+  static constexpr int STAGES = fit_stages(STAGES_BASE);
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + IN_BYTES + BAR_BYTES;
   static_assert(SMEM_BYTES <= SMEM_LIMIT, "shared memory budget exceeded");
 };
@@ -210,6 +224,7 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void named_bar(int id, int threads) {
@@ -494,13 +509,56 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (whole warp walks the loop, one lane issues)
+    // im2col coordinates are carried INCREMENTALLY: ncu's source view of the 3x3 convolutions showed this warp, not the
+    // tensor pipe, pacing the kernel -- five integer divisions per k-block (~160 dependent instructions, ~800 clk) against
+    // 128-256 clk of MMA work per k-block (tensor pipe 14 % / 32 % active, `empty` barrier never waited on).  Now the
+    // per-tile pixel -> (image, row, column) split happens once per tile and (tap row, tap column, channel block) /
+    // (image, row, column of the k-th pixel block) advance with adds and compares.
     int stage = 0;
     uint32_t phase = 0;
+    const int HoWo = p.cHo * p.cWo;
+    const int bk_rows = (B_MN && p.conv_mode == 2) ? BK / p.cWo : 0;          // 64 pixels = bk_rows full rows + bk_cols pixels
+    const int bk_cols = (B_MN && p.conv_mode == 2) ? BK - bk_rows * p.cWo : 0;
     for (int t = w0; t < total_tiles; t += wstep) {
       int split, n_blk, m_blk;
       decode(t, split, n_blk, m_blk);
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      // ---- conv_mode 1 (A = im2col(X)): base coordinates of this tile's first output pixel; tap / channel-block counters
+      int a_w = 0, a_h = 0, a_img = 0, tap_r = 0, tap_s = 0, cb = 0;
+      if (!A_MN && p.conv_mode == 1) {
+        const int pix = m_blk * BM;
+        a_img = pix / HoWo;
+        const int rem = pix - a_img * HoWo;
+        const int ph = rem / p.cWo, pw = rem - ph * p.cWo;
+        a_w = pw * p.c_stride - p.c_pad;
+        a_h = ph * p.c_stride - p.c_pad;
+        const int tap = kb0 / p.c_cblk;          // kb0 == 0 unless split-K
+        cb = kb0 - tap * p.c_cblk;
+        tap_r = tap / p.cS;
+        tap_s = tap - tap_r * p.cS;
+      }
+      // ---- conv_mode 2 (B = im2col(X), wgrad): k-block = 64 consecutive output pixels starting at kb * 64
+      int b_img = 0, b_ph = 0, b_pw = 0;
+      // per-tile (tap row, tap column, channel block) of the up-to-four 64-column sub-tiles of B
+      int bj_r[4] = {0, 0, 0, 0}, bj_s[4] = {0, 0, 0, 0}, bj_c[4] = {0, 0, 0, 0};
+      if (B_MN && p.conv_mode == 2) {
+        const int pix = kb0 * BK;
+        b_img = pix / HoWo;
+        const int rem = pix - b_img * HoWo;
+        b_ph = rem / p.cWo;
+        b_pw = rem - b_ph * p.cWo;
+        constexpr int NJ = CL > 1 ? BN / 128 : BN / 64;
+        const int nb0 = CL > 1 ? (n_blk * BN + cta_rank * (BN / 2)) / 64 : n_blk * (BN / 64);
+#pragma unroll
+        for (int j = 0; j < (NJ > 0 ? NJ : 1); j++) {
+          const int nb = nb0 + j;
+          const int tap = nb / p.c_cblk;
+          bj_c[j] = (nb - tap * p.c_cblk) * 64;
+          bj_r[j] = tap / p.cS;
+          bj_s[j] = tap - bj_r[j] * p.cS;
+        }
+      }
       for (int kb = kb0; kb < kb1; kb++) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t fb = full_bar(stage);
@@ -514,13 +572,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // complete_tx that overtakes the expect_tx of its phase is legal (the phase cannot flip before the arrive)
           if (cta_rank == 0) mbar_expect_tx(fb, 2 * C::STAGE_BYTES);
           if (!A_MN && p.conv_mode == 1) {
-            const int tap = kb / p.c_cblk, cb = kb - tap * p.c_cblk;
-            const int r = tap / p.cS, sx = tap - r * p.cS;
-            const int pix = m_blk * BM;
-            const int img = pix / (p.cHo * p.cWo), rem = pix - img * (p.cHo * p.cWo);
-            const int ph = rem / p.cWo, pw = rem - ph * p.cWo;
-            tma_load_im2col_2sm(sA, &tmA, fbl, cb * 64, pw * p.c_stride - p.c_pad, ph * p.c_stride - p.c_pad, img, (uint16_t)sx,
-                                (uint16_t)r);
+            tma_load_im2col_2sm(sA, &tmA, fbl, cb * 64, a_w, a_h, a_img, (uint16_t)tap_s, (uint16_t)tap_r);
           } else if (!A_MN) {
             tma_load_2d_2sm(sA, &tmA, fbl, kb * BK, m_blk * BM);
           } else {
@@ -531,17 +583,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (!B_MN) {
             tma_load_2d_2sm(sB, &tmB, fbl, kb * BK, n_base);
           } else if (p.conv_mode == 2) {
-            const int pix = kb * BK;
-            const int img = pix / (p.cHo * p.cWo), rem = pix - img * (p.cHo * p.cWo);
-            const int ph = rem / p.cWo, pw = rem - ph * p.cWo;
 #pragma unroll
-            for (int j = 0; j < BN / 128; j++) {
-              const int nb = n_base / 64 + j;
-              const int tap = nb / p.c_cblk, cb = nb - tap * p.c_cblk;
-              const int r = tap / p.cS, sx = tap - r * p.cS;
-              tma_load_im2col_2sm(sB + j * 8192, &tmB, fbl, cb * 64, pw * p.c_stride - p.c_pad, ph * p.c_stride - p.c_pad, img,
-                                  (uint16_t)sx, (uint16_t)r);
-            }
+            for (int j = 0; j < BN / 128; j++)
+              tma_load_im2col_2sm(sB + j * 8192, &tmB, fbl, bj_c[j], b_pw * p.c_stride - p.c_pad, b_ph * p.c_stride - p.c_pad, b_img,
+                                  (uint16_t)bj_s[j], (uint16_t)bj_r[j]);
           } else {
 #pragma unroll
             for (int j = 0; j < BN / 128; j++) tma_load_2d_2sm(sB + j * 8192, &tmB, fbl, n_base + j * 64, kb * BK);
@@ -550,13 +595,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_expect_tx(fb, C::STAGE_BYTES);
         if (!A_MN && p.conv_mode == 1) {
           // k-block = (filter tap, 64-channel block); the tile's first output pixel fixes the base coordinates
-          const int tap = kb / p.c_cblk, cb = kb - tap * p.c_cblk;
-          const int r = tap / p.cS, sx = tap - r * p.cS;
-          const int pix = m_blk * BM;
-          const int img = pix / (p.cHo * p.cWo), rem = pix - img * (p.cHo * p.cWo);
-          const int ph = rem / p.cWo, pw = rem - ph * p.cWo;
-          tma_load_im2col(sA, &tmA, fb, cb * 64, pw * p.c_stride - p.c_pad, ph * p.c_stride - p.c_pad, img, (uint16_t)sx,
-                          (uint16_t)r);
+          tma_load_im2col(sA, &tmA, fb, cb * 64, a_w, a_h, a_img, (uint16_t)tap_s, (uint16_t)tap_r);
         } else if (!A_MN) {
           tma_load_2d(sA, &tmA, fb, kb * BK, m_blk * BM);
         } else {
@@ -567,17 +606,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tma_load_2d(sB, &tmB, fb, kb * BK, n_blk * BN);
         } else if (p.conv_mode == 2) {
           // wgrad: B(n, k) = im2col(X)[pixel k, column n]: 64 pixels x 64 channels per (tap, channel block) sub-tile
-          const int pix = kb * BK;
-          const int img = pix / (p.cHo * p.cWo), rem = pix - img * (p.cHo * p.cWo);
-          const int ph = rem / p.cWo, pw = rem - ph * p.cWo;
 #pragma unroll
-          for (int j = 0; j < BN / 64; j++) {
-            const int nb = n_blk * (BN / 64) + j;
-            const int tap = nb / p.c_cblk, cb = nb - tap * p.c_cblk;
-            const int r = tap / p.cS, sx = tap - r * p.cS;
-            tma_load_im2col(sB + j * 8192, &tmB, fb, cb * 64, pw * p.c_stride - p.c_pad, ph * p.c_stride - p.c_pad, img,
-                            (uint16_t)sx, (uint16_t)r);
-          }
+          for (int j = 0; j < BN / 64; j++)
+            tma_load_im2col(sB + j * 8192, &tmB, fb, bj_c[j], b_pw * p.c_stride - p.c_pad, b_ph * p.c_stride - p.c_pad, b_img,
+                            (uint16_t)bj_s[j], (uint16_t)bj_r[j]);
         } else {
 #pragma unroll
           for (int j = 0; j < BN / 64; j++) tma_load_2d(sB + j * 8192, &tmB, fb, n_blk * BN + j * 64, kb * BK);
@@ -585,6 +617,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         }
         __syncwarp();
+        // ---- advance the im2col counters (uniform across the warp)
+        if (!A_MN && p.conv_mode == 1) {
+          if (++cb == p.c_cblk) {
+            cb = 0;
+            if (++tap_s == p.cS) {
+              tap_s = 0;
+              ++tap_r;
+            }
+          }
+        }
+        if (B_MN && p.conv_mode == 2) {
+          b_pw += bk_cols;                          // next 64 output pixels, traversed W -> H -> N
+          b_ph += bk_rows;
+          if (b_pw >= p.cWo) {
+            b_pw -= p.cWo;
+            ++b_ph;
+          }
+          while (b_ph >= p.cHo) {                   // at most ceil(64 / (Ho * Wo)) + 1 rounds
+            b_ph -= p.cHo;
+            ++b_img;
+          }
+        }
         if (++stage == C::STAGES) {
           stage = 0;
           phase ^= 1u;
@@ -664,11 +718,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int half = (warp - EPI_WARP0) >> 2;  // column half of the tile
     constexpr int HALF_COLS = BN / C::EPI_GROUPS;
     constexpr int PAIRS = HALF_COLS / 64;      // 64-column boxes per warp group and tile (1 or 2)
-    const uint32_t stage_box = staging_base + half * 16384;
+    // staging boxes of this warp group: [group][slot] when ping-ponging, else one per group (AUX: + one aux box per group)
+    const uint32_t stage_box0 = staging_base + (C::PP ? half * 2 : half) * 16384;
     const uint32_t aux_box = staging_base + (2 + half) * 16384;   // AUX kernels only
     const int row_in_box = wq * 32 + lane;
-    const uint32_t stage_row = stage_box + row_in_box * 128;
     const uint32_t aux_row = aux_box + row_in_box * 128;
+    uint32_t box_count = 0;                    // output boxes produced so far by this group (selects the ping-pong slot)
     const int swz = row_in_box & 7;
     const bool issuer = (wq == 0 && lane == 0);
     const int bar_id = 1 + half;               // named barrier of this warp group (128 threads)
@@ -706,7 +761,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (feat == (F_BOX_RES | F_DROP)) feat = F_GENERIC;   // not instantiated
     }
     EpiCtx ec;
-    ec.stage_row = stage_row; ec.aux_row = aux_row; ec.swz = swz; ec.inv_keep = inv_keep;
+    ec.stage_row = stage_box0 + row_in_box * 128; ec.aux_row = aux_row; ec.swz = swz; ec.inv_keep = inv_keep;
     ec.has_bias = has_bias; ec.has_aux_in = has_aux_in; ec.box_is_aux = box_is_aux; ec.box_is_res = box_is_res;
 
     // ---- LD: one operand box per tile and group, prefetched IN_SLOTS tiles ahead of its consumption
@@ -756,9 +811,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // out-of-range columns / rows and every direct global access below is bounds-checked (N % 8 == 0).
         constexpr int NBOX_MAX = 2;
         const int nbox = p.d_f32 ? 2 : 1;        // an fp32 box holds 32 columns, a bf16 box 64
+        uint32_t stage_box = stage_box0;
         for (int hb = 0; hb < NBOX_MAX; hb++) {
           if (hb >= nbox) break;
-          if (issuer) bulk_wait_read0();          // the TMA engine has read the previous contents of the staging boxes
+          // the TMA engine has read the previous contents of the box about to be overwritten (ping-pong: the store issued
+          // TWO boxes ago; the most recent one may still be in flight)
+          if (issuer) {
+            if (C::PP) bulk_wait_read1();
+            else bulk_wait_read0();
+          }
+          stage_box = stage_box0 + (C::PP ? (box_count & 1u) * 16384u : 0u);
+          ec.stage_row = stage_box + row_in_box * 128;
+          box_count++;
           named_bar(bar_id, 128);
           const int it0 = p.d_f32 ? hb * 2 : 0, it1 = p.d_f32 ? hb * 2 + 2 : 4;
           ec.n0 = n0;

@@ -42,7 +42,10 @@ def test_stock_training_loop_matches_oracle():
     _zero_dropout(model)
     model.load_state_dict(sd)      # undo the BN running-stat update of the binding pass
     criterion = nn.CrossEntropyLoss(label_smoothing=0.02)
-    optimizer = torch.optim.AdamW(filter(lambda p: p.requires_grad, model.parameters()), lr=1e-4)
+    # Adam moves every weight by ~lr per step whatever the gradient scale: at the config's 2e-4 an 8-sample batch collapses
+    # the loss from 2.8 to 0.8 in ONE step and the third step is chaotic in the last bf16 bits; 1e-5 keeps the trajectory smooth
+    LR = 1e-5
+    optimizer = torch.optim.AdamW(filter(lambda p: p.requires_grad, model.parameters()), lr=LR)
     ours = []
     for _ in range(3):
         optimizer.zero_grad()
@@ -65,7 +68,7 @@ def test_stock_training_loop_matches_oracle():
             if v.requires_grad and id(v) not in seen:
                 seen.add(id(v))
                 plist.append(v)
-    opt = torch.optim.AdamW(plist, lr=1e-4)
+    opt = torch.optim.AdamW(plist, lr=LR)
     ref = []
     for _ in range(3):
         opt.zero_grad()
@@ -78,8 +81,8 @@ def test_stock_training_loop_matches_oracle():
     assert ours[-1] < ours[0] and ref[-1] < ref[0], "the loss must go down on both sides"
     assert abs(ours[0] - ref[0]) < 2e-2 * max(1.0, abs(ref[0])), (ours, ref)     # same weights: forward parity only
     for a, b in zip(ours[1:], ref[1:]):
-        # after AdamW steps (sign-like updates of size lr amplify bf16 gradient noise) the trajectories stay within 10 %
-        assert abs(a - b) < 1e-1 * max(1.0, abs(b)), (ours, ref)
+        # after AdamW steps (sign-like updates of size lr amplify bf16 gradient noise) the trajectories stay within 5 %
+        assert abs(a - b) < 5e-2 * max(1.0, abs(b)), (ours, ref)
     # the drop in loss over the three steps agrees as well (the optimizer really stepped through .grad views)
     assert abs((ours[0] - ours[-1]) - (ref[0] - ref[-1])) < 0.35 * abs(ref[0] - ref[-1]) + 2e-2
 
