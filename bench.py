@@ -308,8 +308,9 @@ def run_torch_gpu(args):
 # ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
-def build_ours_model(cfg, dev):
-    """Our B200 model + Trainer for one BASELINE configuration."""
+def build_ours_model(cfg, dev, dp_kw=None):
+    """Our B200 model + Trainer for one BASELINE configuration.  dp_kw: data-parallel knobs of the Trainer."""
+    dp_kw = dp_kw or {}
     import torch
     import mdhs_b200
     from mdhs_b200.train import Trainer, mibf_forward_loss
@@ -323,7 +324,7 @@ def build_ours_model(cfg, dev):
                                                       image_weights_path=None, text_model_name=bert_dir(), num_heads=8,
                                                       image_backbone="resnet50", classifier_type="mlp", fusion_type=cfg["fusion"])
             model = model.to(dev)
-            trainer = Trainer(model, optimizer="adamw", lr=2e-4, label_smoothing=0.02)
+            trainer = Trainer(model, optimizer="adamw", lr=2e-4, label_smoothing=0.02, **dp_kw)
         elif fam == "mibf":
             from mdhs_b200.mibf_net.model_resnet import Resnet50WithOurs
             model = Resnet50WithOurs(num_labels=cfg["classes"], bert_path=bert_dir(), pretrained=False).to(dev)
@@ -370,7 +371,10 @@ def run_ours(args):
         bert_dir()
     if world > 1:
         dist.barrier()
-    model, trainer = build_ours_model(cfg, dev)
+    dp_kw = dict(comm_dtype=args.comm_dtype, bert_bucket_layers=args.bert_bucket_layers)
+    if args.sm_reserve >= 0:
+        dp_kw["sm_reserve"] = args.sm_reserve
+    model, trainer = build_ours_model(cfg, dev, dp_kw)
     images, ids, mask, labels = synthetic_batch(B, S, C, seed=123 + rank, image_hw=HW, unit_range=cfg["family"] != "baseline")
     h_in = [t.pin_memory() for t in (images, ids, mask, labels)]
     d_in = [t.to(dev, non_blocking=True) for t in h_in]
@@ -569,6 +573,28 @@ def run_ours(args):
                     "gemm_share_of_step": round(gms / (ms / args.steps), 3),
                     "kernel_busy_ms_per_step": round(other / 1e3, 3) if other else None, "top_kernels_us": top,
                     "model_flops_frac": round(value / world * cfg["gflop"] / 1e3 / peak, 4)}
+    # ---- optional kernel timeline of ONE graph-replayed step (CUPTI through torch.profiler), every rank's view of rank 0:
+    # name / stream / start / duration of every kernel, so that exposed collectives and stretched kernels can be read off
+    if args.timeline and rank == 0 and use_graph:
+        try:
+            from torch.profiler import ProfilerActivity, profile
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                trainer.replay()
+                torch.cuda.synchronize()
+            evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.name]
+            evs.sort(key=lambda e: e.time_range.start)
+            t0 = evs[0].time_range.start
+            rows_ = [{"name": e.name.replace("void ", "").replace("<unnamed>::", "").split("(")[0][:80],
+                      "start_us": round(e.time_range.start - t0, 2), "dur_us": round(e.time_range.end - e.time_range.start, 2)}
+                     for e in evs]
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            json.dump({"world": world, "ms_per_step": ms / args.steps, "kernels": rows_},
+                      open(os.path.join(ROOT, "gpurun_out", args.timeline), "w"))
+        except Exception as e:
+            print(f"[bench] timeline failed: {type(e).__name__}: {e}", file=sys.stderr)
+    elif args.timeline and use_graph:
+        trainer.replay()        # keep the ranks in lock-step with rank 0's profiled replay (the step contains collectives)
+        torch.cuda.synchronize()
     if launches_per_step is None:
         c0 = _lib.launch_count()
         trainer.step(*d_in)
@@ -675,6 +701,11 @@ def main():
     ap.add_argument("--fusion", default=None, choices=["basic", "multiscale", "concat"],
                     help="override the fusion_type of a MultimodalBaselineModel configuration")
     ap.add_argument("--ref-batch", type=int, default=32, help="samples per CPU step of the reference arm (bounded sample)")
+    ap.add_argument("--comm-dtype", default="bf16", choices=["bf16", "fp32"], help="dtype of the gradient buckets on the wire (N > 1)")
+    ap.add_argument("--sm-reserve", type=int, default=-1, help="SMs the persistent GEMM grids leave to NCCL while a bucket is in "
+                                                               "flight (default: MDHS_SM_RESERVE or 16)")
+    ap.add_argument("--bert-bucket-layers", type=int, default=4, help="BERT layers per early gradient bucket (0 = one bucket)")
+    ap.add_argument("--timeline", default=None, help="write the kernel timeline of one replayed step to gpurun_out/<name>")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true")

@@ -286,13 +286,18 @@ int mdhs_sq_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, con
                      const float* probs, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int B, int T,
                      int D, float scale, void* stream);
 
-/* Fused optimizer step on the flat parameter buffer (scripts/train.py:257-309) */
-int mdhs_adam_flat(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, int64_t n,
-                   float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+/* Fused optimizer step on the flat parameter buffer (scripts/train.py:257-309).  grads_bf16 (optional): read the gradient
+ * from this bf16 buffer instead of `grads` (data-parallel runs all-reduce bf16 buckets; `grads` is still zeroed). */
+int mdhs_adam_flat(float* params, float* grads, const void* grads_bf16, float* exp_avg, float* exp_avg_sq, void* shadow_bf16,
+                   int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
                    int adamw, int zero_grad, const float* lr_dev, const int* step_dev, void* stream);
-int mdhs_sgd_flat(float* params, float* grads, float* momentum_buf, void* shadow_bf16, int64_t n, float lr,
-                  float momentum, float weight_decay, float grad_scale, int first_step, int zero_grad,
+int mdhs_sgd_flat(float* params, float* grads, const void* grads_bf16, float* momentum_buf, void* shadow_bf16, int64_t n,
+                  float lr, float momentum, float weight_decay, float grad_scale, int first_step, int zero_grad,
                   const float* lr_dev, const int* step_dev, void* stream);
+/* Persistent GEMM grids leave `n` SMs free (0 = use all): set while a collective kernel (NCCL all-reduce of gradient
+ * buckets, mibf_net/train_resnet.py:84-88's DDP) runs concurrently, so that the GEMM's CTAs are all co-resident instead of
+ * spilling a second wave behind the collective's CTAs. */
+int mdhs_set_sm_reserve(int n);
 /* lr_dev / step_dev (optional device scalars) override lr / step so a captured CUDA graph of the step can be
  * replayed with a changing learning rate and step count.  mdhs_step_begin: once per step before the forward:
  * ++*step_dev and advance the dropout seed tick folded into every stateless dropout mask. */

@@ -104,8 +104,8 @@ SIGNATURES = {
     "mdhs_layer_scale_bwd": "ppppplii" "fup",
     "mdhs_sq_attn_fwd": "plplplpp" "iiifp",
     "mdhs_sq_attn_bwd": "plplplpp" "plplpl" "iiifp",
-    "mdhs_adam_flat": "ppppplfffffifiippp",
-    "mdhs_sgd_flat": "pppplffffiippp",
+    "mdhs_adam_flat": "pppppplfffffifiippp",
+    "mdhs_sgd_flat": "ppppplffffiippp",
     "mdhs_step_begin": "pp",
 }
 _CT = {"p": ctypes.c_void_p, "i": ctypes.c_int32, "l": ctypes.c_int64, "f": ctypes.c_float, "u": ctypes.c_uint64}
@@ -122,6 +122,8 @@ def lib():
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.mdhs_abi_version.restype = ctypes.c_int
         _lib.mdhs_launch_count.restype = ctypes.c_int64
+        _lib.mdhs_set_sm_reserve.argtypes = [ctypes.c_int]
+        _lib.mdhs_set_sm_reserve.restype = ctypes.c_int
         for name, sig in SIGNATURES.items():
             fn = getattr(_lib, name)  # AttributeError here = header / library mismatch
             fn.argtypes = [_CT[c] for c in sig]

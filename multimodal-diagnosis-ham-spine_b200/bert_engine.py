@@ -42,6 +42,9 @@ class BertEngine:
         if cfg.hidden_act not in ("gelu",):
             raise ValueError(f"unsupported BERT activation {cfg.hidden_act!r} (erf GELU only)")
         self.step_seed = 0x5EED0000
+        # called with the layer index right after that encoder layer's backward kernels have been enqueued (its parameter
+        # gradients are final): the data-parallel trainer starts the layer group's gradient bucket early
+        self.on_layer_backward_done = None
         self.layers = []
         C = self.C
         for layer in bert.encoder.layer:
@@ -171,6 +174,8 @@ class BertEngine:
                 d = self._linear_bwd(dqkv, R["x"], None, residual=dpre1, w16=L["wqkv"][1], gw=L["wqkv"][2], gb=L["bqkv"][2])
             else:
                 d = ops.gemm(dqkv, L["wqkv"][1], b_mn=True, residual=dpre1)
+            if self.on_layer_backward_done is not None:
+                self.on_layer_backward_done(li)
         emb = self.bert.embeddings
         if d is None or not emb.word_embeddings.weight.requires_grad:
             return

@@ -35,7 +35,7 @@ constexpr int SMEM_LIMIT = 232448;                           // 227 KiB opt-in m
 // LD = the epilogue reads bf16 operand boxes (act'(aux_in) and / or a bf16 residual): they are prefetched by TMA into a
 // dedicated shared-memory box per epilogue warp group, one tile ahead of the accumulator, so their HBM latency is
 // hidden under the main loop (one pipeline stage is traded for the boxes).  Only BN <= 128 (one 64-column box per group).
-template <int BN, bool LD, int CL = 1, bool AUX = false> struct Cfg {
+template <int BN, int LD, int CL = 1, bool AUX = false> struct Cfg {
   static_assert(!(LD && BN == 256), "operand prefetch needs BN <= 128");
   // (CTA pairs with BN == 64 exist for K-major B only: an MN-major B tile is loaded in 64-column chunks that cannot be halved)
   static constexpr int B_TILE_BYTES = (BN / CL) * BK * 2;     // CL 2: each CTA of the pair stages half of the B tile
@@ -53,11 +53,16 @@ template <int BN, bool LD, int CL = 1, bool AUX = false> struct Cfg {
   // ncu on the output-bound layer-1 GEMMs (K = 64 .. 256, one to four k-blocks per tile): DRAM 40 %, tensor 5-10 %, the
   // epilogue warps parked on the named barrier behind `cp.async.bulk.wait_group.read 0`.  AUX kernels (second output
   // tensor) keep one box per tensor.
-  static constexpr bool PP = !AUX && (MDHS_GEMM_PINGPONG != 0);
+  // (operand-box kernels keep one box and the deeper pipeline: measured 3-5 % slower on the main-loop-bound BERT GEMMs
+  //  with the residual / act' box, and no gain on the residual-carrying layer-1 dgrad, whose limiter is the box latency)
+  static constexpr bool PP = !AUX && !LD && (MDHS_GEMM_PINGPONG != 0);
   static constexpr int STAGING_BYTES = AUX ? 4 * 16384 : (PP ? 2 * EPI_GROUPS : 2) * 16384;
-  // operand boxes in flight per epilogue warp group.  Two slots (and one pipeline stage less) were measured: no gain on
-  // the epilogue-bound GEMMs and -6 % on the main-loop-bound ones, so one slot it is.
-  static constexpr int IN_SLOTS = 1;
+  // operand boxes in flight per epilogue warp group = LD (1 or 2).  Two slots (and one pipeline stage less) were measured
+  // in round 1: no gain on the epilogue-bound BERT GEMMs and -6 % on the main-loop-bound ones, so ONE slot is the default;
+  // LD == 2 is used for short reductions (K <= 256: one to four k-blocks per tile), where a tile lasts less than the HBM
+  // latency of its residual box and a single slot serialises box load and epilogue (401408 x 256 x 64 + residual: 123 us
+  // for 461 MB = 57 % of the HBM peak).
+  static constexpr int IN_SLOTS = LD > 1 ? 2 : 1;
   static constexpr int IN_BYTES = LD ? EPI_GROUPS * IN_SLOTS * 16384 : 0;
   // pipeline depth: the table above, minus what the staging / operand boxes take from the 227 KiB
   static constexpr int fit_stages(int st) {
@@ -433,7 +438,7 @@ __device__ __forceinline__ void epi_chunks(const EpiCtx& ec, const Params& p, in
 // Protocol: `full` barriers live in the leader (one arrival: the leader's expect_tx of both CTAs' bytes; both CTAs'
 // TMA loads complete on it); `empty` / `tmem_full` are signalled in both CTAs by multicast tcgen05.commit; both CTAs'
 // epilogue warps release an accumulator stage on the leader's `tmem_empty`.
-template <int BN, bool A_MN, bool B_MN, bool LD, int CL, bool AUX>
+template <int BN, bool A_MN, bool B_MN, int LD, int CL, bool AUX>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmAux,
@@ -1023,6 +1028,8 @@ int make_im2col_map(CUtensorMap* map, const void* x, int N, int H, int W, int C,
   return r == CUDA_SUCCESS ? MDHS_OK : MDHS_ERR_ARG;
 }
 
+int g_sm_reserve_get();
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -1034,7 +1041,7 @@ int num_sms() {
   return n;
 }
 
-template <int BN, bool A_MN, bool B_MN, bool LD, int CL, bool AUX>
+template <int BN, bool A_MN, bool B_MN, int LD, int CL, bool AUX>
 int launch(const mdhs_gemm_args* a, const Params& p0, cudaStream_t stream) {
   using C = Cfg<BN, LD, CL, AUX>;
   Params p = p0;
@@ -1083,7 +1090,7 @@ int launch(const mdhs_gemm_args* a, const Params& p0, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CL > 1 ? 1 : 0;
-  int cap = num_sms() / CL;
+  int cap = (num_sms() - g_sm_reserve_get()) / CL;
   if (CL > 1) {
     // a persistent grid must be fully co-resident: GPCs with an odd number of usable SMs cannot host every pair
     static int max_clusters = -1;
@@ -1111,31 +1118,31 @@ int launch(const mdhs_gemm_args* a, const Params& p0, cudaStream_t stream) {
   MDHS_RETURN_LAST();
 }
 
-template <int BN, bool LD, int CL>
+template <int BN, int LD, int CL>
 int dispatch_major(const mdhs_gemm_args* a, const Params& p, cudaStream_t s) {
   if (a->aux_out) {
     // a second output tensor only occurs in forward Linear layers (K-major A, no operand boxes)
     if (a->a_mn_major || LD) return MDHS_ERR_ARG;
-    return a->b_mn_major ? launch<BN, false, true, false, CL, true>(a, p, s) : launch<BN, false, false, false, CL, true>(a, p, s);
+    return a->b_mn_major ? launch<BN, false, true, 0, CL, true>(a, p, s) : launch<BN, false, false, 0, CL, true>(a, p, s);
   }
   if (a->a_mn_major) {
     // MN-major A only occurs in weight-gradient GEMMs, which never read epilogue operand boxes
     if (LD) return MDHS_ERR_ARG;
-    return a->b_mn_major ? launch<BN, true, true, false, CL, false>(a, p, s) : launch<BN, true, false, false, CL, false>(a, p, s);
+    return a->b_mn_major ? launch<BN, true, true, 0, CL, false>(a, p, s) : launch<BN, true, false, 0, CL, false>(a, p, s);
   }
   return a->b_mn_major ? launch<BN, false, true, LD, CL, false>(a, p, s) : launch<BN, false, false, LD, CL, false>(a, p, s);
 }
 
 // 64-wide CTA-pair tiles: K-major B only
-template <bool LD>
+template <int LD>
 int dispatch_pair64(const mdhs_gemm_args* a, const Params& p, cudaStream_t s) {
   if (a->aux_out) {
     if (a->a_mn_major || LD) return MDHS_ERR_ARG;
-    return launch<64, false, false, false, 2, true>(a, p, s);
+    return launch<64, false, false, 0, 2, true>(a, p, s);
   }
   if (a->a_mn_major) {
     if (LD) return MDHS_ERR_ARG;
-    return launch<64, true, false, false, 2, false>(a, p, s);
+    return launch<64, true, false, 0, 2, false>(a, p, s);
   }
   return launch<64, false, false, LD, 2, false>(a, p, s);
 }
@@ -1165,6 +1172,17 @@ int cluster_mode() {
 }  // namespace
 
 int64_t g_mdhs_launches = 0;
+static int g_sm_reserve = 0;
+
+namespace {
+int g_sm_reserve_get() { return g_sm_reserve; }
+}  // namespace
+
+extern "C" int mdhs_set_sm_reserve(int n) {
+  if (n < 0 || n > 96) return MDHS_ERR_ARG;
+  g_sm_reserve = n;
+  return MDHS_OK;
+}
 
 extern "C" int mdhs_abi_version(void) { return MDHS_ABI_VERSION; }
 extern "C" int64_t mdhs_launch_count(void) { return g_mdhs_launches; }
@@ -1216,7 +1234,7 @@ extern "C" int mdhs_gemm_bf16(const mdhs_gemm_args* a, void* stream_) {
   int auto_bn = 0;
   if (a->split_k < 0 && a->accumulate && !a->act && !a->dact && !a->aux_out && !a->colsum) {
     // auto: pick (tile width, split count) that fills whole waves of the persistent grid
-    const int sms = num_sms();
+    const int sms = num_sms() - g_sm_reserve_get();
     const int cand[3] = {256, 128, 64};
     double best = -1.0;
     const int max_s = p.kb_total / 4 > 1 ? (p.kb_total / 4 < 32 ? p.kb_total / 4 : 32) : 1;
@@ -1266,7 +1284,7 @@ extern "C" int mdhs_gemm_bf16(const mdhs_gemm_args* a, void* stream_) {
   if (bn != 64 && bn != 128 && bn != 256 && auto_bn) bn = auto_bn;
   if (bn != 64 && bn != 128 && bn != 256) {
     // pick the tile width with the best wave efficiency on this GPU; prefer wider tiles on ties
-    const int sms = num_sms();
+    const int sms = num_sms() - g_sm_reserve_get();
     const int cand[3] = {256, 128, 64};
     double best = -1.0;
     bn = 128;
@@ -1281,7 +1299,14 @@ extern "C" int mdhs_gemm_bf16(const mdhs_gemm_args* a, void* stream_) {
       const int64_t waves = (tiles + units - 1) / units;
       double eff = (double)tiles / (double)(waves * units);
       // wider tiles re-read A less often, need fewer MMA issues per flop and keep the tensor pipe busier per smem byte
-      eff *= tile_width_factor(c, pairs);
+      if (a->conv_mode == 1) {
+        // implicit-GEMM convolutions are paced by the TMA unit's im2col address generation (~700 clk per 128-pixel x 64-channel
+        // box, measured: r02 ncu source view -- the `empty` barrier is never waited on while the tensor pipe idles), i.e. a
+        // tile costs the same whatever its width: time ~ number of waves, so the efficiency is proportional to the width
+        eff *= (double)c / 256.0;
+      } else {
+        eff *= tile_width_factor(c, pairs);
+      }
       // ... but a 256-wide tile gives each epilogue thread 128 columns: with erf-GELU math per element the epilogue, not the
       // tensor pipe, paces the kernel (measured: FFN1 forward 49 us at 128 vs 55 us at 256)
       if (c == 256 && (a->act == MDHS_ACT_GELU || a->act == MDHS_ACT_GELU_DERIV)) eff *= 0.85;
@@ -1302,12 +1327,15 @@ extern "C" int mdhs_gemm_bf16(const mdhs_gemm_args* a, void* stream_) {
   const bool cl2 = cluster_mode() != 0 && (bn >= 128 || !a->b_mn_major) && n_tiles_m >= 2 &&
                    (cluster_mode() == 2 || (int64_t)((n_tiles_m + 1) / 2) * ceil_div(a->N, bn) * p.splits >= num_sms() / 4);
   switch (bn) {
-    case 256: return cl2 ? dispatch_major<256, false, 2>(a, p, stream) : dispatch_major<256, false, 1>(a, p, stream);
+    case 256: return cl2 ? dispatch_major<256, 0, 2>(a, p, stream) : dispatch_major<256, 0, 1>(a, p, stream);
     case 128:
-      if (cl2) return ld ? dispatch_major<128, true, 2>(a, p, stream) : dispatch_major<128, false, 2>(a, p, stream);
-      return ld ? dispatch_major<128, true, 1>(a, p, stream) : dispatch_major<128, false, 1>(a, p, stream);
+      if (cl2) {
+        if (ld && p.kb_total <= 4) return dispatch_major<128, 2, 2>(a, p, stream);   // short reduction: two operand boxes in flight
+        return ld ? dispatch_major<128, 1, 2>(a, p, stream) : dispatch_major<128, 0, 2>(a, p, stream);
+      }
+      return ld ? dispatch_major<128, 1, 1>(a, p, stream) : dispatch_major<128, 0, 1>(a, p, stream);
     default:
-      if (cl2) return ld ? dispatch_pair64<true>(a, p, stream) : dispatch_pair64<false>(a, p, stream);
-      return ld ? dispatch_major<64, true, 1>(a, p, stream) : dispatch_major<64, false, 1>(a, p, stream);
+      if (cl2) return ld ? dispatch_pair64<1>(a, p, stream) : dispatch_pair64<0>(a, p, stream);
+      return ld ? dispatch_major<64, 1, 1>(a, p, stream) : dispatch_major<64, 0, 1>(a, p, stream);
   }
 }

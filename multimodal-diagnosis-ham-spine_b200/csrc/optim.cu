@@ -16,7 +16,8 @@ void mdhs_seed_tick_convnext(uint64_t, cudaStream_t);
 namespace {
 
 // mode 0: AdamW (decoupled decay), 1: Adam (L2 decay folded into the gradient)
-__global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+__global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, float* __restrict__ g,
+                                                        const bf16* __restrict__ g16, float* __restrict__ m,
                                                         float* __restrict__ v, bf16* __restrict__ shadow, int64_t n, float lr,
                                                         float beta1, float beta2, float eps, float wd, float bc1, float bc2,
                                                         float grad_scale, int mode, int zero_grad,
@@ -30,7 +31,14 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, f
   }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
     float4 pp = reinterpret_cast<float4*>(p)[i];
-    float4 gg = reinterpret_cast<float4*>(g)[i];
+    float4 gg;
+    if (g16) {   // data-parallel runs with bf16 gradient buckets: the all-reduced gradient lives in the bf16 comm buffer
+      const bf162* q = reinterpret_cast<const bf162*>(g16) + i * 2;
+      const float2 a = __bfloat1622float2(q[0]), b = __bfloat1622float2(q[1]);
+      gg = make_float4(a.x, a.y, b.x, b.y);
+    } else {
+      gg = reinterpret_cast<float4*>(g)[i];
+    }
     float4 mm = reinterpret_cast<float4*>(m)[i];
     float4 vv = reinterpret_cast<float4*>(v)[i];
     float* P = reinterpret_cast<float*>(&pp);
@@ -59,7 +67,8 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, f
   }
 }
 
-__global__ void __launch_bounds__(256) sgd_flat_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ mom,
+__global__ void __launch_bounds__(256) sgd_flat_kernel(float* __restrict__ p, float* __restrict__ g,
+                                                       const bf16* __restrict__ g16, float* __restrict__ mom,
                                                        bf16* __restrict__ shadow, int64_t n, float lr, float momentum, float wd,
                                                        float grad_scale, int first_step, int zero_grad,
                                                        const float* __restrict__ lr_dev, const int* __restrict__ step_dev) {
@@ -68,7 +77,14 @@ __global__ void __launch_bounds__(256) sgd_flat_kernel(float* __restrict__ p, fl
   if (step_dev) first_step = step_dev[0] <= 1;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
     float4 pp = reinterpret_cast<float4*>(p)[i];
-    float4 gg = reinterpret_cast<float4*>(g)[i];
+    float4 gg;
+    if (g16) {
+      const bf162* q = reinterpret_cast<const bf162*>(g16) + i * 2;
+      const float2 a = __bfloat1622float2(q[0]), b = __bfloat1622float2(q[1]);
+      gg = make_float4(a.x, a.y, b.x, b.y);
+    } else {
+      gg = reinterpret_cast<float4*>(g)[i];
+    }
     float4 bb = mom ? reinterpret_cast<float4*>(mom)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     float* P = reinterpret_cast<float*>(&pp);
     float* G = reinterpret_cast<float*>(&gg);
@@ -102,25 +118,29 @@ int grid_for(int64_t items) {
 }  // namespace
 
 // n must be a multiple of 4 (the flat buffer is padded); all pointers 16-byte aligned.
-extern "C" int mdhs_adam_flat(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, int64_t n,
+extern "C" int mdhs_adam_flat(float* params, float* grads, const void* grads_bf16, float* exp_avg, float* exp_avg_sq,
+                              void* shadow_bf16, int64_t n,
                               float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
                               int adamw, int zero_grad, const float* lr_dev, const int* step_dev, void* stream) {
   if (!params || !grads || !exp_avg || !exp_avg_sq || n <= 0 || (n % 4) || (step < 1 && !step_dev)) return MDHS_ERR_ARG;
   const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
   g_mdhs_launches++;
   adam_flat_kernel<<<grid_for(n / 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      params, grads, exp_avg, exp_avg_sq, (bf16*)shadow_bf16, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale,
+      params, grads, (const bf16*)grads_bf16, exp_avg, exp_avg_sq, (bf16*)shadow_bf16, n, lr, beta1, beta2, eps, weight_decay,
+      bc1, bc2, grad_scale,
       adamw ? 0 : 1, zero_grad, lr_dev, step_dev);
   MDHS_RETURN_LAST();
 }
 
-extern "C" int mdhs_sgd_flat(float* params, float* grads, float* momentum_buf, void* shadow_bf16, int64_t n, float lr,
+extern "C" int mdhs_sgd_flat(float* params, float* grads, const void* grads_bf16, float* momentum_buf, void* shadow_bf16,
+                             int64_t n, float lr,
                              float momentum, float weight_decay, float grad_scale, int first_step, int zero_grad,
                              const float* lr_dev, const int* step_dev, void* stream) {
   if (!params || !grads || n <= 0 || (n % 4)) return MDHS_ERR_ARG;
   g_mdhs_launches++;
   sgd_flat_kernel<<<grid_for(n / 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      params, grads, momentum_buf, (bf16*)shadow_bf16, n, lr, momentum, weight_decay, grad_scale, first_step, zero_grad, lr_dev,
+      params, grads, (const bf16*)grads_bf16, momentum_buf, (bf16*)shadow_bf16, n, lr, momentum, weight_decay, grad_scale,
+      first_step, zero_grad, lr_dev,
       step_dev);
   MDHS_RETURN_LAST();
 }

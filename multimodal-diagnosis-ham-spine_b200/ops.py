@@ -392,16 +392,21 @@ def num_sms(device=None):
     return n
 
 
+def set_sm_reserve(n):
+    """Persistent GEMM grids leave n SMs free (for a concurrently running collective kernel); 0 = all SMs."""
+    _lib.check(_lib.lib().mdhs_set_sm_reserve(int(n)), "mdhs_set_sm_reserve")
+
+
 def adam_flat(params, grads, exp_avg, exp_avg_sq, shadow, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0,
-              adamw=True, zero_grad=True, lr_dev=None, step_dev=None):
-    _lib.call("mdhs_adam_flat", _p(params), _p(grads), _p(exp_avg), _p(exp_avg_sq), _p(shadow), params.numel(), float(lr),
+              adamw=True, zero_grad=True, lr_dev=None, step_dev=None, grads_bf16=None):
+    _lib.call("mdhs_adam_flat", _p(params), _p(grads), _p(grads_bf16), _p(exp_avg), _p(exp_avg_sq), _p(shadow), params.numel(), float(lr),
               float(beta1), float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale), int(adamw),
               int(zero_grad), _p(lr_dev), _p(step_dev), _s())
 
 
 def sgd_flat(params, grads, mom, shadow, lr, momentum, weight_decay, grad_scale=1.0, first_step=False, zero_grad=True,
-             lr_dev=None, step_dev=None):
-    _lib.call("mdhs_sgd_flat", _p(params), _p(grads), _p(mom), _p(shadow), params.numel(), float(lr), float(momentum),
+             lr_dev=None, step_dev=None, grads_bf16=None):
+    _lib.call("mdhs_sgd_flat", _p(params), _p(grads), _p(grads_bf16), _p(mom), _p(shadow), params.numel(), float(lr), float(momentum),
               float(weight_decay), float(grad_scale), int(first_step), int(zero_grad), _p(lr_dev), _p(step_dev), _s())
 
 

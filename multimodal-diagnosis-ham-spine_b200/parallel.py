@@ -7,8 +7,13 @@ the BERT backward returns -- is all-reduced asynchronously while the ResNet trun
 the head slice [0, split) follows when backward ends.  The sum is turned into a mean by the optimizer
 kernel (grad_scale = 1/world), so no extra pass touches the buffer.
 
+`comm_dtype=torch.bfloat16` (the Trainer's default at world > 1): every bucket is cast into a bf16 communication
+buffer by one kernel right before its all-reduce -- half the bytes on the wire and half the time the collective's CTAs share
+the GPU with the backward kernels -- and the fused optimizer reads the reduced gradient straight from that buffer.
+
 Backend-agnostic on purpose: NCCL over NVLink on the GPUs, gloo in the CPU unit tests.
 """
+import torch
 import torch.distributed as dist
 
 
@@ -24,7 +29,7 @@ class GradSync:
     """Buckets are arbitrary [lo, hi) slices of the flat gradient buffer, reduced asynchronously as soon as the caller
     declares them final (`reduce_range`); `finish()` reduces whatever is left and waits for everything."""
 
-    def __init__(self, flat_grad, split, group=None):
+    def __init__(self, flat_grad, split, group=None, comm_dtype=None, on_first_reduce=None):
         self.grad = flat_grad
         self.total = flat_grad.numel()
         self.split = max(0, min(int(split), self.total))
@@ -32,10 +37,36 @@ class GradSync:
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         self._works = []
         self._done = []      # [lo, hi) ranges already handed to the collective this step
+        # bf16 buckets: `comm` holds the (cast, then all-reduced) gradient; None = reduce the fp32 buffer in place
+        self.comm = None
+        if comm_dtype is not None and comm_dtype != flat_grad.dtype and self.world > 1:
+            self.comm = torch.zeros(self.total, device=flat_grad.device, dtype=comm_dtype)
+        self.on_first_reduce = on_first_reduce   # called once per step right before the first collective is enqueued
+        self._started = False
+
+    @property
+    def reduced(self):
+        """Buffer that holds the all-reduced gradient after finish(): the bf16 comm buffer, or None (= the fp32 grad)."""
+        return self.comm
+
+    def _cast(self, lo, hi):
+        if self.grad.is_cuda:
+            from . import ops
+            ops.cast_f32_bf16(self.grad[lo:hi], out=self.comm[lo:hi])
+        else:                       # gloo unit tests on CPU tensors
+            self.comm[lo:hi].copy_(self.grad[lo:hi])
 
     def _reduce(self, lo, hi):
         if self.world > 1 and hi > lo:
-            self._works.append(dist.all_reduce(self.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            if not self._started:
+                self._started = True
+                if self.on_first_reduce is not None:
+                    self.on_first_reduce()
+            buf = self.grad
+            if self.comm is not None:
+                self._cast(lo, hi)
+                buf = self.comm
+            self._works.append(dist.all_reduce(buf[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def reduce_range(self, lo, hi):
         """Call when every gradient in [lo, hi) is final.  Ranges must not overlap within one step."""
@@ -62,6 +93,7 @@ class GradSync:
             w.wait()
         self._works = []
         self._done = []
+        self._started = False
         return 1.0 / self.world   # scale that turns the summed gradient into the data-parallel mean
 
 

@@ -33,10 +33,15 @@ def connext_forward_loss(model, images, ids, mask, labels):
 class Trainer:
     def __init__(self, model, optimizer="adamw", lr=2e-4, weight_decay=None, betas=(0.9, 0.999), eps=1e-8, momentum=0.0,
                  loss="ce", label_smoothing=0.02, focal_gamma=2.0, class_weights=None, process_group=None,
-                 overlap_comm=True, supcon_weight=0.0, supcon_stage="finetune", supcon_temperature=0.07, forward_loss=None):
+                 overlap_comm=True, supcon_weight=0.0, supcon_stage="finetune", supcon_temperature=0.07, forward_loss=None,
+                 comm_dtype="bf16", sm_reserve=None, bert_bucket_layers=4):
         """forward_loss: optional callable (model, images, ids, mask, labels) -> (loss, logits) for the model families whose
         call surface differs from MultimodalBaselineModel (MIBF-Net: batch dict + cal_loss, mibf_net/train_resnet.py:21-41;
         ConNexT: batch dict -> logits).  Everything else -- CUDA graph, gradient sync, fused optimizer -- is shared.
+        Data parallel (world > 1): `comm_dtype` "bf16" (default, SURVEY 8e) | "fp32" = dtype of the gradient buckets on the wire;
+        `bert_bucket_layers` = BERT layers per early bucket (the text-encoder gradients leave in slices while its backward is
+        still running; 0 = one slice after the whole text encoder); `sm_reserve` = SMs the persistent GEMM grids leave to the
+        NCCL kernels while a bucket is in flight (default: MDHS_SM_RESERVE or 16).
         `momentum` only applies to optimizer="sgd": the default 0 is scripts/train.py:301-309's `optim.SGD(params, lr)`;
         MIBF-Net's recipe (mibf_net/train_resnet.py:136-139) passes momentum=0.9 explicitly."""
         self.model = model
@@ -62,6 +67,10 @@ class Trainer:
         # trunk twice in train mode (model.py:292-315), so their stage hooks would fire before the gradients are final
         twice = getattr(model, "global_local_enabled", False) or getattr(model, "sequence_enabled", False)
         self.overlap = overlap_comm and self.world > 1 and forward_loss is None and not twice
+        import os as _os
+        self.comm_dtype = {"bf16": torch.bfloat16, "fp32": None, "f32": None, None: None}[comm_dtype]
+        self.sm_reserve = int(_os.environ.get("MDHS_SM_RESERVE", "16")) if sm_reserve is None else int(sm_reserve)
+        self.bert_bucket_layers = int(bert_bucket_layers)
         self.store = None
         self._graph = None
         self._static = None
@@ -80,7 +89,9 @@ class Trainer:
         self.step_dev = torch.zeros(1, device=device, dtype=torch.int32)
         # slice boundary for the overlapped all-reduce: everything from the text encoder on
         self.split = split_offset(st, getattr(self.model, "text_encoder", None))
-        self.sync = GradSync(st.grad, self.split if self.overlap else 0, self.pg)
+        reserve = (lambda: ops.set_sm_reserve(self.sm_reserve)) if (self.overlap and self.sm_reserve > 0) else None
+        self.sync = GradSync(st.grad, self.split if self.overlap else 0, self.pg, comm_dtype=self.comm_dtype,
+                             on_first_reduce=reserve)
         # the optimizer only touches what torch.optim would: parameters with requires_grad (scripts/train.py builds the
         # optimizer from filter(requires_grad)) and, after the first backward, only those that actually received a gradient
         # (torch skips `grad is None`: the BERT pooler, dead q/k projections of the 1-token attention-pooling head, ...)
@@ -144,10 +155,26 @@ class Trainer:
         if self.overlap and self.split > 0:
             eng = self.model.text_encoder._engine
             orig = eng.backward
+            layers = self.model.text_encoder.model.encoder.layer
+            nb = self.bert_bucket_layers
 
-            def bert_backward_then_reduce(ctx, dh):
-                orig(ctx, dh)
-                self.sync.reduce_tail()
+            def layer_done(li):
+                # gradients of encoder layers [li, li + nb) are final: their slice leaves while the layers below still
+                # back-propagate.  The first call also carries everything behind the encoder layers (fusion, head, pooler).
+                if nb > 0 and li % nb == 0 and li > 0:
+                    lo, _ = param_range(st, layers[li])
+                    hi = self._bert_hi
+                    self._bert_hi = lo
+                    self.sync.reduce_range(lo, hi)
+
+            def bert_backward_then_reduce(ctx, dh, dtaps=None):
+                self._bert_hi = st.total
+                eng.on_layer_backward_done = layer_done
+                try:
+                    orig(ctx, dh, dtaps)
+                finally:
+                    eng.on_layer_backward_done = None
+                self.sync.reduce_range(self.split, self._bert_hi)   # embeddings + the lowest layers
 
             eng.backward = bert_backward_then_reduce
             hook = (eng, orig)
@@ -183,16 +210,21 @@ class Trainer:
             if img_eng is not None:
                 img_eng.on_stage_backward_done = None
         scale = self.sync.finish()
+        if self.sm_reserve > 0 and self.overlap:
+            ops.set_sm_reserve(0)
+        g16 = self.sync.reduced
         if not self._probed_unused and not torch.cuda.is_current_stream_capturing():
             self._probe_unused()
         for lo, hi in self._opt_ranges:
             if self.opt == "sgd":
                 ops.sgd_flat(st.flat[lo:hi], st.grad[lo:hi], self.m[lo:hi] if self.momentum > 0 else None, st.shadow[lo:hi],
-                             self.lr, self.momentum, self.wd, grad_scale=scale, lr_dev=self.lr_dev, step_dev=self.step_dev)
+                             self.lr, self.momentum, self.wd, grad_scale=scale, lr_dev=self.lr_dev, step_dev=self.step_dev,
+                             grads_bf16=None if g16 is None else g16[lo:hi])
             else:
                 ops.adam_flat(st.flat[lo:hi], st.grad[lo:hi], self.m[lo:hi], self.v[lo:hi], st.shadow[lo:hi], self.lr,
                               self.betas[0], self.betas[1], self.eps, self.wd, 1, grad_scale=scale,
-                              adamw=(self.opt == "adamw"), lr_dev=self.lr_dev, step_dev=self.step_dev)
+                              adamw=(self.opt == "adamw"), lr_dev=self.lr_dev, step_dev=self.step_dev,
+                              grads_bf16=None if g16 is None else g16[lo:hi])
         st.mark_fresh()
         return loss.detach(), logits.detach()
 

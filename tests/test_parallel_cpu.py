@@ -43,6 +43,23 @@ def _worker(rank, world, port, ret):
     sync3.reduce_range(120, 200)
     sync3.finish()
     ok = ok and torch.allclose(g3, want, atol=1e-6)
+    # bf16 buckets: every slice is cast into the bf16 communication buffer right before its all-reduce; the
+    # reduced gradient is read from `sync.reduced`, the fp32 buffer keeps the local gradient; the first collective of a step
+    # triggers the `on_first_reduce` callback exactly once (the trainer shrinks the persistent GEMM grids there)
+    g4 = mine.clone()
+    fired = []
+    sync4 = GradSync(g4, split, comm_dtype=torch.bfloat16, on_first_reduce=lambda: fired.append(1))
+    sync4.reduce_range(640, 1000)           # BERT layers 8..11 + fusion + head
+    sync4.reduce_range(470, 640)            # BERT layers 4..7
+    sync4.reduce_range(300, 470)            # embeddings + layers 0..3
+    sync4.finish()
+    want16 = sum(o.bfloat16().float() for o in others)
+    ok = ok and sync4.reduced is not None and sync4.reduced.dtype == torch.bfloat16
+    ok = ok and torch.allclose(sync4.reduced.float(), want16, atol=2e-2, rtol=1e-2) and torch.equal(g4, mine)
+    ok = ok and len(fired) == 1
+    sync4.reduce_tail()
+    sync4.finish()
+    ok = ok and len(fired) == 2
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 
