@@ -360,6 +360,8 @@ def run_ours(args):
         # collectives are captured into the step's CUDA graph: the NCCL watchdog's async error handling must not
         # poll events of a capturing stream (torch CUDA-graphs notes)
         os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
+        # the pipelined optimizer tail leaves 16 SMs to the collective of the next gradient bucket (Trainer.comm_sms)
+        os.environ.setdefault("NCCL_MAX_CTAS", "16")
         dist.init_process_group("nccl", device_id=dev)
     import mdhs_b200  # noqa: F401
     from mdhs_b200 import _lib, ops
@@ -371,7 +373,7 @@ def run_ours(args):
         bert_dir()
     if world > 1:
         dist.barrier()
-    dp_kw = dict(comm_dtype=args.comm_dtype, bert_bucket_layers=args.bert_bucket_layers)
+    dp_kw = dict(comm_dtype=args.comm_dtype, bert_bucket_layers=args.bert_bucket_layers, overlap_comm=args.overlap_comm)
     if args.sm_reserve >= 0:
         dp_kw["sm_reserve"] = args.sm_reserve
     model, trainer = build_ours_model(cfg, dev, dp_kw)
@@ -581,12 +583,25 @@ def run_ours(args):
             with profile(activities=[ProfilerActivity.CUDA]) as prof:
                 trainer.replay()
                 torch.cuda.synchronize()
-            evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.name]
-            evs.sort(key=lambda e: e.time_range.start)
-            t0 = evs[0].time_range.start
-            rows_ = [{"name": e.name.replace("void ", "").replace("<unnamed>::", "").split("(")[0][:80],
-                      "start_us": round(e.time_range.start - t0, 2), "dur_us": round(e.time_range.end - e.time_range.start, 2)}
-                     for e in evs]
+            import re as _re
+
+            def _kname(n):
+                n = n.replace("void ", "").replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
+                m_ = _re.match(r"[A-Za-z_0-9:]+(<[^(]*>)?", n)
+                return (m_.group(0) if m_ else n)[:96]
+            rows_ = []
+            try:        # kineto events carry the stream id
+                for e in prof.profiler.kineto_results.events():
+                    if str(e.device_type()).endswith("CUDA") and e.name():
+                        rows_.append({"name": _kname(e.name()), "start_us": e.start_ns() / 1e3, "dur_us": round(e.duration_ns() / 1e3, 2),
+                                      "stream": int(e.device_resource_id())})
+            except Exception:
+                rows_ = [{"name": _kname(e.name), "start_us": e.time_range.start, "dur_us": round(e.time_range.end - e.time_range.start, 2),
+                          "stream": -1} for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.name]
+            rows_.sort(key=lambda r: r["start_us"])
+            t0 = rows_[0]["start_us"]
+            for r in rows_:
+                r["start_us"] = round(r["start_us"] - t0, 2)
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
             json.dump({"world": world, "ms_per_step": ms / args.steps, "kernels": rows_},
                       open(os.path.join(ROOT, "gpurun_out", args.timeline), "w"))
@@ -705,6 +720,9 @@ def main():
     ap.add_argument("--sm-reserve", type=int, default=-1, help="SMs the persistent GEMM grids leave to NCCL while a bucket is in "
                                                                "flight (default: MDHS_SM_RESERVE or 16)")
     ap.add_argument("--bert-bucket-layers", type=int, default=4, help="BERT layers per early gradient bucket (0 = one bucket)")
+    ap.add_argument("--overlap-comm", default="pipeline", choices=["pipeline", "backward", "none"],
+                    help="N > 1: gradient buckets pipelined with the fused optimizer after backward (default), sent during "
+                         "backward, or one all-reduce before the optimizer")
     ap.add_argument("--timeline", default=None, help="write the kernel timeline of one replayed step to gpurun_out/<name>")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define MDHS_ABI_VERSION 2
+#define MDHS_ABI_VERSION 3
 int mdhs_abi_version(void);
 /* Number of kernels launched through this library since load (for bench.py's gpu_launches). */
 int64_t mdhs_launch_count(void);
@@ -109,6 +109,8 @@ int mdhs_layernorm_bwd(const void* dy, int dy_f32, int64_t lddy, const void* x, 
  * sum_dy_xc = sum(dy' * (x - mean)) (fp64 [C] each) and coef (fp32 [5*C]).
  * With relu != 0 and y == NULL the mask is recomputed from x as fmaf(x, scale, shift) > 0 (bit-identical to what the
  * forward evaluated; only valid for layers without a residual input), which saves one full read of y in both passes.
+ * relu_mask (optional, uint8 [rows, C/8], bit k of byte j = channel 8j+k): mdhs_bn_fwd writes (output > 0) per element and
+ * mdhs_bn_bwd reads it instead of y -- 1 bit instead of 16 per element in both backward passes of the residual layers.
  * training == 0: eval-mode backward, dx = gamma * invstd * dy' (running statistics are constants).
  * sums_ready != 0: the two sums were already produced (by the epilogue of the GEMM that wrote dy, see
  * mdhs_gemm_args.stat_x); the reduce launch is skipped.
@@ -120,9 +122,9 @@ int mdhs_bn_apply(const void* x, const float* scale, const float* shift, const v
                   int64_t rows, int C, int relu, void* stream);
 int mdhs_bn_fwd(const void* x, const double* colsum, const double* colsumsq, const float* gamma, const float* beta,
                 float* running_mean, float* running_var, float momentum, float eps, const void* residual, void* y,
-                float* mean, float* invstd, float* scale, float* shift, int64_t rows, int C, int relu, int training,
-                void* stream);
-int mdhs_bn_bwd(const void* dy, const void* x, const void* y, const float* mean, const float* invstd,
+                float* mean, float* invstd, float* scale, float* shift, void* relu_mask, int64_t rows, int C, int relu,
+                int training, void* stream);
+int mdhs_bn_bwd(const void* dy, const void* x, const void* y, const void* relu_mask, const float* mean, const float* invstd,
                 const float* gamma, const float* scale, const float* shift, double* sum_dy, double* sum_dy_xc,
                 float* coef, void* dx, void* dz, float* dgamma, float* dbeta, int64_t rows, int C, int relu, int training,
                 int sums_ready, void* stream);
@@ -138,6 +140,10 @@ int mdhs_col_stats(const void* x, int64_t ldx, double* sum64, double* sumsq64, f
  */
 int mdhs_im2col_nchw_f32(const float* x, void* col, int B, int C, int H, int W, int R, int S, int stride, int pad,
                          int ldc, void* stream);
+/* stem patch matrix of V test-time-augmentation variants (codes: 4 bits per variant, 0 identity 1 hflip 2 vflip 3 rot90;
+ * scripts/predict.py:33-42) read straight from the un-expanded batch: V * B * Ho * Wo rows */
+int mdhs_im2col_nchw_f32_tta(const float* x, void* col, int B, int C, int H, int W, int R, int S, int stride, int pad,
+                             int ldc, int V, int codes, void* stream);
 int mdhs_im2col_nhwc(const void* x, void* col, int B, int H, int W, int C, int R, int S, int stride, int pad,
                      void* stream);
 int mdhs_col2im_nhwc(const void* dcol, const void* add, void* dx, int B, int H, int W, int C, int R, int S,
@@ -155,6 +161,11 @@ int mdhs_conv_weight_pack_dgrad(const float* w, void* wt, int O, int I, int R, i
 int mdhs_conv_wgrad_unpack(const float* gp, float* g, int O, int I, int R, int S, int ldk, void* stream);
 int mdhs_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream);
 int mdhs_cast_bf16_f32(const void* x, float* y, int64_t n, void* stream);
+/* GPU-side input pipeline (data_loader.py:343-372 after the decode): uint8 [B,Hs,Ws,3] -> per-sample crop box boxes[B,4]
+ * (y0,x0,h,w; NULL = whole image) -> bilinear (align_corners=False) resample to Ho x Wo -> flips[B] (bit0 hflip, bit1 vflip;
+ * NULL = none) -> /255 -> (x - mean) / std -> fp32 [B,3,Ho,Wo].  mean3 / std3 are HOST pointers to 3 floats. */
+int mdhs_preprocess_u8(const uint8_t* src, float* dst, const float* boxes, const uint8_t* flips, int B, int Hs, int Ws, int Ho,
+                       int Wo, const float* mean3, const float* std3, void* stream);
 int mdhs_nhwc_bf16_to_nchw_f32(const void* x, float* y, int B, int H, int W, int C, void* stream);
 int mdhs_nchw_f32_to_nhwc_bf16(const float* x, void* y, int B, int H, int W, int C, void* stream);
 
@@ -287,13 +298,15 @@ int mdhs_sq_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, con
                      int D, float scale, void* stream);
 
 /* Fused optimizer step on the flat parameter buffer (scripts/train.py:257-309).  grads_bf16 (optional): read the gradient
- * from this bf16 buffer instead of `grads` (data-parallel runs all-reduce bf16 buckets; `grads` is still zeroed). */
+ * from this bf16 buffer instead of `grads` (data-parallel runs all-reduce bf16 buckets; `grads` is still zeroed).
+ * blocks_per_sm: > 0 (0 = 16) resident 256-thread blocks per SM; < 0: leave that many SMs free (one 1024-thread block on each
+ * of the others) so that the collective of the next gradient bucket can run beside the optimizer of the current one. */
 int mdhs_adam_flat(float* params, float* grads, const void* grads_bf16, float* exp_avg, float* exp_avg_sq, void* shadow_bf16,
                    int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
-                   int adamw, int zero_grad, const float* lr_dev, const int* step_dev, void* stream);
+                   int adamw, int zero_grad, const float* lr_dev, const int* step_dev, int blocks_per_sm, void* stream);
 int mdhs_sgd_flat(float* params, float* grads, const void* grads_bf16, float* momentum_buf, void* shadow_bf16, int64_t n,
                   float lr, float momentum, float weight_decay, float grad_scale, int first_step, int zero_grad,
-                  const float* lr_dev, const int* step_dev, void* stream);
+                  const float* lr_dev, const int* step_dev, int blocks_per_sm, void* stream);
 /* Persistent GEMM grids leave `n` SMs free (0 = use all): set while a collective kernel (NCCL all-reduce of gradient
  * buckets, mibf_net/train_resnet.py:84-88's DDP) runs concurrently, so that the GEMM's CTAs are all co-resident instead of
  * spilling a second wave behind the collective's CTAs. */

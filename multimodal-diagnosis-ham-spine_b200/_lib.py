@@ -46,10 +46,11 @@ SIGNATURES = {
     "mdhs_layernorm_bwd": "pilpilppp" "plpppp" "iifufup",
     "mdhs_bn_finalize": "pplppppffppppiip",
     "mdhs_bn_apply": "pppppliip",
-    "mdhs_bn_fwd": "ppppppp" "ff" "pppppp" "liii" "p",
-    "mdhs_bn_bwd": "ppppppppppppppp" "liiii" "p",
+    "mdhs_bn_fwd": "ppppppp" "ff" "ppppppp" "liii" "p",
+    "mdhs_bn_bwd": "pppppppppppppppp" "liiii" "p",
     "mdhs_col_stats": "plppplip",
     "mdhs_im2col_nchw_f32": "ppiiiiiiiiip",
+    "mdhs_im2col_nchw_f32_tta": "ppiiiiiiiiiiip",
     "mdhs_im2col_nhwc": "ppiiiiiiiip",
     "mdhs_col2im_nhwc": "pppiiiiiiiip",
     "mdhs_maxpool3x3s2_fwd": "pppiiiip",
@@ -81,6 +82,7 @@ SIGNATURES = {
     "mdhs_level_mix_bwd": "pppppplip",
     "mdhs_axpby_bf16": "ppplffp",
     "mdhs_global_local": "ppiiiifp",
+    "mdhs_preprocess_u8": "ppppiiiiippp",
     "mdhs_lstm_cell_fwd": "pppppiip",
     "mdhs_lstm_cell_bwd": "pppppppiip",
     "mdhs_gru_cell_fwd": "pppppiip",
@@ -104,9 +106,10 @@ SIGNATURES = {
     "mdhs_layer_scale_bwd": "ppppplii" "fup",
     "mdhs_sq_attn_fwd": "plplplpp" "iiifp",
     "mdhs_sq_attn_bwd": "plplplpp" "plplpl" "iiifp",
-    "mdhs_adam_flat": "pppppplfffffifiippp",
-    "mdhs_sgd_flat": "ppppplffffiippp",
+    "mdhs_adam_flat": "pppppplfffffifiippip",
+    "mdhs_sgd_flat": "ppppplffffiippip",
     "mdhs_step_begin": "pp",
+    "mdhs_set_sm_reserve": "i",
 }
 _CT = {"p": ctypes.c_void_p, "i": ctypes.c_int32, "l": ctypes.c_int64, "f": ctypes.c_float, "u": ctypes.c_uint64}
 
@@ -122,8 +125,6 @@ def lib():
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.mdhs_abi_version.restype = ctypes.c_int
         _lib.mdhs_launch_count.restype = ctypes.c_int64
-        _lib.mdhs_set_sm_reserve.argtypes = [ctypes.c_int]
-        _lib.mdhs_set_sm_reserve.restype = ctypes.c_int
         for name, sig in SIGNATURES.items():
             fn = getattr(_lib, name)  # AttributeError here = header / library mismatch
             fn.argtypes = [_CT[c] for c in sig]

@@ -22,9 +22,19 @@ int grid_for(int64_t items, int block) {
 // one-thread-per-8-columns form spent ~60 integer instructions per element on index arithmetic (ncu: 79 % issue-bound,
 // 0.9 ms for the ResNet stem at B = 128).
 constexpr int IM2COL_PIX = 32;
+// Test-time augmentation folded into the addressing (scripts/predict.py:33-42): with V > 1 the output holds V variants of the
+// Bsrc source images stacked on the batch axis (row block v = transform `codes >> 4v & 15` of every image: 0 identity,
+// 1 hflip, 2 vflip, 3 rot90), read straight from the un-expanded batch -- the V x B x 3 x H x W fp32 copy never exists.
+__device__ __forceinline__ void tta_src(int code, int H, int W, int h, int w, int& sh, int& sw) {
+  sh = h;
+  sw = w;
+  if (code == 1) sw = W - 1 - w;
+  else if (code == 2) sh = H - 1 - h;
+  else if (code == 3) { sh = w; sw = W - 1 - h; }   // rot90(k=1): out[i][j] = x[j][W-1-i] (square images)
+}
 __global__ void __launch_bounds__(256) im2col_nchw_f32_kernel(const float* __restrict__ x, bf16* __restrict__ col, int B, int C,
                                                               int H, int W, int R, int S, int stride, int pad, int Ho, int Wo,
-                                                              int ldc) {
+                                                              int ldc, int Bsrc, uint32_t codes) {
   extern __shared__ __align__(16) uint8_t im2col_smem[];
   bf16* tile = reinterpret_cast<bf16*>(im2col_smem);
   const int64_t total_rows = (int64_t)B * Ho * Wo;
@@ -49,11 +59,26 @@ __global__ void __launch_bounds__(256) im2col_nchw_f32_kernel(const float* __res
     const int h = ho * stride - pad + r;
     const int w0 = wo * stride - pad;
     const bool h_ok = (h >= 0 && h < H);
-    const float* src = x + (((int64_t)b * C + c) * H + (h_ok ? h : 0)) * W;
-    for (int sx = 0; sx < S; sx++) {
-      const int w = w0 + sx;
-      const float v = (h_ok && w >= 0 && w < W) ? __ldg(src + w) : 0.f;
-      dst[sx * C] = __float2bfloat16(v);
+    const int code = (codes >> (4 * (b / Bsrc))) & 15;     // B == Bsrc and codes == 0 without TTA
+    if (code == 0) {
+      const float* src = x + (((int64_t)(b % Bsrc) * C + c) * H + (h_ok ? h : 0)) * W;
+      for (int sx = 0; sx < S; sx++) {
+        const int w = w0 + sx;
+        const float v = (h_ok && w >= 0 && w < W) ? __ldg(src + w) : 0.f;
+        dst[sx * C] = __float2bfloat16(v);
+      }
+    } else {
+      const float* plane = x + ((int64_t)(b % Bsrc) * C + c) * H * W;
+      for (int sx = 0; sx < S; sx++) {
+        const int w = w0 + sx;
+        float v = 0.f;
+        if (h_ok && w >= 0 && w < W) {
+          int sh, sw;
+          tta_src(code, H, W, h, w, sh, sw);
+          v = __ldg(plane + (int64_t)sh * W + sw);
+        }
+        dst[sx * C] = __float2bfloat16(v);
+      }
     }
   }
   __syncthreads();
@@ -374,17 +399,33 @@ __global__ void __launch_bounds__(256) tta_expand_kernel(const float* __restrict
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
-extern "C" int mdhs_im2col_nchw_f32(const float* x, void* col, int B, int C, int H, int W, int R, int S, int stride, int pad,
-                                    int ldc, void* stream) {
-  if (!x || !col || ldc < R * S * C || (ldc % 8)) return MDHS_ERR_ARG;
+static int im2col_nchw_launch(const float* x, void* col, int Bsrc, int V, uint32_t codes, int C, int H, int W, int R, int S,
+                              int stride, int pad, int ldc, void* stream) {
+  if (!x || !col || ldc < R * S * C || (ldc % 8) || V < 1 || V > 8 || Bsrc <= 0) return MDHS_ERR_ARG;
+  for (int v = 0; v < V; v++) {
+    const int code = (codes >> (4 * v)) & 15;
+    if (code > 3 || (code == 3 && H != W)) return MDHS_ERR_ARG;
+  }
   const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
   g_mdhs_launches++;
+  const int B = Bsrc * V;
   const int64_t rows = (int64_t)B * Ho * Wo;
   const size_t smem = (size_t)IM2COL_PIX * ldc * sizeof(bf16);
   if (smem > 48 * 1024 || ((uintptr_t)col & 15)) return MDHS_ERR_ARG;
-  im2col_nchw_f32_kernel<<<(unsigned)((rows + IM2COL_PIX - 1) / IM2COL_PIX), 256, smem, ST(stream)>>>(x, (bf16*)col, B, C, H, W, R, S,
-                                                                                                  stride, pad, Ho, Wo, ldc);
+  im2col_nchw_f32_kernel<<<(unsigned)((rows + IM2COL_PIX - 1) / IM2COL_PIX), 256, smem, ST(stream)>>>(
+      x, (bf16*)col, B, C, H, W, R, S, stride, pad, Ho, Wo, ldc, Bsrc, codes);
   MDHS_RETURN_LAST();
+}
+
+extern "C" int mdhs_im2col_nchw_f32(const float* x, void* col, int B, int C, int H, int W, int R, int S, int stride, int pad,
+                                    int ldc, void* stream) {
+  return im2col_nchw_launch(x, col, B, 1, 0u, C, H, W, R, S, stride, pad, ldc, stream);
+}
+
+// V test-time-augmentation variants of the B source images, stacked on the batch axis of the patch matrix (V * B * Ho * Wo rows)
+extern "C" int mdhs_im2col_nchw_f32_tta(const float* x, void* col, int B, int C, int H, int W, int R, int S, int stride, int pad,
+                                        int ldc, int V, int codes, void* stream) {
+  return im2col_nchw_launch(x, col, B, V, (uint32_t)codes, C, H, W, R, S, stride, pad, ldc, stream);
 }
 
 extern "C" int mdhs_im2col_nhwc(const void* x, void* col, int B, int H, int W, int C, int R, int S, int stride, int pad,

@@ -272,3 +272,70 @@ extern "C" int mdhs_dropout_f32(const float* x, float* y, int64_t n, float p, ui
   dropout_f32_kernel<<<grid_for(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, n, p, seed);
   MDHS_RETURN_LAST();
 }
+
+// ---------------------------------------------------------------------------------------------
+// GPU-side input pipeline (replaces the per-sample torchvision transforms of data_loader.py:343-372 after the
+// JPEG decode): uint8 HWC batch -> per-sample crop box (RandomResizedCrop / Resize + CenterCrop geometry chosen by the
+// host) -> bilinear resample to (out_h, out_w) (F.interpolate(align_corners=False) sampling, like `_center_crop` +
+// interpolate of model.py:292-301) -> optional horizontal / vertical flip -> ToTensor (/255) -> Normalize(mean, std)
+// -> fp32 NCHW, the layout ImageEncoder.forward receives.  One thread = one output pixel (3 channels).
+// boxes: [B, 4] fp32 (y0, x0, h, w) in source pixels; flips: [B] uint8, bit 0 = hflip, bit 1 = vflip (both may be NULL).
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void preprocess_u8_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, const float* __restrict__ boxes,
+                                     const uint8_t* __restrict__ flips, int B, int Hs, int Ws, int Ho, int Wo, float3 mean,
+                                     float3 inv_std) {
+  const int64_t total = (int64_t)B * Ho * Wo;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / ((int64_t)Ho * Wo));
+    const int rem = (int)(i - (int64_t)b * Ho * Wo);
+    int oy = rem / Wo, ox = rem - oy * Wo;
+    const uint8_t f = flips ? flips[b] : 0;
+    const int sy_o = (f & 2) ? Ho - 1 - oy : oy, sx_o = (f & 1) ? Wo - 1 - ox : ox;   // flip = read the mirrored output pixel
+    float y0 = 0.f, x0 = 0.f, bh = (float)Hs, bw = (float)Ws;
+    if (boxes) {
+      y0 = boxes[b * 4 + 0];
+      x0 = boxes[b * 4 + 1];
+      bh = boxes[b * 4 + 2];
+      bw = boxes[b * 4 + 3];
+    }
+    // align_corners = False: source coordinate of the output pixel centre, clamped at 0 like ATen's area_pixel_compute
+    float fy = ((float)sy_o + 0.5f) * (bh / (float)Ho) - 0.5f;
+    float fx = ((float)sx_o + 0.5f) * (bw / (float)Wo) - 0.5f;
+    fy = fy < 0.f ? 0.f : fy;
+    fx = fx < 0.f ? 0.f : fx;
+    int iy = (int)fy, ix = (int)fx;
+    const float wy = fy - (float)iy, wx = fx - (float)ix;
+    const int bhi = (int)bh, bwi = (int)bw;
+    const int iy1 = iy + (iy < bhi - 1 ? 1 : 0), ix1 = ix + (ix < bwi - 1 ? 1 : 0);
+    const int by = (int)y0, bx = (int)x0;
+    auto at = [&](int yy, int xx, int c) -> float {
+      int Y = by + yy, X = bx + xx;
+      Y = Y < 0 ? 0 : (Y >= Hs ? Hs - 1 : Y);
+      X = X < 0 ? 0 : (X >= Ws ? Ws - 1 : X);
+      return (float)src[(((int64_t)b * Hs + Y) * Ws + X) * 3 + c];
+    };
+    const float m[3] = {mean.x, mean.y, mean.z}, is[3] = {inv_std.x, inv_std.y, inv_std.z};
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const float top = at(iy, ix, c) * (1.f - wx) + at(iy, ix1, c) * wx;
+      const float bot = at(iy1, ix, c) * (1.f - wx) + at(iy1, ix1, c) * wx;
+      const float v = (top * (1.f - wy) + bot * wy) * (1.f / 255.f);
+      dst[(((int64_t)b * 3 + c) * Ho + oy) * Wo + ox] = (v - m[c]) * is[c];
+    }
+  }
+}
+}  // namespace
+
+extern "C" int mdhs_preprocess_u8(const uint8_t* src, float* dst, const float* boxes, const uint8_t* flips, int B, int Hs, int Ws,
+                                  int Ho, int Wo, const float* mean3, const float* std3, void* stream) {
+  if (!src || !dst || !mean3 || !std3 || B <= 0 || Hs <= 0 || Ws <= 0 || Ho <= 0 || Wo <= 0) return MDHS_ERR_ARG;
+  const int64_t total = (int64_t)B * Ho * Wo;
+  int64_t g = (total + 255) / 256;
+  if (g > (int64_t)mdhs_num_sms() * 16) g = (int64_t)mdhs_num_sms() * 16;
+  g_mdhs_launches++;
+  preprocess_u8_kernel<<<(int)g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src, dst, boxes, flips, B, Hs, Ws, Ho, Wo, make_float3(mean3[0], mean3[1], mean3[2]),
+      make_float3(1.f / std3[0], 1.f / std3[1], 1.f / std3[2]));
+  MDHS_RETURN_LAST();
+}

@@ -304,9 +304,18 @@ __device__ __forceinline__ void stvec8(float* __restrict__ p, const float* v) {
 
 // Shared streaming body of the two forward kernels: y = act(x * sc + sh (+ residual)), 8 channels per thread held in
 // registers (the grid stride is a multiple of C/8), two independent 16-byte streams in flight per thread.
+// mask_out (optional, relu only): one byte per 8-channel vector, bit k = (output k > 0) -- the backward of a layer WITH a
+// residual input reads this 1-bit/element mask instead of the whole bf16 output (2 bytes/element, twice).
+__device__ __forceinline__ uint8_t relu_bits(const float* v) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) m |= (v[k] > 0.f ? 1u : 0u) << k;
+  return (uint8_t)m;
+}
+template <bool MASK>
 __device__ __forceinline__ void bn_apply_stream(const bf16* __restrict__ x, const bf16* __restrict__ residual,
                                                 bf16* __restrict__ y, const float* sc, const float* sh, int64_t i0,
-                                                int64_t stride, int64_t total_vec, int relu) {
+                                                int64_t stride, int64_t total_vec, int relu, uint8_t* __restrict__ mask_out) {
   int64_t i = i0;
   for (; i + stride < total_vec; i += 2 * stride) {
     float v0[8], v1[8], r0[8], r1[8];
@@ -339,6 +348,10 @@ __device__ __forceinline__ void bn_apply_stream(const bf16* __restrict__ x, cons
     }
     store8(y + i * 8, v0);
     store8(y + (i + stride) * 8, v1);
+    if (MASK) {
+      mask_out[i] = relu_bits(v0);
+      mask_out[i + stride] = relu_bits(v1);
+    }
   }
   if (i < total_vec) {
     float v[8], r[8];
@@ -352,15 +365,18 @@ __device__ __forceinline__ void bn_apply_stream(const bf16* __restrict__ x, cons
       v[k] = o;
     }
     store8(y + i * 8, v);
+    if (MASK) mask_out[i] = relu_bits(v);
   }
 }
 
 // y = act(x * scale[c] + shift[c] (+ residual)); 8 channels per thread, grid-stride over rows*C/8.  The host sizes the
 // grid so that the stride is a multiple of C/8: a thread then stays on ONE channel vector and its scale / shift live in
 // registers (per-iteration parameter loads made this kernel L1-bound: ncu l1tex 89 % at 65 % of HBM peak).
-__global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ scale,
+template <bool MASK>
+__global__ void __launch_bounds__(256, 3) bn_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ scale,
                                                        const float* __restrict__ shift, const bf16* __restrict__ residual,
-                                                       bf16* __restrict__ y, int64_t total_vec, int C, int relu) {
+                                                       bf16* __restrict__ y, int64_t total_vec, int C, int relu,
+                                                       uint8_t* __restrict__ mask_out) {
   const int cvec = C >> 3;
   const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -370,7 +386,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ 
   *reinterpret_cast<float4*>(sc + 4) = *reinterpret_cast<const float4*>(scale + c0 + 4);
   *reinterpret_cast<float4*>(sh) = *reinterpret_cast<const float4*>(shift + c0);
   *reinterpret_cast<float4*>(sh + 4) = *reinterpret_cast<const float4*>(shift + c0 + 4);
-  bn_apply_stream(x, residual, y, sc, sh, i0, stride, total_vec, relu);
+  bn_apply_stream<MASK>(x, residual, y, sc, sh, i0, stride, total_vec, relu, mask_out);
 }
 
 // Per-channel reductions for BN backward: sum(dy') and sum(dy' * (x - mean)), dy' = dy * [y > 0] when relu.  The ReLU
@@ -385,7 +401,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ 
 // 25 MB layer).  The (x - mean) centring happens here; the 1/sigma factor is applied by the consumer.
 template <int RL>
 __global__ void __launch_bounds__(32 * RL, 512 / (32 * RL)) bn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
-                                                            const bf16* __restrict__ y, const float* __restrict__ mean,
+                                                            const bf16* __restrict__ y, const uint8_t* __restrict__ mbits,
+                                                            const float* __restrict__ mean,
                                                             const float* __restrict__ scale, const float* __restrict__ shift,
                                                             double* __restrict__ sum_dy, double* __restrict__ sum_dy_xc,
                                                             int64_t rows, int C, int Cw, int rows_per_block, int relu) {
@@ -395,7 +412,10 @@ __global__ void __launch_bounds__(32 * RL, 512 / (32 * RL)) bn_bwd_reduce_kernel
   const int c0 = blockIdx.x * 256 + cv * 8;
   const bool ok = c0 < Cw;
   const int ch0 = c0 % C;
-  const bool remask = relu && (y == nullptr);
+  const bool use_bits = relu && (mbits != nullptr);          // 1-bit/element ReLU mask written by the forward
+  const bool remask = relu && !use_bits && (y == nullptr);
+  const bool use_y = relu && !use_bits && !remask;
+  const int cw8 = Cw >> 3, cv0 = c0 >> 3;
   float a[8], b[8], mu[8], sc[8], sf[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) {
@@ -406,11 +426,13 @@ __global__ void __launch_bounds__(32 * RL, 512 / (32 * RL)) bn_bwd_reduce_kernel
   }
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
   const int64_t r1 = min(rows, r0 + rows_per_block);
-  auto accum = [&](const float* d, const float* xv, const float* yv) {
+  auto accum = [&](const float* d, const float* xv, const float* yv, uint32_t bits) {
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      const float act = remask ? fmaf(xv[k], sc[k], sf[k]) : yv[k];
-      const float dd = (relu && !(act > 0.f)) ? 0.f : d[k];
+      bool on = true;
+      if (use_bits) on = (bits >> k) & 1u;
+      else if (relu) on = (remask ? fmaf(xv[k], sc[k], sf[k]) : yv[k]) > 0.f;
+      const float dd = on ? d[k] : 0.f;
       a[k] += dd;
       b[k] = fmaf(dd, xv[k] - mu[k], b[k]);
     }
@@ -420,27 +442,29 @@ __global__ void __launch_bounds__(32 * RL, 512 / (32 * RL)) bn_bwd_reduce_kernel
     int64_t r = r0 + rl;
     for (; r + (U - 1) * RL < r1; r += U * RL) {
       bf16x8 rd[U], rx[U], ry[U];
+      uint32_t mb[U];
 #pragma unroll
       for (int u = 0; u < U; u++) {
         rd[u] = ldraw8(dy + (r + u * RL) * Cw + c0);
         rx[u] = ldraw8(x + (r + u * RL) * Cw + c0);
-        if (relu && !remask) ry[u] = ldraw8(y + (r + u * RL) * Cw + c0);
+        if (use_y) ry[u] = ldraw8(y + (r + u * RL) * Cw + c0);
+        mb[u] = use_bits ? mbits[(r + u * RL) * cw8 + cv0] : 0u;
       }
 #pragma unroll
       for (int u = 0; u < U; u++) {
         float d[8], xv[8], yv[8];
         cvt8(rd[u], d);
         cvt8(rx[u], xv);
-        if (relu && !remask) cvt8(ry[u], yv);
-        accum(d, xv, yv);
+        if (use_y) cvt8(ry[u], yv);
+        accum(d, xv, yv, mb[u]);
       }
     }
     for (; r < r1; r += RL) {
       float d[8], xv[8], yv[8];
       load8(dy + r * Cw + c0, d);
       load8(x + r * Cw + c0, xv);
-      if (relu && !remask) load8(y + r * Cw + c0, yv);
-      accum(d, xv, yv);
+      if (use_y) load8(y + r * Cw + c0, yv);
+      accum(d, xv, yv, use_bits ? mbits[r * cw8 + cv0] : 0u);
     }
   }
   // cross-lane reduction through shared memory, 8 row lanes per round
@@ -520,13 +544,17 @@ __global__ void bn_bwd_coeff_kernel(const float* __restrict__ mean, const float*
 // identity branch.  Pure streaming, 8 channels per thread; the grid stride is a multiple of C/8 (see bn_apply), so the
 // five coefficient vectors of a thread's channel group are loaded once (128-bit loads).  coef rows 3 and 4 hold the forward
 // scale / shift when the ReLU mask is recomputed from x (y == nullptr).
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
-                                                           const bf16* __restrict__ y, const float* __restrict__ coef,
-                                                           bf16* __restrict__ dx, bf16* __restrict__ dz, int64_t rows, int C,
-                                                           int relu) {
+// MODE: where the ReLU mask comes from -- 0 no ReLU, 1 recomputed from (x, scale, shift), 2 the bf16 output y, 3 the forward's
+// bit mask.  (Compile-time: with run-time flags every launch carried the code and registers of all four paths.)
+template <int MODE, bool DZ>
+__global__ void __launch_bounds__(256, 3) bn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                              const bf16* __restrict__ y, const uint8_t* __restrict__ mbits,
+                                                              const float* __restrict__ coef, bf16* __restrict__ dx,
+                                                              bf16* __restrict__ dz_, int64_t rows, int C) {
   const int cvec = C >> 3;
   const int64_t total_vec = rows * cvec;
-  const bool remask = relu && (y == nullptr);
+  constexpr bool relu = MODE != 0, use_bits = MODE == 3, remask = MODE == 1, use_y = MODE == 2;
+  bf16* dz = DZ ? dz_ : nullptr;
   const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int c0 = (int)(i0 % cvec) * 8;
@@ -541,22 +569,26 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restric
   int64_t i = i0;
   for (; i + stride < total_vec; i += 2 * stride) {   // two independent row groups in flight per thread
     bf16x8 rd[2], rx[2], ry[2];
+    uint32_t mb[2];
 #pragma unroll
     for (int u = 0; u < 2; u++) {
       rd[u] = ldraw8(dy + (i + u * stride) * 8);
       rx[u] = ldraw8(x + (i + u * stride) * 8);
-      if (relu && !remask) ry[u] = ldraw8(y + (i + u * stride) * 8);
+      if (use_y) ry[u] = ldraw8(y + (i + u * stride) * 8);
+      mb[u] = use_bits ? mbits[i + u * stride] : 0u;
     }
 #pragma unroll
     for (int u = 0; u < 2; u++) {
       float d[8], xv[8], yv[8], o[8];
       cvt8(rd[u], d);
       cvt8(rx[u], xv);
-      if (relu && !remask) cvt8(ry[u], yv);
+      if (use_y) cvt8(ry[u], yv);
 #pragma unroll
       for (int k = 0; k < 8; k++) {
-        const float act = remask ? fmaf(xv[k], sc[k], sf[k]) : yv[k];
-        const float dd = (relu && !(act > 0.f)) ? 0.f : d[k];
+        bool on = true;
+        if (use_bits) on = (mb[u] >> k) & 1u;
+        else if (relu) on = (remask ? fmaf(xv[k], sc[k], sf[k]) : yv[k]) > 0.f;
+        const float dd = on ? d[k] : 0.f;
         d[k] = dd;
         o[k] = fmaf(ca[k], dd, fmaf(cb[k], xv[k], cc[k]));
       }
@@ -568,11 +600,14 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restric
     float d[8], xv[8], yv[8], o[8];
     load8(dy + i * 8, d);
     load8(x + i * 8, xv);
-    if (relu && !remask) load8(y + i * 8, yv);
+    if (use_y) load8(y + i * 8, yv);
+    const uint32_t bits = use_bits ? mbits[i] : 0u;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      const float act = remask ? fmaf(xv[k], sc[k], sf[k]) : yv[k];
-      const float dd = (relu && !(act > 0.f)) ? 0.f : d[k];
+      bool on = true;
+      if (use_bits) on = (bits >> k) & 1u;
+      else if (relu) on = (remask ? fmaf(xv[k], sc[k], sf[k]) : yv[k]) > 0.f;
+      const float dd = on ? d[k] : 0.f;
       d[k] = dd;
       o[k] = fmaf(ca[k], dd, fmaf(cb[k], xv[k], cc[k]));
     }
@@ -776,17 +811,18 @@ extern "C" int mdhs_bn_apply(const void* x, const float* scale, const float* shi
   if (!x || !scale || !shift || !y || rows <= 0 || (C % 8)) return MDHS_ERR_ARG;
   const int64_t total_vec = rows * (C / 8);
   g_mdhs_launches++;
-  bn_apply_kernel<<<grid_for_channels(total_vec, C), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      (const bf16*)x, scale, shift, (const bf16*)residual, (bf16*)y, total_vec, C, relu);
+  bn_apply_kernel<false><<<grid_for_channels(total_vec, C), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      (const bf16*)x, scale, shift, (const bf16*)residual, (bf16*)y, total_vec, C, relu, nullptr);
   MDHS_RETURN_LAST();
 }
 
 // finalize + apply as one C-ABI call (two launches: the per-channel fp64 work runs once per channel, not once per thread)
 extern "C" int mdhs_bn_fwd(const void* x, const double* colsum, const double* colsumsq, const float* gamma, const float* beta,
                            float* running_mean, float* running_var, float momentum, float eps, const void* residual, void* y,
-                           float* mean, float* invstd, float* scale, float* shift, int64_t rows, int C, int relu, int training,
-                           void* stream) {
+                           float* mean, float* invstd, float* scale, float* shift, void* relu_mask, int64_t rows, int C,
+                           int relu, int training, void* stream) {
   if (!x || !y || !gamma || !beta || !scale || !shift || rows <= 0 || C <= 0 || (C % 8)) return MDHS_ERR_ARG;
+  if (relu_mask && !relu) return MDHS_ERR_ARG;
   if (training && (!colsum || !colsumsq)) return MDHS_ERR_ARG;
   if (!training && (!running_mean || !running_var)) return MDHS_ERR_ARG;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -794,8 +830,12 @@ extern "C" int mdhs_bn_fwd(const void* x, const double* colsum, const double* co
   g_mdhs_launches += 2;
   bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(colsum, colsumsq, rows, gamma, beta, running_mean, running_var, momentum,
                                                        eps, mean, invstd, scale, shift, C, training);
-  bn_apply_kernel<<<grid_for_channels(total_vec, C), 256, 0, st>>>((const bf16*)x, scale, shift, (const bf16*)residual, (bf16*)y,
-                                                                  total_vec, C, relu);
+  if (relu_mask)
+    bn_apply_kernel<true><<<grid_for_channels(total_vec, C), 256, 0, st>>>((const bf16*)x, scale, shift, (const bf16*)residual,
+                                                                          (bf16*)y, total_vec, C, relu, (uint8_t*)relu_mask);
+  else
+    bn_apply_kernel<false><<<grid_for_channels(total_vec, C), 256, 0, st>>>((const bf16*)x, scale, shift, (const bf16*)residual,
+                                                                           (bf16*)y, total_vec, C, relu, nullptr);
   MDHS_RETURN_LAST();
 }
 
@@ -818,12 +858,14 @@ static void bn_reduce_cfg(int* rl, int* bps) {
   *bps = s_bps;
 }
 
-extern "C" int mdhs_bn_bwd(const void* dy, const void* x, const void* y, const float* mean, const float* invstd,
+extern "C" int mdhs_bn_bwd(const void* dy, const void* x, const void* y, const void* relu_mask, const float* mean,
+                           const float* invstd,
                            const float* gamma, const float* scale, const float* shift, double* sum_dy, double* sum_dy_xc,
                            float* coef, void* dx, void* dz, float* dgamma, float* dbeta, int64_t rows, int C, int relu,
                            int training, int sums_ready, void* stream) {
   if (!dy || !x || !mean || !invstd || !gamma || !sum_dy || !sum_dy_xc || !coef || !dx || rows <= 0 || (C % 8)) return MDHS_ERR_ARG;
-  if (relu && !y && (!scale || !shift)) return MDHS_ERR_ARG;   // the mask comes from y or is recomputed from scale / shift
+  // the ReLU mask comes from the forward's bit mask, from y, or is recomputed from (x, scale, shift)
+  if (relu && !y && !relu_mask && (!scale || !shift)) return MDHS_ERR_ARG;
   if ((dgamma == nullptr) != (dbeta == nullptr)) return MDHS_ERR_ARG;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (!sums_ready) {
@@ -851,19 +893,35 @@ extern "C" int mdhs_bn_bwd(const void* dy, const void* x, const void* y, const f
     g_mdhs_launches++;
     const dim3 grid(cslabs, row_blocks);
     if (rl == 16)
-      bn_bwd_reduce_kernel<16><<<grid, 512, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, mean, scale, shift, sum_dy,
+      bn_bwd_reduce_kernel<16><<<grid, 512, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, (const uint8_t*)relu_mask, mean, scale, shift, sum_dy,
                                                      sum_dy_xc, rows_w, C, Cw, rpb, relu);
     else
-      bn_bwd_reduce_kernel<8><<<grid, 256, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, mean, scale, shift, sum_dy,
+      bn_bwd_reduce_kernel<8><<<grid, 256, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, (const uint8_t*)relu_mask, mean, scale, shift, sum_dy,
                                                     sum_dy_xc, rows_w, C, Cw, rpb, relu);
   }
   g_mdhs_launches += 2;
-  const bool remask = relu && !y;
+  const bool remask = relu && !y && !relu_mask;
   bn_bwd_coeff_kernel<<<ceil_div(C, 128), 128, 0, st>>>(mean, invstd, gamma, sum_dy, sum_dy_xc, remask ? scale : nullptr,
                                                         remask ? shift : nullptr, coef, dgamma, dbeta, rows, C, training);
   const int64_t total_vec = rows * (C / 8);
-  bn_bwd_apply_kernel<<<grid_for_channels(total_vec, C), 256, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, coef,
-                                                                       (bf16*)dx, (bf16*)dz, rows, C, relu);
+  const int mode = !relu ? 0 : (relu_mask ? 3 : (y ? 2 : 1));
+  const int grid = grid_for_channels(total_vec, C);
+#define BN_APPLY(MODE, DZ)                                                                                                  \
+  bn_bwd_apply_kernel<MODE, DZ><<<grid, 256, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, (const uint8_t*)relu_mask, \
+                                                     coef, (bf16*)dx, (bf16*)dz, rows, C)
+#define BN_APPLY_DZ(MODE)              \
+  do {                                 \
+    if (dz) BN_APPLY(MODE, true);      \
+    else BN_APPLY(MODE, false);        \
+  } while (0)
+  switch (mode) {
+    case 0: BN_APPLY_DZ(0); break;
+    case 1: BN_APPLY_DZ(1); break;
+    case 2: BN_APPLY_DZ(2); break;
+    default: BN_APPLY_DZ(3); break;
+  }
+#undef BN_APPLY_DZ
+#undef BN_APPLY
   MDHS_RETURN_LAST();
 }
 

@@ -16,7 +16,7 @@ void mdhs_seed_tick_convnext(uint64_t, cudaStream_t);
 namespace {
 
 // mode 0: AdamW (decoupled decay), 1: Adam (L2 decay folded into the gradient)
-__global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, float* __restrict__ g,
+__global__ void __launch_bounds__(1024) adam_flat_kernel(float* __restrict__ p, float* __restrict__ g,
                                                         const bf16* __restrict__ g16, float* __restrict__ m,
                                                         float* __restrict__ v, bf16* __restrict__ shadow, int64_t n, float lr,
                                                         float beta1, float beta2, float eps, float wd, float bc1, float bc2,
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, f
   }
 }
 
-__global__ void __launch_bounds__(256) sgd_flat_kernel(float* __restrict__ p, float* __restrict__ g,
+__global__ void __launch_bounds__(1024) sgd_flat_kernel(float* __restrict__ p, float* __restrict__ g,
                                                        const bf16* __restrict__ g16, float* __restrict__ mom,
                                                        bf16* __restrict__ shadow, int64_t n, float lr, float momentum, float wd,
                                                        float grad_scale, int first_step, int zero_grad,
@@ -109,10 +109,24 @@ __global__ void __launch_bounds__(256) sgd_flat_kernel(float* __restrict__ p, fl
   }
 }
 
-int grid_for(int64_t items) {
+// Launch shape.  blocks_per_sm > 0 (default 16): that many 256-thread blocks per SM.  blocks_per_sm < 0: "leave -blocks_per_sm
+// SMs free" -- ONE 1024-thread block per SM on (num_sms + blocks_per_sm) SMs.  A data-parallel step runs this kernel next to
+// NCCL's all-reduce of the NEXT gradient bucket; NCCL's CTAs (hundreds of threads x ~100 registers) need an SM to themselves,
+// so with blocks on every SM the collective only started when the optimizer had drained (CUPTI timeline, 2 x B200: the two
+// simply alternated).  With whole SMs left free they run side by side; 1024 threads x 64 B keep 64 KB of loads in flight per SM.
+void launch_shape(int64_t items, int blocks_per_sm, int* grid, int* block) {
+  if (blocks_per_sm < 0) {
+    int sms = mdhs_num_sms() + blocks_per_sm;
+    if (sms < 1) sms = 1;
+    int64_t g = (items + 1023) / 1024;
+    *grid = (int)(g < 1 ? 1 : (g > sms ? sms : g));
+    *block = 1024;
+    return;
+  }
   int64_t g = (items + 255) / 256;
-  const int64_t cap = (int64_t)mdhs_num_sms() * 16;
-  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+  const int64_t cap = (int64_t)mdhs_num_sms() * (blocks_per_sm > 0 ? blocks_per_sm : 16);
+  *grid = (int)(g < 1 ? 1 : (g > cap ? cap : g));
+  *block = 256;
 }
 
 }  // namespace
@@ -121,11 +135,14 @@ int grid_for(int64_t items) {
 extern "C" int mdhs_adam_flat(float* params, float* grads, const void* grads_bf16, float* exp_avg, float* exp_avg_sq,
                               void* shadow_bf16, int64_t n,
                               float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
-                              int adamw, int zero_grad, const float* lr_dev, const int* step_dev, void* stream) {
+                              int adamw, int zero_grad, const float* lr_dev, const int* step_dev, int blocks_per_sm,
+                              void* stream) {
   if (!params || !grads || !exp_avg || !exp_avg_sq || n <= 0 || (n % 4) || (step < 1 && !step_dev)) return MDHS_ERR_ARG;
   const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
   g_mdhs_launches++;
-  adam_flat_kernel<<<grid_for(n / 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  int grid, block;
+  launch_shape(n / 4, blocks_per_sm, &grid, &block);
+  adam_flat_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       params, grads, (const bf16*)grads_bf16, exp_avg, exp_avg_sq, (bf16*)shadow_bf16, n, lr, beta1, beta2, eps, weight_decay,
       bc1, bc2, grad_scale,
       adamw ? 0 : 1, zero_grad, lr_dev, step_dev);
@@ -135,10 +152,12 @@ extern "C" int mdhs_adam_flat(float* params, float* grads, const void* grads_bf1
 extern "C" int mdhs_sgd_flat(float* params, float* grads, const void* grads_bf16, float* momentum_buf, void* shadow_bf16,
                              int64_t n, float lr,
                              float momentum, float weight_decay, float grad_scale, int first_step, int zero_grad,
-                             const float* lr_dev, const int* step_dev, void* stream) {
+                             const float* lr_dev, const int* step_dev, int blocks_per_sm, void* stream) {
   if (!params || !grads || n <= 0 || (n % 4)) return MDHS_ERR_ARG;
   g_mdhs_launches++;
-  sgd_flat_kernel<<<grid_for(n / 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  int grid, block;
+  launch_shape(n / 4, blocks_per_sm, &grid, &block);
+  sgd_flat_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       params, grads, (const bf16*)grads_bf16, momentum_buf, (bf16*)shadow_bf16, n, lr, momentum, weight_decay, grad_scale,
       first_step, zero_grad, lr_dev,
       step_dev);

@@ -83,8 +83,8 @@ class MdhsModule(nn.Module):
 
 class _TrunkFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, anchor, images, engine, training, names, need):
-        feats, c = engine.forward(images, training, need)
+    def forward(ctx, anchor, images, engine, training, names, need, tta=None):
+        feats, c = engine.forward(images, training, need, tta=tta)
         # frozen trunk (need == False): nothing was saved, the backward below must be a no-op
         ctx.engine, ctx.c, ctx.names = engine, (c if need else None), names
         return tuple(feats[n][0] for n in names)
@@ -94,7 +94,7 @@ class _TrunkFn(torch.autograd.Function):
         if ctx.c is not None:  # frozen trunk: outputs still carry grad so that downstream Functions run backward
             ctx.engine.backward(ctx.c, {n: (g.contiguous() if g is not None else None) for n, g in zip(ctx.names, grads)})
         ctx.c = None
-        return None, None, None, None, None, None
+        return None, None, None, None, None, None, None
 
 
 # ---- stage-wise trunk (only used while analysis hooks are registered on image_encoder.stem / layerN / layerN[-1]) ----------
@@ -315,18 +315,26 @@ class ImageEncoder(MdhsModule):
         eng.end_forward()
         return tuple(feats[n] for n in names)
 
-    def forward(self, x):
+    def forward(self, x, tta=None):
+        """tta: optional tuple of transform names (scripts/predict.py:33-42: "hflip", "vflip", "rot90"): inference only; the
+        returned tokens then hold [identity] + transforms variants stacked on the batch axis ((1 + len(tta)) * B samples),
+        produced by the stem's im2col addressing instead of a materialised augmented batch."""
         st = self.store(x.device)
+        if tta:
+            if self.is_convnext or torch.is_grad_enabled() or self._hooked_stages():
+                x, tta = ops.tta_expand(x, tta), None       # generic path: materialise the variants
+            else:
+                tta = ops.tta_codes(tta)
         if self.is_convnext:
             return self._forward_convnext(st, x)
-        B = x.shape[0]
+        B = x.shape[0] * (tta[0] if tta else 1)
         names = ("layer2", "layer3", "layer4") if self.multi_scale else ("layer4",)
         need = self._trainable() and torch.is_grad_enabled()
         hooked = self._hooked_stages()
         if hooked:
             feats = self._forward_staged(st, x.float(), hooked, names, need)
         else:
-            feats = _TrunkFn.apply(st.anchor, x.float(), self._engine, self.training, names, need)
+            feats = _TrunkFn.apply(st.anchor, x.float(), self._engine, self.training, names, need, tta or None)
         if self.multi_scale:
             out = {}
             for name, f, proj in zip(names, feats, (self.proj2, self.proj3, self.proj4)):

@@ -154,19 +154,23 @@ def bn_apply(x, scale, shift, residual=None, relu=True, out=None):
     return y
 
 
-def bn_fwd(x, colsum, colsumsq, gamma, beta, running_mean, running_var, momentum, eps, residual=None, relu=True, training=True):
-    """Finalize + apply in one C-ABI call.  Returns (y, mean, invstd, scale, shift)."""
+def bn_fwd(x, colsum, colsumsq, gamma, beta, running_mean, running_var, momentum, eps, residual=None, relu=True, training=True,
+           want_mask=False):
+    """Finalize + apply in one C-ABI call.  Returns (y, mean, invstd, scale, shift[, relu bit mask uint8 [rows, C/8]])."""
     rows, C = x.shape
     stats = torch.empty((4, C), device=x.device, dtype=torch.float32)
     y = torch.empty_like(x)
+    mask = torch.empty((rows, C // 8), device=x.device, dtype=torch.uint8) if (want_mask and relu) else None
     _lib.call("mdhs_bn_fwd", _p(x), _p(colsum), _p(colsumsq), _p(gamma), _p(beta), _p(running_mean), _p(running_var),
               float(momentum), float(eps), _p(residual), _p(y), stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(),
-              stats[3].data_ptr(), rows, C, int(relu), int(training), _s())
+              stats[3].data_ptr(), _p(mask), rows, C, int(relu), int(training), _s())
+    if want_mask:
+        return y, stats[0], stats[1], stats[2], stats[3], mask
     return y, stats[0], stats[1], stats[2], stats[3]
 
 
 def bn_bwd(dy, x, y, mean, invstd, gamma, dgamma, dbeta, relu=True, want_dz=False, scale=None, shift=None, training=True,
-           sums=None):
+           sums=None, mask=None):
     """y may be None when relu and the layer had no residual input: the mask is recomputed from (x, scale, shift).
     sums: optional fp64 [2, C] workspace already holding sum(dy'), sum(dy' * (x - mean)) (GEMM-epilogue fused reduction)."""
     rows, C = x.shape
@@ -174,7 +178,7 @@ def bn_bwd(dy, x, y, mean, invstd, gamma, dgamma, dbeta, relu=True, want_dz=Fals
     coef = torch.empty((5, C), device=x.device, dtype=torch.float32)
     dx = torch.empty_like(x)
     dz = torch.empty_like(x) if want_dz else None
-    _lib.call("mdhs_bn_bwd", _p(dy), _p(x), _p(y), _p(mean), _p(invstd), _p(gamma), _p(scale), _p(shift), ws[0].data_ptr(),
+    _lib.call("mdhs_bn_bwd", _p(dy), _p(x), _p(y), _p(mask), _p(mean), _p(invstd), _p(gamma), _p(scale), _p(shift), ws[0].data_ptr(),
               ws[1].data_ptr(), _p(coef), _p(dx), _p(dz), _p(dgamma), _p(dbeta), rows, C, int(relu), int(training),
               int(sums is not None), _s())
     return dx, dz
@@ -185,11 +189,30 @@ def col_stats(x, sum64=None, sumsq64=None, sum32=None):
     _lib.call("mdhs_col_stats", _p(x), x.stride(0), _p(sum64), _p(sumsq64), _p(sum32), rows, C, _s())
 
 
-def im2col_nchw_f32(x, R, S, stride, pad, ldc):
+TTA_CODES = {"identity": 0, "hflip": 1, "vflip": 2, "rot90": 3}
+
+
+def tta_codes(transforms):
+    """Packed 4-bit transform ids of [identity] + transforms (scripts/predict.py:33-42)."""
+    names = ["identity"] + list(transforms)
+    codes = 0
+    for v, n in enumerate(names):
+        if n not in TTA_CODES:
+            raise ValueError(f"unknown TTA transform {n!r}")
+        codes |= TTA_CODES[n] << (4 * v)
+    return len(names), codes
+
+
+def im2col_nchw_f32(x, R, S, stride, pad, ldc, tta=None):
+    """tta = (V, codes): the patch matrix holds V augmented variants of every image (variant-major), read from x directly."""
     B, C, H, W = x.shape
     Ho, Wo = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
-    col = torch.empty((B * Ho * Wo, ldc), device=x.device, dtype=torch.bfloat16)
-    _lib.call("mdhs_im2col_nchw_f32", _p(x), _p(col), B, C, H, W, R, S, stride, pad, ldc, _s())
+    V = 1 if tta is None else tta[0]
+    col = torch.empty((V * B * Ho * Wo, ldc), device=x.device, dtype=torch.bfloat16)
+    if tta is None:
+        _lib.call("mdhs_im2col_nchw_f32", _p(x), _p(col), B, C, H, W, R, S, stride, pad, ldc, _s())
+    else:
+        _lib.call("mdhs_im2col_nchw_f32_tta", _p(x), _p(col), B, C, H, W, R, S, stride, pad, ldc, V, int(tta[1]), _s())
     return col, Ho, Wo
 
 
@@ -394,20 +417,21 @@ def num_sms(device=None):
 
 def set_sm_reserve(n):
     """Persistent GEMM grids leave n SMs free (for a concurrently running collective kernel); 0 = all SMs."""
-    _lib.check(_lib.lib().mdhs_set_sm_reserve(int(n)), "mdhs_set_sm_reserve")
+    _lib.call("mdhs_set_sm_reserve", int(n))
 
 
 def adam_flat(params, grads, exp_avg, exp_avg_sq, shadow, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0,
-              adamw=True, zero_grad=True, lr_dev=None, step_dev=None, grads_bf16=None):
+              adamw=True, zero_grad=True, lr_dev=None, step_dev=None, grads_bf16=None, blocks_per_sm=0):
     _lib.call("mdhs_adam_flat", _p(params), _p(grads), _p(grads_bf16), _p(exp_avg), _p(exp_avg_sq), _p(shadow), params.numel(), float(lr),
               float(beta1), float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale), int(adamw),
-              int(zero_grad), _p(lr_dev), _p(step_dev), _s())
+              int(zero_grad), _p(lr_dev), _p(step_dev), int(blocks_per_sm), _s())
 
 
 def sgd_flat(params, grads, mom, shadow, lr, momentum, weight_decay, grad_scale=1.0, first_step=False, zero_grad=True,
-             lr_dev=None, step_dev=None, grads_bf16=None):
+             lr_dev=None, step_dev=None, grads_bf16=None, blocks_per_sm=0):
     _lib.call("mdhs_sgd_flat", _p(params), _p(grads), _p(grads_bf16), _p(mom), _p(shadow), params.numel(), float(lr), float(momentum),
-              float(weight_decay), float(grad_scale), int(first_step), int(zero_grad), _p(lr_dev), _p(step_dev), _s())
+              float(weight_decay), float(grad_scale), int(first_step), int(zero_grad), _p(lr_dev), _p(step_dev),
+              int(blocks_per_sm), _s())
 
 
 def step_begin(step_dev=None):
@@ -599,9 +623,6 @@ def sq_attn_bwd(q, k, v, dout, probs, B, T, scale=1.0):
     return dq, dk, dv
 
 
-TTA_CODES = {"identity": 0, "hflip": 1, "vflip": 2, "rot90": 3}
-
-
 def tta_expand(images, transforms):
     """[B,3,H,W] fp32 -> [V*B,3,H,W]: identity followed by the named transforms (scripts/predict.py:33-42)."""
     B, C, H, W = images.shape
@@ -656,6 +677,28 @@ def global_local(images, crop_ratio):
     y = torch.empty((2 * B, C, H, W), device=x.device, dtype=torch.float32)
     _lib.call("mdhs_global_local", _p(x), _p(y), B, C, H, W, float(crop_ratio), _s())
     return y
+
+
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)   # data_loader.py:358
+
+
+def preprocess_u8(images_u8, out_hw=(224, 224), boxes=None, flips=None, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+    """GPU-side replacement of the per-sample torchvision transforms after the decode (data_loader.py:343-372):
+    uint8 [B, Hs, Ws, 3] CUDA batch -> crop boxes [B, 4] (y0, x0, h, w) -> bilinear resize -> flips [B] uint8 (bit 0 h, bit 1 v)
+    -> ToTensor -> Normalize -> fp32 [B, 3, H, W].  The host only decodes and draws the random crop / flip parameters."""
+    import ctypes as _ct
+    B, Hs, Ws, C = images_u8.shape
+    assert C == 3 and images_u8.dtype == torch.uint8 and images_u8.is_cuda and images_u8.is_contiguous()
+    out = torch.empty((B, 3, out_hw[0], out_hw[1]), device=images_u8.device, dtype=torch.float32)
+    m3 = (_ct.c_float * 3)(*[float(v) for v in mean])
+    s3 = (_ct.c_float * 3)(*[float(v) for v in std])
+    if boxes is not None:
+        boxes = boxes.to(device=images_u8.device, dtype=torch.float32).contiguous()
+    if flips is not None:
+        flips = flips.to(device=images_u8.device, dtype=torch.uint8).contiguous()
+    _lib.call("mdhs_preprocess_u8", _p(images_u8), _p(out), _p(boxes), _p(flips), B, Hs, Ws, out_hw[0], out_hw[1],
+              _ct.cast(m3, _ct.c_void_p), _ct.cast(s3, _ct.c_void_p), _s())
+    return out
 
 
 def lstm_cell_fwd(gates, c_prev):

@@ -82,6 +82,11 @@ class GradSync:
         """Call when every gradient in [split, total) is final (after the text-encoder backward)."""
         self.reduce_range(self.split, self.total)
 
+    def wait(self, i):
+        """Block the current stream until the i-th collective issued this step has completed (pipelined optimizer tail)."""
+        if i < len(self._works):
+            self._works[i].wait()
+
     def finish(self):
         """Call after backward: reduces what is left and waits for all outstanding collectives."""
         pos = 0

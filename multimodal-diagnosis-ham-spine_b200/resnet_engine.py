@@ -118,10 +118,10 @@ class ResNetEngine:
         self.on_stage_backward_done = None
 
     # ------------------------------------------------------------------ forward pieces
-    def _conv_bn(self, c, x, B, H, W, relu, residual, training, need_grad):
+    def _conv_bn(self, c, x, B, H, W, relu, residual, training, need_grad, tta=None):
         """x: [B*H*W, Cin] bf16 (or the NCHW fp32 image for the stem).  Returns y, Ho, Wo, record-for-backward."""
         if c.stem:
-            A, Ho, Wo = ops.im2col_nchw_f32(x, c.R, c.S, c.stride, c.pad, c.ldk)
+            A, Ho, Wo = ops.im2col_nchw_f32(x, c.R, c.S, c.stride, c.pad, c.ldk, tta=tta)
         elif c.direct:
             A, Ho, Wo = x, H, W
         elif c.implicit:
@@ -130,6 +130,9 @@ class ResNetEngine:
             A, Ho, Wo = ops.im2col_nhwc(x, B, H, W, c.I, c.R, c.S, c.stride, c.pad)
         rows = B * Ho * Wo
         bn = c.bn
+        # layers with a residual input cannot rebuild their ReLU mask from (raw, scale, shift): the forward leaves a 1-bit
+        # mask for the backward (instead of the backward re-reading the whole bf16 output twice)
+        want_mask = need_grad and relu and residual is not None
         gkw = dict(conv=c.conv_desc(1, B, H, W), M=rows, K=c.K) if c.implicit else {}
         track = bn.track_running_stats and bn.running_mean is not None
         if training:
@@ -140,20 +143,22 @@ class ResNetEngine:
                 raw = ops.gemm(A, c.wp, N=c.O, **gkw)
                 ops.col_stats(raw, st[0], st[1])
             mom = bn.momentum if bn.momentum is not None else 0.1
-            y, mean, invstd, scale, shift = ops.bn_fwd(raw, st[0], st[1], bn.weight.data, bn.bias.data,
-                                                       bn.running_mean if track else None, bn.running_var if track else None,
-                                                       mom, bn.eps, residual=residual, relu=relu, training=True)
+            out = ops.bn_fwd(raw, st[0], st[1], bn.weight.data, bn.bias.data, bn.running_mean if track else None,
+                             bn.running_var if track else None, mom, bn.eps, residual=residual, relu=relu, training=True,
+                             want_mask=want_mask)
             if track and bn.num_batches_tracked is not None:
                 self._nbt.append(bn.num_batches_tracked)
         else:
             raw = ops.gemm(A, c.wp, N=c.O, **gkw)
-            y, mean, invstd, scale, shift = ops.bn_fwd(raw, None, None, bn.weight.data, bn.bias.data, bn.running_mean,
-                                                       bn.running_var, 0.0, bn.eps, residual=residual, relu=relu, training=False)
+            out = ops.bn_fwd(raw, None, None, bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, 0.0, bn.eps,
+                             residual=residual, relu=relu, training=False, want_mask=want_mask)
+        y, mean, invstd, scale, shift = out[:5]
+        mask = out[5] if want_mask else None
         rec = None
         if need_grad:
             # y is only kept for the backward ReLU mask when a residual entered the activation; otherwise the mask is
             # recomputed from (raw, scale, shift)
-            rec = dict(c=c, A=A, raw=raw, y=y if (relu and residual is not None) else None, mean=mean, invstd=invstd,
+            rec = dict(c=c, A=A, raw=raw, y=None, mask=mask, mean=mean, invstd=invstd,
                        scale=scale, shift=shift, relu=relu, B=B, H=H, W=W, Ho=Ho, Wo=Wo, has_res=residual is not None,
                        training=training, sums=None)
         return y, Ho, Wo, rec
@@ -168,10 +173,12 @@ class ResNetEngine:
             torch._foreach_add_(self._nbt, 1)
             self._nbt = []
 
-    def forward_stem(self, images, training, need_grad):
-        """images [B,3,H,W] fp32 -> (x [B*H2*W2, 64] bf16 after the 3x3/2 max-pool, H2, W2, ctx)."""
+    def forward_stem(self, images, training, need_grad, tta=None):
+        """images [B,3,H,W] fp32 -> (x [B*H2*W2, 64] bf16 after the 3x3/2 max-pool, H2, W2, ctx).  tta = (V, codes): the
+        trunk runs on V test-time-augmentation variants of every image (batch V*B), generated by the stem's im2col."""
         B, _, H, W = images.shape
-        x, H1, W1, rec = self._conv_bn(self.stem, images.contiguous(), B, H, W, True, None, training, need_grad)
+        B = B * (tta[0] if tta else 1)
+        x, H1, W1, rec = self._conv_bn(self.stem, images.contiguous(), B, H, W, True, None, training, need_grad, tta=tta)
         y, idx, H2, W2 = ops.maxpool_fwd(x, B, H1, W1, self.stem.O)
         ctx = dict(rec=rec, pool=(idx, H1, W1, self.stem.O), B=B) if need_grad else None
         return y, H2, W2, ctx
@@ -197,11 +204,13 @@ class ResNetEngine:
                 blocks.append(dict(main=main, down=rdown))
         return x, H, W, self.layers[li][-1][0][-1].O, (dict(blocks=blocks, B=B) if need_grad else None)
 
-    def forward(self, images, training, need_grad):
-        """images: [B,3,H,W] fp32 CUDA.  Returns ({name: (feat2d bf16, h, w, C)}, ctx)."""
-        B = images.shape[0]
+    def forward(self, images, training, need_grad, tta=None):
+        """images: [B,3,H,W] fp32 CUDA.  Returns ({name: (feat2d bf16, h, w, C)}, ctx).  tta: see forward_stem (inference)."""
+        if tta is not None and need_grad:
+            raise ValueError("test-time augmentation inside the stem is an inference path (no backward)")
+        B = images.shape[0] * (tta[0] if tta else 1)
         self.begin_forward(images, training)
-        x, H, W, sctx = self.forward_stem(images, training, need_grad)
+        x, H, W, sctx = self.forward_stem(images, training, need_grad, tta=tta)
         feats, lctx = {}, []
         for li in range(4):
             x, H, W, C, c = self.forward_layer(li, x, B, H, W, training, need_grad)
@@ -251,7 +260,7 @@ class ResNetEngine:
         dbeta = st.g32(c.bn.bias) if bnw.requires_grad else None
         draw, dz = ops.bn_bwd(dy, rec["raw"], rec["y"], rec["mean"], rec["invstd"], bnw.data, dgamma, dbeta,
                               relu=rec["relu"], want_dz=rec["has_res"], scale=rec["scale"], shift=rec["shift"],
-                              training=rec["training"], sums=rec["sums"])
+                              training=rec["training"], sums=rec["sums"], mask=rec["mask"])
         A = rec["A"]
         rows = rec["B"] * rec["Ho"] * rec["Wo"]
         side = None
@@ -267,7 +276,7 @@ class ResNetEngine:
             #  but an epilogue-bound 1x1 dgrad with a short reduction pays more for it than the separate reduce kernel costs:
             #  401408x64x256: 43 -> 86 us against a 28 us reduce; 25088x256x1024: 19 -> 27 us against 13 us)
             if (producer is not None and self._bwd_ws is not None and c.dgrad_fusable and add_to_dx is None
-                    and producer["y"] is None and (c.implicit_dgrad or c.O >= FUSE_BN_BWD_MIN_K)):
+                    and not producer["has_res"] and (c.implicit_dgrad or c.O >= FUSE_BN_BWD_MIN_K)):
                 pc = producer["c"]
                 sums = self._bwd_ws[pc.stats_off:pc.stats_off + 2 * pc.O].view(2, pc.O)
                 skw = dict(stat_x=producer["raw"], stat_mean=producer["mean"], stat_scale=producer["scale"],

@@ -33,7 +33,7 @@ def connext_forward_loss(model, images, ids, mask, labels):
 class Trainer:
     def __init__(self, model, optimizer="adamw", lr=2e-4, weight_decay=None, betas=(0.9, 0.999), eps=1e-8, momentum=0.0,
                  loss="ce", label_smoothing=0.02, focal_gamma=2.0, class_weights=None, process_group=None,
-                 overlap_comm=True, supcon_weight=0.0, supcon_stage="finetune", supcon_temperature=0.07, forward_loss=None,
+                 overlap_comm="pipeline", supcon_weight=0.0, supcon_stage="finetune", supcon_temperature=0.07, forward_loss=None,
                  comm_dtype="bf16", sm_reserve=None, bert_bucket_layers=4):
         """forward_loss: optional callable (model, images, ids, mask, labels) -> (loss, logits) for the model families whose
         call surface differs from MultimodalBaselineModel (MIBF-Net: batch dict + cal_loss, mibf_net/train_resnet.py:21-41;
@@ -41,7 +41,8 @@ class Trainer:
         Data parallel (world > 1): `comm_dtype` "bf16" (default, SURVEY 8e) | "fp32" = dtype of the gradient buckets on the wire;
         `bert_bucket_layers` = BERT layers per early bucket (the text-encoder gradients leave in slices while its backward is
         still running; 0 = one slice after the whole text encoder); `sm_reserve` = SMs the persistent GEMM grids leave to the
-        NCCL kernels while a bucket is in flight (default: MDHS_SM_RESERVE or 16).
+        NCCL kernels while a bucket is in flight in "backward" mode (default: MDHS_SM_RESERVE or 0 -- measured on 2 x B200, a
+        reserve of 16 costs more on the un-overlapped GEMMs than it gains on the overlapped ones).
         `momentum` only applies to optimizer="sgd": the default 0 is scripts/train.py:301-309's `optim.SGD(params, lr)`;
         MIBF-Net's recipe (mibf_net/train_resnet.py:136-139) passes momentum=0.9 explicitly."""
         self.model = model
@@ -66,11 +67,22 @@ class Trainer:
         # ... and assume ONE image-encoder / text-encoder backward per step: the global-local and multi-slice branches run the
         # trunk twice in train mode (model.py:292-315), so their stage hooks would fire before the gradients are final
         twice = getattr(model, "global_local_enabled", False) or getattr(model, "sequence_enabled", False)
-        self.overlap = overlap_comm and self.world > 1 and forward_loss is None and not twice
+        # overlap_comm: "pipeline" (default) = all buckets are reduced after backward, the fused optimizer of bucket k running
+        # while bucket k+1 is on the wire; "backward" (or True) = buckets leave DURING backward (round-1 behaviour);
+        # False = one all-reduce, then the optimizer.  Measured on 2 x B200 (profiles/r02_summary.md): collectives that run
+        # next to the backward GEMMs slow those by more than the transfer they hide (the persistent tcgen05 grids and the
+        # split-K reduce-add wgrads lose ~0.9 ms to ~0.8 ms of NCCL kernels), while the HBM-bound optimizer shares the GPU well.
+        mode = {True: "backward", False: "none", None: "none"}.get(overlap_comm, overlap_comm)
+        if mode not in ("pipeline", "backward", "none"):
+            raise ValueError(f"Unsupported overlap_comm: {overlap_comm}")
+        self.comm_mode = mode if self.world > 1 else "none"
+        self.overlap = self.comm_mode == "backward" and forward_loss is None and not twice
         import os as _os
         self.comm_dtype = {"bf16": torch.bfloat16, "fp32": None, "f32": None, None: None}[comm_dtype]
-        self.sm_reserve = int(_os.environ.get("MDHS_SM_RESERVE", "16")) if sm_reserve is None else int(sm_reserve)
+        self.sm_reserve = int(_os.environ.get("MDHS_SM_RESERVE", "0")) if sm_reserve is None else int(sm_reserve)
         self.bert_bucket_layers = int(bert_bucket_layers)
+        # SMs the pipelined optimizer leaves to NCCL (its CTAs need an SM to themselves); pair with NCCL_MAX_CTAS <= comm_sms
+        self.comm_sms = int(_os.environ.get("MDHS_COMM_SMS", "16"))
         self.store = None
         self._graph = None
         self._static = None
@@ -97,6 +109,7 @@ class Trainer:
         # (torch skips `grad is None`: the BERT pooler, dead q/k projections of the 1-token attention-pooling head, ...)
         self._opt_ranges = self._trainable_ranges(None)
         self._probed_unused = False
+        self._buckets = self._pipeline_buckets(n)
         if self.world > 1:
             # same initial weights everywhere (rank 0 wins), like DistributedDataParallel's constructor
             dist.broadcast(st.flat, src=0, group=self.pg)
@@ -125,6 +138,39 @@ class Trainer:
             lo4, hi4 = lo // 4 * 4, min(st.total, (hi + 3) // 4 * 4)
             out.append((lo4, hi4))
         return out
+
+    def _pipeline_buckets(self, total, sizes=(0.06, 0.12, 0.2, 0.2, 0.2, 0.22)):
+        """[lo, hi) slices of the flat buffer for the pipelined reduce -> optimizer tail: a small first bucket (the optimizer
+        starts early), boundaries on parameter slots (64-element aligned)."""
+        st = self.store
+        starts = sorted(st.offsets[id(p)] for p in st.params)
+        cuts, acc = [0], 0.0
+        for f in sizes[:-1]:
+            acc += f
+            target = acc * total
+            c = min(starts, key=lambda o: abs(o - target))
+            if c > cuts[-1]:
+                cuts.append(c)
+        cuts.append(total)
+        return [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+
+    def _opt_update(self, lo, hi, scale, g16):
+        """Fused optimizer over the trainable spans inside [lo, hi)."""
+        st = self.store
+        bps = -self.comm_sms if self.comm_mode == "pipeline" else 0    # whole SMs left to the next bucket's collective
+        for a, b in self._opt_ranges:
+            a, b = max(a, lo), min(b, hi)
+            if b <= a:
+                continue
+            if self.opt == "sgd":
+                ops.sgd_flat(st.flat[a:b], st.grad[a:b], self.m[a:b] if self.momentum > 0 else None, st.shadow[a:b],
+                             self.lr, self.momentum, self.wd, grad_scale=scale, lr_dev=self.lr_dev, step_dev=self.step_dev,
+                             grads_bf16=None if g16 is None else g16[a:b], blocks_per_sm=bps)
+            else:
+                ops.adam_flat(st.flat[a:b], st.grad[a:b], self.m[a:b], self.v[a:b], st.shadow[a:b], self.lr,
+                              self.betas[0], self.betas[1], self.eps, self.wd, 1, grad_scale=scale,
+                              adamw=(self.opt == "adamw"), lr_dev=self.lr_dev, step_dev=self.step_dev,
+                              grads_bf16=None if g16 is None else g16[a:b], blocks_per_sm=bps)
 
     def _probe_unused(self):
         """One-time (first eager step, after backward): parameters whose whole gradient is exactly zero never took part in
@@ -209,22 +255,23 @@ class Trainer:
                 hook[0].backward = hook[1]
             if img_eng is not None:
                 img_eng.on_stage_backward_done = None
-        scale = self.sync.finish()
-        if self.sm_reserve > 0 and self.overlap:
-            ops.set_sm_reserve(0)
-        g16 = self.sync.reduced
         if not self._probed_unused and not torch.cuda.is_current_stream_capturing():
-            self._probe_unused()
-        for lo, hi in self._opt_ranges:
-            if self.opt == "sgd":
-                ops.sgd_flat(st.flat[lo:hi], st.grad[lo:hi], self.m[lo:hi] if self.momentum > 0 else None, st.shadow[lo:hi],
-                             self.lr, self.momentum, self.wd, grad_scale=scale, lr_dev=self.lr_dev, step_dev=self.step_dev,
-                             grads_bf16=None if g16 is None else g16[lo:hi])
-            else:
-                ops.adam_flat(st.flat[lo:hi], st.grad[lo:hi], self.m[lo:hi], self.v[lo:hi], st.shadow[lo:hi], self.lr,
-                              self.betas[0], self.betas[1], self.eps, self.wd, 1, grad_scale=scale,
-                              adamw=(self.opt == "adamw"), lr_dev=self.lr_dev, step_dev=self.step_dev,
-                              grads_bf16=None if g16 is None else g16[lo:hi])
+            self._probe_unused()            # on the LOCAL gradients, before any collective touches them
+        if self.comm_mode == "pipeline":
+            # every bucket goes on the wire in order; the optimizer of bucket k runs while bucket k + 1 is being reduced
+            for lo, hi in self._buckets:
+                self.sync.reduce_range(lo, hi)
+            g16 = self.sync.reduced
+            scale = 1.0 / self.world
+            for i, (lo, hi) in enumerate(self._buckets):
+                self.sync.wait(i)
+                self._opt_update(lo, hi, scale, g16)
+            self.sync.finish()
+        else:
+            scale = self.sync.finish()
+            if self.sm_reserve > 0 and self.overlap:
+                ops.set_sm_reserve(0)
+            self._opt_update(0, st.total, scale, self.sync.reduced)
         st.mark_fresh()
         return loss.detach(), logits.detach()
 

@@ -527,3 +527,56 @@ def test_gemm_epilogue_bn_backward_reduction(ops, M, N, K, conv):
     dx1, _ = ops.bn_bwd(dy, x, None, mean, invstd, gamma, dg1, db1, relu=True, scale=scale, shift=shift, sums=sums)
     assert relerr(dx1, dx0) < 4e-3
     assert relerr(dg1, dg0) < 1e-4 and relerr(db1, db0) < 1e-4
+
+
+def test_preprocess_u8_matches_torch(ops):
+    """GPU input pipeline: crop box + bilinear resize + flips + ToTensor + Normalize of a uint8 HWC batch vs the
+    same chain in torch (crop -> F.interpolate(bilinear, align_corners=False) -> flip -> normalise)."""
+    torch.manual_seed(0)
+    B, Hs, Ws = 5, 300, 260
+    src = torch.randint(0, 256, (B, Hs, Ws, 3), dtype=torch.uint8, device="cuda")
+    boxes = torch.tensor([[0, 0, 300, 260], [10, 20, 200, 180], [38, 18, 224, 224], [100, 60, 90, 150], [5, 7, 64, 64]], dtype=torch.float32)
+    flips = torch.tensor([0, 1, 2, 3, 0], dtype=torch.uint8)
+    got = ops.preprocess_u8(src, (224, 224), boxes=boxes, flips=flips)
+    mean = torch.tensor(ops.IMAGENET_MEAN, device="cuda").view(1, 3, 1, 1)
+    std = torch.tensor(ops.IMAGENET_STD, device="cuda").view(1, 3, 1, 1)
+    for b in range(B):
+        y0, x0, h, w = [int(v) for v in boxes[b]]
+        crop = src[b, y0:y0 + h, x0:x0 + w].permute(2, 0, 1).float().unsqueeze(0)
+        ref = F.interpolate(crop, size=(224, 224), mode="bilinear", align_corners=False)
+        if int(flips[b]) & 1:
+            ref = ref.flip(-1)
+        if int(flips[b]) & 2:
+            ref = ref.flip(-2)
+        ref = (ref / 255.0 - mean) / std
+        assert (got[b:b + 1] - ref).abs().max().item() < 2e-4, b
+    # whole image, no boxes / flips: identity geometry when the sizes match
+    same = ops.preprocess_u8(src[:, :224, :224].contiguous(), (224, 224))
+    ref = (src[:, :224, :224].permute(0, 3, 1, 2).float() / 255.0 - mean) / std
+    assert (same - ref).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("rows,C", [(4 * 56 * 56, 256), (1001, 64), (392, 2048)])
+def test_batchnorm_relu_bitmask_equals_y_mask(ops, rows, C):
+    """Residual layers: the forward's 1-bit/element ReLU mask (uint8 [rows, C/8]) gives the backward exactly what re-reading
+    the bf16 output gave (bit-identical dx / dz, same reductions)."""
+    torch.manual_seed(5)
+    x = (torch.randn(rows, C, device="cuda") * 1.5 + 0.3).bfloat16()
+    res = torch.randn(rows, C, device="cuda").bfloat16()
+    gamma = torch.rand(C, device="cuda") + 0.5
+    beta = torch.randn(C, device="cuda") * 0.3
+    cs = torch.zeros(C, device="cuda", dtype=torch.float64)
+    cq = torch.zeros(C, device="cuda", dtype=torch.float64)
+    ops.col_stats(x, cs, cq)
+    y, mean, invstd, scale, shift, mask = ops.bn_fwd(x, cs, cq, gamma, beta, None, None, 0.1, 1e-5, residual=res, relu=True,
+                                                     want_mask=True)
+    assert mask.shape == (rows, C // 8) and mask.dtype == torch.uint8
+    bits = ((mask.unsqueeze(-1) >> torch.arange(8, device="cuda", dtype=torch.uint8)) & 1).reshape(rows, C).bool()
+    assert torch.equal(bits, y > 0)
+    dy = torch.randn(rows, C, device="cuda").bfloat16()
+    dg0, db0 = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dg1, db1 = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dx0, dz0 = ops.bn_bwd(dy, x, y, mean, invstd, gamma, dg0, db0, relu=True, want_dz=True)
+    dx1, dz1 = ops.bn_bwd(dy, x, None, mean, invstd, gamma, dg1, db1, relu=True, want_dz=True, mask=mask)
+    assert torch.equal(dz0, dz1)
+    assert relerr(dx1, dx0) < 1e-3 and relerr(dg1, dg0) < 1e-5 and relerr(db1, db0) < 1e-5

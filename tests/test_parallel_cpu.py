@@ -60,6 +60,17 @@ def _worker(rank, world, port, ret):
     sync4.reduce_tail()
     sync4.finish()
     ok = ok and len(fired) == 2
+    # pipelined tail (Trainer overlap_comm="pipeline"): buckets go out in order, each is waited for individually
+    g5 = mine.clone()
+    sync5 = GradSync(g5, 0)
+    bk = [(0, 100), (100, 400), (400, 1000)]
+    for lo, hi in bk:
+        sync5.reduce_range(lo, hi)
+    for i, (lo, hi) in enumerate(bk):
+        sync5.wait(i)
+        ok = ok and torch.allclose(g5[lo:hi], want[lo:hi], atol=1e-6)
+    sync5.finish()
+    ok = ok and torch.allclose(g5, want, atol=1e-6)
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 
