@@ -360,8 +360,6 @@ def run_ours(args):
         # collectives are captured into the step's CUDA graph: the NCCL watchdog's async error handling must not
         # poll events of a capturing stream (torch CUDA-graphs notes)
         os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
-        # the pipelined optimizer tail leaves 16 SMs to the collective of the next gradient bucket (Trainer.comm_sms)
-        os.environ.setdefault("NCCL_MAX_CTAS", "16")
         dist.init_process_group("nccl", device_id=dev)
     import mdhs_b200  # noqa: F401
     from mdhs_b200 import _lib, ops
@@ -719,9 +717,9 @@ def main():
     ap.add_argument("--comm-dtype", default="bf16", choices=["bf16", "fp32"], help="dtype of the gradient buckets on the wire (N > 1)")
     ap.add_argument("--sm-reserve", type=int, default=-1, help="SMs the persistent GEMM grids leave to NCCL while a bucket is in "
                                                                "flight (default: MDHS_SM_RESERVE or 16)")
-    ap.add_argument("--bert-bucket-layers", type=int, default=4, help="BERT layers per early gradient bucket (0 = one bucket)")
-    ap.add_argument("--overlap-comm", default="pipeline", choices=["pipeline", "backward", "none"],
-                    help="N > 1: gradient buckets pipelined with the fused optimizer after backward (default), sent during "
+    ap.add_argument("--bert-bucket-layers", type=int, default=0, help="BERT layers per early gradient bucket (0 = one bucket)")
+    ap.add_argument("--overlap-comm", default="backward", choices=["pipeline", "backward", "none"],
+                    help="N > 1: gradient buckets sent during backward (default), pipelined with the fused optimizer after "
                          "backward, or one all-reduce before the optimizer")
     ap.add_argument("--timeline", default=None, help="write the kernel timeline of one replayed step to gpurun_out/<name>")
     ap.add_argument("--no-graph", action="store_true")

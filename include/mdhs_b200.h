@@ -87,14 +87,15 @@ int mdhs_gemm_bf16(const mdhs_gemm_args* args, void* stream);
  * transformers BertEmbeddings/BertSelfOutput/BertOutput LayerNorm, eps 1e-12).  x is bf16 or fp32
  * [rows, C]; statistics fp32; optional inverted dropout on the output (BERT embeddings).
  * Backward accumulates (+=) dgamma/dbeta and can emit a second dx copy masked by the dropout of the
- * dense branch that fed the residual sum.  C % 8 == 0, C <= 2048.
+ * dense branch that fed the residual sum; dbias (optional) += column sums of that copy (dx_drop, else dx) = the bias
+ * gradient of that dense layer.  C % 8 == 0, C <= 2048.
  */
 int mdhs_layernorm_fwd(const void* x, int x_f32, int64_t ldx, const float* gamma, const float* beta, void* y_bf16,
                        int64_t ldy, float* y_f32, float* mean, float* rstd, int rows, int C, float eps,
                        float drop_p, uint64_t seed, void* stream);
 int mdhs_layernorm_bwd(const void* dy, int dy_f32, int64_t lddy, const void* x, int x_f32, int64_t ldx,
                        const float* mean, const float* rstd, const float* gamma, void* dx_bf16, int64_t lddx,
-                       void* dx_drop_bf16, float* dx_f32, float* dgamma, float* dbeta, int rows, int C,
+                       void* dx_drop_bf16, float* dx_f32, float* dgamma, float* dbeta, float* dbias, int rows, int C,
                        float drop_p, uint64_t seed, float drop2_p, uint64_t seed2, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

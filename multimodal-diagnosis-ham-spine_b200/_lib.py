@@ -43,7 +43,7 @@ class GemmArgs(ctypes.Structure):
 SIGNATURES = {
     "mdhs_gemm_bf16": "pp",
     "mdhs_layernorm_fwd": "pilpppl" "ppp" "iiffup",
-    "mdhs_layernorm_bwd": "pilpilppp" "plpppp" "iifufup",
+    "mdhs_layernorm_bwd": "pilpilppp" "plppppp" "iifufup",
     "mdhs_bn_finalize": "pplppppffppppiip",
     "mdhs_bn_apply": "pppppliip",
     "mdhs_bn_fwd": "ppppppp" "ff" "ppppppp" "liii" "p",

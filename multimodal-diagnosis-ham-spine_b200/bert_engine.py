@@ -107,7 +107,7 @@ class BertEngine:
 
     # ------------------------------------------------------------------ backward
     def _linear_bwd(self, dy, x_in, lin, need_dx=True, residual=None, aux_in=None, dact=ops.ACT_NONE, w16=None,
-                    gw=None, gb=None):
+                    gw=None, gb=None, bias_done=False):
         """dy [T,N], x_in [T,K]: accumulates dW, db; returns dx = dy.W (* act'(aux_in)) (+ residual)."""
         st = self.store
         w = lin.weight if lin is not None else None
@@ -124,7 +124,8 @@ class BertEngine:
                 side = runtime.fork_side()
             with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
                 ops.gemm(dy, x_in, a_mn=True, b_mn=True, out=gw, accumulate=True, split_k=-1, M=N, N=K, K=T)
-                ops.col_stats(dy, sum32=gb)
+                if not bias_done:      # (the LayerNorm backward that produced dy already summed its columns)
+                    ops.col_stats(dy, sum32=gb)
         if not need_dx:
             return None
         dx = ops.gemm(dy, w16, b_mn=True, residual=residual, aux_in=aux_in, dact=dact, M=T, N=K, K=N)
@@ -152,18 +153,20 @@ class BertEngine:
             s0 = R["s0"]
             ln2, ln1 = L["ln2"], L["ln1"]
             tr2 = ln2.weight.requires_grad
+            b2 = st.g32(L["wo2"].bias) if L["wo2"].weight.requires_grad else None
             dpre2, dpre2_d, _ = ops.layernorm_bwd(d, R["pre2"], R["m2"], R["r2"], ln2.weight.data,
                                                   st.g32(ln2.weight) if tr2 else None, st.g32(ln2.bias) if tr2 else None,
-                                                  drop2_p=ph, seed2=s0 + 3, want_dx_drop=ph > 0)
+                                                  drop2_p=ph, seed2=s0 + 3, want_dx_drop=ph > 0, dbias=b2)
             g2 = dpre2_d if ph > 0 else dpre2
-            dipre = self._linear_bwd(g2, R["inter"], L["wo2"], aux_in=R["ipre"], dact=ops.ACT_MUL)
+            dipre = self._linear_bwd(g2, R["inter"], L["wo2"], aux_in=R["ipre"], dact=ops.ACT_MUL, bias_done=True)
             dh1 = self._linear_bwd(dipre, R["h1"], L["wi"], residual=dpre2)
             tr1 = ln1.weight.requires_grad
+            b1 = st.g32(L["wo"].bias) if L["wo"].weight.requires_grad else None
             dpre1, dpre1_d, _ = ops.layernorm_bwd(dh1, R["pre1"], R["m1"], R["r1"], ln1.weight.data,
                                                   st.g32(ln1.weight) if tr1 else None, st.g32(ln1.bias) if tr1 else None,
-                                                  drop2_p=ph, seed2=s0 + 2, want_dx_drop=ph > 0)
+                                                  drop2_p=ph, seed2=s0 + 2, want_dx_drop=ph > 0, dbias=b1)
             g1 = dpre1_d if ph > 0 else dpre1
-            datt = self._linear_bwd(g1, R["att"], L["wo"])
+            datt = self._linear_bwd(g1, R["att"], L["wo"], bias_done=True)
             qkv = R["qkv"]
             dqkv = torch.empty_like(qkv)
             ops.attention_bwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], R["att"], datt, R["lse"], B, H, S, S, D, scale,

@@ -191,20 +191,30 @@ __global__ void __launch_bounds__(256) ln_bwd_param_kernel(const void* __restric
                                                            int64_t ldx, const float* __restrict__ mean_in,
                                                            const float* __restrict__ rstd_in, float* __restrict__ dgamma,
                                                            float* __restrict__ dbeta, int rows, int C, int rows_per_block,
-                                                           float drop_p, uint64_t seed) {
-  __shared__ float sh[2][8][256 + 8];
+                                                           float drop_p, uint64_t seed, const bf16* __restrict__ bsrc,
+                                                           int64_t ldb, float* __restrict__ dbias) {
+  // bsrc / dbias (optional): dbias[c] += sum_r bsrc[r, c] -- the bias gradient of the dense layer that fed this LayerNorm's
+  // residual sum (its output gradient is the dx / dx_drop that ln_bwd_dx just wrote): one more bf16 read here instead of a
+  // separate column-sum launch (24 of the 61 col_stats launches of a BERT-base step).
+  __shared__ float sh[3][8][256 + 8];
   const int cv = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c0 = blockIdx.x * 256 + cv * 8;
   const bool ok = c0 < C;
   const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  float a[8], b[8];
+  float a[8], b[8], cb[8];
 #pragma unroll
-  for (int k = 0; k < 8; k++) a[k] = b[k] = 0.f;
+  for (int k = 0; k < 8; k++) a[k] = b[k] = cb[k] = 0.f;
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(rows, r0 + rows_per_block);
   if (ok) {
     for (int r = r0 + rl; r < r1; r += 8) {
       float xv[8], dyv[8];
+      if (bsrc) {
+        float bv[8];
+        load8(bsrc + (int64_t)r * ldb + c0, bv);
+#pragma unroll
+        for (int k = 0; k < 8; k++) cb[k] += bv[k];
+      }
       if (XF32) {
         const float* xp = reinterpret_cast<const float*>(x_) + (int64_t)r * ldx + c0;
         *reinterpret_cast<float4*>(xv) = *reinterpret_cast<const float4*>(xp);
@@ -235,18 +245,21 @@ __global__ void __launch_bounds__(256) ln_bwd_param_kernel(const void* __restric
   for (int k = 0; k < 8; k++) {
     sh[0][rl][cv * 8 + k] = a[k];
     sh[1][rl][cv * 8 + k] = b[k];
+    sh[2][rl][cv * 8 + k] = cb[k];
   }
   __syncthreads();
   const int c = blockIdx.x * 256 + threadIdx.x;
   if (c < C) {
-    float s0 = 0.f, s1 = 0.f;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; w++) {
       s0 += sh[0][w][threadIdx.x];
       s1 += sh[1][w][threadIdx.x];
+      s2 += sh[2][w][threadIdx.x];
     }
     if (dgamma) atomicAdd(dgamma + c, s0);
     if (dbeta) atomicAdd(dbeta + c, s1);
+    if (dbias) atomicAdd(dbias + c, s2);
   }
 }
 
@@ -750,12 +763,15 @@ extern "C" int mdhs_layernorm_fwd(const void* x, int x_f32, int64_t ldx, const f
 
 extern "C" int mdhs_layernorm_bwd(const void* dy, int dy_f32, int64_t lddy, const void* x, int x_f32, int64_t ldx,
                                   const float* mean, const float* rstd, const float* gamma, void* dx_bf16, int64_t lddx,
-                                  void* dx_drop_bf16, float* dx_f32, float* dgamma, float* dbeta, int rows, int C,
+                                  void* dx_drop_bf16, float* dx_f32, float* dgamma, float* dbeta, float* dbias, int rows, int C,
                                   float drop_p, uint64_t seed, float drop2_p, uint64_t seed2, void* stream) {
   if (!dy || !x || !mean || !rstd || !gamma || rows <= 0 || (C % 8) || C > LN_MAXCH * 256) return MDHS_ERR_ARG;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int blocks = ceil_div(rows, 8);
-  const bool params = (dgamma != nullptr) || (dbeta != nullptr);
+  // dbias: column sums of the gradient handed to the dense branch (dx_drop when given, else dx)
+  const bf16* bsrc = dbias ? (const bf16*)(dx_drop_bf16 ? dx_drop_bf16 : dx_bf16) : nullptr;
+  if (dbias && !bsrc) return MDHS_ERR_ARG;
+  const bool params = (dgamma != nullptr) || (dbeta != nullptr) || (dbias != nullptr);
   g_mdhs_launches += params ? 2 : 1;
 #define LNB1(XF, DF, N)                                                                                                       \
   ln_bwd_dx_kernel<XF, DF, N><<<blocks, 256, 0, st>>>(dy, lddy, x, ldx, mean, rstd, gamma, (bf16*)dx_bf16, lddx,               \
@@ -783,7 +799,7 @@ extern "C" int mdhs_layernorm_bwd(const void* dy, int dy_f32, int64_t lddy, cons
     rpb = ((rpb + 7) / 8) * 8;
     row_blocks = ceil_div(rows, rpb);
     const dim3 grid(cslabs, row_blocks);
-#define LNP(XF, DF) ln_bwd_param_kernel<XF, DF><<<grid, 256, 0, st>>>(dy, lddy, x, ldx, mean, rstd, dgamma, dbeta, rows, C, rpb, drop_p, seed)
+#define LNP(XF, DF) ln_bwd_param_kernel<XF, DF><<<grid, 256, 0, st>>>(dy, lddy, x, ldx, mean, rstd, dgamma, dbeta, rows, C, rpb, drop_p, seed, bsrc, lddx, dbias)
     if (x_f32) {
       if (dy_f32) LNP(true, true); else LNP(true, false);
     } else {

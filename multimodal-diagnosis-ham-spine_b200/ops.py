@@ -124,14 +124,16 @@ def layernorm_fwd(x, gamma, beta, eps, *, out_bf16=True, out_f32=False, drop_p=0
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, *, dx_bf16=True, dx_f32=False, drop_p=0.0, seed=0,
-                  drop2_p=0.0, seed2=0, want_dx_drop=False):
+                  drop2_p=0.0, seed2=0, want_dx_drop=False, dbias=None):
+    """dbias (optional fp32 [C]): += column sums of the gradient handed on to the dense branch (dx_drop if requested, else
+    dx), i.e. the bias gradient of the Linear that fed this LayerNorm's residual sum."""
     rows, C = x.shape
     dx = torch.empty((rows, C), device=x.device, dtype=torch.bfloat16) if dx_bf16 else None
     dxd = torch.empty((rows, C), device=x.device, dtype=torch.bfloat16) if want_dx_drop else None
     dx32 = torch.empty((rows, C), device=x.device, dtype=torch.float32) if dx_f32 else None
     _lib.call("mdhs_layernorm_bwd", _p(dy), int(dy.dtype == torch.float32), dy.stride(0), _p(x),
               int(x.dtype == torch.float32), x.stride(0), _p(mean), _p(rstd), _p(gamma), _p(dx), C, _p(dxd), _p(dx32),
-              _p(dgamma), _p(dbeta), rows, C, float(drop_p), int(seed), float(drop2_p), int(seed2), _s())
+              _p(dgamma), _p(dbeta), _p(dbias), rows, C, float(drop_p), int(seed), float(drop2_p), int(seed2), _s())
     return dx, dxd, dx32
 
 

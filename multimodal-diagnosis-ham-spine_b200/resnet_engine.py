@@ -26,7 +26,9 @@ from . import runtime
 # registers across the persistent CTA's tiles) or, when False, one extra column pass (col_stats) over the raw conv output.
 FUSE_BN_STATS_IN_GEMM = _os.environ.get("MDHS_FUSE_BN_STATS", "1") != "0"
 # convolutions with a shorter reduction than this take the separate col_stats pass (their GEMM is epilogue / HBM paced)
-FUSE_BN_STATS_MIN_K = int(_os.environ.get("MDHS_FUSE_BN_MIN_K", "100"))
+# (round 2, tools/bench_gemm_step.py: even the most output-bound shape, 401408 x 256 x 64, pays 32 us for the fused column pass
+#  against 60 us for the separate one, so everything is fused by default now)
+FUSE_BN_STATS_MIN_K = int(_os.environ.get("MDHS_FUSE_BN_MIN_K", "0"))
 # backward: sum(dy'), sum(dy' (x - mean)) of the PRODUCER layer's BatchNorm taken in the epilogue of the dgrad GEMM that
 # writes dy (the raw activation arrives through the prefetched operand box), so the separate reduce pass disappears
 FUSE_BN_BWD_REDUCE = _os.environ.get("MDHS_FUSE_BN_BWD", "1") != "0"

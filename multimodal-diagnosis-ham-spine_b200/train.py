@@ -33,8 +33,8 @@ def connext_forward_loss(model, images, ids, mask, labels):
 class Trainer:
     def __init__(self, model, optimizer="adamw", lr=2e-4, weight_decay=None, betas=(0.9, 0.999), eps=1e-8, momentum=0.0,
                  loss="ce", label_smoothing=0.02, focal_gamma=2.0, class_weights=None, process_group=None,
-                 overlap_comm="pipeline", supcon_weight=0.0, supcon_stage="finetune", supcon_temperature=0.07, forward_loss=None,
-                 comm_dtype="bf16", sm_reserve=None, bert_bucket_layers=4):
+                 overlap_comm="backward", supcon_weight=0.0, supcon_stage="finetune", supcon_temperature=0.07, forward_loss=None,
+                 comm_dtype="bf16", sm_reserve=None, bert_bucket_layers=0):
         """forward_loss: optional callable (model, images, ids, mask, labels) -> (loss, logits) for the model families whose
         call surface differs from MultimodalBaselineModel (MIBF-Net: batch dict + cal_loss, mibf_net/train_resnet.py:21-41;
         ConNexT: batch dict -> logits).  Everything else -- CUDA graph, gradient sync, fused optimizer -- is shared.
@@ -67,11 +67,12 @@ class Trainer:
         # ... and assume ONE image-encoder / text-encoder backward per step: the global-local and multi-slice branches run the
         # trunk twice in train mode (model.py:292-315), so their stage hooks would fire before the gradients are final
         twice = getattr(model, "global_local_enabled", False) or getattr(model, "sequence_enabled", False)
-        # overlap_comm: "pipeline" (default) = all buckets are reduced after backward, the fused optimizer of bucket k running
-        # while bucket k+1 is on the wire; "backward" (or True) = buckets leave DURING backward (round-1 behaviour);
-        # False = one all-reduce, then the optimizer.  Measured on 2 x B200 (profiles/r02_summary.md): collectives that run
-        # next to the backward GEMMs slow those by more than the transfer they hide (the persistent tcgen05 grids and the
-        # split-K reduce-add wgrads lose ~0.9 ms to ~0.8 ms of NCCL kernels), while the HBM-bound optimizer shares the GPU well.
+        # overlap_comm: "backward" (default, or True) = buckets leave DURING backward ([text encoder | fusion | head] when the
+        # BERT backward returns, ResNet layer4 / layer3 per stage, the rest at the end); "pipeline" = all buckets are reduced
+        # after backward, the fused optimizer of bucket k alternating with the collective of bucket k+1; False / "none" = one
+        # all-reduce, then the optimizer.  Measured (profiles/r02_summary.md section 5): 8 x B200 21.82 / 22.44 / 21.98 ms,
+        # 2 x B200 22.03 / 21.99 / 22.29 ms against 20.65-21.4 ms on one GPU.  What the overlap costs: NCCL's CTAs need whole
+        # SMs, and a statically scheduled persistent GEMM grid that loses even one SM to them runs a second round.
         mode = {True: "backward", False: "none", None: "none"}.get(overlap_comm, overlap_comm)
         if mode not in ("pipeline", "backward", "none"):
             raise ValueError(f"Unsupported overlap_comm: {overlap_comm}")
@@ -81,8 +82,11 @@ class Trainer:
         self.comm_dtype = {"bf16": torch.bfloat16, "fp32": None, "f32": None, None: None}[comm_dtype]
         self.sm_reserve = int(_os.environ.get("MDHS_SM_RESERVE", "0")) if sm_reserve is None else int(sm_reserve)
         self.bert_bucket_layers = int(bert_bucket_layers)
-        # SMs the pipelined optimizer leaves to NCCL (its CTAs need an SM to themselves); pair with NCCL_MAX_CTAS <= comm_sms
-        self.comm_sms = int(_os.environ.get("MDHS_COMM_SMS", "16"))
+        # SMs the pipelined optimizer leaves to NCCL (its CTAs need an SM to themselves; pair with NCCL_MAX_CTAS <= comm_sms).
+        # 0 (default) = normal optimizer grid: measured on 2 x B200, running the collective NEXT TO the HBM-bound optimizer
+        # stretches the NCCL kernels 2.5x (320 vs 130 us per 54 MB bucket) and loses to letting them alternate
+        # (21.81 vs 21.99 - 0.35 ms/step, profiles/r02_summary.md)
+        self.comm_sms = int(_os.environ.get("MDHS_COMM_SMS", "0"))
         self.store = None
         self._graph = None
         self._static = None
@@ -157,7 +161,7 @@ class Trainer:
     def _opt_update(self, lo, hi, scale, g16):
         """Fused optimizer over the trainable spans inside [lo, hi)."""
         st = self.store
-        bps = -self.comm_sms if self.comm_mode == "pipeline" else 0    # whole SMs left to the next bucket's collective
+        bps = -self.comm_sms if (self.comm_mode == "pipeline" and self.comm_sms > 0) else 0
         for a, b in self._opt_ranges:
             a, b = max(a, lo), min(b, hi)
             if b <= a:

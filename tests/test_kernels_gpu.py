@@ -580,3 +580,23 @@ def test_batchnorm_relu_bitmask_equals_y_mask(ops, rows, C):
     dx1, dz1 = ops.bn_bwd(dy, x, None, mean, invstd, gamma, dg1, db1, relu=True, want_dz=True, mask=mask)
     assert torch.equal(dz0, dz1)
     assert relerr(dx1, dx0) < 1e-3 and relerr(dg1, dg0) < 1e-5 and relerr(db1, db0) < 1e-5
+
+
+def test_layernorm_bwd_fused_dense_bias_gradient(ops):
+    """mdhs_layernorm_bwd(dbias=...): the bias gradient of the dense layer behind the LayerNorm = column sums of the
+    (dropout-masked) input gradient the same call writes -- equal to the separate col_stats pass it replaces."""
+    torch.manual_seed(6)
+    rows, C = 1000, 768
+    x = torch.randn(rows, C, device="cuda").bfloat16()
+    g = torch.rand(C, device="cuda") + 0.5
+    b = torch.randn(C, device="cuda")
+    _, _, mean, rstd = ops.layernorm_fwd(x, g, b, 1e-12)
+    dy = torch.randn(rows, C, device="cuda").bfloat16()
+    for p2 in (0.0, 0.1):
+        dg, db, dbias = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+        dx, dxd, _ = ops.layernorm_bwd(dy, x, mean, rstd, g, dg, db, drop2_p=p2, seed2=77, want_dx_drop=p2 > 0, dbias=dbias)
+        src = dxd if p2 > 0 else dx
+        want = torch.zeros(C, device="cuda")
+        ops.col_stats(src, sum32=want)
+        assert relerr(dbias, want) < 1e-5
+        assert relerr(dbias, src.float().sum(0)) < 1e-4
