@@ -224,3 +224,19 @@ def test_bert_hidden_states_4_8_12_match_hf():
             got = port.bert_last_hidden(sd, "text_encoder.model.", ids, mask, num_layers=n)
             valid = mask.bool()
             assert rel(got[valid], hs[n][valid]) < 1e-5, n
+
+
+def test_convnext_stage_taps_match_torchvision():
+    """ImageEncoder(backbone="convnext_*") takes the outputs of the residual stages 2 / 3 / 4 as layer2 / 3 / 4:
+    the oracle's stage taps equal torchvision's `features[:4]`, `[:6]`, `[:8]`."""
+    import torchvision
+    net = torchvision.models.convnext_tiny(weights=None).eval()
+    sd = {"features." + k: v for k, v in weights.synth_state_dict(net.features.state_dict(), seed=2).items()}
+    net.features.load_state_dict({k[len("features."):]: v for k, v in sd.items()})
+    x = torch.rand(2, 3, 64, 64, generator=torch.Generator().manual_seed(1))
+    taps = []
+    with torch.no_grad():
+        out = port.convnext_features(sd, "features.", x, taps=taps)
+        assert rel(out, net.features(x)) < 1e-5
+        for tap, upto in zip(taps[1:], (4, 6, 8)):
+            assert rel(tap, net.features[:upto](x)) < 1e-5
