@@ -84,7 +84,7 @@ def _nchw(t2d, B, H, W):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("B,C,H,W", [(2, 96, 14, 14), (3, 192, 7, 7), (2, 72, 9, 13), (1, 128, 5, 3)])
+@pytest.mark.parametrize("B,C,H,W", [(2, 96, 14, 14), (3, 192, 7, 7), (2, 72, 9, 13), (1, 128, 5, 3), (2, 96, 56, 56), (5, 64, 16, 10)])
 def test_dwconv7_fwd_bwd(ops, B, C, H, W):
     torch.manual_seed(0)
     x = torch.randn(B, C, H, W).bfloat16().float()
