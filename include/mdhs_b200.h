@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define MDHS_ABI_VERSION 3
+#define MDHS_ABI_VERSION 4
 int mdhs_abi_version(void);
 /* Number of kernels launched through this library since load (for bench.py's gpu_launches). */
 int64_t mdhs_launch_count(void);
@@ -215,6 +215,9 @@ int mdhs_act_dropout_bwd(const void* dy, const void* aux, void* g, int64_t n, in
                          void* stream);
 int mdhs_relu_bwd_f32(const float* dy, const float* y, float* dx, int64_t n, void* stream);
 int mdhs_mul_f32(const float* a, const float* b, float* c, int64_t n, void* stream);
+/* grad[i] += sum64[i], then sum64 / sumsq64 (optional) are zeroed: turns the fp64 column sums a GEMM epilogue produced
+ * (mdhs_gemm_args.colsum on the dgrad that writes the pre-activation gradient) into a Linear bias gradient */
+int mdhs_sum64_to_grad(double* sum64, double* sumsq64, float* grad, int n, void* stream);
 /* adaptive level weighting of the hierarchical fusion (README.md:15; fusion_type "hierarchical"): out = sum_l softmax(logits)_l
  * p[l] over L <= 4 fp32 vectors of n elements (p / dp are HOST arrays of device pointers); backward writes dp[l] = w_l * dout
  * and accumulates dlogits (+=); g_ws = fp32 [4] workspace. */
@@ -290,8 +293,9 @@ int mdhs_dwconv7_fwd(const void* x, const float* w, const float* bias, void* y, 
 int mdhs_dwconv7_wgrad(const void* x, const void* dy, float* dw, float* db, int B, int H, int W, int C, void* stream);
 int mdhs_layer_scale_fwd(const void* x, const void* z, const float* ls, void* out, int64_t rows, int C, int rows_per_sample,
                          float p, uint64_t seed, void* stream);
-int mdhs_layer_scale_bwd(const void* dy, const void* z, const float* ls, void* dz, float* dls, int64_t rows, int C,
-                         int rows_per_sample, float p, uint64_t seed, void* stream);
+/* dbias (optional): += column sums of dz, the bias gradient of the Linear that produced z (CNBlock block.5) */
+int mdhs_layer_scale_bwd(const void* dy, const void* z, const float* ls, void* dz, float* dls, float* dbias, int64_t rows,
+                         int C, int rows_per_sample, float p, uint64_t seed, void* stream);
 int mdhs_sq_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, float* out,
                      float* probs, int B, int T, int D, float scale, void* stream);
 int mdhs_sq_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const float* dout,

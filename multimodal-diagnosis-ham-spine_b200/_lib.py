@@ -77,6 +77,7 @@ SIGNATURES = {
     "mdhs_act_dropout_bwd": "ppplifup",
     "mdhs_relu_bwd_f32": "ppplp",
     "mdhs_mul_f32": "ppplp",
+    "mdhs_sum64_to_grad": "pppip",
     "mdhs_dropout_f32": "pplfup",
     "mdhs_level_mix_fwd": "ppplip",
     "mdhs_level_mix_bwd": "pppppplip",
@@ -103,7 +104,7 @@ SIGNATURES = {
     "mdhs_dwconv7_fwd": "ppppiiiiip",
     "mdhs_dwconv7_wgrad": "ppppiiiip",
     "mdhs_layer_scale_fwd": "pppplii" "fup",
-    "mdhs_layer_scale_bwd": "ppppplii" "fup",
+    "mdhs_layer_scale_bwd": "pppppplii" "fup",
     "mdhs_sq_attn_fwd": "plplplpp" "iiifp",
     "mdhs_sq_attn_bwd": "plplplpp" "plplpl" "iiifp",
     "mdhs_adam_flat": "pppppplfffffifiippip",

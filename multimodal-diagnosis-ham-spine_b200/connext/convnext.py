@@ -89,24 +89,50 @@ class _DwConvFn(torch.autograd.Function):
         return dx, None, None, None, None, None, None, None
 
 
-class _LayerScaleFn(torch.autograd.Function):
-    """out = x + ls * keep(sample) * z  (CNBlock tail: layer_scale, StochasticDepth("row"), residual)."""
+class _MlpScaleFn(torch.autograd.Function):
+    """CNBlock after its LayerNorm (torchvision CNBlock.block[3:], layer_scale, StochasticDepth("row"), residual):
+        out = x + ls * keep(sample) * (GELU(y W1^T + b1) W2^T + b2)
+    Forward: the first GEMM's epilogue also stores GELU'(pre-activation); backward: the layer-scale kernel emits dz, dls and
+    the second Linear's bias gradient, the dgrad GEMM of the second Linear multiplies by the saved GELU' and column-sums its
+    output (= the first Linear's bias gradient), so no separate activation-backward or bias-reduction pass runs."""
 
     @staticmethod
-    def forward(ctx, x, z, ls, gls, rows_per_sample, p, seed):
-        x, z = x.contiguous(), z.contiguous()
+    def forward(ctx, x, y, p1, p2, lsp, scratch, rows_per_sample, p, seed, need):
+        x, y = x.contiguous(), y.contiguous()
+        w1, gw1, b1, gb1 = p1
+        w2, gw2, b2, gb2 = p2
+        ls, gls = lsp
+        T, N1 = y.shape[0], w1.shape[0]
+        deriv = torch.empty((T, N1), device=y.device, dtype=torch.bfloat16) if need else None
+        h = ops.gemm(y, w1, bias=b1, act=ops.ACT_GELU_DERIV if need else ops.ACT_GELU, aux_out=deriv)
+        z = ops.gemm(h, w2, bias=b2)
         out = ops.layer_scale_fwd(x, z, ls, rows_per_sample, p, seed)
-        ctx.ls, ctx.gls, ctx.cfg = ls, gls, (rows_per_sample, p, seed)
-        ctx.save_for_backward(z)
+        ctx.p1, ctx.p2, ctx.lsp, ctx.scratch, ctx.cfg = p1, p2, lsp, scratch, (rows_per_sample, p, seed)
+        ctx.save_for_backward(y, h, deriv, z)
         return out
 
     @staticmethod
-    def backward(ctx, dy):
-        (z,) = ctx.saved_tensors
+    def backward(ctx, dout):
+        y, h, deriv, z = ctx.saved_tensors
+        w1, gw1, b1, gb1 = ctx.p1
+        w2, gw2, b2, gb2 = ctx.p2
+        ls, gls = ctx.lsp
         rps, p, seed = ctx.cfg
-        dy = dy.contiguous()
-        dz = ops.layer_scale_bwd(dy, z, ctx.ls, ctx.gls, rps, p, seed)
-        return dy, dz, None, None, None, None, None
+        dout = dout.contiguous()
+        T, C = dout.shape
+        N1 = w1.shape[0]
+        dz = ops.layer_scale_bwd(dout, z, ls, gls, rps, p, seed, dbias=gb2)
+        if gw2 is not None:
+            ops.gemm(dz, h, a_mn=True, b_mn=True, out=gw2, accumulate=True, split_k=-1, M=C, N=N1, K=T)
+        s64 = ctx.scratch[:, :N1] if gb1 is not None else None
+        g = ops.gemm(dz, w2, b_mn=True, aux_in=deriv, dact=ops.ACT_MUL, M=T, N=N1, K=C,
+                     colsum=None if s64 is None else s64[0], colsumsq=None if s64 is None else s64[1])
+        if gb1 is not None:
+            ops.sum64_to_grad(s64[0], s64[1], gb1)
+        if gw1 is not None:
+            ops.gemm(g, y, a_mn=True, b_mn=True, out=gw1, accumulate=True, split_k=-1, M=N1, N=C, K=T)
+        dy = ops.gemm(g, w1, b_mn=True, M=T, N=C, K=N1) if ctx.needs_input_grad[1] else None
+        return dout, dy, None, None, None, None, None, None, None, None
 
 
 class SqAttnFn(torch.autograd.Function):
@@ -134,6 +160,7 @@ class ConvNeXtEngine:
     def __init__(self, store, features):
         self.store, self.features = store, features
         self.step_seed = 0x5D000000
+        self._s64 = None
         self.stages = []   # ("stem" | "down" | "blocks", payload)
         for i, stage in enumerate(features):
             first = stage[0]
@@ -157,11 +184,25 @@ class ConvNeXtEngine:
                             st.g32(dw.weight) if tr else None, st.g32(dw.bias) if (tr and dw.bias is not None) else None,
                             B, H, W)
         y = Fm.layernorm(y, st, ln)
-        y = Fm.linear(y, st, fc1.weight, fc1.bias, act=ops.ACT_GELU)
-        z = Fm.linear(y, st, fc2.weight, fc2.bias)
         ls = blk.layer_scale
         p = float(blk.stochastic_depth.p) if training else 0.0
-        return _LayerScaleFn.apply(x, z, ls.data.view(-1), st.g32(ls).view(-1) if ls.requires_grad else None, H * W, p, seed)
+        return _MlpScaleFn.apply(x, y, self._lin(fc1), self._lin(fc2),
+                                 (ls.data.view(-1), st.g32(ls).view(-1) if ls.requires_grad else None),
+                                 self._scratch64(fc1.weight.shape[0]), H * W, p, seed, torch.is_grad_enabled())
+
+    def _lin(self, lin):
+        """(bf16 shadow weight, fp32 weight-gradient view, fp32 bias, fp32 bias-gradient view) of an nn.Linear."""
+        st = self.store
+        tr = lin.weight.requires_grad
+        has_b = lin.bias is not None
+        return (st.w16(lin.weight), st.g32(lin.weight) if tr else None, lin.bias.data if has_b else None,
+                st.g32(lin.bias) if (has_b and lin.bias.requires_grad) else None)
+
+    def _scratch64(self, n):
+        """fp64 [2, n] column-sum workspace of the bias-gradient epilogue; zero between uses (mdhs_sum64_to_grad clears it)."""
+        if self._s64 is None or self._s64.shape[1] < n:
+            self._s64 = torch.zeros((2, max(n, 4096)), device=self.store.device, dtype=torch.float64)
+        return self._s64
 
     def forward(self, images, training, taps=None):
         """images: [B,3,H,W] fp32 CUDA -> (tokens [B*h*w, C] bf16, h, w).  taps: optional list that receives

@@ -464,20 +464,23 @@ __global__ void __launch_bounds__(256) layer_scale_fwd_kernel(const bf16* __rest
   }
 }
 
-// dz = dy * ls[c] * keep(b);  dls[c] += sum_rows dy * z * keep(b).  Column-reduction layout of bn_bwd_reduce.
+// dz = dy * ls[c] * keep(b);  dls[c] += sum_rows dy * z * keep(b);  dbias[c] += sum_rows dz (the bias gradient of the
+// Linear that produced z).  Column-reduction layout of bn_bwd_reduce.
 __global__ void __launch_bounds__(256) layer_scale_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z,
                                                               const float* __restrict__ ls, bf16* __restrict__ dz,
-                                                              float* __restrict__ dls, int64_t rows, int C, int rows_per_sample,
-                                                              int rows_per_block, float p, uint64_t seed) {
+                                                              float* __restrict__ dls, float* __restrict__ dbias, int64_t rows,
+                                                              int C, int rows_per_sample, int rows_per_block, float p,
+                                                              uint64_t seed) {
   __shared__ float sh[8][256 + 8];
   const int cv = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c0 = blockIdx.x * 256 + cv * 8;
   const bool ok = c0 < C;
   const float inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
-  float a[8], s[8];
+  float a[8], s[8], bsum[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) {
     a[k] = 0.f;
+    bsum[k] = 0.f;
     s[k] = ok ? ls[c0 + k] : 0.f;
   }
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
@@ -492,6 +495,7 @@ __global__ void __launch_bounds__(256) layer_scale_bwd_kernel(const bf16* __rest
       for (int k = 0; k < 8; k++) {
         o[k] = d[k] * s[k] * keep;
         a[k] = fmaf(d[k] * keep, zv[k], a[k]);
+        bsum[k] += o[k];
       }
       store8(dz + r * C + c0, o);
     }
@@ -505,6 +509,17 @@ __global__ void __launch_bounds__(256) layer_scale_bwd_kernel(const bf16* __rest
 #pragma unroll
     for (int w8 = 0; w8 < 8; w8++) t += sh[w8][threadIdx.x];
     atomicAdd(dls + c, t);
+  }
+  if (dbias == nullptr) return;   // uniform
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 8; k++) sh[rl][cv * 8 + k] = bsum[k];
+  __syncthreads();
+  if (c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; w8++) t += sh[w8][threadIdx.x];
+    atomicAdd(dbias + c, t);
   }
 }
 
@@ -778,7 +793,7 @@ extern "C" int mdhs_layer_scale_fwd(const void* x, const void* z, const float* l
   MDHS_RETURN_LAST();
 }
 
-extern "C" int mdhs_layer_scale_bwd(const void* dy, const void* z, const float* ls, void* dz, float* dls, int64_t rows, int C,
+extern "C" int mdhs_layer_scale_bwd(const void* dy, const void* z, const float* ls, void* dz, float* dls, float* dbias, int64_t rows, int C,
                                     int rows_per_sample, float p, uint64_t seed, void* stream) {
   if (!dy || !z || !ls || !dz || rows <= 0 || C <= 0 || (C % 8) || rows_per_sample <= 0 || p < 0.f || p >= 1.f) return MDHS_ERR_ARG;
   const int cslabs = (C + 255) / 256;
@@ -788,8 +803,8 @@ extern "C" int mdhs_layer_scale_bwd(const void* dy, const void* z, const float* 
   rpb = ((rpb + 7) / 8) * 8;
   row_blocks = (int)((rows + rpb - 1) / rpb);
   g_mdhs_launches++;
-  layer_scale_bwd_kernel<<<dim3(cslabs, row_blocks), 256, 0, ST(stream)>>>((const bf16*)dy, (const bf16*)z, ls, (bf16*)dz, dls, rows, C,
-                                                                          rows_per_sample, (int)rpb, p, seed);
+  layer_scale_bwd_kernel<<<dim3(cslabs, row_blocks), 256, 0, ST(stream)>>>((const bf16*)dy, (const bf16*)z, ls, (bf16*)dz, dls, dbias, rows,
+                                                                          C, rows_per_sample, (int)rpb, p, seed);
   MDHS_RETURN_LAST();
 }
 

@@ -53,6 +53,15 @@ __global__ void dropout_f32_kernel(const float* __restrict__ x, float* __restric
     y[i] = x[i] * dropout_scale(seed, (uint64_t)i, p, inv_keep);
 }
 
+// grad[i] += (float)sum64[i]; the fp64 workspaces (column sums written by a GEMM epilogue) are cleared for their next use
+__global__ void sum64_to_grad_kernel(double* __restrict__ sum64, double* __restrict__ sumsq64, float* __restrict__ grad, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  grad[i] += (float)sum64[i];
+  sum64[i] = 0.0;
+  if (sumsq64 != nullptr) sumsq64[i] = 0.0;
+}
+
 }  // namespace
 
 namespace {
@@ -256,6 +265,13 @@ extern "C" int mdhs_relu_bwd_f32(const float* dy, const float* y, float* dx, int
   if (!dy || !y || !dx || n <= 0) return MDHS_ERR_ARG;
   g_mdhs_launches++;
   relu_bwd_f32_kernel<<<grid_for(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dy, y, dx, n);
+  MDHS_RETURN_LAST();
+}
+
+extern "C" int mdhs_sum64_to_grad(double* sum64, double* sumsq64, float* grad, int n, void* stream) {
+  if (!sum64 || !grad || n <= 0) return MDHS_ERR_ARG;
+  g_mdhs_launches++;
+  sum64_to_grad_kernel<<<(n + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(sum64, sumsq64, grad, n);
   MDHS_RETURN_LAST();
 }
 

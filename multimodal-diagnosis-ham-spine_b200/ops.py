@@ -452,6 +452,12 @@ def relu_bwd_f32(dy, y):
     return dx
 
 
+def sum64_to_grad(sum64, sumsq64, grad):
+    """grad += sum64 (fp64 column sums from a GEMM epilogue); clears both workspaces."""
+    assert sum64.dtype == torch.float64 and grad.dtype == torch.float32 and sum64.is_contiguous() and grad.is_contiguous()
+    _lib.call("mdhs_sum64_to_grad", _p(sum64), _p(sumsq64), _p(grad), grad.numel(), _s())
+
+
 def mul_f32(a, b):
     c = torch.empty_like(a)
     _lib.call("mdhs_mul_f32", _p(a), _p(b), _p(c), a.numel(), _s())
@@ -599,10 +605,10 @@ def layer_scale_fwd(x, z, ls, rows_per_sample, p=0.0, seed=0):
     return out
 
 
-def layer_scale_bwd(dy, z, ls, dls, rows_per_sample, p=0.0, seed=0):
+def layer_scale_bwd(dy, z, ls, dls, rows_per_sample, p=0.0, seed=0, dbias=None):
     rows, C = dy.shape
     dz = torch.empty_like(dy)
-    _lib.call("mdhs_layer_scale_bwd", _p(dy), _p(z), _p(ls), _p(dz), _p(dls), rows, C, int(rows_per_sample), float(p), int(seed), _s())
+    _lib.call("mdhs_layer_scale_bwd", _p(dy), _p(z), _p(ls), _p(dz), _p(dls), _p(dbias), rows, C, int(rows_per_sample), float(p), int(seed), _s())
     return dz
 
 

@@ -45,7 +45,7 @@ def test_library_exports_every_declared_symbol():
         assert _lib.SIGNATURES.get(name) == sig, (name, _lib.SIGNATURES.get(name), sig)
     for name in _lib.SIGNATURES:
         assert name in protos, f"{name} bound in _lib.py but missing from the header"
-    assert lib.mdhs_abi_version() == 3
+    assert lib.mdhs_abi_version() == 4
 
 
 def test_product_never_imports_the_oracle():

@@ -121,11 +121,58 @@ def test_layer_scale_residual(ops, p):
     assert rel(out, ref) < 1e-2
     dy = torch.randn(B * T, C).bfloat16()
     dls = torch.zeros(C, device="cuda")
-    dz = ops.layer_scale_bwd(dy.cuda(), z.cuda(), ls.cuda(), dls, T, p, 77)
+    dbias = torch.ones(C, device="cuda")     # accumulates (+=)
+    dz = ops.layer_scale_bwd(dy.cuda(), z.cuda(), ls.cuda(), dls, T, p, 77, dbias=dbias)
     kk = keep.round(decimals=3).view(B, 1).repeat_interleave(T, 0)
     kk = torch.where(kk > 0.5, torch.full_like(kk, 1.0 / (1.0 - p)), torch.zeros_like(kk))
     assert rel(dz, dy.float() * ls * kk) < 1e-2
     assert rel(dls, (dy.float() * z.float() * kk).sum(0)) < 2e-3
+    assert rel(dbias - 1.0, (dy.float() * ls * kk).sum(0)) < 2e-3
+
+
+@pytest.mark.gpu
+def test_sum64_to_grad(ops):
+    torch.manual_seed(5)
+    s64 = torch.randn(2, 200, device="cuda", dtype=torch.float64)
+    ref = s64[0].clone()
+    g = torch.full((200,), 0.5, device="cuda")
+    ops.sum64_to_grad(s64[0], s64[1], g)
+    assert torch.equal(g, 0.5 + ref.float()) and not s64.any()
+
+
+@pytest.mark.gpu
+def test_cnblock_matches_torch(ops):
+    """One torchvision CNBlock (dwconv -> LN -> MLP -> layer scale -> residual), forward and every gradient, against the
+    fp32 module on the same bf16-rounded parameters."""
+    import torchvision
+    from mdhs_b200.connext.convnext import ConvNeXtEngine
+    from mdhs_b200.runtime import ParamStore
+    torch.manual_seed(3)
+    B, C, H, W = 3, 64, 14, 14
+    blk = torchvision.models.convnext.CNBlock(C, 1.0, 0.0).cuda()
+    with torch.no_grad():
+        blk.layer_scale.uniform_(0.2, 0.6)
+        for prm in blk.parameters():
+            prm.copy_(prm.bfloat16().float())
+    feats = torch.nn.Sequential(torch.nn.Sequential(torch.nn.Conv2d(3, C, 4, 4), torch.nn.LayerNorm(C)),
+                                torch.nn.Sequential(blk)).cuda()
+    x = torch.randn(B, C, H, W, device="cuda").bfloat16().float()
+    xr = x.clone().requires_grad_(True)
+    ref = blk(xr)
+    dy = torch.randn_like(ref).bfloat16().float()
+    ref.backward(dy)
+    want = {n: prm.grad.clone() for n, prm in blk.named_parameters()}
+    for prm in blk.parameters():
+        prm.grad = None
+    store = ParamStore(feats, "cuda")
+    eng = ConvNeXtEngine(store, feats)
+    tok = x.permute(0, 2, 3, 1).reshape(B * H * W, C).bfloat16().requires_grad_(True)
+    out = eng._block(blk, tok, B, H, W, True, 11)
+    assert rel(out.float().view(B, H, W, C).permute(0, 3, 1, 2), ref) < 1e-2
+    out.backward(dy.permute(0, 2, 3, 1).reshape(B * H * W, C).bfloat16())
+    assert rel(tok.grad.float().view(B, H, W, C).permute(0, 3, 1, 2), xr.grad) < 2e-2
+    for n, prm in blk.named_parameters():
+        assert rel(store.g32(prm), want[n]) < 2e-2, n
 
 
 @pytest.mark.gpu
