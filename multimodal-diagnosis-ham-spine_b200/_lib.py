@@ -67,6 +67,7 @@ SIGNATURES = {
     "mdhs_nchw_f32_to_nhwc_bf16": "ppiiiip",
     "mdhs_attention_fwd": "plplplplpp" "iiiii" "ffup",
     "mdhs_attention_bwd": "plplplpplpp" "ppppp" "iiiii" "ffup",
+    "mdhs_attention_bwd_workspace": "iii",
     "mdhs_embed_gather": "ppppppiiiip",
     "mdhs_embed_scatter": "ppppppiiiip",
     "mdhs_linear_f32_fwd": "plpppliiiip",

@@ -331,7 +331,7 @@ def attention_bwd(q, k, v, o, d_o, lse, B, H, Sq, Sk, D, scale, key_mask=None, d
     assert dq.stride(0) == q.stride(0) and dk.stride(0) == k.stride(0) and dv.stride(0) == v.stride(0)
     assert d_o.stride(0) == o.stride(0)
     dk32 = dv32 = None
-    if Sq > 64:
+    if _lib.lib().mdhs_attention_bwd_workspace(Sq, Sk, D):   # a query, not a status: 1 = fp32 accumulation path
         dk32 = torch.zeros((B * Sk, k.stride(0)), device=q.device, dtype=torch.float32)
         dv32 = torch.zeros((B * Sk, v.stride(0)), device=q.device, dtype=torch.float32)
     _lib.call("mdhs_attention_bwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), _p(d_o), o.stride(0),

@@ -280,22 +280,30 @@ def test_attention_dropout_statistics(ops):
     assert torch.equal(o, o2)
 
 
-def test_attention_dropout_backward_matches_autograd(ops):
-    """The dropout mask is a pure function of (seed, element index): recover it from a forward pass with V = I, then
-    check forward and backward of a random-V problem against autograd with that explicit mask."""
+@pytest.mark.parametrize("S,D", [(64, 64), (256, 64), (200, 32)])
+def test_attention_dropout_backward_matches_autograd(ops, S, D):
+    """The dropout mask is a pure function of (seed, element index): recover it from forward passes whose V holds an
+    identity block (one pass per D-wide block of keys), then check forward and backward of a random-V problem against
+    autograd with that explicit mask.  S > 64 runs the long-sequence kernels (dQ pass + transposed dK/dV pass), whose
+    dropout indexing must agree with the forward's."""
     torch.manual_seed(0)
-    B, H, S, D, p, seed = 2, 3, 64, 64, 0.2, 99
+    B, H, p, seed = 2, 3, 0.2, 99
     q = torch.randn(B * S, H * D, device="cuda").bfloat16()
     k = torch.randn(B * S, H * D, device="cuda").bfloat16()
     scale = 1.0 / math.sqrt(D)
-    eye = torch.eye(S, device="cuda").repeat(B, H).bfloat16()            # [B*S, H*D] with V_bh = I
-    o_eye, _ = ops.attention_fwd(q, k, eye, B, H, S, S, D, scale, drop_p=p, seed=seed)
 
     def heads(t):
         return t.float().reshape(B, S, H, D).permute(0, 2, 1, 3).contiguous()
     qh, kh = heads(q).requires_grad_(True), heads(k).requires_grad_(True)
     probs = torch.softmax(qh @ kh.transpose(-1, -2) * scale, dim=-1)
-    pm = heads(o_eye)                                                    # = probs * mask (bf16-rounded)
+    pm = torch.zeros(B, H, S, S, device="cuda")
+    for c0 in range(0, S, D):
+        n = min(D, S - c0)
+        blk = torch.zeros(S, D, device="cuda")
+        blk[c0:c0 + n, :n] = torch.eye(n, device="cuda")
+        vsel = blk.repeat(B, H).bfloat16()                               # [B*S, H*D] with V_bh = the identity block
+        o_sel, _ = ops.attention_fwd(q, k, vsel, B, H, S, S, D, scale, drop_p=p, seed=seed)
+        pm[..., c0:c0 + n] = heads(o_sel)[..., :n]                        # = probs * mask (bf16-rounded)
     mask = torch.where(pm > 0.5 * probs.detach() / (1 - p), torch.full_like(pm, 1.0 / (1 - p)), torch.zeros_like(pm))
     assert abs((mask == 0).float().mean().item() - p) < 0.02
     v = torch.randn(B * S, H * D, device="cuda").bfloat16()
