@@ -184,9 +184,11 @@ int mdhs_attention_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, c
                        void* dq, void* dk, void* dv, float* dk32, float* dv32, int B, int H, int Sq, int Sk, int D,
                        float scale, float drop_p, uint64_t seed, void* stream);
 /* dq / dk / dv are bf16 outputs with the strides of q / k / v.  Sq <= 64: one CTA per head.  Sq > 64: a dQ pass (CTAs own
- * 128 queries) and a dK/dV pass (CTAs own 128 keys and walk every query) -- no atomics, dk32 / dv32 unused (NULL).  Only
- * when mdhs_attention_bwd_workspace(Sq, Sk, D) returns 1 (query sets too long for the dK/dV pass's shared memory) must the
- * caller pass zeroed fp32 workspaces dk32 [B*Sk, ldk] / dv32 [B*Sk, ldv], which then receive dK / dV instead of dk / dv. */
+ * 128 queries) and a dK/dV pass (CTAs own 64 keys and stream every query block past them) -- no atomics; dk32, if given,
+ * is a [B*H*Sq] fp32 scratch through which the dQ pass hands delta = rowsum(dO * O) to the dK/dV pass (NULL: recomputed),
+ * dv32 is unused.  Only when mdhs_attention_bwd_workspace(Sq, Sk, D) returns 1 (shapes whose tiles do not fit in shared
+ * memory) must the caller pass zeroed fp32 workspaces dk32 [B*Sk, ldk] / dv32 [B*Sk, ldv], which then receive dK / dV
+ * instead of dk / dv. */
 int mdhs_attention_bwd_workspace(int Sq, int Sk, int D);
 
 /* BERT embeddings (transformers BertEmbeddings via encoder.py:130-134): gather + gradient scatter */

@@ -520,7 +520,7 @@ __device__ __forceinline__ void stage_delta_lse(const AttnParams& p, int b, int 
 }
 
 template <int D, bool DROP>
-__global__ void __launch_bounds__(LNW * 32) attn_fwd_long_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(LNW * 32, 2) attn_fwd_long_kernel(const AttnParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   constexpr int LD = D + 8, QTL = LNW * 16;
   const int skp = (p.Sk + KB - 1) / KB * KB, nkb = skp / KB;
@@ -690,6 +690,10 @@ __global__ void __launch_bounds__(LNW * 32, 2) attn_bwd_dq_kernel(const AttnPara
   }
   stage_mask(p, b, skp, sMask);
   stage_delta_lse<D>(p, b, h, bh, q0, QTL, sDelta, sLse);
+  if (p.dk32 != nullptr) {   // scratch given: publish delta for the dK/dV pass (same thread that wrote sDelta[i])
+    __syncthreads();
+    for (int i = threadIdx.x; i < nq; i += blockDim.x) p.dk32[(int64_t)bh * p.Sq + q0 + i] = sDelta[i];
+  }
 
   const int r0 = warp * 16;
   uint32_t qa[D / 16][4], doa[D / 16][4];
@@ -775,15 +779,20 @@ __global__ void __launch_bounds__(LNW * 32, 2) attn_bwd_dq_kernel(const AttnPara
   }
 }
 
-// dK / dV pass: one CTA = (batch, head, 16 * NW keys); warps own 16 key rows and walk all queries in 64-query blocks.
-template <int D, int NW, bool DROP>
-__global__ void __launch_bounds__(NW * 32) attn_bwd_dkv_kernel(const AttnParams p) {
+// dK / dV pass: one CTA = (batch, head, 64 keys), 4 warps, warps own 16 key rows.  Q / dO stream through a two-stage
+// cp.async ring of 64-query blocks (so three CTAs fit an SM: ~58 KB of shared memory, <= 168 registers); each block is
+// consumed as two 32-query halves to keep the S^T / dP^T accumulators small.  delta / lse / dropout row keys of every
+// query of the head sit in shared memory (delta comes from the dQ pass through `p.dk32` when the caller gave scratch).
+constexpr int DKV_NW = 4, DKV_KT = DKV_NW * 16, DKV_QH = 32;
+
+template <int D, bool DROP>
+__global__ void __launch_bounds__(DKV_NW * 32, 3) attn_bwd_dkv_kernel(const AttnParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
-  constexpr int LD = D + 8, KT = NW * 16;
+  constexpr int LD = D + 8, KT = DKV_KT;
   const int sqp = (p.Sq + KB - 1) / KB * KB, nqb = sqp / KB;
-  bf16* sQ = reinterpret_cast<bf16*>(smem);
-  bf16* sdO = sQ + (size_t)sqp * LD;
-  bf16* sK = sdO + (size_t)sqp * LD;
+  bf16* sQ = reinterpret_cast<bf16*>(smem);          // [2][KB][LD]
+  bf16* sdO = sQ + 2 * KB * LD;                      // [2][KB][LD]
+  bf16* sK = sdO + 2 * KB * LD;
   bf16* sV = sK + KT * LD;
   float* sLse = reinterpret_cast<float*>(sV + KT * LD);
   float* sDelta = sLse + sqp;
@@ -800,14 +809,22 @@ __global__ void __launch_bounds__(NW * 32) attn_bwd_dkv_kernel(const AttnParams 
 
   stage_rows_range<D>(p.k + ((int64_t)b * p.Sk + k0) * p.ldk + h * D, p.ldk, 0, KT, nk, sK);
   stage_rows_range<D>(p.v + ((int64_t)b * p.Sk + k0) * p.ldv + h * D, p.ldv, 0, KT, nk, sV);
-  // query blocks beyond the 8 outstanding groups cp.async allows share the last group
-  const int ngroups = nqb < 8 ? nqb : 8;
-  for (int j = 0; j < nqb; j++) {
-    stage_rows_range<D>(qg, p.ldq, j * KB, (j + 1) * KB, p.Sq, sQ);
-    stage_rows_range<D>(og, p.ldo, j * KB, (j + 1) * KB, p.Sq, sdO);
-    if (j < ngroups - 1 || j == nqb - 1) cp_commit();
+  for (int j = 0; j < 2; j++) {
+    if (j < nqb) {
+      stage_rows_range<D>(qg + (int64_t)j * KB * p.ldq, p.ldq, 0, KB, p.Sq - j * KB, sQ + j * KB * LD);
+      stage_rows_range<D>(og + (int64_t)j * KB * p.ldo, p.ldo, 0, KB, p.Sq - j * KB, sdO + j * KB * LD);
+    }
+    cp_commit();
   }
-  stage_delta_lse<D>(p, b, h, bh, 0, sqp, sDelta, sLse);
+  if (p.dk32 != nullptr) {   // delta from the dQ pass
+    for (int i = threadIdx.x; i < sqp; i += blockDim.x) {
+      const bool ok = i < p.Sq;
+      sDelta[i] = ok ? p.dk32[(int64_t)bh * p.Sq + i] : 0.f;
+      sLse[i] = ok ? p.lse[(int64_t)bh * p.Sq + i] * LOG2E : INFINITY;
+    }
+  } else {
+    stage_delta_lse<D>(p, b, h, bh, 0, sqp, sDelta, sLse);
+  }
   if (DROP)
     for (int i = threadIdx.x; i < sqp; i += blockDim.x) sRowKey[i] = attn_row_key(p.seed, (uint64_t)bh * p.Sq + i);
 
@@ -831,11 +848,12 @@ __global__ void __launch_bounds__(NW * 32) attn_bwd_dkv_kernel(const AttnParams 
   const uint32_t key0 = (uint32_t)(k0 + r0 + g);
 
   for (int j = 0; j < nqb; j++) {
-    const int qb = j * KB;
-    if (j < ngroups) {
-      cp_wait_pending(j < ngroups - 1 ? ngroups - 1 - j : 0);
-      __syncthreads();
-    }
+    const int buf = j & 1;
+    const bf16* bQ = sQ + buf * KB * LD;
+    const bf16* bdO = sdO + buf * KB * LD;
+    if (j + 1 < nqb) cp_wait_pending(1);
+    else cp_wait_pending(0);
+    __syncthreads();
     if (j == 0) {
 #pragma unroll
       for (int kk = 0; kk < D / 16; kk++) {
@@ -843,60 +861,72 @@ __global__ void __launch_bounds__(NW * 32) attn_bwd_dkv_kernel(const AttnParams 
         lda_rowmajor(va[kk], sV, LD, r0, kk * 16, lane);
       }
     }
-    if (!active) continue;
-    float st[KB / 8][4], dpt[KB / 8][4];
+    if (active) {
 #pragma unroll
-    for (int i = 0; i < KB / 8; i++) {
-      st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f;
-      dpt[i][0] = dpt[i][1] = dpt[i][2] = dpt[i][3] = 0.f;
-    }
+      for (int half = 0; half < KB / DKV_QH; half++) {
+        const int ql = half * DKV_QH;        // first query row of this half inside the stage
+        const int qb = j * KB + ql;          // ... and inside the head
+        float st[DKV_QH / 8][4], dpt[DKV_QH / 8][4];
 #pragma unroll
-    for (int kk = 0; kk < D / 16; kk++) {
+        for (int i = 0; i < DKV_QH / 8; i++) {
+          st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f;
+          dpt[i][0] = dpt[i][1] = dpt[i][2] = dpt[i][3] = 0.f;
+        }
 #pragma unroll
-      for (int np = 0; np < KB / 16; np++) {
-        uint32_t bb[4];
-        ldb_nk(bb, sQ, LD, qb + np * 16, kk * 16, lane);
-        mma16816(st[2 * np], ka[kk], bb[0], bb[1]);
-        mma16816(st[2 * np + 1], ka[kk], bb[2], bb[3]);
-        ldb_nk(bb, sdO, LD, qb + np * 16, kk * 16, lane);
-        mma16816(dpt[2 * np], va[kk], bb[0], bb[1]);
-        mma16816(dpt[2 * np + 1], va[kk], bb[2], bb[3]);
+        for (int kk = 0; kk < D / 16; kk++) {
+#pragma unroll
+          for (int np = 0; np < DKV_QH / 16; np++) {
+            uint32_t bb[4];
+            ldb_nk(bb, bQ, LD, ql + np * 16, kk * 16, lane);
+            mma16816(st[2 * np], ka[kk], bb[0], bb[1]);
+            mma16816(st[2 * np + 1], ka[kk], bb[2], bb[3]);
+            ldb_nk(bb, bdO, LD, ql + np * 16, kk * 16, lane);
+            mma16816(dpt[2 * np], va[kk], bb[0], bb[1]);
+            mma16816(dpt[2 * np + 1], va[kk], bb[2], bb[3]);
+          }
+        }
+        uint32_t pta[DKV_QH / 16][4], dsta[DKV_QH / 16][4];
+#pragma unroll
+        for (int nt = 0; nt < DKV_QH / 8; nt++) {
+          const int qi = qb + nt * 8 + 2 * tig;
+          const float2 ls = *reinterpret_cast<const float2*>(sLse + qi);
+          const float2 dl = *reinterpret_cast<const float2*>(sDelta + qi);
+          float p0 = ex2f(fmaf(st[nt][0], c2, mk0 - ls.x)), p1 = ex2f(fmaf(st[nt][1], c2, mk0 - ls.y));
+          float p2 = ex2f(fmaf(st[nt][2], c2, mk1 - ls.x)), p3 = ex2f(fmaf(st[nt][3], c2, mk1 - ls.y));
+          float m0 = 1.f, m1 = 1.f, m2 = 1.f, m3 = 1.f;
+          if (DROP) {
+            const uint2 rk = *reinterpret_cast<const uint2*>(sRowKey + qi);
+            m0 = attn_drop_one(rk.x, key0, drop_thr, inv_keep);
+            m1 = attn_drop_one(rk.y, key0, drop_thr, inv_keep);
+            m2 = attn_drop_one(rk.x, key0 + 8, drop_thr, inv_keep);
+            m3 = attn_drop_one(rk.y, key0 + 8, drop_thr, inv_keep);
+          }
+          dsta[nt >> 1][(nt & 1) * 2] = pack2(p0 * (dpt[nt][0] * m0 - dl.x), p1 * (dpt[nt][1] * m1 - dl.y));
+          dsta[nt >> 1][(nt & 1) * 2 + 1] = pack2(p2 * (dpt[nt][2] * m2 - dl.x), p3 * (dpt[nt][3] * m3 - dl.y));
+          pta[nt >> 1][(nt & 1) * 2] = pack2(p0 * m0, p1 * m1);
+          pta[nt >> 1][(nt & 1) * 2 + 1] = pack2(p2 * m2, p3 * m3);
+        }
+#pragma unroll
+        for (int kk = 0; kk < DKV_QH / 16; kk++) {
+#pragma unroll
+          for (int dd = 0; dd < D / 16; dd++) {
+            uint32_t bb[4];
+            ldb_kn(bb, bdO, LD, ql + kk * 16, dd * 16, lane);
+            mma16816(dv[2 * dd], pta[kk], bb[0], bb[1]);
+            mma16816(dv[2 * dd + 1], pta[kk], bb[2], bb[3]);
+            ldb_kn(bb, bQ, LD, ql + kk * 16, dd * 16, lane);
+            mma16816(dk[2 * dd], dsta[kk], bb[0], bb[1]);
+            mma16816(dk[2 * dd + 1], dsta[kk], bb[2], bb[3]);
+          }
+        }
       }
     }
-    uint32_t pta[KB / 16][4], dsta[KB / 16][4];
-#pragma unroll
-    for (int nt = 0; nt < KB / 8; nt++) {
-      const int qi = qb + nt * 8 + 2 * tig;
-      const float2 ls = *reinterpret_cast<const float2*>(sLse + qi);
-      const float2 dl = *reinterpret_cast<const float2*>(sDelta + qi);
-      float p0 = ex2f(fmaf(st[nt][0], c2, mk0 - ls.x)), p1 = ex2f(fmaf(st[nt][1], c2, mk0 - ls.y));
-      float p2 = ex2f(fmaf(st[nt][2], c2, mk1 - ls.x)), p3 = ex2f(fmaf(st[nt][3], c2, mk1 - ls.y));
-      float m0 = 1.f, m1 = 1.f, m2 = 1.f, m3 = 1.f;
-      if (DROP) {
-        const uint2 rk = *reinterpret_cast<const uint2*>(sRowKey + qi);
-        m0 = attn_drop_one(rk.x, key0, drop_thr, inv_keep);
-        m1 = attn_drop_one(rk.y, key0, drop_thr, inv_keep);
-        m2 = attn_drop_one(rk.x, key0 + 8, drop_thr, inv_keep);
-        m3 = attn_drop_one(rk.y, key0 + 8, drop_thr, inv_keep);
-      }
-      dsta[nt >> 1][(nt & 1) * 2] = pack2(p0 * (dpt[nt][0] * m0 - dl.x), p1 * (dpt[nt][1] * m1 - dl.y));
-      dsta[nt >> 1][(nt & 1) * 2 + 1] = pack2(p2 * (dpt[nt][2] * m2 - dl.x), p3 * (dpt[nt][3] * m3 - dl.y));
-      pta[nt >> 1][(nt & 1) * 2] = pack2(p0 * m0, p1 * m1);
-      pta[nt >> 1][(nt & 1) * 2 + 1] = pack2(p2 * m2, p3 * m3);
+    __syncthreads();   // every warp is done with this stage: refill it with the block two ahead
+    if (j + 2 < nqb) {
+      stage_rows_range<D>(qg + (int64_t)(j + 2) * KB * p.ldq, p.ldq, 0, KB, p.Sq - (j + 2) * KB, sQ + buf * KB * LD);
+      stage_rows_range<D>(og + (int64_t)(j + 2) * KB * p.ldo, p.ldo, 0, KB, p.Sq - (j + 2) * KB, sdO + buf * KB * LD);
     }
-#pragma unroll
-    for (int kk = 0; kk < KB / 16; kk++) {
-#pragma unroll
-      for (int dd = 0; dd < D / 16; dd++) {
-        uint32_t bb[4];
-        ldb_kn(bb, sdO, LD, qb + kk * 16, dd * 16, lane);
-        mma16816(dv[2 * dd], pta[kk], bb[0], bb[1]);
-        mma16816(dv[2 * dd + 1], pta[kk], bb[2], bb[3]);
-        ldb_kn(bb, sQ, LD, qb + kk * 16, dd * 16, lane);
-        mma16816(dk[2 * dd], dsta[kk], bb[0], bb[1]);
-        mma16816(dk[2 * dd + 1], dsta[kk], bb[2], bb[3]);
-      }
-    }
+    cp_commit();
   }
   if (!active) return;
 #pragma unroll
@@ -966,11 +996,10 @@ size_t dq_smem(int Sk) {
   return (size_t)2 * skp * (D + 8) * 2 + (size_t)2 * LNW * 16 * (D + 8) * 2 + (size_t)skp * 4 + (size_t)2 * LNW * 16 * 4;
 }
 template <int D>
-size_t dkv_smem(int Sq, int nw) {
+size_t dkv_smem(int Sq) {
   const int sqp = (Sq + KB - 1) / KB * KB;
-  return (size_t)2 * sqp * (D + 8) * 2 + (size_t)2 * nw * 16 * (D + 8) * 2 + (size_t)3 * sqp * 4;
+  return (size_t)4 * KB * (D + 8) * 2 + (size_t)2 * DKV_KT * (D + 8) * 2 + (size_t)3 * sqp * 4;
 }
-inline int dkv_warps(int Sk) { return Sk <= 64 ? 4 : LNW; }
 
 template <class K>
 int set_smem(K kern, size_t sm, size_t& configured) {
@@ -986,7 +1015,7 @@ template <int D>
 bool long_fwd_ok(int Sq, int Sk) { return Sq > QT && fwd_long_smem<D>(Sk) <= SMEM_LIMIT; }
 template <int D>
 bool long_bwd_ok(int Sq, int Sk) {
-  return Sq > QT && dq_smem<D>(Sk) <= SMEM_LIMIT && dkv_smem<D>(Sq, dkv_warps(Sk)) <= SMEM_LIMIT;
+  return Sq > QT && dq_smem<D>(Sk) <= SMEM_LIMIT && dkv_smem<D>(Sq) <= SMEM_LIMIT;
 }
 
 template <int D>
@@ -1002,23 +1031,16 @@ int launch_fwd_long(const AttnParams& p, cudaStream_t st) {
 template <int D>
 int launch_bwd_long(const AttnParams& p, cudaStream_t st) {
   const size_t sm = dq_smem<D>(p.Sk);
-  static size_t c0[2] = {0, 0}, c1[2] = {0, 0}, c2[2] = {0, 0};
+  static size_t c0[2] = {0, 0}, c1[2] = {0, 0};
   const bool drop = p.drop_p > 0.f;
   auto kq = drop ? attn_bwd_dq_kernel<D, true> : attn_bwd_dq_kernel<D, false>;
   if (int rc = set_smem(kq, sm, c0[drop])) return rc;
   kq<<<dim3(p.B * p.H, ceil_div(p.Sq, LNW * 16)), LNW * 32, sm, st>>>(p);
-  const int nw = dkv_warps(p.Sk);
-  const size_t sk = dkv_smem<D>(p.Sq, nw);
+  const size_t sk = dkv_smem<D>(p.Sq);
   g_mdhs_launches++;
-  if (nw == 4) {
-    auto kk = drop ? attn_bwd_dkv_kernel<D, 4, true> : attn_bwd_dkv_kernel<D, 4, false>;
-    if (int rc = set_smem(kk, sk, c1[drop])) return rc;
-    kk<<<dim3(p.B * p.H, ceil_div(p.Sk, 64)), 128, sk, st>>>(p);
-  } else {
-    auto kk = drop ? attn_bwd_dkv_kernel<D, LNW, true> : attn_bwd_dkv_kernel<D, LNW, false>;
-    if (int rc = set_smem(kk, sk, c2[drop])) return rc;
-    kk<<<dim3(p.B * p.H, ceil_div(p.Sk, LNW * 16)), LNW * 32, sk, st>>>(p);
-  }
+  auto kk = drop ? attn_bwd_dkv_kernel<D, true> : attn_bwd_dkv_kernel<D, false>;
+  if (int rc = set_smem(kk, sk, c1[drop])) return rc;
+  kk<<<dim3(p.B * p.H, ceil_div(p.Sk, DKV_KT)), DKV_NW * 32, sk, st>>>(p);
   MDHS_RETURN_LAST();
 }
 

@@ -319,7 +319,8 @@ def attention_fwd(q, k, v, B, H, Sq, Sk, D, scale, key_mask=None, drop_p=0.0, se
     return o, lse
 
 
-def attention_bwd(q, k, v, o, d_o, lse, B, H, Sq, Sk, D, scale, key_mask=None, drop_p=0.0, seed=0, dq=None, dk=None, dv=None):
+def attention_bwd(q, k, v, o, d_o, lse, B, H, Sq, Sk, D, scale, key_mask=None, drop_p=0.0, seed=0, dq=None, dk=None, dv=None,
+                  delta_scratch=True):
     """dq/dk/dv: optional pre-allocated bf16 views with the same row strides as q/k/v."""
     if dq is None:
         dq = torch.empty((B * Sq, H * D), device=q.device, dtype=torch.bfloat16)
@@ -331,13 +332,16 @@ def attention_bwd(q, k, v, o, d_o, lse, B, H, Sq, Sk, D, scale, key_mask=None, d
     assert dq.stride(0) == q.stride(0) and dk.stride(0) == k.stride(0) and dv.stride(0) == v.stride(0)
     assert d_o.stride(0) == o.stride(0)
     dk32 = dv32 = None
-    if _lib.lib().mdhs_attention_bwd_workspace(Sq, Sk, D):   # a query, not a status: 1 = fp32 accumulation path
+    fp32_path = bool(_lib.lib().mdhs_attention_bwd_workspace(Sq, Sk, D))   # a query, not a status
+    if fp32_path:
         dk32 = torch.zeros((B * Sk, k.stride(0)), device=q.device, dtype=torch.float32)
         dv32 = torch.zeros((B * Sk, v.stride(0)), device=q.device, dtype=torch.float32)
+    elif Sq > 64 and delta_scratch:
+        dk32 = torch.empty((B * H * Sq,), device=q.device, dtype=torch.float32)   # delta, dQ pass -> dK/dV pass
     _lib.call("mdhs_attention_bwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), _p(d_o), o.stride(0),
               _p(key_mask), _p(lse), _p(dq), _p(dk), _p(dv), _p(dk32), _p(dv32), B, H, Sq, Sk, D, float(scale),
               float(drop_p), int(seed), _s())
-    if dk32 is not None:
+    if fp32_path:
         # fp32 accumulators cover the full row stride; copy the head columns back as bf16
         dk.copy_(cast_f32_bf16(dk32)[:, :dk.shape[1]])
         dv.copy_(cast_f32_bf16(dv32)[:, :dv.shape[1]])

@@ -265,6 +265,11 @@ def test_attention(ops, B, H, Sq, Sk, D, masked):
     assert relerr(dq, tok(qr.grad, Sq)) < 2e-2
     assert relerr(dk, tok(kr.grad, Sk)) < 2e-2
     assert relerr(dv, tok(vr.grad, Sk)) < 2e-2
+    if Sq > 64:   # long path without the delta scratch: the dK/dV pass recomputes rowsum(dO * O) itself
+        dkv2 = torch.empty_like(kv)
+        dq2, dk2, dv2 = ops.attention_bwd(q, k, v, o, do, lse, B, H, Sq, Sk, D, scale, key_mask=mask, delta_scratch=False,
+                                          dk=dkv2[:, :H * D], dv=dkv2[:, H * D:])
+        assert torch.equal(dq2, dq) and relerr(dk2, dk) < 1e-3 and relerr(dv2, dv) < 1e-3
 
 
 def test_attention_dropout_statistics(ops):
