@@ -183,10 +183,130 @@ __global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const void* __restrict__
   }
 }
 
+// ---- narrow rows (C <= 128, bf16, no dropout: the ConvNeXt stage-1 / stem LayerNorms with C = 96 / 128 over 401408 rows).
+// A warp per 192-byte row leaves 20 of 32 lanes idle and too few bytes in flight (ncu-less arithmetic: 154 MB in 95 us =
+// 1.6 TB/s).  Here half a warp owns a row and keeps two rows in flight.
+__device__ __forceinline__ float half_sum(float v, unsigned mask) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) ln_fwd_small_kernel(const bf16* __restrict__ x, int64_t ldx, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, bf16* __restrict__ y, int64_t ldy,
+                                                           float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows,
+                                                           int C, float eps) {
+  const int sub = threadIdx.x & 15;
+  const unsigned hmask = 0xffffu << (threadIdx.x & 16);
+  const int64_t row0 = ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 4) * 2;
+  if (row0 >= rows) return;   // whole half-warps leave together
+  const int col = sub * 8;
+  const bool ok = col < C;
+  const bool two = row0 + 1 < rows;
+  float v[2][8];
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    if (ok && (r == 0 || two)) load8(x + (row0 + r) * ldx + col, v[r]);
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; i++) v[r][i] = 0.f;
+    }
+  }
+  float gm[8], bt[8];
+  if (ok) {
+    *reinterpret_cast<float4*>(gm) = *reinterpret_cast<const float4*>(gamma + col);
+    *reinterpret_cast<float4*>(gm + 4) = *reinterpret_cast<const float4*>(gamma + col + 4);
+    *reinterpret_cast<float4*>(bt) = *reinterpret_cast<const float4*>(beta + col);
+    *reinterpret_cast<float4*>(bt + 4) = *reinterpret_cast<const float4*>(beta + col + 4);
+  }
+  const float inv_c = 1.f / (float)C;
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += v[r][i];
+    const float mean = half_sum(s, hmask) * inv_c;
+    float q = 0.f;
+    if (ok) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const float d = v[r][i] - mean;
+        q += d * d;
+      }
+    }
+    const float rstd = rsqrtf(half_sum(q, hmask) * inv_c + eps);
+    if (r == 1 && !two) break;
+    if (sub == 0) {
+      if (mean_out) mean_out[row0 + r] = mean;
+      if (rstd_out) rstd_out[row0 + r] = rstd;
+    }
+    if (ok) {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) o[i] = (v[r][i] - mean) * rstd * gm[i] + bt[i];
+      store8(y + (row0 + r) * ldy + col, o);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) ln_bwd_dx_small_kernel(const bf16* __restrict__ dy, int64_t lddy, const bf16* __restrict__ x,
+                                                              int64_t ldx, const float* __restrict__ mean_in,
+                                                              const float* __restrict__ rstd_in, const float* __restrict__ gamma,
+                                                              bf16* __restrict__ dx, int64_t lddx, int rows, int C) {
+  const int sub = threadIdx.x & 15;
+  const unsigned hmask = 0xffffu << (threadIdx.x & 16);
+  const int64_t row0 = ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 4) * 2;
+  if (row0 >= rows) return;
+  const int col = sub * 8;
+  const bool ok = col < C;
+  const bool two = row0 + 1 < rows;
+  float xv[2][8], dv[2][8];
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    if (ok && (r == 0 || two)) {
+      load8(x + (row0 + r) * ldx + col, xv[r]);
+      load8(dy + (row0 + r) * lddy + col, dv[r]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; i++) xv[r][i] = dv[r][i] = 0.f;
+    }
+  }
+  float gm[8];
+  if (ok) {
+    *reinterpret_cast<float4*>(gm) = *reinterpret_cast<const float4*>(gamma + col);
+    *reinterpret_cast<float4*>(gm + 4) = *reinterpret_cast<const float4*>(gamma + col + 4);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; i++) gm[i] = 0.f;
+  }
+  const float inv_c = 1.f / (float)C;
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    const bool live = r == 0 || two;
+    const float mean = live ? mean_in[row0 + r] : 0.f, rstd = live ? rstd_in[row0 + r] : 0.f;
+    float xh[8], g[8], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      xh[i] = ok ? (xv[r][i] - mean) * rstd : 0.f;
+      g[i] = dv[r][i] * gm[i];
+      s1 += g[i];
+      s2 = fmaf(g[i], xh[i], s2);
+    }
+    s1 = half_sum(s1, hmask) * inv_c;
+    s2 = half_sum(s2, hmask) * inv_c;
+    if (live && ok) {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) o[i] = rstd * (g[i] - s1 - xh[i] * s2);
+      store8(dx + (row0 + r) * lddx + col, o);
+    }
+  }
+}
+
 // Backward, parameter gradients: dgamma[c] += sum_r dy'[r,c] * xhat[r,c], dbeta[c] += sum_r dy'[r,c] (dy' = dy times the
 // forward output-dropout mask).  Column reduction with the bn_bwd_reduce thread layout: block = 32 channel vectors(8) x 8
 // row lanes over a 256-column slab, grid = (slabs, row blocks), fp32 atomics at the end.
-template <bool XF32, bool DYF32>
+template <bool XF32, bool DYF32, int CVW>
 __global__ void __launch_bounds__(256) ln_bwd_param_kernel(const void* __restrict__ dy_, int64_t lddy, const void* __restrict__ x_,
                                                            int64_t ldx, const float* __restrict__ mean_in,
                                                            const float* __restrict__ rstd_in, float* __restrict__ dgamma,
@@ -196,9 +316,12 @@ __global__ void __launch_bounds__(256) ln_bwd_param_kernel(const void* __restric
   // bsrc / dbias (optional): dbias[c] += sum_r bsrc[r, c] -- the bias gradient of the dense layer that fed this LayerNorm's
   // residual sum (its output gradient is the dx / dx_drop that ln_bwd_dx just wrote): one more bf16 read here instead of a
   // separate column-sum launch (24 of the 61 col_stats launches of a BERT-base step).
-  __shared__ float sh[3][8][256 + 8];
-  const int cv = threadIdx.x & 31, rl = threadIdx.x >> 5;
-  const int c0 = blockIdx.x * 256 + cv * 8;
+  // CVW channel vectors x (256 / CVW) row lanes: 32 x 8 in general, 16 x 16 for C <= 128 (C = 96: 12 of 16 lanes busy
+  // instead of 12 of 32)
+  constexpr int RL = 256 / CVW, SLAB = CVW * 8;
+  __shared__ float sh[3][RL][SLAB + 8];
+  const int cv = threadIdx.x % CVW, rl = threadIdx.x / CVW;
+  const int c0 = blockIdx.x * SLAB + cv * 8;
   const bool ok = c0 < C;
   const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   float a[8], b[8], cb[8];
@@ -207,7 +330,8 @@ __global__ void __launch_bounds__(256) ln_bwd_param_kernel(const void* __restric
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(rows, r0 + rows_per_block);
   if (ok) {
-    for (int r = r0 + rl; r < r1; r += 8) {
+#pragma unroll 2
+    for (int r = r0 + rl; r < r1; r += RL) {
       float xv[8], dyv[8];
       if (bsrc) {
         float bv[8];
@@ -248,11 +372,11 @@ __global__ void __launch_bounds__(256) ln_bwd_param_kernel(const void* __restric
     sh[2][rl][cv * 8 + k] = cb[k];
   }
   __syncthreads();
-  const int c = blockIdx.x * 256 + threadIdx.x;
-  if (c < C) {
+  const int c = blockIdx.x * SLAB + threadIdx.x;
+  if (threadIdx.x < SLAB && c < C) {
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; w++) {
+    for (int w = 0; w < RL; w++) {
       s0 += sh[0][w][threadIdx.x];
       s1 += sh[1][w][threadIdx.x];
       s2 += sh[2][w][threadIdx.x];
@@ -755,6 +879,11 @@ extern "C" int mdhs_layernorm_fwd(const void* x, int x_f32, int64_t ldx, const f
     else if (C <= 1024) LNF(XF, 4);    \
     else LNF(XF, 8);                   \
   } while (0)
+  if (!x_f32 && C <= 128 && y_bf16 && !y_f32 && drop_p <= 0.f) {
+    ln_fwd_small_kernel<<<ceil_div(rows, 32), 256, 0, st>>>((const bf16*)x, ldx, gamma, beta, (bf16*)y_bf16, ldy, mean, rstd, rows, C,
+                                                            eps);
+    MDHS_RETURN_LAST();
+  }
   if (x_f32) LNF_N(true); else LNF_N(false);
 #undef LNF_N
 #undef LNF
@@ -784,7 +913,11 @@ extern "C" int mdhs_layernorm_bwd(const void* dy, int dy_f32, int64_t lddy, cons
     else if (C <= 1024) LNB1(XF, DF, 4);\
     else LNB1(XF, DF, 8);               \
   } while (0)
-  if (x_f32) {
+  const bool narrow = !x_f32 && !dy_f32 && C <= 128;
+  if (narrow && dx_bf16 && !dx_drop_bf16 && !dx_f32 && drop_p <= 0.f) {
+    ln_bwd_dx_small_kernel<<<ceil_div(rows, 32), 256, 0, st>>>((const bf16*)dy, lddy, (const bf16*)x, ldx, mean, rstd, gamma,
+                                                               (bf16*)dx_bf16, lddx, rows, C);
+  } else if (x_f32) {
     if (dy_f32) LNB(true, true); else LNB(true, false);
   } else {
     if (dy_f32) LNB(false, true); else LNB(false, false);
@@ -792,15 +925,19 @@ extern "C" int mdhs_layernorm_bwd(const void* dy, int dy_f32, int64_t lddy, cons
 #undef LNB
 #undef LNB1
   if (params) {
-    const int cslabs = ceil_div(C, 256);
+    const int slab = narrow ? 128 : 256;
+    const int cslabs = ceil_div(C, slab);
     int row_blocks = ((int64_t)mdhs_num_sms() * 4) / cslabs;
     if (row_blocks < 1) row_blocks = 1;
     int rpb = ceil_div(rows, row_blocks);
-    rpb = ((rpb + 7) / 8) * 8;
+    rpb = ((rpb + 15) / 16) * 16;
     row_blocks = ceil_div(rows, rpb);
     const dim3 grid(cslabs, row_blocks);
-#define LNP(XF, DF) ln_bwd_param_kernel<XF, DF><<<grid, 256, 0, st>>>(dy, lddy, x, ldx, mean, rstd, dgamma, dbeta, rows, C, rpb, drop_p, seed, bsrc, lddx, dbias)
-    if (x_f32) {
+#define LNP(XF, DF) ln_bwd_param_kernel<XF, DF, 32><<<grid, 256, 0, st>>>(dy, lddy, x, ldx, mean, rstd, dgamma, dbeta, rows, C, rpb, drop_p, seed, bsrc, lddx, dbias)
+    if (narrow) {
+      ln_bwd_param_kernel<false, false, 16><<<grid, 256, 0, st>>>(dy, lddy, x, ldx, mean, rstd, dgamma, dbeta, rows, C, rpb, drop_p,
+                                                                  seed, bsrc, lddx, dbias);
+    } else if (x_f32) {
       if (dy_f32) LNP(true, true); else LNP(true, false);
     } else {
       if (dy_f32) LNP(false, true); else LNP(false, false);

@@ -44,6 +44,30 @@ def test_layernorm(ops, rows, C, xf32):
     assert relerr(db, br.grad) < 1e-4
 
 
+@pytest.mark.parametrize("rows,C", [(401, 96), (64, 128), (7, 64), (1, 96), (130, 104)])
+def test_layernorm_narrow_rows(ops, rows, C):
+    """C <= 128, bf16 in / out: the half-warp-per-row kernels (ConvNeXt stage-1 LayerNorms), forward, dx, dgamma / dbeta
+    and the fused dense-bias gradient; odd row counts exercise the unpaired last row."""
+    torch.manual_seed(1)
+    x = (torch.randn(rows, C, device="cuda") * 2 + 0.5).bfloat16()
+    g = torch.randn(C, device="cuda")
+    b = torch.randn(C, device="cuda")
+    y, _, mean, rstd = ops.layernorm_fwd(x, g, b, 1e-6)
+    xr = x.float().requires_grad_(True)
+    gr, br = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = F.layer_norm(xr, (C,), gr, br, 1e-6)
+    assert relerr(y, ref) < 1e-2
+    assert relerr(mean, xr.detach().mean(1)) < 1e-5
+    dy = torch.randn(rows, C, device="cuda").bfloat16()
+    ref.backward(dy.float())
+    dg, db, dbias = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dx, _, _ = ops.layernorm_bwd(dy, x, mean, rstd, g, dg, db, dbias=dbias)
+    assert relerr(dx, xr.grad) < 1e-2
+    assert relerr(dg, gr.grad) < 1e-4
+    assert relerr(db, br.grad) < 1e-4
+    assert relerr(dbias, dx.float().sum(0)) < 1e-4
+
+
 def test_layernorm_dropout_consistency(ops):
     """Forward output dropout and the backward mask come from the same stateless hash."""
     torch.manual_seed(1)
@@ -168,6 +192,34 @@ def test_stem_im2col(ops):
     y = ops.gemm(col, wp)
     ref = F.conv2d(x.bfloat16().float(), w.bfloat16().float(), stride=2, padding=3)
     assert relerr(ops.nhwc_bf16_to_nchw_f32(y, B, Ho, Wo, 64), ref) < 1e-2
+
+
+@pytest.mark.parametrize("R,stride,pad,H,W", [(7, 2, 3, 224, 224), (4, 4, 0, 64, 96), (3, 1, 1, 17, 23)])
+def test_stem_im2col_matches_unfold(ops, R, stride, pad, H, W):
+    """Patch matrix of an NCHW fp32 image (ResNet stem 7x7/2, ConvNeXt patchify 4x4/4, an odd 3x3) against F.unfold, including
+    the zero padding columns up to ldk."""
+    torch.manual_seed(0)
+    B, C = 3, 3
+    x = torch.randn(B, C, H, W, device="cuda")
+    K = R * R * C
+    ldk = (K + 7) // 8 * 8
+    col, Ho, Wo = ops.im2col_nchw_f32(x, R, R, stride, pad, ldk)
+    ref = F.unfold(x.bfloat16().float(), R, padding=pad, stride=stride)            # [B, C*R*R, L], rows ordered (c, r, s)
+    ref = ref.view(B, C, R * R, Ho * Wo).permute(0, 3, 2, 1).reshape(B * Ho * Wo, K)  # -> (r, s, c)
+    assert torch.equal(col[:, :K].float(), ref)
+    assert not col[:, K:].any()
+
+
+def test_stem_im2col_tta_variants(ops):
+    """TTA variants through the patch-matrix addressing equal the patch matrix of the explicitly augmented batch."""
+    torch.manual_seed(0)
+    B, H = 2, 32
+    x = torch.randn(B, 3, H, H, device="cuda")
+    names = ["hflip", "vflip", "rot90"]
+    col, Ho, Wo = ops.im2col_nchw_f32(x, 7, 7, 2, 3, 152, tta=ops.tta_codes(names))
+    aug = torch.cat([x, x.flip(3), x.flip(2), torch.rot90(x, 1, (2, 3))])
+    ref, _, _ = ops.im2col_nchw_f32(aug.contiguous(), 7, 7, 2, 3, 152)
+    assert torch.equal(col, ref)
 
 
 def test_maxpool(ops):
