@@ -45,6 +45,7 @@ class BertEngine:
         # called with the layer index right after that encoder layer's backward kernels have been enqueued (its parameter
         # gradients are final): the data-parallel trainer starts the layer group's gradient bucket early
         self.on_layer_backward_done = None
+        self._s64 = None   # fp64 [2, K] column-sum workspace of the bias-gradient epilogue
         self.layers = []
         C = self.C
         for layer in bert.encoder.layer:
@@ -107,8 +108,10 @@ class BertEngine:
 
     # ------------------------------------------------------------------ backward
     def _linear_bwd(self, dy, x_in, lin, need_dx=True, residual=None, aux_in=None, dact=ops.ACT_NONE, w16=None,
-                    gw=None, gb=None, bias_done=False):
-        """dy [T,N], x_in [T,K]: accumulates dW, db; returns dx = dy.W (* act'(aux_in)) (+ residual)."""
+                    gw=None, gb=None, bias_done=False, colsum_to=None):
+        """dy [T,N], x_in [T,K]: accumulates dW, db; returns dx = dy.W (* act'(aux_in)) (+ residual).
+        colsum_to (fp32 [K] gradient view): += column sums of dx, taken in the dgrad GEMM's epilogue -- dx is the output
+        gradient of the Linear below, so this is that Linear's bias gradient without a separate pass over dx."""
         st = self.store
         w = lin.weight if lin is not None else None
         w16 = st.w16(w) if w16 is None else w16
@@ -128,7 +131,15 @@ class BertEngine:
                     ops.col_stats(dy, sum32=gb)
         if not need_dx:
             return None
-        dx = ops.gemm(dy, w16, b_mn=True, residual=residual, aux_in=aux_in, dact=dact, M=T, N=K, K=N)
+        s64 = None
+        if colsum_to is not None:
+            if self._s64 is None or self._s64.shape[1] < K:
+                self._s64 = torch.zeros((2, K), device=dy.device, dtype=torch.float64)   # kept zero by sum64_to_grad
+            s64 = self._s64[:, :K]
+        dx = ops.gemm(dy, w16, b_mn=True, residual=residual, aux_in=aux_in, dact=dact, M=T, N=K, K=N,
+                      colsum=None if s64 is None else s64[0], colsumsq=None if s64 is None else s64[1])
+        if s64 is not None:
+            ops.sum64_to_grad(s64[0], s64[1], colsum_to)
         if side is not None:
             runtime.join_side(side)
         return dx
@@ -158,8 +169,9 @@ class BertEngine:
                                                   st.g32(ln2.weight) if tr2 else None, st.g32(ln2.bias) if tr2 else None,
                                                   drop2_p=ph, seed2=s0 + 3, want_dx_drop=ph > 0, dbias=b2)
             g2 = dpre2_d if ph > 0 else dpre2
-            dipre = self._linear_bwd(g2, R["inter"], L["wo2"], aux_in=R["ipre"], dact=ops.ACT_MUL, bias_done=True)
-            dh1 = self._linear_bwd(dipre, R["h1"], L["wi"], residual=dpre2)
+            gbi = st.g32(L["wi"].bias) if L["wi"].weight.requires_grad else None
+            dipre = self._linear_bwd(g2, R["inter"], L["wo2"], aux_in=R["ipre"], dact=ops.ACT_MUL, bias_done=True, colsum_to=gbi)
+            dh1 = self._linear_bwd(dipre, R["h1"], L["wi"], residual=dpre2, bias_done=gbi is not None)
             tr1 = ln1.weight.requires_grad
             b1 = st.g32(L["wo"].bias) if L["wo"].weight.requires_grad else None
             dpre1, dpre1_d, _ = ops.layernorm_bwd(dh1, R["pre1"], R["m1"], R["r1"], ln1.weight.data,

@@ -304,6 +304,56 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_bwd_kernel(const bf16* __res
   }
 }
 
+// Even H and W (the 112 x 112 stem map): a thread owns a 2 x 2 input block and 8 channels.  The block's pixels are reached
+// only from the four windows (i, j), (i, j+1), (i+1, j), (i+1, j+1), through nine (window, tap) pairs in total -- four dy / idx
+// loads serve four input pixels (the per-pixel gather above loads 2.25 windows per pixel on average).
+__global__ void __launch_bounds__(256) maxpool3x3s2_bwd_block_kernel(const bf16* __restrict__ dy, const uint8_t* __restrict__ idx,
+                                                                     bf16* __restrict__ dx, int B, int H, int W, int C, int Ho,
+                                                                     int Wo) {
+  const int cvec = C >> 3, H2 = H >> 1, W2 = W >> 1;
+  const int64_t total = (int64_t)B * H2 * W2 * cvec;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(t % cvec);
+    int64_t q = t / cvec;
+    const int j = (int)(q % W2);
+    q /= W2;
+    const int i = (int)(q % H2);
+    const int b = (int)(q / H2);
+    float g[4][8];       // dy of windows (i,j), (i,j+1), (i+1,j), (i+1,j+1)
+    uint2 tp[4];         // their winning taps (one byte per channel)
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int ho = i + (k >> 1), wo = j + (k & 1);
+      if (ho < Ho && wo < Wo) {
+        const int64_t o = ((((int64_t)b * Ho + ho) * Wo + wo) * cvec + cv) * 8;
+        load8(dy + o, g[k]);
+        tp[k] = *reinterpret_cast<const uint2*>(idx + o);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; c++) g[k][c] = 0.f;
+        tp[k] = make_uint2(0xffffffffu, 0xffffffffu);
+      }
+    }
+    float o00[8], o01[8], o10[8], o11[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      const int sh = (c & 3) * 8;
+      uint32_t t0 = ((c < 4 ? tp[0].x : tp[0].y) >> sh) & 0xffu, t1 = ((c < 4 ? tp[1].x : tp[1].y) >> sh) & 0xffu;
+      uint32_t t2 = ((c < 4 ? tp[2].x : tp[2].y) >> sh) & 0xffu, t3 = ((c < 4 ? tp[3].x : tp[3].y) >> sh) & 0xffu;
+      // tap = r * 3 + s of the input pixel (2 ho - 1 + r, 2 wo - 1 + s) inside window (ho, wo)
+      o00[c] = t0 == 4u ? g[0][c] : 0.f;
+      o01[c] = (t0 == 5u ? g[0][c] : 0.f) + (t1 == 3u ? g[1][c] : 0.f);
+      o10[c] = (t0 == 7u ? g[0][c] : 0.f) + (t2 == 1u ? g[2][c] : 0.f);
+      o11[c] = (t0 == 8u ? g[0][c] : 0.f) + (t1 == 6u ? g[1][c] : 0.f) + (t2 == 2u ? g[2][c] : 0.f) + (t3 == 0u ? g[3][c] : 0.f);
+    }
+    bf16* p = dx + ((((int64_t)b * H + 2 * i) * W + 2 * j) * cvec + cv) * 8;
+    store8(p, o00);
+    store8(p + (int64_t)cvec * 8, o01);
+    store8(p + (int64_t)W * cvec * 8, o10);
+    store8(p + (int64_t)(W + 1) * cvec * 8, o11);
+  }
+}
+
 // Mean over the token axis: x [B, T, C] bf16 -> y [B, C] (fp32 and/or bf16), scaled by `scale`
 // (1/T for a mean; multi-scale fusion averages three pooled vectors with an extra 1/3).
 __global__ void __launch_bounds__(256) mean_tokens_fwd_kernel(const bf16* __restrict__ x, float* __restrict__ y32,
@@ -535,6 +585,11 @@ extern "C" int mdhs_maxpool3x3s2_bwd(const void* dy, const void* idx, void* dx, 
   if (!dy || !dx || !idx || (C % 8)) return MDHS_ERR_ARG;
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   g_mdhs_launches++;
+  if ((H % 2) == 0 && (W % 2) == 0) {
+    maxpool3x3s2_bwd_block_kernel<<<grid_for((int64_t)B * (H / 2) * (W / 2) * (C / 8), 256), 256, 0, ST(stream)>>>(
+        (const bf16*)dy, (const uint8_t*)idx, (bf16*)dx, B, H, W, C, Ho, Wo);
+    MDHS_RETURN_LAST();
+  }
   maxpool3x3s2_bwd_kernel<<<grid_for((int64_t)B * H * W * (C / 8), 256), 256, 0, ST(stream)>>>((const bf16*)dy, (const uint8_t*)idx,
                                                                                                (bf16*)dx, B, H, W, C, Ho, Wo);
   MDHS_RETURN_LAST();

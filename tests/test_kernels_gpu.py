@@ -222,9 +222,11 @@ def test_stem_im2col_tta_variants(ops):
     assert torch.equal(col, ref)
 
 
-def test_maxpool(ops):
+@pytest.mark.parametrize("H", [30, 31, 112])
+def test_maxpool(ops, H):
+    """even sizes: the 2 x 2-block backward; odd: the per-pixel gather"""
     torch.manual_seed(0)
-    B, H, C = 3, 30, 64
+    B, C = 3, 64
     x = torch.randn(B, C, H, H, device="cuda").bfloat16().float()
     xr = x.clone().requires_grad_(True)
     ref = F.max_pool2d(xr, 3, 2, 1)
