@@ -323,6 +323,11 @@ int mdhs_sgd_flat(float* params, float* grads, const void* grads_bf16, float* mo
  * buckets, mibf_net/train_resnet.py:84-88's DDP) runs concurrently, so that the GEMM's CTAs are all co-resident instead of
  * spilling a second wave behind the collective's CTAs. */
 int mdhs_set_sm_reserve(int n);
+/* Work distribution of the persistent GEMM grids: 1 (default; MDHS_GEMM_DYNAMIC=0 in the environment starts with 0) = CTAs
+ * draw work items from a global counter, so a grid that does not get all of its SMs at once (a collective's CTAs, another
+ * stream's kernels) loses nothing but those SMs; 0 = static round-robin.  GEMMs with column statistics in the epilogue and
+ * GEMMs of at most one round of tiles always use the static schedule. */
+int mdhs_set_gemm_dynamic(int on);
 /* lr_dev / step_dev (optional device scalars) override lr / step so a captured CUDA graph of the step can be
  * replayed with a changing learning rate and step count.  mdhs_step_begin: once per step before the forward:
  * ++*step_dev and advance the dropout seed tick folded into every stateless dropout mask. */

@@ -112,6 +112,7 @@ SIGNATURES = {
     "mdhs_sgd_flat": "ppppplffffiippip",
     "mdhs_step_begin": "pp",
     "mdhs_set_sm_reserve": "i",
+    "mdhs_set_gemm_dynamic": "i",
 }
 _CT = {"p": ctypes.c_void_p, "i": ctypes.c_int32, "l": ctypes.c_int64, "f": ctypes.c_float, "u": ctypes.c_uint64}
 

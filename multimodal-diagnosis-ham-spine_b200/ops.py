@@ -426,6 +426,11 @@ def set_sm_reserve(n):
     _lib.call("mdhs_set_sm_reserve", int(n))
 
 
+def set_gemm_dynamic(on):
+    """Dynamic (work-counter) vs static tile scheduling of the persistent GEMM grids."""
+    _lib.call("mdhs_set_gemm_dynamic", int(bool(on)))
+
+
 def adam_flat(params, grads, exp_avg, exp_avg_sq, shadow, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0,
               adamw=True, zero_grad=True, lr_dev=None, step_dev=None, grads_bf16=None, blocks_per_sm=0):
     _lib.call("mdhs_adam_flat", _p(params), _p(grads), _p(grads_bf16), _p(exp_avg), _p(exp_avg_sq), _p(shadow), params.numel(), float(lr),

@@ -203,3 +203,40 @@ def test_gemm_cta_pair_tiles(mdhs, M, N, K, a_mn, b_mn, bn):
         y = ops.gemm(a, b, b_mn=b_mn, colsum=cs, colsumsq=cq, bn_hint=bn)
         assert torch.allclose(cs, y.double().sum(0), rtol=1e-5, atol=2e-2)
         assert torch.allclose(cq, (y.double() ** 2).sum(0), rtol=1e-5, atol=2e-2)
+
+
+@pytest.mark.parametrize("M,N,K", [(16384, 512, 256), (40000 + 72, 256, 64), (20000, 1024, 128), (3000, 4096, 1024)])
+def test_gemm_dynamic_tile_scheduler_matches_static(mdhs, M, N, K):
+    """Several rounds of tiles per CTA: the work-counter schedule (default) must produce exactly what the static round-robin
+    produces -- plain, bias + residual through the prefetched operand box (short K: two box slots), GELU' second output,
+    act' multiply, fp32 output -- and launches must leave their counter slot clean (the same shapes run repeatedly)."""
+    from mdhs_b200 import ops
+    torch.manual_seed(11)
+    a = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda") * 0.1).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda").bfloat16()
+
+    def run():
+        out = {}
+        out["plain"] = ops.gemm(a, w)
+        out["f32"] = ops.gemm(a, w, out_dtype=torch.float32)
+        out["res"] = ops.gemm(a, w, bias=bias, residual=res)
+        aux = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        out["gelu"] = ops.gemm(a, w, bias=bias, act=ops.ACT_GELU_DERIV, aux_out=aux)
+        out["aux"] = aux
+        out["mul"] = ops.gemm(a, w, aux_in=aux, dact=ops.ACT_MUL)
+        out["dgrad"] = ops.gemm(res, w, b_mn=True, M=M, N=K, K=N)          # [M, K] = res . W
+        return out
+    try:
+        ops.set_gemm_dynamic(False)
+        want = run()
+        ops.set_gemm_dynamic(True)
+        for _ in range(3):
+            got = run()
+            for k in want:
+                assert torch.equal(got[k], want[k]), k
+    finally:
+        ops.set_gemm_dynamic(True)
+    ref = a.float() @ w.float().t()
+    assert (want["f32"] - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-3
