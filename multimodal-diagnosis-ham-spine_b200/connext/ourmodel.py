@@ -15,6 +15,7 @@ import torch.nn as nn
 from torchvision import models
 
 from .. import functional as Fm
+from .. import runtime
 from ..encoder import MdhsModule
 from ..mibf_net.bert import BertEncoder as _BertEncoder
 from .convnext import ConvNeXtEngine, SqAttnFn
@@ -143,9 +144,20 @@ class ConvNeXtMoEClassifier(MdhsModule):
         images = batch_data["transformed_image"]
         self.store(images.device)
         B = images.shape[0]
+        branch = None
+        if self.text_encoder is not None and runtime.DUAL_STREAM and images.is_cuda:
+            main = torch.cuda.current_stream()
+            branch = runtime.fork_branch()     # BERT on a second stream, overlapping the ConvNeXt trunk
         tokens, h, w = self.image_encoder.forward_tokens(images)
         feat = Fm.mean_tokens(tokens, B, h * w)                                   # (B, C) fp32
         if self.text_encoder is not None:
-            cls = self.text_encoder(batch_data["input_ids"], batch_data["attention_mask"]).contiguous()
+            if branch is not None:
+                with torch.cuda.stream(branch):
+                    cls = self.text_encoder(batch_data["input_ids"], batch_data["attention_mask"]).contiguous()
+                    cls = runtime.gate_branch_outputs(cls, main, branch)
+                runtime.join_side(branch)
+                runtime.record_on_current(cls)
+            else:
+                cls = self.text_encoder(batch_data["input_ids"], batch_data["attention_mask"]).contiguous()
             feat = torch.cat([Fm.to_f32(cls), feat], dim=1)                      # text first, as moe.py:297 orders it
         return self.moe(feat, loss_coef)

@@ -7,6 +7,7 @@ from torchvision import models
 
 from .. import functional as Fm
 from .. import ops
+from .. import runtime
 from ..encoder import MdhsModule, _TrunkFn
 from ..resnet_engine import ResNetEngine
 from .attention import MultiHeadCrossAttention_v2, SelfAttention
@@ -62,10 +63,21 @@ class Resnet50WithOurs(MdhsModule):
         images = batch_data["transformed_image"]
         st = self.store(images.device)
         B = images.shape[0]
-        text = self.text_encoder(batch_data["input_ids"], batch_data["attention_mask"])          # (B, 768) bf16 view
+        branch = None
+        if runtime.DUAL_STREAM and images.is_cuda:     # BERT on a second stream, overlapping the ResNet trunk
+            main = torch.cuda.current_stream()
+            branch = runtime.fork_branch()
+        else:
+            text = self.text_encoder(batch_data["input_ids"], batch_data["attention_mask"])      # (B, 768) bf16 view
         trainable = any(p.requires_grad for p in self.image_encoder.parameters())
         need = trainable and torch.is_grad_enabled()
         (f4,) = _TrunkFn.apply(st.anchor, images.float(), self._trunk, self.training, ("layer4",), need)
+        if branch is not None:
+            with torch.cuda.stream(branch):
+                text = self.text_encoder(batch_data["input_ids"], batch_data["attention_mask"])
+                text = runtime.gate_branch_outputs(text, main, branch)
+            runtime.join_side(branch)
+            runtime.record_on_current(text)
         pooled = Fm.mean_tokens(f4, B, f4.shape[0] // B)                                          # avg-pool -> (B, 2048) fp32
         fc = self.image_encoder.fc
         image = Fm.linear(Fm.to_bf16(pooled), st, fc.weight, fc.bias)                             # (B, 768) bf16

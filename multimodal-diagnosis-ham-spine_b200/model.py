@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 
 from . import functional as Fm
+from . import runtime
 from .encoder import ImageEncoder, MdhsModule, TextEncoder
 from .modules.fusion_blocks import (BilinearFusionModule, ConcatFusionModule, FusionModule, HadamardFusionModule,
                                     HierarchicalFusionModule, MultiScaleFusionModule, SSMFusionModule, VMambaFusionModule,
@@ -139,9 +140,22 @@ class MultimodalBaselineModel(MdhsModule):
     # ------------------------------------------------------------------ reference call surface
     def forward_features(self, image_input, text_input_ids, text_attention_mask, tabular_input=None, ablation_mode=None):
         self.store(image_input.device)
+        branch = None
+        if runtime.DUAL_STREAM and ablation_mode != "image_only" and image_input.is_cuda:
+            main = torch.cuda.current_stream()
+            branch = runtime.fork_branch()     # forked BEFORE the image encoder is enqueued: the two encoders overlap
         image_tokens, pooled_image = self._encode_image_tokens(image_input, want_pooled=(ablation_mode == "image_only"))
+        text_tokens = None
+        if branch is not None:
+            # enqueued second so that autograd (latest node first) back-propagates the text encoder FIRST, on its stream:
+            # its gradient bucket can leave while the trunk's backward is still being enqueued (train.py)
+            with torch.cuda.stream(branch):
+                text_tokens = self._encode_text(text_input_ids, text_attention_mask)
+                text_tokens = runtime.gate_branch_outputs(text_tokens, main, branch)
+            runtime.join_side(branch)
+            runtime.record_on_current(text_tokens)
         return self._features_from_tokens(image_tokens, pooled_image, text_input_ids, text_attention_mask, tabular_input,
-                                          ablation_mode)
+                                          ablation_mode, text_tokens)
 
     def _features_from_tokens(self, image_tokens, pooled_image, text_input_ids, text_attention_mask, tabular_input,
                               ablation_mode, text_tokens=None):

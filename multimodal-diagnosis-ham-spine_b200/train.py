@@ -217,7 +217,14 @@ class Trainer:
                     self._bert_hi = lo
                     self.sync.reduce_range(lo, hi)
 
+            main_stream = torch.cuda.current_stream()
+
             def bert_backward_then_reduce(ctx, dh, dtaps=None):
+                # with the text encoder on its own stream (runtime.DUAL_STREAM) this runs in that stream's context: the
+                # bucket below also carries the fusion / head gradients, whose kernels were enqueued on the step's stream
+                cur = torch.cuda.current_stream()
+                if cur != main_stream:
+                    cur.wait_stream(main_stream)
                 self._bert_hi = st.total
                 eng.on_layer_backward_done = layer_done
                 try:
