@@ -66,7 +66,9 @@ class Trainer:
         # other model families reduce everything after backward
         # ... and assume ONE image-encoder / text-encoder backward per step: the global-local and multi-slice branches run the
         # trunk twice in train mode (model.py:292-315), so their stage hooks would fire before the gradients are final
-        twice = getattr(model, "global_local_enabled", False) or getattr(model, "sequence_enabled", False)
+        # (the gated model runs the whole feature path twice in train mode, model.py:257-271: same reason)
+        self.gated = bool(getattr(model, "gate_enabled", False))
+        twice = getattr(model, "global_local_enabled", False) or getattr(model, "sequence_enabled", False) or self.gated
         # overlap_comm: "backward" (default, or True) = buckets leave DURING backward ([text encoder | fusion | head] when the
         # BERT backward returns, ResNet layer4 / layer3 per stage, the rest at the end); "pipeline" = all buckets are reduced
         # after backward, the fused optimizer of bucket k alternating with the collective of bucket k+1; False / "none" = one
@@ -251,6 +253,10 @@ class Trainer:
         try:
             if self.forward_loss is not None:
                 loss, logits = self.forward_loss(self.model, images, ids, mask, labels)
+            elif self.gated and self.supcon_weight == 0.0:
+                # scripts/train.py:378 calls model(...): with the dual-expert gate that is NOT classifier(forward_features)
+                logits = self.model(images, ids, mask)
+                loss = self._loss(logits, labels)
             else:
                 feats = self.model.forward_features(images, ids, mask)
                 logits = self.model.classifier(feats)
