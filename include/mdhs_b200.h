@@ -326,7 +326,9 @@ int mdhs_set_sm_reserve(int n);
 /* Work distribution of the persistent GEMM grids: 1 (default; MDHS_GEMM_DYNAMIC=0 in the environment starts with 0) = CTAs
  * draw work items from a global counter, so a grid that does not get all of its SMs at once (a collective's CTAs, another
  * stream's kernels) loses nothing but those SMs; 0 = static round-robin.  GEMMs with column statistics in the epilogue and
- * GEMMs of at most one round of tiles always use the static schedule. */
+ * GEMMs of at most one round of tiles always use the static schedule.  The counter slots (32 KB) are allocated on the device
+ * that is current at the first large GEMM issued outside stream capture: one device per process, like the reference's
+ * one-process-per-GPU DDP launch. */
 int mdhs_set_gemm_dynamic(int on);
 /* lr_dev / step_dev (optional device scalars) override lr / step so a captured CUDA graph of the step can be
  * replayed with a changing learning rate and step count.  mdhs_step_begin: once per step before the forward:
