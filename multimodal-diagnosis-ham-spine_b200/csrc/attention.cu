@@ -1,10 +1,11 @@
 // Fused small-sequence attention (forward + backward) on the tensor cores for every multi-head attention on the
 // path: BERT self-attention (S <= 512, d = 64), nn.MultiheadAttention self/cross attention of the fusion blocks
-// (d = 32; 49..784 queries, <= 512 keys).  One CTA = one (batch, head, 64-query tile); the whole K/V of that head
+// (d = 32; 49..784 queries, <= 512 keys).  Up to 64 queries: one CTA = one (batch, head); the whole K/V of that head
 // stays in shared memory; each warp owns 16 query rows: S = Q K^T and O = P V (and the five products of the
 // backward) are mma.sync m16n8k16 bf16 tiles fed by ldmatrix, with scale + key mask + online softmax + dropout in
-// registers between them.  Probabilities never reach HBM (the backward recomputes them from the saved
-// log-sum-exp).  Buffers are token-major [B*S, ld] bf16 with head h in columns [h*D, (h+1)*D).
+// registers between them.  More than 64 queries: 8-warp forward CTAs and a two-pass backward (dQ pass, then a dK/dV pass
+// whose warps own key rows) -- see "long sequences" below.  Probabilities never reach HBM (the backward recomputes them
+// from the saved log-sum-exp).  Buffers are token-major [B*S, ld] bf16 with head h in columns [h*D, (h+1)*D).
 #include "common.cuh"
 #include "../../include/mdhs_b200.h"
 

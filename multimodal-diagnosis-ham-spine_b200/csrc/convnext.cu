@@ -1,10 +1,11 @@
 // ConvNeXt-specific kernels (torchvision CNBlock as used by ConNexT/models/ourmodel.py:57-62 and the ConvNeXt image
 // encoders of configs 4): NHWC bf16 activations [B*H*W, C].
 //   * depthwise 7x7 convolution (pad 3, groups = C): forward, input gradient (same kernel, mirrored taps) and
-//     weight / bias gradient.  HBM / L1-bound: each thread owns 8 channels (one 16-byte vector) x 4 adjacent output
-//     pixels, so a filter row costs 10 vector loads for 28 tap applications.
+//     weight / bias gradient.  C % 32 == 0 (every ConvNeXt width): TMA-staged halo boxes, a channel pair and a 4 x 7
+//     output tile per thread, the 49 taps in registers, packed fp32 FMAs (dwconv7_tma_kernel / dwconv7_wgrad_tma_kernel).
+//     Other widths: the older kernels (8 channels x 4 pixels per thread, taps read from shared memory).
 //   * layer-scale + stochastic-depth + residual:  out = x + ls[c] * keep(b) * z   and its backward
-//     (dz, dls; dx = dy is the identity branch and needs no kernel).
+//     (dz, dls and the bias gradient of the Linear that produced z; dx = dy is the identity branch and needs no kernel).
 //   * single-query attention (ourmodel.py:17-31 with a 1-token query: the text -> image direction): softmax over the
 //     T image positions of q.k_t (no 1/sqrt(d) in the reference), out = sum_t p_t v_t; forward + backward.
 // The 1x1 / patchify convolutions, LayerNorms and MLPs of the block run on the shared GEMM / LayerNorm kernels.
