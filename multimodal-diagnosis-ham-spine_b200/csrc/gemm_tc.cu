@@ -1,9 +1,11 @@
 // bf16 GEMM for sm_100a: tcgen05.mma with TMEM accumulators, TMA-fed shared-memory pipeline, persistent warp-specialised
 // CTAs (one per SM), optionally paired (cta_group::2).  See include/mdhs_b200.h for the contract, DESIGN.md section 3.1 and
-// profiles/r01_summary.md for the measurements behind each design point.
+// profiles/r01_summary.md / r02_summary.md for the measurements behind each design point.
 //
 //   warp 0      : TMA producer -- the whole warp walks the loop, one elected lane issues -> smem ring of STAGES {A tile, B tile}
-//                 (tiled maps, or im2col maps for implicit-GEMM convolutions; 2SM loads in pair mode)
+//                 (tiled maps, or im2col maps for implicit-GEMM convolutions; 2SM loads in pair mode); also the work-item
+//                 source: it draws items from a global counter and publishes them to the other roles through a shared ring
+//                 (dynamic schedule; the static round-robin remains for GEMMs with per-CTA column statistics)
 //   warp 1      : MMA issuer (elect.sync; the pair's leader CTA only) -> tcgen05.mma into one of two TMEM accumulator stages
 //   warp 2      : TMEM allocator / deallocator
 //   warps 4..11 : epilogue, two groups of four warps (one TMEM lane quarter each): per 64-column box a compact loop over
